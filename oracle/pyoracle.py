@@ -1,0 +1,82 @@
+"""ctypes front-end of oracle/liboracle.so (TEST INFRASTRUCTURE ONLY; see oracle/__init__.py)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def _graph_args(g, se3, pt):
+    d, i = C.c_double, C.c_int
+    return [len(se3), _p(se3, d), len(pt), _p(pt, d),
+            len(g["prior_v"]), _p(g["prior_v"], i), _p(g["prior_Z"], d), _p(g["prior_w"], d),
+            len(g["se3e_ij"]), _p(g["se3e_ij"], i), _p(g["se3e_Z"], d), _p(g["se3e_w"], d), _p(g["se3e_delta"], d),
+            len(g["obs_cp"]), _p(g["obs_cp"], i), _p(g["obs_z"], d), _p(g["obs_w"], d), _p(g["obs_delta"], d),
+            len(g["ter_pph"]), _p(g["ter_pph"], i), _p(g["ter_w"], d), _p(g["ter_delta"], d)]
+
+
+def ba_optimize(g, max_iters=300, gain_threshold=1e-4, verbose=False):
+    """Runs the oracle LM on graph dict `g` (vdo_slam_b200.synth.make_batch_graph layout).
+    Returns dict(se3, pt, iters, chi2 (len iters+1), stats)."""
+    L = lib()
+    se3 = g["se3"].copy()
+    pt = g["pt"].copy()
+    hist = np.zeros(max_iters + 1)
+    stats = np.zeros(8)
+    L.vdo_oracle_ba_optimize.restype = C.c_int
+    n = L.vdo_oracle_ba_optimize(*_graph_args(g, se3, pt), C.c_int(max_iters), C.c_double(gain_threshold),
+                                 C.c_int(int(verbose)), _p(hist, C.c_double), _p(stats, C.c_double))
+    return dict(se3=se3, pt=pt, iters=n, chi2=hist[: n + 1].copy(),
+                stats=dict(lam=stats[0], trials=int(stats[1]), lnz=int(stats[2]), t_linear=stats[3], t_total=stats[4]))
+
+
+def ba_dense_system(g):
+    L = lib()
+    se3 = g["se3"].copy()
+    pt = g["pt"].copy()
+    n = 3 * len(pt) + 6 * len(se3)
+    H = np.zeros((n, n))
+    b = np.zeros(n)
+    chi = C.c_double(0)
+    L.vdo_oracle_ba_dense_system(*_graph_args(g, se3, pt), _p(H, C.c_double), _p(b, C.c_double), C.byref(chi))
+    return H, b, chi.value
+
+
+def edge_eval(kind, a, b, c):
+    L = lib()
+    a, b, c = (np.ascontiguousarray(x, np.float64) for x in (a, b, c))
+    err = np.zeros(6)
+    Ja, Jb, Jc = np.zeros(36), np.zeros(36), np.zeros(36)
+    L.vdo_oracle_edge_eval(C.c_int(kind), *(_p(x, C.c_double) for x in (a, b, c, err, Ja, Jb, Jc)))
+    return err, Ja, Jb, Jc
+
+
+def iso_oplus(T, upd):
+    T = np.ascontiguousarray(T, np.float64).copy()
+    upd = np.ascontiguousarray(upd, np.float64)
+    lib().vdo_oracle_iso_oplus(_p(T, C.c_double), _p(upd, C.c_double))
+    return T

@@ -1,0 +1,218 @@
+"""Seeded synthetic inputs shaped like the reference's workloads.
+
+`make_batch_graph` emits the factor graph that `Optimizer::FullBatchOptimization` builds from a `Map`
+(/root/reference/src/Optimizer.cc:1350-1755): camera-pose and per-frame object-motion SE(3) vertices,
+static points (one vertex per track) and dynamic points (one vertex per observation), with
+EdgeSE3Prior / EdgeSE3 (odometry, motion smoothness) / EdgeSE3PointXYZ / LandmarkMotionTernaryEdge factors and
+the information / Huber constants of Optimizer.cc:1330-1335,1352 (full) or :190-195,213 (partial window).
+
+No dataset is on disk (KITTI / OMD demo data are external downloads), so everything is procedural.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# float constants exactly as the reference declares them (`const float ...`), promoted to double on use
+FULL_BATCH = dict(sigma2_cam=np.float32(0.001), sigma2_3d_sta=np.float32(80), sigma2_obj_smo=np.float32(0.001),
+                  sigma2_obj=np.float32(100), sigma2_3d_dyn=np.float32(80), huber=np.float32(0.0001), prior_w=100000.0)
+PARTIAL_BATCH = dict(sigma2_cam=np.float32(0.0001), sigma2_3d_sta=np.float32(16), sigma2_obj_smo=np.float32(0.1),
+                     sigma2_obj=np.float32(20), sigma2_3d_dyn=np.float32(16), huber=np.float32(0.0001), prior_w=100000.0)
+
+
+def _rot(axis: np.ndarray, ang: np.ndarray) -> np.ndarray:
+    """Rodrigues; axis (...,3) unit, ang (...) -> (...,3,3)."""
+    axis = np.asarray(axis, np.float64)
+    ang = np.asarray(ang, np.float64)
+    x, y, z = axis[..., 0], axis[..., 1], axis[..., 2]
+    c, s = np.cos(ang), np.sin(ang)
+    C = 1 - c
+    R = np.stack([
+        np.stack([c + x * x * C, x * y * C - z * s, x * z * C + y * s], -1),
+        np.stack([y * x * C + z * s, c + y * y * C, y * z * C - x * s], -1),
+        np.stack([z * x * C - y * s, z * y * C + x * s, c + z * z * C], -1)], -2)
+    return R
+
+
+def iso(R: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """(…,3,3),(…,3) -> (…,12) row-major R then t (the layout every C entry point uses)."""
+    return np.concatenate([R.reshape(R.shape[:-2] + (9,)), t], -1)
+
+
+def iso_R(T):
+    return T[..., :9].reshape(T.shape[:-1] + (3, 3))
+
+
+def iso_t(T):
+    return T[..., 9:12]
+
+
+def iso_mul(A, B):
+    Ra, Rb = iso_R(A), iso_R(B)
+    return iso(Ra @ Rb, (Ra @ iso_t(B)[..., None])[..., 0] + iso_t(A))
+
+
+def iso_inv(A):
+    Rt = np.swapaxes(iso_R(A), -1, -2)
+    return iso(Rt, -(Rt @ iso_t(A)[..., None])[..., 0])
+
+
+def iso_apply(A, p):
+    return (iso_R(A) @ p[..., None])[..., 0] + iso_t(A)
+
+
+def _small_iso(rng, n, sig_t, sig_r):
+    ax = rng.normal(size=(n, 3))
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    return iso(_rot(ax, rng.normal(scale=sig_r, size=n)), rng.normal(scale=sig_t, size=(n, 3)))
+
+
+def make_batch_graph(n_frames=200, n_objects=5, n_static=40000, n_dynamic=10000, seed=4, consts=FULL_BATCH,
+                     obj_span=None, geom_p=0.35, max_len=30, obs_sigma=0.05, odo_sigma_t=0.01,
+                     odo_sigma_r=np.deg2rad(0.1)):
+    """Config 4 (defaults) / config 5 (n_frames=1000, n_objects=50, n_static=800000, n_dynamic=200000,
+    obj_span=(100, 400), seed=5) generator.  Returns a dict of C-contiguous arrays:
+
+      se3 (C,12) f64 initial estimates [cameras 0..N-1, then motion vertices]; se3_gt
+      pt (P,3) f64 initial estimates [static tracks, then dynamic observations in chain order]; pt_gt
+      prior_v (1,) i32, prior_Z (1,12), prior_w (1,)
+      se3e_ij (E,2) i32, se3e_Z (E,12), se3e_w (E,), se3e_delta (E,)      odometry then smoothness edges
+      obs_cp (E,2) i32 [se3 idx, point idx], obs_z (E,3), obs_w, obs_delta
+      ter_pph (E,3) i32 [p1, p2, motion se3 idx], ter_w, ter_delta
+    """
+    rng = np.random.default_rng(seed)
+    N = int(n_frames)
+    # ---- ground-truth camera trajectory: 1 m / frame along a gentle arc (0.3 deg / frame yaw) ----
+    yaw = np.deg2rad(0.3) * np.arange(N)
+    Rwc = _rot(np.tile([0.0, 1.0, 0.0], (N, 1)), yaw)
+    fwd = (Rwc @ np.array([0.0, 0.0, 1.0]))
+    twc = np.concatenate([np.zeros((1, 3)), np.cumsum(fwd[:-1], 0)], 0)
+    cam_gt = iso(Rwc, twc)
+    # odometry measurements Z_i = T_i^-1 T_{i+1} (+ noise); initial estimates = chained odometry from Identity
+    Z = iso_mul(iso_mul(iso_inv(cam_gt[:-1]), cam_gt[1:]), _small_iso(rng, N - 1, odo_sigma_t, odo_sigma_r))
+    cam_est = np.empty_like(cam_gt)
+    cam_est[0] = cam_gt[0]
+    for i in range(N - 1):
+        cam_est[i + 1] = iso_mul(cam_est[i], Z[i])
+
+    # ---- objects: constant world-frame rigid motion, visible over a frame span ----
+    K = int(n_objects)
+    if obj_span is None or K == 0:
+        o_s = np.zeros(K, np.int64)
+        o_e = np.full(K, N - 1, np.int64)
+    else:
+        lo, hi = obj_span
+        span = rng.integers(min(lo, N - 1), min(hi, N - 1) + 1, size=K)
+        o_s = np.array([rng.integers(0, N - s) for s in span], np.int64)
+        o_e = o_s + span
+    # pivot = object centre at its first frame, placed in front of the camera
+    piv = iso_apply(cam_gt[o_s], np.stack([rng.uniform(-8, 8, K), rng.uniform(-1, 1, K), rng.uniform(8, 22, K)], -1)) if K else np.zeros((0, 3))
+    Ro = _rot(np.tile([0.0, 1.0, 0.0], (K, 1)), rng.normal(scale=np.deg2rad(0.4), size=K)) if K else np.zeros((0, 3, 3))
+    vel = (iso_R(cam_gt[o_s]) @ np.stack([rng.normal(scale=0.05, size=K), np.zeros(K), rng.uniform(0.7, 1.3, K)], -1)[..., None])[..., 0] if K else np.zeros((0, 3))
+    Hobj = iso(Ro, piv - (Ro @ piv[..., None])[..., 0] + vel) if K else np.zeros((0, 12))
+    # motion vertex index table: mot_idx[o, k] for transition k -> k+1, k in [o_s, o_e-1]
+    mot_idx = -np.ones((K, max(N - 1, 1)), np.int64)
+    nxt = N
+    mot_obj, mot_k = [], []
+    for k in range(N - 1):                       # frame-major like the reference's vertex creation order
+        for o in range(K):
+            if o_s[o] <= k < o_e[o]:
+                mot_idx[o, k] = nxt
+                nxt += 1
+                mot_obj.append(o)
+                mot_k.append(k)
+    C = nxt
+    mot_obj = np.asarray(mot_obj, np.int64)
+    mot_k = np.asarray(mot_k, np.int64)
+    se3_gt = np.concatenate([cam_gt, Hobj[mot_obj]], 0) if len(mot_obj) else cam_gt.copy()
+    se3 = np.concatenate([cam_est, np.tile(iso(np.eye(3), np.zeros(3)), (len(mot_obj), 1))], 0)  # motions start at Identity (Optimizer.cc:1581)
+
+    def track_lengths(n, cap):
+        L = 3 + rng.geometric(geom_p, size=n) - 1
+        return np.minimum(np.minimum(L, max_len), cap)
+
+    # ---- static tracks ----
+    Ns = int(n_static)
+    Ls = track_lengths(Ns, N)
+    s_start = (rng.random(Ns) * (N - Ls + 1)).astype(np.int64)
+    s_pt_gt = iso_apply(cam_gt[s_start], np.stack([rng.uniform(-15, 15, Ns), rng.uniform(-2, 2, Ns), rng.uniform(5, 40, Ns)], -1))
+    s_tid = np.repeat(np.arange(Ns), Ls)
+    s_frame = s_start[s_tid] + (np.arange(Ls.sum()) - np.repeat(np.cumsum(Ls) - Ls, Ls))
+    s_z = iso_apply(iso_inv(cam_gt[s_frame]), s_pt_gt[s_tid]) + rng.normal(scale=obs_sigma, size=(len(s_tid), 3))
+    first = np.cumsum(Ls) - Ls
+    s_pt_est = iso_apply(cam_est[s_frame[first]], s_z[first])          # Map::vp3DPointSta of the first sighting
+
+    # ---- dynamic tracks ----
+    Nd = int(n_dynamic) if K else 0
+    d_obj = rng.integers(0, K, size=Nd) if Nd else np.zeros(0, np.int64)
+    span_len = (o_e - o_s + 1)
+    Ld = track_lengths(Nd, 10 ** 9)
+    Ld = np.minimum(Ld, span_len[d_obj]) if Nd else Ld
+    d_start = o_s[d_obj] + (rng.random(Nd) * (span_len[d_obj] - Ld + 1)).astype(np.int64) if Nd else np.zeros(0, np.int64)
+    # object centre at frame k: apply H repeatedly to the pivot; tabulate per object
+    centre = np.zeros((K, N, 3))
+    for o in range(K):
+        c = piv[o].copy()
+        for k in range(o_s[o], o_e[o] + 1):
+            centre[o, k] = c
+            c = Ro[o] @ c + iso_t(Hobj[o])
+    p0 = centre[d_obj, d_start] + rng.uniform(-1.0, 1.0, size=(Nd, 3)) if Nd else np.zeros((0, 3))
+    nd_obs = int(Ld.sum()) if Nd else 0
+    d_tid = np.repeat(np.arange(Nd), Ld)
+    d_pos = np.arange(nd_obs) - np.repeat(np.cumsum(Ld) - Ld, Ld)
+    d_frame = d_start[d_tid] + d_pos
+    d_pt_gt = np.zeros((nd_obs, 3))
+    cur = p0.copy()
+    offs = np.cumsum(Ld) - Ld
+    for j in range(int(Ld.max()) if Nd else 0):      # propagate p_{k+1} = H p_k for all tracks still alive
+        alive = np.nonzero(Ld > j)[0]
+        d_pt_gt[offs[alive] + j] = cur[alive]
+        cur[alive] = (Ro[d_obj[alive]] @ cur[alive][..., None])[..., 0] + iso_t(Hobj[d_obj[alive]])
+    d_z = iso_apply(iso_inv(cam_gt[d_frame]), d_pt_gt) + rng.normal(scale=obs_sigma, size=(nd_obs, 3))
+    d_pt_est = iso_apply(cam_est[d_frame], d_z)
+
+    pt_gt = np.concatenate([s_pt_gt, d_pt_gt], 0)
+    pt = np.concatenate([s_pt_est, d_pt_est], 0)
+    P = len(pt)
+
+    # ---- edges ----
+    f = lambda v: 1.0 / float(v)
+    hub = float(consts["huber"])
+    obs_cp = np.concatenate([np.stack([s_frame, s_tid], -1), np.stack([d_frame, Ns + np.arange(nd_obs)], -1)], 0).astype(np.int32)
+    obs_z = np.concatenate([s_z, d_z], 0)
+    obs_w = np.concatenate([np.full(len(s_tid), f(consts["sigma2_3d_sta"])), np.full(nd_obs, f(consts["sigma2_3d_dyn"]))])
+    obs_delta = np.full(len(obs_w), hub)
+    not_last = d_pos < (Ld[d_tid] - 1) if Nd else np.zeros(0, bool)
+    t_p1 = Ns + np.nonzero(not_last)[0]
+    ter_pph = np.stack([t_p1, t_p1 + 1, mot_idx[d_obj[d_tid[not_last]], d_frame[not_last]]], -1).astype(np.int32) if Nd else np.zeros((0, 3), np.int32)
+    assert (ter_pph[:, 2] >= N).all() if len(ter_pph) else True
+    ter_w = np.full(len(ter_pph), f(consts["sigma2_obj"]))
+    ter_delta = np.full(len(ter_pph), hub)
+    # odometry + smoothness (Optimizer.cc:1383-1399, :1596-1623; smoothness only for frame index i>2, i.e. k>=2)
+    odo_ij = np.stack([np.arange(N - 1), np.arange(1, N)], -1)
+    sm = [(mot_idx[o, k - 1], mot_idx[o, k]) for k in range(2, N - 1) for o in range(K) if mot_idx[o, k] >= 0 and mot_idx[o, k - 1] >= 0]
+    sm_ij = np.asarray(sm, np.int64).reshape(-1, 2)
+    se3e_ij = np.concatenate([odo_ij, sm_ij], 0).astype(np.int32)
+    se3e_Z = np.concatenate([Z, np.tile(iso(np.eye(3), np.zeros(3)), (len(sm_ij), 1))], 0)
+    se3e_w = np.concatenate([np.full(N - 1, f(consts["sigma2_cam"])), np.full(len(sm_ij), f(consts["sigma2_obj_smo"]))])
+    se3e_delta = np.full(len(se3e_w), hub)
+
+    g = dict(se3=se3, se3_gt=se3_gt, pt=pt, pt_gt=pt_gt, n_cam=N,
+             prior_v=np.zeros(1, np.int32), prior_Z=cam_est[:1].copy(), prior_w=np.array([float(consts["prior_w"])]),
+             se3e_ij=se3e_ij, se3e_Z=se3e_Z, se3e_w=se3e_w, se3e_delta=se3e_delta,
+             obs_cp=obs_cp, obs_z=obs_z, obs_w=obs_w, obs_delta=obs_delta,
+             ter_pph=ter_pph, ter_w=ter_w, ter_delta=ter_delta)
+    for k, v in list(g.items()):
+        if isinstance(v, np.ndarray):
+            g[k] = np.ascontiguousarray(v, dtype=np.int32 if v.dtype.kind == "i" else np.float64)
+    assert P == g["pt"].shape[0] and C == g["se3"].shape[0]
+    return g
+
+
+def graph_sizes(g) -> dict:
+    return dict(C=len(g["se3"]), P=len(g["pt"]), E_p=len(g["obs_cp"]), E_t=len(g["ter_pph"]), E_o=len(g["se3e_ij"]), E_prior=len(g["prior_v"]))
+
+
+def algorithmic_bytes_per_iter(g) -> int:
+    """bytes one LM linearisation must move in the explicit-block formulation."""
+    s = graph_sizes(g)
+    return 216 * s["E_p"] + 412 * s["E_t"] + 416 * s["E_o"] + 96 * s["P"] + 272 * s["C"]
