@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/sec of the batch factor-graph solve (BASELINE.json metric) on synthetic config-5 data.
+
+A "step" is one complete vdo_graph_optimize() call (the reference's Optimizer::FullBatchOptimization solve: LM up to
+300 iterations, terminate action gain < 1e-4) on the config-5 factor graph, restarted from the same initial estimates
+every step; value = LM iterations executed / device time.  See DESIGN.md section "Measurement".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config5|config4|small]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: generator kwargs
+    "config5": dict(n_frames=1000, n_objects=50, n_static=800000, n_dynamic=200000, seed=5, obj_span=(100, 400)),
+    "config4": dict(n_frames=200, n_objects=5, n_static=40000, n_dynamic=10000, seed=4),
+    "small": dict(n_frames=60, n_objects=3, n_static=6000, n_dynamic=1500, seed=4),
+    # bounded CPU sample of the same generator (about 1/80 of config 5 by edge count)
+    "cpu_sample": dict(n_frames=100, n_objects=3, n_static=10000, n_dynamic=2500, seed=4),
+}
+LM_MAX_ITERS, LM_GAIN = 300, 1e-4
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def graph_h2d_bytes(g) -> int:
+    return int(sum(v.nbytes for k, v in g.items() if isinstance(v, np.ndarray) and not k.endswith("_gt")))
+
+
+def my_algorithmic_bytes(sz) -> dict:
+    """Compulsory HBM bytes per launch of each linearisation kernel in THIS implementation's formulation (DESIGN.md
+    section 'Kernels'): inputs that must be read once + outputs that must be written once; se3 state gathers (<=1.3 MB,
+    L2 resident) are not counted."""
+    Ep, Et, P, C = sz["E_p"], sz["E_t"], sz["P"], sz["C"]
+    return {
+        "k_lin_tracklets": 37 * Ep + 73 * P,                 # edge: cam 4 + z 24 + cls 1 + omega 8 ; landmark: p 24 + begin 4 + h 4 + cls 1 + hll 8 + bl 24 + omega 8
+        "k_vertex_sym_obs": 61 * Ep + 16 * (Ep // 512 + C),   # edge: pt 4 + z 24 + cls 1 + p gather 24 + omega 8 ; chunk descriptor
+        "k_vertex_sym_ter": 61 * Et,                          # edge: p1 4 + cls 1 + two landmark gathers 48 + omega 8
+        "k_schur_landmarks": 12 * Ep + 64 * P,                # edge: cam 4 + omega 8 ; landmark: p 24 + begin 4 + h 4 + omega 8 + s 8 (+bl 24 in modes 0/2) ... + out 24 (x2: fwd+bwd)
+        "k_schur_vertex_obs": 60 * Ep,                        # edge: pt 4 + omega 8 + p 24 + zl 24
+    }
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from vdo_slam_b200 import capi
+    from vdo_slam_b200.synth import make_batch_graph, graph_sizes, algorithmic_bytes_per_iter
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    g = make_batch_graph(**WORKLOADS[args.workload])
+    sz = graph_sizes(g)
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    # ---- device-resident arm: graph already in HBM, each step = reset estimates (D2D) + full LM solve ----
+    G = capi.BatchGraph(ctx, g)
+    info = G.info()
+
+    def step():
+        G.reset()
+        return G.optimize(max_iterations=LM_MAX_ITERS, gain_threshold=LM_GAIN)
+
+    for _ in range(args.warmup):
+        r = step()
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = launches = pcg = 0
+    ms_lin = ms_solve = 0.0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            r = step()
+            iters += r["iterations"]; launches += r["kernel_launches"]; pcg += r["pcg_iterations"]
+            ms_lin += r["ms_linearize"]; ms_solve += r["ms_solve"]
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        t = torch.tensor([float(iters)], device="cuda"); dist.all_reduce(t); iters_all = float(t.item())
+    else:
+        iters_all = float(iters)
+    value = iters_all / (ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers -> C ABI (ingest, H2D, solve, D2H) every step ----
+    h2d = graph_h2d_bytes(g)
+    d2h = int(g["se3"].nbytes + g["pt"].nbytes)
+    e2e_steps = max(1, min(args.steps, 3))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e_iters = 0
+    for _ in range(e2e_steps):
+        G2 = capi.BatchGraph(ctx, g)
+        r2 = G2.optimize(max_iterations=LM_MAX_ITERS, gain_threshold=LM_GAIN)
+        G2.vertices()
+        e_iters += r2["iterations"]
+        G2.close()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+        t = torch.tensor([float(e_iters)], device="cuda"); dist.all_reduce(t); e_iters = float(t.item())
+    e2e_val = e_iters / e2e_s
+
+    # ---- roofline of the linearisation (Jacobian assembly) kernels: CUDA events inside the library, on its stream ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    lin_ms_per_iter = ms_lin / max(iters, 1)
+    mine = my_algorithmic_bytes(sz)
+    lin_bytes = mine["k_lin_tracklets"] + mine["k_vertex_sym_obs"] + mine["k_vertex_sym_ter"]
+    achieved = lin_bytes / (lin_ms_per_iter * 1e-3) / 1e9 if lin_ms_per_iter > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "linearisation = k_lin_tracklets<1> + k_vertex_sym<0,obs> + k_vertex_sym<0,ter> + k_lin_se3_edges<1>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": lin_bytes,
+                "survey_formula_bytes": algorithmic_bytes_per_iter(g), "ms_per_launch": lin_ms_per_iter}
+
+    out = None
+    if rank == 0:
+        cpu = cpu_baseline(args)
+        out = {"metric": "LM iterations/sec (batch factor-graph solve)", "value": value, "unit": "LM iters/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"{args.workload}: " + json.dumps(WORKLOADS[args.workload]), "sizes": sz,
+                          "step": f"one full LM solve (<= {LM_MAX_ITERS} iterations, gain < {LM_GAIN}) from the same initial estimates",
+                          "l2": "edge streams (%.0f MB) exceed the 126 MB L2; no explicit flush" % (info["device_bytes"] / 1e6),
+                          "multi_gpu": "replicas (landmark sharding lands in a later round)" if world > 1 else "single GPU"},
+               "lm_iters_per_step": iters / args.steps, "pcg_iters_per_lm_iter": pcg / max(iters, 1),
+               "ms_linearize_per_lm_iter": lin_ms_per_iter, "ms_solve_per_lm_iter": ms_solve / max(iters, 1),
+               "clocks": clocks, "gpu_launches": launches,
+               "e2e": {"value": e2e_val, "unit": "LM iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "steps": e2e_steps, "note": "host numpy buffers -> vdo_graph_* C ABI (ingest + H2D + solve + D2H) each step"},
+               "roofline": roofline, "cpu_baseline": cpu}
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_baseline(args, budget_iters=6):
+    """The CPU oracle (restatement of the reference's g2o path; the reference itself cannot be built here) on a bounded
+    sample of the same generator, single thread like the reference (G2O_OPENMP off)."""
+    from oracle import pyoracle as po
+    from vdo_slam_b200.synth import make_batch_graph, graph_sizes
+    gs = make_batch_graph(**WORKLOADS["cpu_sample"])
+    sz_s = graph_sizes(gs)
+    full = graph_sizes_cached(args.workload)
+    t0 = time.perf_counter()
+    r = po.ba_optimize(gs, max_iters=budget_iters, gain_threshold=0.0)
+    dt = time.perf_counter() - t0
+    its = r["iters"] / dt
+    scale = (sz_s["E_p"] + sz_s["E_t"]) / float(full["E_p"] + full["E_t"])
+    return {"value": its * scale, "unit": "LM iters/s", "cores": 1, "kind": "port",
+            "sample": f"oracle (oracle/ba_lm.c) on {json.dumps(WORKLOADS['cpu_sample'])}: {r['iters']} LM iterations in {dt:.1f} s = "
+                      f"{its:.3f} it/s on a graph with {scale:.4f} of the workload's edges; value = that rate x edge ratio "
+                      f"(assumes linear cost; the sparse Cholesky is super-linear, so this flatters the CPU)",
+            "sample_iters_per_s": its, "host_cores": os.cpu_count()}
+
+
+_SZ = {}
+
+
+def graph_sizes_cached(name):
+    if name not in _SZ:
+        from vdo_slam_b200.synth import make_batch_graph, graph_sizes
+        _SZ[name] = graph_sizes(make_batch_graph(**WORKLOADS[name]))
+    return _SZ[name]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    w = max(args.warmup, 0)
+    from oracle import pyoracle as po
+    from vdo_slam_b200.synth import make_batch_graph, graph_sizes
+    gs = make_batch_graph(**WORKLOADS["cpu_sample"])
+    sz_s, full = graph_sizes(gs), graph_sizes_cached(args.workload)
+    scale = (sz_s["E_p"] + sz_s["E_t"]) / float(full["E_p"] + full["E_t"])
+    per_step = 2
+    for _ in range(min(w, 1)):
+        po.ba_optimize(gs, max_iters=1, gain_threshold=0.0)
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        its += po.ba_optimize(gs, max_iters=per_step, gain_threshold=0.0)["iters"]
+    dt = time.perf_counter() - t0
+    v = its / dt * scale
+    return {"impl": "reference", "metric": "LM iterations/sec (batch factor-graph solve)", "value": v, "unit": "LM iters/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: " + json.dumps(WORKLOADS[args.workload])},
+            "cpu_baseline": {"value": v, "unit": "LM iters/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                             "sample": f"CPU oracle (restatement of the reference g2o path; the reference cannot be built here: no Eigen3/"
+                                       f"OpenCV/CSparse) on {json.dumps(WORKLOADS['cpu_sample'])}, {per_step} LM iterations per step, "
+                                       f"rate x edge ratio {scale:.4f} to express it in workload-sized iterations"},
+            "e2e": {"value": v, "unit": "LM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config5", choices=[k for k in WORKLOADS if k != "cpu_sample"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+    else:
+        out = run_ours(args, rank, world, local_rank)
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+/*
+ * vdo_b200.h -- C ABI of the B200-native VDO-SLAM hot path (libvdo_b200.so).
+ *
+ * The reference (halajun/VDO_SLAM) has no FFI layer: its hot path is plain C++ inside libObjSLAM.so.
+ * Each entry point below names the reference interface it replaces (paths relative to the reference root;
+ * g2o/ = dependencies/g2o/g2o/).  Host wrappers with the reference's own C++ signatures
+ * (VDO_SLAM::Optimizer, ORBextractor, ...) sit above this ABI; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers + sizes, caller-allocated outputs, int status return (0 = VDO_OK, <0 = error;
+ *     vdo_last_error() gives the text).  No exceptions cross the boundary, nothing calls exit().
+ *   - every pointer is a HOST pointer unless the parameter name ends in _dev.
+ *   - an SE(3) value ("iso") is 12 doubles: rotation row-major (9) then translation (3) -- the memory
+ *     image of g2o's Isometry3 estimate (g2o/types/vertex_se3.h:50) without Eigen's column-major packing.
+ *   - there is NO CPU fallback: every compute entry point fails with VDO_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef VDO_B200_H
+#define VDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDO_OK 0
+#define VDO_ERR_CUDA (-1)        /* CUDA runtime / no device */
+#define VDO_ERR_ARG (-2)         /* bad argument */
+#define VDO_ERR_UNSUPPORTED (-3) /* graph shape outside what the reference's optimisers build */
+#define VDO_ERR_STATE (-4)       /* call order violated */
+#define VDO_ERR_NCCL (-5)
+
+typedef struct vdo_ctx vdo_ctx;     /* one per VDO_SLAM::System (src/System.cc:22-48): device, stream, arenas */
+typedef struct vdo_graph vdo_graph; /* one per g2o::SparseOptimizer instance of the batch optimisers */
+
+int vdo_ctx_create(int device, vdo_ctx **out);
+void vdo_ctx_destroy(vdo_ctx *ctx);
+const char *vdo_last_error(const vdo_ctx *ctx);
+/* cudaStream_t of the context as an integer handle (so torch / callers can order work against it) */
+uint64_t vdo_ctx_stream(const vdo_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch factor-graph optimisation.  Replaces the g2o::SparseOptimizer + OptimizationAlgorithmLevenberg +
+ * BlockSolverX + LinearSolverCSparse stack as driven by Optimizer::FullBatchOptimization
+ * (src/Optimizer.cc:1232-2175) and Optimizer::PartialBatchOptimization (src/Optimizer.cc:42-1230).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* new g2o::SparseOptimizer (src/Optimizer.cc:1312-1323, :172-183) */
+int vdo_graph_create(vdo_ctx *ctx, vdo_graph **out);
+void vdo_graph_destroy(vdo_graph *g);
+
+/* optimizer.addVertex(VertexSE3 / VertexPointXYZ) with setEstimate (src/Optimizer.cc:1359-1363, 1412-1416,
+ * 1571-1582).  se3: n_se3 x 12 iso (camera poses and object motions share one index space), pt: n_pt x 3. */
+int vdo_graph_set_vertices(vdo_graph *g, int n_se3, const double *se3, int n_pt, const double *pt);
+
+/* EdgeSE3Prior, identity offset parameter, information = w * I6, no kernel (src/Optimizer.cc:1364-1373;
+ * g2o/types/edge_se3_prior.cpp:89-102).  v: n se3 indices, Z: n x 12 iso, w: n */
+int vdo_graph_add_edges_se3_prior(vdo_graph *g, int n, const int *v, const double *Z, const double *w);
+
+/* EdgeSE3 (odometry and motion-smoothness edges; src/Optimizer.cc:1383-1399, 1596-1623;
+ * g2o/types/edge_se3.cpp:77-104).  ij: n x 2 se3 indices, Z: n x 12, information = w * I6,
+ * Huber delta (<= 0: no robust kernel). */
+int vdo_graph_add_edges_se3(vdo_graph *g, int n, const int *ij, const double *Z, const double *w, const double *delta);
+
+/* EdgeSE3PointXYZ, identity offset (src/Optimizer.cc:1421-1435; g2o/types/edge_se3_pointxyz.cpp:99-140).
+ * cp: n x 2 (se3 index, point index), z: n x 3 measured point in the camera frame, information = w * I3 */
+int vdo_graph_add_edges_se3_pointxyz(vdo_graph *g, int n, const int *cp, const double *z, const double *w, const double *delta);
+
+/* LandmarkMotionTernaryEdge, measurement 0 (src/Optimizer.cc:1724-1741; g2o/types/types_dyn_slam3d.cpp:53-85).
+ * pph: n x 3 (point p1, point p2, motion se3 index), information = w * I3 */
+int vdo_graph_add_edges_landmark_motion(vdo_graph *g, int n, const int *pph, const double *w, const double *delta);
+
+/* optimizer.initializeOptimization() + BlockSolver::buildStructure (src/Optimizer.cc:1768;
+ * g2o/core/block_solver.hpp:142-295): orders landmarks by tracklet, builds the edge streams, uploads to HBM. */
+int vdo_graph_finalize(vdo_graph *g);
+
+typedef struct vdo_lm_options {
+  int max_iterations;       /* optimizer.optimize(N): 300 full batch, 100 partial (src/Optimizer.cc:1935, :807) */
+  double gain_threshold;    /* SparseOptimizerTerminateAction::setGainThreshold; <= 0: action not installed */
+  int max_trials;           /* maxTrialsAfterFailure, g2o default 10 */
+  double pcg_rel_tol;       /* reduced-camera PCG: stop when sqrt(r.M^-1 r) <= tol * initial; default 1e-10 */
+  int pcg_max_iterations;   /* default 2000 */
+  int verbose;              /* per-iteration line on stderr, like optimizer.setVerbose(true) */
+  int force_all_iterations; /* benchmarking: ignore every stop rule and run exactly max_iterations */
+} vdo_lm_options;
+
+typedef struct vdo_lm_stats {
+  int iterations;           /* return value of SparseOptimizer::optimize */
+  int trials;               /* total LM trials (linear solves) */
+  int pcg_iterations;       /* total PCG iterations over all solves */
+  double initial_chi2, final_chi2, final_lambda;
+  double ms_linearize, ms_solve, ms_total; /* CUDA-event times on the context stream */
+  int kernel_launches;      /* kernels launched by this optimize() call */
+} vdo_lm_stats;
+
+void vdo_lm_options_default(vdo_lm_options *o);
+
+/* optimizer.optimize(max_iterations) (g2o/core/sparse_optimizer.cpp:354-427 with
+ * OptimizationAlgorithmLevenberg::solve, g2o/core/optimization_algorithm_levenberg.cpp:61-164).
+ * chi2_history (may be NULL): max_iterations+1 doubles, [0] = initial robust chi2. */
+int vdo_graph_optimize(vdo_graph *g, const vdo_lm_options *opt, vdo_lm_stats *stats, double *chi2_history);
+
+/* vertex->getEstimateData() (src/Optimizer.cc:2094-2172) */
+int vdo_graph_get_vertices(const vdo_graph *g, double *se3, double *pt);
+/* restore the estimates given to vdo_graph_set_vertices (device-to-device; used to repeat a solve) */
+int vdo_graph_reset_vertices(vdo_graph *g);
+
+/* sizes after finalize: out[0]=n_se3 out[1]=n_pt out[2]=n_pointxyz_edges out[3]=n_motion_edges out[4]=n_se3_edges
+ * out[5]=n_prior out[6]=n_tracklets out[7]=device bytes held */
+int vdo_graph_info(const vdo_graph *g, int64_t out[8]);
+
+/* Test hooks: one linearisation at the current estimates, returned in the caller's vertex numbering.
+ * Hpp_diag: n_se3 x 36 (row-major 6x6 diagonal blocks), bp: n_se3 x 6, Hll_diag: n_pt (scalar: the 3x3
+ * diagonal blocks are that scalar times I3 for scalar information), bl: n_pt x 3, chi2: robust chi2. */
+int vdo_graph_debug_linearize(vdo_graph *g, double *Hpp_diag, double *bp, double *Hll_diag, double *bl, double *chi2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,228 @@
+// tests/emul/ba_backend_emul.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// A serial stand-in for the CUDA backend (vdo_slam_b200/csrc/ba_kernels.cu): "device memory" is malloc, every
+// "kernel" is a for-loop over the same VDO_HD per-thread bodies (ba_bodies.cuh) the CUDA kernels call, and the
+// reductions the kernels do with warp shuffles + atomics are plain sums.  It exists so the -m "not gpu" test-suite
+// can exercise the host logic of the product (graph ingestion, tracklet ordering, LM / Schur / PCG driver in
+// ba_driver.cpp, the C ABI glue in vdo_capi.cpp) in a container without a GPU.  It is compiled into
+// tests/emul/libvdo_emul.so, never into libvdo_b200.so; the product has no CPU path.
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../vdo_slam_b200/csrc/ba_bodies.cuh"
+
+namespace vdo {
+
+struct EmulBackend : BaBackend {
+  int n_launch = 0;
+  std::chrono::steady_clock::time_point t0[4];
+  void* alloc(size_t b) override { return std::calloc(1, b ? b : 1); }
+  void free_(void* p) override { std::free(p); }
+  void h2d(void* d, const void* s, size_t b) override { std::memcpy(d, s, b); }
+  void d2h(void* d, const void* s, size_t b) override { std::memcpy(d, s, b); }
+  void d2d(void* d, const void* s, size_t b) override { std::memcpy(d, s, b); }
+  void zero(void* d, size_t b) override { std::memset(d, 0, b); }
+  void sync() override {}
+  int launches() const override { return n_launch; }
+  void* stream() const override { return nullptr; }
+  void timer_start(int s) override { t0[s] = std::chrono::steady_clock::now(); }
+  float timer_stop_ms(int s) override { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0[s]).count(); }
+
+  void lin_tracklets(BaDev& d, bool write) override {
+    ++n_launch;
+    double chi = 0;
+    for (int t = 0; t < d.T; ++t) chi += body_lin_tracklet(d, t, write);
+    d.scal[SC_CHI2] += chi;
+  }
+  static void add_sym(double* H36, const double* A21) {
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c) {
+        double v = A21[sym6_idx(r, c)];
+        H36[6 * r + c] += v;
+        if (c != r) H36[6 * c + r] += v;
+      }
+  }
+  void lin_vertex_obs(BaDev& d) override {
+    ++n_launch;
+    for (int ci = 0; ci < d.n_obs_chunks; ++ci) {
+      Chunk ch = d.obs_chunks[ci];
+      Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+      double A[21] = {0}, g[6] = {0};
+      for (int e = ch.begin; e < ch.end; ++e) body_lin_vertex_obs(d, T, e, A, g);
+      add_sym(d.Hpp + 36 * (size_t)ch.v, A);
+      for (int i = 0; i < 6; ++i) d.bp[6 * (size_t)ch.v + i] += g[i];
+    }
+  }
+  void lin_vertex_ter(BaDev& d) override {
+    ++n_launch;
+    for (int ci = 0; ci < d.n_ter_chunks; ++ci) {
+      Chunk ch = d.ter_chunks[ci];
+      Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+      double A[21] = {0}, g[6] = {0};
+      for (int e = ch.begin; e < ch.end; ++e) body_lin_vertex_ter(d, T, e, A, g);
+      add_sym(d.Hpp + 36 * (size_t)ch.v, A);
+      for (int i = 0; i < 6; ++i) d.bp[6 * (size_t)ch.v + i] += g[i];
+    }
+  }
+  void lin_se3_edges(BaDev& d, bool write) override {
+    ++n_launch;
+    double chi_tot = 0;
+    for (int e = 0; e < d.Ese; ++e) {
+      double chi, Hi[36], Hj[36], Ho[36], gi[6], gj[6];
+      bool binary = body_se3_edge(d, e, write, chi, Hi, Hj, Ho, gi, gj);
+      chi_tot += chi;
+      if (!write) continue;
+      int i = d.se_i[e];
+      for (int k = 0; k < 36; ++k) d.Hpp[36 * (size_t)i + k] += Hi[k];
+      for (int k = 0; k < 6; ++k) d.bp[6 * (size_t)i + k] += gi[k];
+      if (binary) {
+        int j = d.se_j[e];
+        for (int k = 0; k < 36; ++k) { d.Hpp[36 * (size_t)j + k] += Hj[k]; d.se_Hoff[36 * (size_t)e + k] = Ho[k]; }
+        for (int k = 0; k < 6; ++k) d.bp[6 * (size_t)j + k] += gj[k];
+      }
+    }
+    d.scal[SC_CHI2] += chi_tot;
+  }
+  void max_diagonal(BaDev& d) override {
+    ++n_launch;
+    double m = 0;
+    for (int v = 0; v < d.C; ++v) for (int i = 0; i < 6; ++i) m = std::fmax(m, std::fabs(d.Hpp[36 * (size_t)v + 7 * i]));
+    for (int k = 0; k < d.P; ++k) m = std::fmax(m, std::fabs(d.hll[k]));
+    d.scal[SC_MAXDIAG] = m;
+  }
+  void factor_landmarks(BaDev& d, double lambda) override { ++n_launch; for (int t = 0; t < d.T; ++t) body_factor_tracklet(d, t, lambda); }
+  void precond_begin(BaDev& d, double lambda) override {
+    ++n_launch;
+    for (int v = 0; v < d.C; ++v) {
+      for (int i = 0; i < 36; ++i) d.Minv[36 * (size_t)v + i] = d.Hpp[36 * (size_t)v + i];
+      for (int i = 0; i < 6; ++i) d.Minv[36 * (size_t)v + 7 * i] += lambda;
+    }
+  }
+  void precond_vertex_obs(BaDev& d) override {
+    ++n_launch;
+    for (int ci = 0; ci < d.n_obs_chunks; ++ci) {
+      Chunk ch = d.obs_chunks[ci];
+      Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+      double A[21] = {0};
+      for (int e = ch.begin; e < ch.end; ++e) body_precond_vertex_obs(d, T, e, A);
+      for (int i = 0; i < 21; ++i) A[i] = -A[i];
+      add_sym(d.Minv + 36 * (size_t)ch.v, A);
+    }
+  }
+  void precond_vertex_ter(BaDev& d) override {
+    ++n_launch;
+    for (int ci = 0; ci < d.n_ter_chunks; ++ci) {
+      Chunk ch = d.ter_chunks[ci];
+      Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+      double A[21] = {0};
+      for (int e = ch.begin; e < ch.end; ++e) body_precond_vertex_ter(d, T, e, A);
+      for (int i = 0; i < 21; ++i) A[i] = -A[i];
+      add_sym(d.Minv + 36 * (size_t)ch.v, A);
+    }
+  }
+  void precond_factor(BaDev& d, double lambda) override {
+    ++n_launch;
+    const size_t N36 = 36 * (size_t)d.C;
+    for (int pth = 0; pth < d.n_paths; ++pth) {
+      const int pb = d.path_begin[pth], pe = d.path_begin[pth + 1], nl = pcr_num_levels(pe - pb);
+      int cur = 0;
+      for (int v = pb; v < pe; ++v) body_pcr_setup(d, v, d.pcr_D, d.pcr_L);
+      for (int l = 0; l < nl; ++l) {
+        const double *D = d.pcr_D + cur * N36, *L = d.pcr_L + cur * N36;
+        double *Dn = d.pcr_D + (1 - cur) * N36, *Ln = d.pcr_L + (1 - cur) * N36;
+        for (int v = pb; v < pe; ++v) { int bad = 0; body_pcr_invert(d, v, D, d.pcr_Dinv, lambda, &bad); d.scal[SC_BAD] += bad; }
+        for (int v = pb; v < pe; ++v) body_pcr_reduce(v, pb, pe, 1 << l, D, L, d.pcr_Dinv, Dn, Ln, d.pcr_A + l * N36, d.pcr_G + l * N36);
+        cur = 1 - cur;
+      }
+      for (int v = pb; v < pe; ++v) { int bad = 0; body_pcr_invert(d, v, d.pcr_D + cur * N36, d.Minv, lambda, &bad); d.scal[SC_BAD] += bad; }
+    }
+  }
+  // z = M^-1 r
+  void precond_apply(BaDev& d, const double* r, double* z) {
+    const size_t N6 = 6 * (size_t)d.C, N36 = 36 * (size_t)d.C;
+    for (int pth = 0; pth < d.n_paths; ++pth) {
+      const int pb = d.path_begin[pth], pe = d.path_begin[pth + 1], nl = pcr_num_levels(pe - pb);
+      int cur = 0;
+      for (int v = pb; v < pe; ++v) for (int i = 0; i < 6; ++i) d.pcr_b[6 * (size_t)v + i] = r[6 * (size_t)v + i];
+      for (int l = 0; l < nl; ++l) {
+        for (int v = pb; v < pe; ++v) body_pcr_apply(v, pb, pe, 1 << l, d.pcr_A + l * N36, d.pcr_G + l * N36, d.pcr_b + cur * N6, d.pcr_b + (1 - cur) * N6);
+        cur = 1 - cur;
+      }
+      for (int v = pb; v < pe; ++v) mul6(d.Minv + 36 * (size_t)v, d.pcr_b + cur * N6 + 6 * (size_t)v, z + 6 * (size_t)v);
+    }
+  }
+  void schur_landmarks(BaDev& d, int mode, const double* v) override {
+    ++n_launch;
+    if (mode == 1 && d.scal[SC_DONE] != 0.0) return;
+    double* out = mode == 2 ? d.xl : d.zl;
+    for (int t = 0; t < d.T; ++t) body_schur_tracklet(d, t, mode, v, out);
+  }
+  void schur_vertex_obs(BaDev& d, double sign, double* out) override {
+    ++n_launch;
+    for (int ci = 0; ci < d.n_obs_chunks; ++ci) {
+      Chunk ch = d.obs_chunks[ci];
+      Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+      double a[6] = {0};
+      for (int e = ch.begin; e < ch.end; ++e) body_schur_vertex_obs(d, T, e, a);
+      for (int i = 0; i < 6; ++i) out[6 * (size_t)ch.v + i] += sign * a[i];
+    }
+  }
+  void schur_vertex_ter(BaDev& d, double sign, double* out) override {
+    ++n_launch;
+    for (int ci = 0; ci < d.n_ter_chunks; ++ci) {
+      Chunk ch = d.ter_chunks[ci];
+      Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+      double a[6] = {0};
+      for (int e = ch.begin; e < ch.end; ++e) body_schur_vertex_ter(d, T, e, a);
+      for (int i = 0; i < 6; ++i) out[6 * (size_t)ch.v + i] += sign * a[i];
+    }
+  }
+  void hpp_mul(BaDev& d, double lambda, const double* x, double* out) override {
+    ++n_launch;
+    for (int v = 0; v < d.C; ++v) body_hpp_mul(d, v, lambda, x, out);
+  }
+  void pcg_init(BaDev& d) override {
+    ++n_launch;
+    double rz = 0;
+    for (size_t i = 0; i < 6 * (size_t)d.C; ++i) { d.r[i] = d.rhs[i]; d.xp[i] = 0; }
+    precond_apply(d, d.r, d.z);
+    for (size_t i = 0; i < 6 * (size_t)d.C; ++i) { d.p[i] = d.z[i]; rz += d.z[i] * d.r[i]; }
+    d.scal[SC_RZ] = rz; d.scal[SC_RZ0] = rz; d.scal[SC_RZ_NEW] = 0; d.scal[SC_PAP] = 0; d.scal[SC_ITERS] = 0;
+    d.scal[SC_DONE] = (rz > 0) ? 0.0 : 1.0;
+  }
+  void pcg_dot_pAp(BaDev& d) override {
+    ++n_launch;
+    if (d.scal[SC_DONE] != 0.0) return;
+    double s = 0;
+    for (size_t i = 0; i < 6 * (size_t)d.C; ++i) s += d.p[i] * d.Ap[i];
+    d.scal[SC_PAP] = s;
+  }
+  void pcg_step(BaDev& d, double tol2) override {
+    n_launch += 2;
+    if (d.scal[SC_DONE] != 0.0) return;
+    double pAp = d.scal[SC_PAP], rz = d.scal[SC_RZ];
+    if (!(pAp > 0) || !std::isfinite(pAp)) { d.scal[SC_DONE] = 2.0; return; }
+    double alpha = rz / pAp, rzn = 0;
+    for (size_t q = 0; q < 6 * (size_t)d.C; ++q) { d.xp[q] += alpha * d.p[q]; d.r[q] -= alpha * d.Ap[q]; }
+    precond_apply(d, d.r, d.z);
+    for (size_t q = 0; q < 6 * (size_t)d.C; ++q) rzn += d.z[q] * d.r[q];
+    double beta = rzn / rz;
+    for (size_t i = 0; i < 6 * (size_t)d.C; ++i) d.p[i] = d.z[i] + beta * d.p[i];
+    d.scal[SC_RZ] = rzn; d.scal[SC_ITERS] += 1;
+    if (rzn <= tol2 * d.scal[SC_RZ0]) d.scal[SC_DONE] = 1.0;
+    if (!std::isfinite(rzn)) d.scal[SC_DONE] = 2.0;
+  }
+  void apply_update(BaDev& d, double lambda, bool reortho) override {
+    ++n_launch;
+    double s = 0;
+    for (int v = 0; v < d.C; ++v) s += body_update_se3(d, v, lambda, reortho);
+    for (int k = 0; k < d.P; ++k) s += body_update_pt(d, k, lambda);
+    d.scal[SC_SCALE] += s;
+  }
+};
+
+BaBackend* make_backend(int, char*, size_t) { return new EmulBackend; }
+
+}  // namespace vdo

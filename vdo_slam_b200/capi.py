@@ -1,0 +1,168 @@
+"""ctypes binding of libvdo_b200.so (C ABI in include/vdo_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is no CPU fallback: if the
+shared object is missing or no CUDA device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvdo_b200.so")
+
+
+class LMOptions(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("gain_threshold", C.c_double), ("max_trials", C.c_int),
+                ("pcg_rel_tol", C.c_double), ("pcg_max_iterations", C.c_int), ("verbose", C.c_int),
+                ("force_all_iterations", C.c_int)]
+
+
+class LMStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("trials", C.c_int), ("pcg_iterations", C.c_int),
+                ("initial_chi2", C.c_double), ("final_chi2", C.c_double), ("final_lambda", C.c_double),
+                ("ms_linearize", C.c_double), ("ms_solve", C.c_double), ("ms_total", C.c_double),
+                ("kernel_launches", C.c_int)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class VdoError(RuntimeError):
+    pass
+
+
+_libs = {}
+
+
+def load(path: str | None = None) -> C.CDLL:
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise VdoError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                       "There is no CPU fallback.")
+    L = C.CDLL(path)
+    L.vdo_last_error.restype = C.c_char_p
+    L.vdo_ctx_stream.restype = C.c_uint64
+    _libs[path] = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """vdo_ctx: one per System (device + stream)."""
+
+    def __init__(self, device: int = 0, lib_path: str | None = None):
+        self.L = load(lib_path)
+        self.h = C.c_void_p()
+        rc = self.L.vdo_ctx_create(C.c_int(device), C.byref(self.h))
+        if rc != 0:
+            raise VdoError(f"vdo_ctx_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise VdoError(f"{what} failed with {rc}: {self.L.vdo_last_error(self.h).decode()}")
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.vdo_ctx_stream(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.vdo_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchGraph:
+    """vdo_graph: the factor graph of Optimizer::FullBatchOptimization / PartialBatchOptimization."""
+
+    def __init__(self, ctx: Context, g: dict):
+        """g: dict in the layout of vdo_slam_b200.synth.make_batch_graph."""
+        self.ctx, L = ctx, ctx.L
+        self.h = C.c_void_p()
+        ctx.check(L.vdo_graph_create(ctx.h, C.byref(self.h)), "vdo_graph_create")
+        se3, pt = _f64(g["se3"]), _f64(g["pt"])
+        self.n_se3, self.n_pt = len(se3), len(pt)
+        ctx.check(L.vdo_graph_set_vertices(self.h, len(se3), _dp(se3), len(pt), _dp(pt)), "vdo_graph_set_vertices")
+        if len(g["prior_v"]):
+            v, Z, w = _i32(g["prior_v"]), _f64(g["prior_Z"]), _f64(g["prior_w"])
+            ctx.check(L.vdo_graph_add_edges_se3_prior(self.h, len(v), _ip(v), _dp(Z), _dp(w)), "add_edges_se3_prior")
+        if len(g["se3e_ij"]):
+            ij, Z, w, dl = _i32(g["se3e_ij"]), _f64(g["se3e_Z"]), _f64(g["se3e_w"]), _f64(g["se3e_delta"])
+            ctx.check(L.vdo_graph_add_edges_se3(self.h, len(w), _ip(ij), _dp(Z), _dp(w), _dp(dl)), "add_edges_se3")
+        if len(g["obs_cp"]):
+            cp, z, w, dl = _i32(g["obs_cp"]), _f64(g["obs_z"]), _f64(g["obs_w"]), _f64(g["obs_delta"])
+            ctx.check(L.vdo_graph_add_edges_se3_pointxyz(self.h, len(w), _ip(cp), _dp(z), _dp(w), _dp(dl)), "add_edges_se3_pointxyz")
+        if len(g["ter_pph"]):
+            pph, w, dl = _i32(g["ter_pph"]), _f64(g["ter_w"]), _f64(g["ter_delta"])
+            ctx.check(L.vdo_graph_add_edges_landmark_motion(self.h, len(w), _ip(pph), _dp(w), _dp(dl)), "add_edges_landmark_motion")
+        ctx.check(L.vdo_graph_finalize(self.h), "vdo_graph_finalize")
+
+    def optimize(self, max_iterations=300, gain_threshold=1e-4, pcg_rel_tol=1e-10, pcg_max_iterations=2000,
+                 verbose=False, force_all_iterations=False):
+        o = LMOptions()
+        self.ctx.L.vdo_lm_options_default(C.byref(o))
+        o.max_iterations, o.gain_threshold = int(max_iterations), float(gain_threshold)
+        o.pcg_rel_tol, o.pcg_max_iterations = float(pcg_rel_tol), int(pcg_max_iterations)
+        o.verbose, o.force_all_iterations = int(verbose), int(force_all_iterations)
+        st = LMStats()
+        hist = np.zeros(max_iterations + 1)
+        self.ctx.check(self.ctx.L.vdo_graph_optimize(self.h, C.byref(o), C.byref(st), _dp(hist)), "vdo_graph_optimize")
+        d = st.asdict()
+        d["chi2"] = hist[: st.iterations + 1].copy()
+        return d
+
+    def vertices(self):
+        se3 = np.zeros((self.n_se3, 12))
+        pt = np.zeros((self.n_pt, 3))
+        self.ctx.check(self.ctx.L.vdo_graph_get_vertices(self.h, _dp(se3), _dp(pt)), "vdo_graph_get_vertices")
+        return se3, pt
+
+    def reset(self):
+        self.ctx.check(self.ctx.L.vdo_graph_reset_vertices(self.h), "vdo_graph_reset_vertices")
+
+    def info(self):
+        out = (C.c_int64 * 8)()
+        self.ctx.check(self.ctx.L.vdo_graph_info(self.h, out), "vdo_graph_info")
+        return dict(zip(["n_se3", "n_pt", "n_pointxyz_edges", "n_motion_edges", "n_se3_edges", "n_prior", "n_tracklets", "device_bytes"], list(out)))
+
+    def debug_linearize(self):
+        Hpp = np.zeros((self.n_se3, 6, 6)); bp = np.zeros((self.n_se3, 6)); Hll = np.zeros(self.n_pt); bl = np.zeros((self.n_pt, 3))
+        chi = C.c_double(0)
+        self.ctx.check(self.ctx.L.vdo_graph_debug_linearize(self.h, _dp(Hpp), _dp(bp), _dp(Hll), _dp(bl), C.byref(chi)), "debug_linearize")
+        return Hpp, bp, Hll, bl, chi.value
+
+    def close(self):
+        if self.h:
+            self.ctx.L.vdo_graph_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

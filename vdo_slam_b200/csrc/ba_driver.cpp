@@ -1,0 +1,478 @@
+// ba_driver.cpp -- see ba_driver.h.  Pure host C++: no CUDA calls here, everything device-side goes through BaBackend.
+#include "ba_driver.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+namespace vdo {
+
+BaGraph::~BaGraph() {
+  for (void* p : owned_) be_->free_(p);
+}
+
+int BaGraph::set_vertices(int n_se3, const double* se3, int n_pt, const double* pt) {
+  if (finalized_) return fail(VDO_ERR_STATE, "set_vertices after finalize");
+  if (n_se3 < 0 || n_pt < 0 || (n_se3 && !se3) || (n_pt && !pt)) return fail(VDO_ERR_ARG, "set_vertices: bad arguments");
+  n_se3_ = n_se3; n_pt_ = n_pt;
+  h_se3_.assign(se3, se3 + 12 * (size_t)n_se3);
+  h_pt_.assign(pt, pt + 3 * (size_t)n_pt);
+  return VDO_OK;
+}
+int BaGraph::add_prior(int n, const int* v, const double* Z, const double* w) {
+  if (finalized_) return fail(VDO_ERR_STATE, "add after finalize");
+  for (int i = 0; i < n; ++i) if (v[i] < 0 || v[i] >= n_se3_) return fail(VDO_ERR_ARG, "prior edge: vertex out of range");
+  pr_v_.insert(pr_v_.end(), v, v + n); pr_Z_.insert(pr_Z_.end(), Z, Z + 12 * (size_t)n); pr_w_.insert(pr_w_.end(), w, w + n);
+  return VDO_OK;
+}
+int BaGraph::add_se3(int n, const int* ij, const double* Z, const double* w, const double* delta) {
+  if (finalized_) return fail(VDO_ERR_STATE, "add after finalize");
+  for (int i = 0; i < 2 * n; ++i) if (ij[i] < 0 || ij[i] >= n_se3_) return fail(VDO_ERR_ARG, "se3 edge: vertex out of range");
+  for (int i = 0; i < n; ++i) if (ij[2 * i] == ij[2 * i + 1]) return fail(VDO_ERR_ARG, "se3 edge: self loop");
+  se_ij_.insert(se_ij_.end(), ij, ij + 2 * (size_t)n); se_Z_.insert(se_Z_.end(), Z, Z + 12 * (size_t)n);
+  se_w_.insert(se_w_.end(), w, w + n); se_d_.insert(se_d_.end(), delta, delta + n);
+  return VDO_OK;
+}
+int BaGraph::add_obs(int n, const int* cp, const double* z, const double* w, const double* delta) {
+  if (finalized_) return fail(VDO_ERR_STATE, "add after finalize");
+  for (int i = 0; i < n; ++i)
+    if (cp[2 * i] < 0 || cp[2 * i] >= n_se3_ || cp[2 * i + 1] < 0 || cp[2 * i + 1] >= n_pt_) return fail(VDO_ERR_ARG, "pointxyz edge: vertex out of range");
+  ob_cp_.insert(ob_cp_.end(), cp, cp + 2 * (size_t)n); ob_z_.insert(ob_z_.end(), z, z + 3 * (size_t)n);
+  ob_w_.insert(ob_w_.end(), w, w + n); ob_d_.insert(ob_d_.end(), delta, delta + n);
+  return VDO_OK;
+}
+int BaGraph::add_ter(int n, const int* pph, const double* w, const double* delta) {
+  if (finalized_) return fail(VDO_ERR_STATE, "add after finalize");
+  for (int i = 0; i < n; ++i)
+    if (pph[3 * i] < 0 || pph[3 * i] >= n_pt_ || pph[3 * i + 1] < 0 || pph[3 * i + 1] >= n_pt_ || pph[3 * i + 2] < 0 || pph[3 * i + 2] >= n_se3_)
+      return fail(VDO_ERR_ARG, "landmark-motion edge: vertex out of range");
+  te_pph_.insert(te_pph_.end(), pph, pph + 3 * (size_t)n); te_w_.insert(te_w_.end(), w, w + n); te_d_.insert(te_d_.end(), delta, delta + n);
+  return VDO_OK;
+}
+
+namespace {
+struct ClassTable {
+  std::map<std::pair<double, double>, int> ids;
+  std::vector<double> w, d;
+  int get(double ww, double dd) {
+    auto key = std::make_pair(ww, dd > 0 ? dd : 0.0);
+    auto it = ids.find(key);
+    if (it != ids.end()) return it->second;
+    int id = (int)w.size();
+    ids[key] = id; w.push_back(ww); d.push_back(key.second);
+    return id;
+  }
+};
+void make_chunks(const std::vector<int>& begin, std::vector<Chunk>& out) {
+  for (int v = 0; v + 1 < (int)begin.size(); ++v)
+    for (int b = begin[v]; b < begin[v + 1]; b += VDO_CHUNK) out.push_back(Chunk{v, b, std::min(b + VDO_CHUNK, begin[v + 1]), 0});
+}
+}  // namespace
+
+int BaGraph::finalize() {
+  if (finalized_) return fail(VDO_ERR_STATE, "finalize called twice");
+  const int C = n_se3_, P = n_pt_;
+  const int Eo = (int)ob_w_.size(), Et = (int)te_w_.size(), Es = (int)se_w_.size(), Ep = (int)pr_w_.size();
+  // ---- se3 vertices: renumber so that every path of the se3-se3 edge graph (camera odometry chain, per-object
+  //      motion-smoothness chains) is a contiguous, ordered index range; other vertices become singleton paths ----
+  std::vector<int> path_begin;
+  {
+    std::vector<int> deg(C, 0), nb0(C, -1), nb1(C, -1), comp(C);
+    std::iota(comp.begin(), comp.end(), 0);
+    auto find = [&](int x) { while (comp[x] != x) { comp[x] = comp[comp[x]]; x = comp[x]; } return x; };
+    std::vector<char> bad_comp(C, 0);
+    for (int e = 0; e < Es; ++e) {
+      int a = se_ij_[2 * e], b = se_ij_[2 * e + 1];
+      int ra = find(a), rb = find(b);
+      if (ra == rb) bad_comp[ra] = 1;            // cycle or duplicate edge
+      else { comp[ra] = rb; if (bad_comp[ra]) bad_comp[rb] = 1; }
+      if (deg[a] == 0) nb0[a] = b; else if (deg[a] == 1) nb1[a] = b;
+      if (deg[b] == 0) nb0[b] = a; else if (deg[b] == 1) nb1[b] = a;
+      deg[a]++; deg[b]++;
+    }
+    for (int v = 0; v < C; ++v) if (deg[v] > 2) bad_comp[find(v)] = 1;
+    for (int v = 0; v < C; ++v) if (bad_comp[v] && comp[v] == v) { /* propagated below through find() */ }
+    new_se3_of_old_.assign(C, -1);
+    int cnt = 0;
+    for (int v = 0; v < C; ++v) {
+      if (new_se3_of_old_[v] != -1) continue;
+      const bool is_path = !bad_comp[find(v)];
+      if (!is_path || deg[v] == 0) { path_begin.push_back(cnt); new_se3_of_old_[v] = cnt++; continue; }
+      if (deg[v] == 2) continue;                 // interior vertex: reached from its path's smaller endpoint
+      path_begin.push_back(cnt);
+      int prev = -1, cur = v;
+      while (cur != -1) {
+        new_se3_of_old_[cur] = cnt++;
+        int nx = (nb0[cur] != prev) ? nb0[cur] : nb1[cur];
+        if (deg[cur] == 1 && prev != -1) nx = -1;
+        prev = cur; cur = nx;
+      }
+    }
+    for (int v = 0; v < C; ++v) if (new_se3_of_old_[v] == -1) { path_begin.push_back(cnt); new_se3_of_old_[v] = cnt++; }  // safety
+    path_begin.push_back(cnt);
+  }
+  auto S3 = [&](int old_id) { return new_se3_of_old_[old_id]; };
+  // ---- tracklets: chains of landmarks linked by ternary edges ----
+  std::vector<int> next(P, -1), prev(P, -1), ter_of(P, -1);
+  for (int e = 0; e < Et; ++e) {
+    int p1 = te_pph_[3 * e], p2 = te_pph_[3 * e + 1];
+    if (p1 == p2 || next[p1] != -1 || prev[p2] != -1)
+      return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges must form simple chains (one predecessor / successor per landmark)");
+    next[p1] = p2; prev[p2] = p1; ter_of[p1] = e;
+  }
+  new_of_old_.assign(P, -1);
+  std::vector<int> old_of_new(P), tk_begin;
+  int cnt = 0;
+  for (int p = 0; p < P; ++p) {
+    if (prev[p] != -1) continue;
+    tk_begin.push_back(cnt);
+    for (int q = p; q != -1; q = next[q]) { new_of_old_[q] = cnt; old_of_new[cnt++] = q; }
+  }
+  if (cnt != P) return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges contain a cycle");
+  tk_begin.push_back(cnt);
+  const int T = (int)tk_begin.size() - 1;
+
+  ClassTable oc, tc;
+  // ---- landmark-major pointxyz stream ----
+  std::vector<int> lm_begin(P + 1, 0);
+  for (int e = 0; e < Eo; ++e) lm_begin[new_of_old_[ob_cp_[2 * e + 1]] + 1]++;
+  for (int k = 0; k < P; ++k) lm_begin[k + 1] += lm_begin[k];
+  std::vector<int> fill(lm_begin.begin(), lm_begin.end() - 1), lm_cam(Eo), lm_pos(Eo);
+  std::vector<double> lm_z(3 * (size_t)Eo);
+  std::vector<uint8_t> lm_cls(Eo);
+  for (int e = 0; e < Eo; ++e) {
+    int k = new_of_old_[ob_cp_[2 * e + 1]], pos = fill[k]++;
+    lm_pos[e] = pos; lm_cam[pos] = S3(ob_cp_[2 * e]);
+    for (int i = 0; i < 3; ++i) lm_z[3 * (size_t)pos + i] = ob_z_[3 * (size_t)e + i];
+    int cls = oc.get(ob_w_[e], ob_d_[e]);
+    if (cls > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on pointxyz edges");
+    lm_cls[pos] = (uint8_t)cls;
+  }
+  // ---- vertex-major pointxyz stream: walk the landmark-major stream so each vertex's edges stay landmark-sorted ----
+  std::vector<int> vm_begin(C + 1, 0);
+  for (int pos = 0; pos < Eo; ++pos) vm_begin[lm_cam[pos] + 1]++;
+  for (int v = 0; v < C; ++v) vm_begin[v + 1] += vm_begin[v];
+  std::vector<int> vfill(vm_begin.begin(), vm_begin.end() - 1), vm_pt(Eo);
+  std::vector<double> vm_z(3 * (size_t)Eo);
+  std::vector<uint8_t> vm_cls(Eo);
+  {
+    int k = 0;
+    for (int pos = 0; pos < Eo; ++pos) {
+      while (lm_begin[k + 1] <= pos) ++k;
+      int q = vfill[lm_cam[pos]]++;
+      vm_pt[q] = k; vm_cls[q] = lm_cls[pos];
+      for (int i = 0; i < 3; ++i) vm_z[3 * (size_t)q + i] = lm_z[3 * (size_t)pos + i];
+    }
+  }
+  std::vector<Chunk> obs_chunks; make_chunks(vm_begin, obs_chunks);
+  // ---- ternary edges: per landmark (as p1) and motion-vertex-major ----
+  std::vector<int> tk_h(P, -1);
+  std::vector<uint8_t> tk_cls(P, 0);
+  std::vector<int> hm_begin(C + 1, 0);
+  for (int e = 0; e < Et; ++e) {
+    int k = new_of_old_[te_pph_[3 * e]];
+    tk_h[k] = S3(te_pph_[3 * e + 2]);
+    int cls = tc.get(te_w_[e], te_d_[e]);
+    if (cls > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on landmark-motion edges");
+    tk_cls[k] = (uint8_t)cls;
+    hm_begin[S3(te_pph_[3 * e + 2]) + 1]++;
+  }
+  for (int v = 0; v < C; ++v) hm_begin[v + 1] += hm_begin[v];
+  std::vector<int> hfill(hm_begin.begin(), hm_begin.end() - 1), hm_p1(Et);
+  std::vector<uint8_t> hm_cls(Et);
+  for (int k = 0; k < P; ++k) {   // landmark order keeps each motion vertex's edges landmark-sorted
+    if (tk_h[k] < 0) continue;
+    int q = hfill[tk_h[k]]++;
+    hm_p1[q] = k; hm_cls[q] = tk_cls[k];
+  }
+  std::vector<Chunk> ter_chunks; make_chunks(hm_begin, ter_chunks);
+  // ---- se3-se3 edges (priors first, j = -1) and H_pp adjacency ----
+  const int Ese = Ep + Es;
+  std::vector<int> se_i(Ese), se_j(Ese);
+  std::vector<double> se_Z(12 * (size_t)Ese), se_w(Ese), se_d(Ese);
+  for (int e = 0; e < Ep; ++e) { se_i[e] = S3(pr_v_[e]); se_j[e] = -1; se_w[e] = pr_w_[e]; se_d[e] = 0; std::memcpy(&se_Z[12 * (size_t)e], &pr_Z_[12 * (size_t)e], 96); }
+  for (int e = 0; e < Es; ++e) {
+    int q = Ep + e;
+    se_i[q] = S3(se_ij_[2 * e]); se_j[q] = S3(se_ij_[2 * e + 1]); se_w[q] = se_w_[e]; se_d[q] = se_d_[e] > 0 ? se_d_[e] : 0;
+    std::memcpy(&se_Z[12 * (size_t)q], &se_Z_[12 * (size_t)e], 96);
+  }
+  std::vector<int> nbr_begin(C + 1, 0);
+  for (int e = Ep; e < Ese; ++e) { nbr_begin[se_i[e] + 1]++; nbr_begin[se_j[e] + 1]++; }
+  for (int v = 0; v < C; ++v) nbr_begin[v + 1] += nbr_begin[v];
+  std::vector<int> nfill(nbr_begin.begin(), nbr_begin.end() - 1), nbr_edge(2 * (size_t)Es), nbr_other(2 * (size_t)Es);
+  std::vector<uint8_t> nbr_tr(2 * (size_t)Es);
+  for (int e = Ep; e < Ese; ++e) {
+    int a = nfill[se_i[e]]++; nbr_edge[a] = e; nbr_other[a] = se_j[e]; nbr_tr[a] = 0;
+    int b = nfill[se_j[e]]++; nbr_edge[b] = e; nbr_other[b] = se_i[e]; nbr_tr[b] = 1;
+  }
+  // ---- chain-preconditioner wiring: edge between internal vertices v-1 and v of the same path ----
+  const int n_paths = (int)path_begin.size() - 1;
+  std::vector<int> path_of(C), pcr_edge(C, -1);
+  std::vector<uint8_t> pcr_tr(C, 0);
+  int max_len = 1;
+  for (int pth = 0; pth < n_paths; ++pth) {
+    for (int v = path_begin[pth]; v < path_begin[pth + 1]; ++v) path_of[v] = pth;
+    max_len = std::max(max_len, path_begin[pth + 1] - path_begin[pth]);
+  }
+  for (int e = Ep; e < Ese; ++e) {
+    int a = se_i[e], b = se_j[e];
+    if (path_of[a] != path_of[b]) continue;       // (only inside non-path components, which were split into singletons)
+    if (b == a + 1) { pcr_edge[b] = e; pcr_tr[b] = 1; }        // M(b, a) = H_ab^T
+    else if (a == b + 1) { pcr_edge[a] = e; pcr_tr[a] = 0; }   // M(a, b) = H_ab
+  }
+  int pcr_levels = 0; while ((1 << pcr_levels) < max_len) ++pcr_levels;
+  std::vector<double> se3_int(12 * (size_t)C);
+  for (int o = 0; o < C; ++o) std::memcpy(&se3_int[12 * (size_t)S3(o)], &h_se3_[12 * (size_t)o], 96);
+  // ---- states in internal landmark order ----
+  std::vector<double> pt_int(3 * (size_t)P);
+  for (int k = 0; k < P; ++k) for (int i = 0; i < 3; ++i) pt_int[3 * (size_t)k + i] = h_pt_[3 * (size_t)old_of_new[k] + i];
+
+  // ---- upload ----
+  BaDev& d = d_;
+  d.C = C; d.P = P; d.T = T; d.Eobs = Eo; d.Eter = Et; d.Ese = Ese;
+  d.n_obs_chunks = (int)obs_chunks.size(); d.n_ter_chunks = (int)ter_chunks.size(); d.n_nbr = (int)nbr_edge.size();
+  d.se3 = upload(se3_int); d.pt = upload(pt_int);
+  d.se3_init = upload(se3_int); d.pt_init = upload(pt_int);
+  d.se3_bk = dalloc<double>(12 * (size_t)C); d.pt_bk = dalloc<double>(3 * (size_t)P);
+  d.tk_begin = upload(tk_begin);
+  d.lm_obs_begin = upload(lm_begin); d.lm_cam = upload(lm_cam); d.lm_z = upload(lm_z); d.lm_cls = upload(lm_cls); d.lm_omega = dalloc<double>(Eo);
+  d.tk_h = upload(tk_h); d.tk_cls = upload(tk_cls); d.tk_omega = dalloc<double>(P);
+  d.vm_pt = upload(vm_pt); d.vm_z = upload(vm_z); d.vm_cls = upload(vm_cls); d.vm_omega = dalloc<double>(Eo); d.obs_chunks = upload(obs_chunks);
+  d.hm_p1 = upload(hm_p1); d.hm_cls = upload(hm_cls); d.hm_omega = dalloc<double>(Et); d.ter_chunks = upload(ter_chunks);
+  d.se_i = upload(se_i); d.se_j = upload(se_j); d.se_Z = upload(se_Z); d.se_w = upload(se_w); d.se_delta = upload(se_d); d.se_Hoff = dalloc<double>(36 * (size_t)Ese);
+  d.nbr_begin = upload(nbr_begin); d.nbr_edge = upload(nbr_edge); d.nbr_other = upload(nbr_other); d.nbr_tr = upload(nbr_tr);
+  d.Hpp = dalloc<double>(36 * (size_t)C); d.bp = dalloc<double>(6 * (size_t)C); d.hll = dalloc<double>(P); d.bl = dalloc<double>(3 * (size_t)P);
+  d.pt_s = dalloc<double>(P); d.Minv = dalloc<double>(36 * (size_t)C);
+  d.pt_g = dalloc<double>(P); d.tk_gamma = dalloc<double>(P);
+  d.n_paths = n_paths; d.pcr_levels = pcr_levels;
+  d.path_begin = upload(path_begin); d.path_of = upload(path_of); d.pcr_edge = upload(pcr_edge); d.pcr_tr = upload(pcr_tr);
+  d.pcr_D = dalloc<double>(72 * (size_t)C); d.pcr_L = dalloc<double>(72 * (size_t)C); d.pcr_Dinv = dalloc<double>(36 * (size_t)C);
+  d.pcr_A = dalloc<double>(36 * (size_t)C * std::max(pcr_levels, 1)); d.pcr_G = dalloc<double>(36 * (size_t)C * std::max(pcr_levels, 1));
+  d.pcr_b = dalloc<double>(12 * (size_t)C);
+  d.xp = dalloc<double>(6 * (size_t)C); d.r = dalloc<double>(6 * (size_t)C); d.z = dalloc<double>(6 * (size_t)C);
+  d.p = dalloc<double>(6 * (size_t)C); d.Ap = dalloc<double>(6 * (size_t)C); d.rhs = dalloc<double>(6 * (size_t)C);
+  d.zl = dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P);
+  oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
+  d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
+  d.scal = dalloc<double>(SC_N);
+  be_->sync();
+  // host staging is no longer needed (keep the landmark map for read-back)
+  std::vector<double>().swap(ob_z_); std::vector<double>().swap(ob_w_); std::vector<double>().swap(ob_d_); std::vector<int>().swap(ob_cp_);
+  std::vector<int>().swap(te_pph_); std::vector<double>().swap(te_w_); std::vector<double>().swap(te_d_);
+  std::vector<double>().swap(se_Z_); std::vector<double>().swap(pr_Z_);
+  std::vector<double>().swap(h_se3_); std::vector<double>().swap(h_pt_);
+  finalized_ = true;
+  return VDO_OK;
+}
+
+int BaGraph::get_vertices(double* se3, double* pt) {
+  if (!finalized_) return fail(VDO_ERR_STATE, "get_vertices before finalize");
+  if (se3) {
+    std::vector<double> tmp(12 * (size_t)d_.C);
+    be_->d2h(tmp.data(), d_.se3, 96 * (size_t)d_.C);
+    for (int o = 0; o < d_.C; ++o) std::memcpy(se3 + 12 * (size_t)o, &tmp[12 * (size_t)new_se3_of_old_[o]], 96);
+  }
+  if (pt) {
+    std::vector<double> tmp(3 * (size_t)d_.P);
+    be_->d2h(tmp.data(), d_.pt, 24 * (size_t)d_.P);
+    for (int o = 0; o < d_.P; ++o) {
+      int k = new_of_old_[o];
+      pt[3 * (size_t)o] = tmp[3 * (size_t)k]; pt[3 * (size_t)o + 1] = tmp[3 * (size_t)k + 1]; pt[3 * (size_t)o + 2] = tmp[3 * (size_t)k + 2];
+    }
+  }
+  return VDO_OK;
+}
+int BaGraph::reset_vertices() {
+  if (!finalized_) return fail(VDO_ERR_STATE, "reset_vertices before finalize");
+  be_->d2d(d_.se3, d_.se3_init, 96 * (size_t)d_.C);
+  be_->d2d(d_.pt, d_.pt_init, 24 * (size_t)d_.P);
+  oplus_calls_ = 0;
+  return VDO_OK;
+}
+int BaGraph::info(int64_t out[8]) const {
+  out[0] = d_.C; out[1] = d_.P; out[2] = d_.Eobs; out[3] = d_.Eter; out[4] = d_.Ese; out[5] = (int64_t)pr_w_.size(); out[6] = d_.T; out[7] = (int64_t)bytes_;
+  return VDO_OK;
+}
+
+// ---- buildSystem (g2o/core/block_solver.hpp:501-560) ----
+void BaGraph::linearize() {
+  be_->zero(d_.Hpp, 288 * (size_t)d_.C);
+  be_->zero(d_.bp, 48 * (size_t)d_.C);
+  be_->zero(d_.scal, sizeof(double) * SC_N);
+  be_->lin_tracklets(d_, true);
+  be_->lin_vertex_obs(d_);
+  be_->lin_vertex_ter(d_);
+  be_->lin_se3_edges(d_, true);
+}
+double BaGraph::robust_chi2() {
+  be_->zero(d_.scal + SC_CHI2, sizeof(double));
+  be_->lin_tracklets(d_, false);
+  be_->lin_se3_edges(d_, false);
+  double c; be_->d2h(&c, d_.scal + SC_CHI2, sizeof(double));
+  return c;
+}
+
+// ---- one linear solve (H + lambda I) x = b by landmark elimination + PCG on the reduced se3 system ----
+bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
+  BaDev& d = d_;
+  be_->factor_landmarks(d, lambda);
+  be_->zero(d.scal + SC_BAD, sizeof(double));
+  be_->precond_begin(d, lambda);
+  be_->precond_vertex_obs(d);
+  be_->precond_vertex_ter(d);
+  be_->precond_factor(d, lambda);
+  // rhs = bp - Hpl Hll^-1 bl
+  be_->schur_landmarks(d, 0, nullptr);
+  be_->d2d(d.rhs, d.bp, 48 * (size_t)d.C);
+  be_->schur_vertex_obs(d, -1.0, d.rhs);
+  be_->schur_vertex_ter(d, -1.0, d.rhs);
+  be_->pcg_init(d);
+  const double tol2 = opt.pcg_rel_tol * opt.pcg_rel_tol;
+  const int batch = 8;
+  double sc[SC_N];
+  int it = 0;
+  bool ok = true;
+  while (it < opt.pcg_max_iterations) {
+    for (int b = 0; b < batch; ++b) {
+      be_->hpp_mul(d, lambda, d.p, d.Ap);
+      be_->schur_landmarks(d, 1, d.p);
+      be_->schur_vertex_obs(d, -1.0, d.Ap);
+      be_->schur_vertex_ter(d, -1.0, d.Ap);
+      be_->pcg_dot_pAp(d);
+      be_->pcg_step(d, tol2);
+    }
+    it += batch;
+    be_->d2h(sc, d.scal, sizeof(sc));
+    if (sc[SC_DONE] != 0.0) break;
+  }
+  *pcg_iters = (int)sc[SC_ITERS];
+  if (sc[SC_DONE] == 2.0 || !std::isfinite(sc[SC_RZ])) ok = false;   // breakdown (p.Ap <= 0 or NaN)
+  // back substitution: xl = Hll^-1 (bl - Hlp xp)
+  be_->schur_landmarks(d, 2, d.xp);
+  return ok;
+}
+
+int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* hist) {
+  if (!finalized_) return fail(VDO_ERR_STATE, "optimize before finalize");
+  vdo_lm_options opt = o_in;
+  if (opt.max_trials <= 0) opt.max_trials = 10;
+  if (opt.pcg_rel_tol <= 0) opt.pcg_rel_tol = 1e-10;
+  if (opt.pcg_max_iterations <= 0) opt.pcg_max_iterations = 2000;
+  BaDev& d = d_;
+  const int launches0 = be_->launches();
+  be_->timer_start(0);
+  float ms_lin = 0, ms_solve = 0;
+  double lambda = -1, ni = 2; int nbad = 0, trials = 0, pcg_total = 0;
+  int iters_done = 0; bool stop_flag = false, ok = true;
+  double chi2_check = 0, last_chi_action = 0;
+  double chi_cur = robust_chi2();
+  const double chi_init = chi_cur;
+  if (hist) hist[0] = chi_cur;
+  for (int it = 0; it < opt.max_iterations && ((!stop_flag && ok) || opt.force_all_iterations); ++it) {
+    const double ini = chi_cur;
+    double current = chi_cur, temp = chi_cur;
+    be_->timer_start(1);
+    linearize();
+    if (it == 0) {
+      be_->max_diagonal(d);
+      double md; be_->d2h(&md, d.scal + SC_MAXDIAG, sizeof(double));
+      lambda = 1e-5 * md; ni = 2; nbad = 0;
+    }
+    ms_lin += be_->timer_stop_ms(1);
+    double rho = 0; int qmax = 0; bool result_ok = true;
+    be_->timer_start(2);
+    do {
+      be_->d2d(d.se3_bk, d.se3, 96 * (size_t)d.C);        // push
+      be_->d2d(d.pt_bk, d.pt, 24 * (size_t)d.P);
+      int pit = 0;
+      bool ok2 = solve(lambda, opt, &pit);
+      pcg_total += pit;
+      ++oplus_calls_;
+      bool reortho = false;
+      if (oplus_calls_ > 1000) { oplus_calls_ = 0; reortho = true; }   // vertex_se3.h:110-113
+      be_->zero(d.scal + SC_SCALE, sizeof(double));
+      be_->apply_update(d, lambda, reortho);
+      be_->zero(d.scal + SC_CHI2, sizeof(double));
+      be_->lin_tracklets(d, false);
+      be_->lin_se3_edges(d, false);
+      double sc[SC_N]; be_->d2h(sc, d.scal, sizeof(sc));
+      temp = sc[SC_CHI2];
+      if (!ok2) temp = DBL_MAX;
+      rho = current - temp;
+      double scale = sc[SC_SCALE] + 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(temp)) {
+        double alpha = 1. - std::pow(2 * rho - 1, 3);
+        alpha = std::min(alpha, 2. / 3.);
+        double sf = std::max(1. / 3., alpha);
+        lambda *= sf; ni = 2; current = temp;
+      } else {
+        lambda *= ni; ni *= 2;
+        be_->d2d(d.se3, d.se3_bk, 96 * (size_t)d.C);      // pop
+        be_->d2d(d.pt, d.pt_bk, 24 * (size_t)d.P);
+      }
+      ++qmax; ++trials;
+    } while (rho < 0 && qmax < opt.max_trials && !stop_flag);
+    ms_solve += be_->timer_stop_ms(2);
+    if (qmax == opt.max_trials || rho == 0) result_ok = false;
+    else {
+      if ((ini - current) * 1e3 < ini) nbad++; else nbad = 0;
+      if (nbad >= 3) result_ok = false;
+    }
+    ok = result_ok;
+    const double chi_now = current;     // errors at the (restored) estimate == last accepted chi2
+    if (chi2_check < chi_now && it > 0) ok = false;
+    chi2_check = chi_now;
+    chi_cur = chi_now;
+    if (hist) hist[it + 1] = chi_now;
+    if (opt.verbose) std::fprintf(stderr, "[vdo_b200] iteration= %d\t chi2= %.9g\t lambda= %.6g\t levenbergIter= %d\t pcg= %d\n", it, chi_now, lambda, qmax, pcg_total);
+    ++iters_done;
+    if (opt.gain_threshold > 0) {
+      if (it == 0) last_chi_action = chi_now;
+      else {
+        double gain = (last_chi_action - chi_now) / chi_now;
+        last_chi_action = chi_now;
+        if (gain >= 0 && gain < opt.gain_threshold) stop_flag = true;
+      }
+    }
+  }
+  float ms_total = be_->timer_stop_ms(0);
+  if (stats) {
+    stats->iterations = iters_done; stats->trials = trials; stats->pcg_iterations = pcg_total;
+    stats->initial_chi2 = chi_init; stats->final_chi2 = chi_cur; stats->final_lambda = lambda;
+    stats->ms_linearize = ms_lin; stats->ms_solve = ms_solve; stats->ms_total = ms_total;
+    stats->kernel_launches = be_->launches() - launches0;
+  }
+  return VDO_OK;
+}
+
+int BaGraph::debug_linearize(double* Hpp, double* bp, double* Hll, double* bl, double* chi2) {
+  if (!finalized_) return fail(VDO_ERR_STATE, "debug_linearize before finalize");
+  linearize();
+  {
+    std::vector<double> tH(36 * (size_t)d_.C), tg(6 * (size_t)d_.C);
+    be_->d2h(tH.data(), d_.Hpp, 288 * (size_t)d_.C);
+    be_->d2h(tg.data(), d_.bp, 48 * (size_t)d_.C);
+    for (int o = 0; o < d_.C; ++o) {
+      int v = new_se3_of_old_[o];
+      if (Hpp) std::memcpy(Hpp + 36 * (size_t)o, &tH[36 * (size_t)v], 288);
+      if (bp) std::memcpy(bp + 6 * (size_t)o, &tg[6 * (size_t)v], 48);
+    }
+  }
+  std::vector<double> th(d_.P), tb(3 * (size_t)d_.P);
+  be_->d2h(th.data(), d_.hll, 8 * (size_t)d_.P);
+  be_->d2h(tb.data(), d_.bl, 24 * (size_t)d_.P);
+  for (int o = 0; o < d_.P; ++o) {
+    int k = new_of_old_[o];
+    if (Hll) Hll[o] = th[k];
+    if (bl) for (int i = 0; i < 3; ++i) bl[3 * (size_t)o + i] = tb[3 * (size_t)k + i];
+  }
+  if (chi2) be_->d2h(chi2, d_.scal + SC_CHI2, sizeof(double));
+  return VDO_OK;
+}
+
+}  // namespace vdo

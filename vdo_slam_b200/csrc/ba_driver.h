@@ -1,0 +1,55 @@
+// ba_driver.h -- host side of the batch factor-graph optimiser: graph ingestion (the analogue of
+// g2o::SparseOptimizer::initializeOptimization + BlockSolver::buildStructure) and the Levenberg-Marquardt loop
+// (g2o/core/optimization_algorithm_levenberg.cpp:61-164, sparse_optimizer.cpp:354-427) driving backend kernels.
+#pragma once
+#include <string>
+#include <vector>
+#include "ba_types.h"
+#include "../../include/vdo_b200.h"
+
+namespace vdo {
+
+class BaGraph {
+ public:
+  explicit BaGraph(BaBackend* be) : be_(be) {}
+  ~BaGraph();
+  int set_vertices(int n_se3, const double* se3, int n_pt, const double* pt);
+  int add_prior(int n, const int* v, const double* Z, const double* w);
+  int add_se3(int n, const int* ij, const double* Z, const double* w, const double* delta);
+  int add_obs(int n, const int* cp, const double* z, const double* w, const double* delta);
+  int add_ter(int n, const int* pph, const double* w, const double* delta);
+  int finalize();
+  int optimize(const vdo_lm_options& opt, vdo_lm_stats* stats, double* chi2_history);
+  int get_vertices(double* se3, double* pt);
+  int reset_vertices();
+  int info(int64_t out[8]) const;
+  int debug_linearize(double* Hpp, double* bp, double* Hll, double* bl, double* chi2);
+  const std::string& error() const { return err_; }
+
+ private:
+  template <typename T> T* dalloc(size_t n) { bytes_ += n * sizeof(T); T* p = (T*)be_->alloc(n ? n * sizeof(T) : sizeof(T)); owned_.push_back(p); return p; }
+  template <typename T> T* upload(const std::vector<T>& v) { T* p = dalloc<T>(v.size()); if (!v.empty()) be_->h2d(p, v.data(), v.size() * sizeof(T)); return p; }
+  void linearize();                 // buildSystem
+  double robust_chi2();             // computeActiveErrors + activeRobustChi2
+  bool solve(double lambda, const vdo_lm_options& opt, int* pcg_iters);   // Schur + PCG + back-substitution -> xp, xl
+  int fail(int code, const std::string& m) { err_ = m; return code; }
+
+  BaBackend* be_;
+  BaDev d_;
+  std::vector<void*> owned_;
+  size_t bytes_ = 0;
+  bool finalized_ = false;
+  std::string err_;
+  long oplus_calls_ = 0;
+  // host staging (until finalize)
+  int n_se3_ = 0, n_pt_ = 0;
+  std::vector<double> h_se3_, h_pt_;
+  std::vector<int> pr_v_; std::vector<double> pr_Z_, pr_w_;
+  std::vector<int> se_ij_; std::vector<double> se_Z_, se_w_, se_d_;
+  std::vector<int> ob_cp_; std::vector<double> ob_z_, ob_w_, ob_d_;
+  std::vector<int> te_pph_; std::vector<double> te_w_, te_d_;
+  std::vector<int> new_of_old_;     // landmark renumbering
+  std::vector<int> new_se3_of_old_; // se3 renumbering (path order)
+};
+
+}  // namespace vdo

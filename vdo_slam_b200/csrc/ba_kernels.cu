@@ -1,0 +1,371 @@
+// ba_kernels.cu -- sm_100a kernels of the batch factor-graph path and the CUDA implementation of BaBackend.
+//
+// All arithmetic is fp64 (g2o runs in double).  The path is HBM/L2-bound stream-gather-reduce work over
+// edge streams, so the kernels are organised around coalesced edge streams and shuffle reductions, not tensor cores:
+//   * landmark side  : one thread per tracklet walks its landmark-major edge stream (k_lin_tracklets, k_schur_landmarks)
+//   * se3-vertex side: one CTA per <=512-edge chunk of a vertex's edge stream, per-thread accumulation of the 21+6
+//                      (or 6) entries, warp-shuffle tree + one smem hop, then <=36 atomics per chunk
+//   * reduced system : matrix-free S*v (above two passes) inside a PCG whose preconditioner is block-tridiagonal along
+//                      the se3-se3 edge chains, solved by parallel cyclic reduction (one CTA per chain)
+// Kernel bodies live in ba_bodies.cuh (shared with the serial emulation under tests/emul).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "ba_bodies.cuh"
+
+namespace vdo {
+
+#define CK(x)                                                                                       \
+  do {                                                                                              \
+    cudaError_t e_ = (x);                                                                           \
+    if (e_ != cudaSuccess) { std::fprintf(stderr, "[vdo_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); } \
+  } while (0)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum; result valid in thread 0.  smem must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? smem[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <bool WRITE>
+__global__ void __launch_bounds__(128) k_lin_tracklets(BaDev d) {
+  __shared__ double red[32];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double chi = 0.0;
+  if (t < d.T) chi = body_lin_tracklet(d, t, WRITE);
+  chi = block_sum(chi, red);
+  if (threadIdx.x == 0 && chi != 0.0) atomicAdd(d.scal + SC_CHI2, chi);
+}
+
+// reduce NV per-thread values over the CTA into smem out[NV]
+template <int NV>
+__device__ __forceinline__ void block_reduce_vec(double* acc, double* smem /*[nwarps*NV]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double v = warp_sum(acc[i]);
+    if (lane == 0) smem[w * NV + i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int k = 0; k < nw; ++k) s += smem[k * NV + threadIdx.x];
+    smem[threadIdx.x] = s;   // safe: thread i only reads column i of every row, and row 0 column i is its own
+  }
+  __syncthreads();
+}
+
+// MODE 0: linearise (Hpp += A, bp += g) ; MODE 1: preconditioner (Minv -= A) ;  OBS: pointxyz vs ternary stream
+template <int MODE, bool OBS>
+__global__ void __launch_bounds__(128) k_vertex_sym(BaDev d) {
+  __shared__ double sm[4 * 27];
+  const Chunk ch = OBS ? d.obs_chunks[blockIdx.x] : d.ter_chunks[blockIdx.x];
+  Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+  double acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+  for (int e = ch.begin + threadIdx.x; e < ch.end; e += blockDim.x) {
+    if (MODE == 0) { if (OBS) body_lin_vertex_obs(d, T, e, acc, acc + 21); else body_lin_vertex_ter(d, T, e, acc, acc + 21); }
+    else { if (OBS) body_precond_vertex_obs(d, T, e, acc); else body_precond_vertex_ter(d, T, e, acc); }
+  }
+  block_reduce_vec<27>(acc, sm);
+  if (threadIdx.x < 36) {
+    const int r = threadIdx.x / 6, c = threadIdx.x % 6;
+    const double v = sm[r <= c ? sym6_idx(r, c) : sym6_idx(c, r)];
+    if (MODE == 0) atomicAdd(d.Hpp + 36 * (size_t)ch.v + threadIdx.x, v);
+    else atomicAdd(d.Minv + 36 * (size_t)ch.v + threadIdx.x, -v);
+  } else if (MODE == 0 && threadIdx.x < 42) {
+    atomicAdd(d.bp + 6 * (size_t)ch.v + (threadIdx.x - 36), sm[21 + threadIdx.x - 36]);
+  }
+}
+
+template <bool OBS>
+__global__ void __launch_bounds__(128) k_schur_vertex(BaDev d, double sign, double* __restrict__ out, int check_done) {
+  __shared__ double sm[4 * 6];
+  if (check_done && d.scal[SC_DONE] != 0.0) return;
+  const Chunk ch = OBS ? d.obs_chunks[blockIdx.x] : d.ter_chunks[blockIdx.x];
+  Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = ch.begin + threadIdx.x; e < ch.end; e += blockDim.x) {
+    if (OBS) body_schur_vertex_obs(d, T, e, acc); else body_schur_vertex_ter(d, T, e, acc);
+  }
+  block_reduce_vec<6>(acc, sm);
+  if (threadIdx.x < 6) atomicAdd(out + 6 * (size_t)ch.v + threadIdx.x, sign * sm[threadIdx.x]);
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(64) k_lin_se3_edges(BaDev d) {
+  __shared__ double red[32];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double chi = 0.0;
+  if (e < d.Ese) {
+    double Hi[36], Hj[36], Ho[36], gi[6], gj[6];
+    const bool binary = body_se3_edge(d, e, WRITE, chi, Hi, Hj, Ho, gi, gj);
+    if (WRITE) {
+      const int i = d.se_i[e];
+      for (int k = 0; k < 36; ++k) atomicAdd(d.Hpp + 36 * (size_t)i + k, Hi[k]);
+      for (int k = 0; k < 6; ++k) atomicAdd(d.bp + 6 * (size_t)i + k, gi[k]);
+      if (binary) {
+        const int j = d.se_j[e];
+        for (int k = 0; k < 36; ++k) { atomicAdd(d.Hpp + 36 * (size_t)j + k, Hj[k]); d.se_Hoff[36 * (size_t)e + k] = Ho[k]; }
+        for (int k = 0; k < 6; ++k) atomicAdd(d.bp + 6 * (size_t)j + k, gj[k]);
+      }
+    }
+  }
+  chi = block_sum(chi, red);
+  if (threadIdx.x == 0 && chi != 0.0) atomicAdd(d.scal + SC_CHI2, chi);
+}
+
+__global__ void __launch_bounds__(256) k_max_diagonal(BaDev d) {
+  __shared__ double red[32];
+  const int n1 = d.C * 6, n = n1 + d.P;
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = fmax(m, i < n1 ? fabs(d.Hpp[36 * (size_t)(i / 6) + 7 * (i % 6)]) : fabs(d.hll[i - n1]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmax(m, red[k]);
+    atomicMax(reinterpret_cast<unsigned long long*>(d.scal + SC_MAXDIAG), (unsigned long long)__double_as_longlong(m));  // m >= 0
+  }
+}
+
+__global__ void __launch_bounds__(128) k_factor_landmarks(BaDev d, double lambda) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < d.T) body_factor_tracklet(d, t, lambda);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_schur_landmarks(BaDev d, const double* __restrict__ v, double* __restrict__ out) {
+  if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < d.T) body_schur_tracklet(d, t, MODE, v, out);
+}
+
+__global__ void __launch_bounds__(128) k_precond_begin(BaDev d, double lambda) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d.C * 36) { const int k = i % 36; d.Minv[i] = d.Hpp[i] + ((k % 7) == 0 ? lambda : 0.0); }
+}
+
+__global__ void __launch_bounds__(128) k_hpp_mul(BaDev d, double lambda, const double* __restrict__ x, double* __restrict__ out) {
+  if (d.scal[SC_DONE] != 0.0) return;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < d.C) body_hpp_mul(d, v, lambda, x, out);
+}
+
+// ---- parallel cyclic reduction, one CTA per path ----
+__global__ void __launch_bounds__(256) k_pcr_factor(BaDev d, double lambda) {
+  const int pb = d.path_begin[blockIdx.x], pe = d.path_begin[blockIdx.x + 1];
+  const int nl = pcr_num_levels(pe - pb);
+  const size_t N36 = 36 * (size_t)d.C;
+  int bad = 0, cur = 0;
+  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_setup(d, v, d.pcr_D, d.pcr_L);
+  __syncthreads();
+  for (int l = 0; l < nl; ++l) {
+    const double *D = d.pcr_D + cur * N36, *L = d.pcr_L + cur * N36;
+    double *Dn = d.pcr_D + (1 - cur) * N36, *Ln = d.pcr_L + (1 - cur) * N36;
+    for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_invert(d, v, D, d.pcr_Dinv, lambda, &bad);
+    __syncthreads();
+    for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_reduce(v, pb, pe, 1 << l, D, L, d.pcr_Dinv, Dn, Ln, d.pcr_A + l * N36, d.pcr_G + l * N36);
+    __syncthreads();
+    cur = 1 - cur;
+  }
+  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_invert(d, v, d.pcr_D + cur * N36, d.Minv, lambda, &bad);
+  if (bad) atomicAdd(d.scal + SC_BAD, 1.0);
+}
+
+// z = M^-1 r for the CTA's path (r must already be final for the whole path); returns this thread's share of r.z
+__device__ __forceinline__ double pcr_solve_path(const BaDev& d, int pb, int pe, const double* __restrict__ r, double* __restrict__ z) {
+  const int nl = pcr_num_levels(pe - pb);
+  const size_t N6 = 6 * (size_t)d.C, N36 = 36 * (size_t)d.C;
+  int cur = 0;
+  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d.pcr_b[6 * (size_t)v + i] = r[6 * (size_t)v + i];
+  __syncthreads();
+  for (int l = 0; l < nl; ++l) {
+    for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
+      body_pcr_apply(v, pb, pe, 1 << l, d.pcr_A + l * N36, d.pcr_G + l * N36, d.pcr_b + cur * N6, d.pcr_b + (1 - cur) * N6);
+    __syncthreads();
+    cur = 1 - cur;
+  }
+  double rz = 0.0;
+  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) {
+    double zz[6];
+    mul6(d.Minv + 36 * (size_t)v, d.pcr_b + cur * N6 + 6 * (size_t)v, zz);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { z[6 * (size_t)v + i] = zz[i]; rz += zz[i] * r[6 * (size_t)v + i]; }
+  }
+  return rz;
+}
+
+__global__ void __launch_bounds__(256) k_pcg_init(BaDev d) {
+  __shared__ double red[32];
+  const int pb = d.path_begin[blockIdx.x], pe = d.path_begin[blockIdx.x + 1];
+  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { d.r[6 * (size_t)v + i] = d.rhs[6 * (size_t)v + i]; d.xp[6 * (size_t)v + i] = 0.0; }
+  __syncthreads();
+  double rz = pcr_solve_path(d, pb, pe, d.r, d.z);
+  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d.p[6 * (size_t)v + i] = d.z[6 * (size_t)v + i];
+  rz = block_sum(rz, red);
+  if (threadIdx.x == 0) atomicAdd(d.scal + SC_RZ, rz);
+}
+__global__ void k_pcg_init_fin(BaDev d) {
+  const double rz = d.scal[SC_RZ];
+  d.scal[SC_RZ0] = rz; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] = 0.0;
+  d.scal[SC_DONE] = (rz > 0.0) ? 0.0 : 1.0;
+}
+__global__ void __launch_bounds__(256) k_pcg_dot(BaDev d) {
+  __shared__ double red[32];
+  if (d.scal[SC_DONE] != 0.0) return;
+  const int n = d.C * 6;
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += d.p[i] * d.Ap[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(d.scal + SC_PAP, s);
+}
+// x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new += r.z
+__global__ void __launch_bounds__(256) k_pcg_step_a(BaDev d) {
+  __shared__ double red[32];
+  if (d.scal[SC_DONE] != 0.0) return;
+  const double pap = d.scal[SC_PAP], rz = d.scal[SC_RZ];
+  const double alpha = (pap > 0.0) ? rz / pap : 0.0;
+  const int pb = d.path_begin[blockIdx.x], pe = d.path_begin[blockIdx.x + 1];
+  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const size_t q = 6 * (size_t)v + i; d.xp[q] += alpha * d.p[q]; d.r[q] -= alpha * d.Ap[q]; }
+  __syncthreads();
+  double rzn = pcr_solve_path(d, pb, pe, d.r, d.z);
+  rzn = block_sum(rzn, red);
+  if (threadIdx.x == 0) atomicAdd(d.scal + SC_RZ_NEW, rzn);
+}
+__global__ void __launch_bounds__(256) k_pcg_step_b(BaDev d) {
+  if (d.scal[SC_DONE] != 0.0) return;
+  const double beta = d.scal[SC_RZ_NEW] / d.scal[SC_RZ];
+  const int n = d.C * 6;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d.p[i] = d.z[i] + beta * d.p[i];
+}
+__global__ void k_pcg_scalars(BaDev d, double tol2) {
+  if (d.scal[SC_DONE] != 0.0) return;
+  const double pap = d.scal[SC_PAP], rzn = d.scal[SC_RZ_NEW];
+  if (!(pap > 0.0) || !isfinite(pap) || !isfinite(rzn)) { d.scal[SC_DONE] = 2.0; return; }
+  d.scal[SC_RZ] = rzn; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] += 1.0;
+  if (rzn <= tol2 * d.scal[SC_RZ0]) d.scal[SC_DONE] = 1.0;
+}
+
+__global__ void __launch_bounds__(128) k_apply_update(BaDev d, double lambda, int reortho) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (i < d.C) s = body_update_se3(d, i, lambda, reortho != 0);
+  else if (i < d.C + d.P) s = body_update_pt(d, i - d.C, lambda);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0 && s != 0.0) atomicAdd(d.scal + SC_SCALE, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct CudaBackend : BaBackend {
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  int n_launch = 0;
+  cudaEvent_t ev0[4], ev1[4];
+  ~CudaBackend() override {
+    for (int i = 0; i < 4; ++i) { cudaEventDestroy(ev0[i]); cudaEventDestroy(ev1[i]); }
+    if (st) cudaStreamDestroy(st);
+  }
+  void* alloc(size_t b) override { void* p = nullptr; CK(cudaMalloc(&p, b ? b : 8)); CK(cudaMemsetAsync(p, 0, b ? b : 8, st)); return p; }
+  void free_(void* p) override { cudaFree(p); }
+  void h2d(void* d, const void* s, size_t b) override { CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+  void d2h(void* d, const void* s, size_t b) override { CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+  void d2d(void* d, const void* s, size_t b) override { CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); }
+  void zero(void* d, size_t b) override { CK(cudaMemsetAsync(d, 0, b, st)); }
+  void sync() override { CK(cudaStreamSynchronize(st)); }
+  int launches() const override { return n_launch; }
+  void* stream() const override { return (void*)st; }
+  void timer_start(int s) override { CK(cudaEventRecord(ev0[s], st)); }
+  float timer_stop_ms(int s) override { float ms = 0; CK(cudaEventRecord(ev1[s], st)); CK(cudaEventSynchronize(ev1[s])); CK(cudaEventElapsedTime(&ms, ev0[s], ev1[s])); return ms; }
+
+  static int nblk(int n, int b) { return n > 0 ? (n + b - 1) / b : 0; }
+#define LAUNCH(kern, grid, block, ...)                         \
+  do {                                                         \
+    if ((grid) > 0) { kern<<<(grid), (block), 0, st>>>(__VA_ARGS__); ++n_launch; } \
+  } while (0)
+
+  void lin_tracklets(BaDev& d, bool write) override {
+    if (write) LAUNCH(k_lin_tracklets<true>, nblk(d.T, 128), 128, d); else LAUNCH(k_lin_tracklets<false>, nblk(d.T, 128), 128, d);
+  }
+  void lin_vertex_obs(BaDev& d) override { auto k = k_vertex_sym<0, true>; LAUNCH(k, d.n_obs_chunks, 128, d); }
+  void lin_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<0, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
+  void lin_se3_edges(BaDev& d, bool write) override {
+    if (write) LAUNCH(k_lin_se3_edges<true>, nblk(d.Ese, 64), 64, d); else LAUNCH(k_lin_se3_edges<false>, nblk(d.Ese, 64), 64, d);
+  }
+  void max_diagonal(BaDev& d) override {
+    zero(d.scal + SC_MAXDIAG, sizeof(double));
+    int n = d.C * 6 + d.P;
+    LAUNCH(k_max_diagonal, min(nblk(n, 256), 148 * 8), 256, d);
+  }
+  void factor_landmarks(BaDev& d, double lambda) override { LAUNCH(k_factor_landmarks, nblk(d.T, 128), 128, d, lambda); }
+  void precond_begin(BaDev& d, double lambda) override { LAUNCH(k_precond_begin, nblk(d.C * 36, 128), 128, d, lambda); }
+  void precond_vertex_obs(BaDev& d) override { auto k = k_vertex_sym<1, true>; LAUNCH(k, d.n_obs_chunks, 128, d); }
+  void precond_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
+  void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_paths, 256, d, lambda); }
+  void schur_landmarks(BaDev& d, int mode, const double* v) override {
+    const int g = nblk(d.T, 128);
+    if (mode == 0) LAUNCH(k_schur_landmarks<0>, g, 128, d, v, d.zl);
+    else if (mode == 1) LAUNCH(k_schur_landmarks<1>, g, 128, d, v, d.zl);
+    else LAUNCH(k_schur_landmarks<2>, g, 128, d, v, d.xl);
+  }
+  void schur_vertex_obs(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
+  void schur_vertex_ter(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<false>, d.n_ter_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
+  void hpp_mul(BaDev& d, double lambda, const double* x, double* out) override { LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, lambda, x, out); }
+  void pcg_init(BaDev& d) override {
+    zero(d.scal + SC_PAP, 6 * sizeof(double));   // PAP, RZ, RZ_NEW, RZ0, DONE, ITERS
+    LAUNCH(k_pcg_init, d.n_paths, 256, d);
+    LAUNCH(k_pcg_init_fin, 1, 1, d);
+  }
+  void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, min(nblk(d.C * 6, 256), 148), 256, d); }
+  void pcg_step(BaDev& d, double tol2) override {
+    LAUNCH(k_pcg_step_a, d.n_paths, 256, d);
+    LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
+    LAUNCH(k_pcg_scalars, 1, 1, d, tol2);
+  }
+  void apply_update(BaDev& d, double lambda, bool reortho) override { LAUNCH(k_apply_update, nblk(d.C + d.P, 128), 128, d, lambda, reortho ? 1 : 0); }
+};
+
+BaBackend* make_backend(int device, char* err, size_t errlen) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) { std::snprintf(err, errlen, "no CUDA device (%s); libvdo_b200 has no CPU path", cudaGetErrorString(e)); return nullptr; }
+  if (device < 0 || device >= n) { std::snprintf(err, errlen, "device %d out of range (%d visible)", device, n); return nullptr; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { std::snprintf(err, errlen, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return nullptr; }
+  if (prop.major != 10) { std::snprintf(err, errlen, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor); return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { std::snprintf(err, errlen, "cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+  CudaBackend* b = new CudaBackend;
+  b->dev = device;
+  if ((e = cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking)) != cudaSuccess) { std::snprintf(err, errlen, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete b; return nullptr; }
+  for (int i = 0; i < 4; ++i) { cudaEventCreate(&b->ev0[i]); cudaEventCreate(&b->ev1[i]); }
+  return b;
+}
+
+}  // namespace vdo

@@ -1,0 +1,116 @@
+// ba_types.h -- HBM data layout of one batch factor graph and the backend interface the LM driver runs on.
+//
+// Layout (all fp64 unless noted).  "Landmark" = VertexPointXYZ.  Landmarks are renumbered so that each tracklet
+// (a static point, or the chain p_0 - p_1 - ... of per-frame copies of one dynamic point tied by
+// LandmarkMotionTernaryEdges) is contiguous and in chain order; that makes H_ll block-tridiagonal per tracklet.
+//
+//   se3[C*12]            vertex estimates (camera poses + object motions), AoS iso
+//   pt[P*3]              landmark estimates, tracklet order
+//   tk_begin[T+1]        landmark range of tracklet t
+//   landmark-major EdgeSE3PointXYZ stream (sorted by landmark): lm_obs_begin[P+1], lm_cam[E], lm_z[E*3], lm_cls[E] (u8),
+//                        lm_omega[E] (robustified weight, rewritten by every linearisation)
+//   per landmark k:      tk_h[k]  = motion vertex of the ternary edge (k, k+1), or -1;  tk_cls[k]; tk_omega[k]
+//   vertex-major EdgeSE3PointXYZ stream (sorted by se3 vertex): vm_pt[E], vm_z[E*3], vm_cls[E], vm_omega[E],
+//                        cut into chunks {vertex, begin, end} of at most VDO_CHUNK edges
+//   vertex-major ternary stream (sorted by motion vertex): hm_p1[Et] (landmark index of p1; p2 = p1 + 1), hm_cls, hm_omega,
+//                        chunks likewise
+//   se3-se3 edges (prior: j = -1): se_i, se_j, se_Z[*12], se_w, se_delta, se_Hoff[*36] (J_i^T W J_j, written by linearise)
+//   adjacency for H_pp * v: nbr_begin[C+1], nbr_edge[], nbr_other[], nbr_tr[] (1: use block transposed)
+//   system: Hpp[C*36] (diagonal blocks, full row-major), bp[C*6], hll[P] (H_ll diagonal blocks are hll*I3), bl[P*3],
+//           pt_s[P] (Schur pivots of the per-tracklet tridiagonal for the current lambda), pt_g[P], tk_gamma[P]
+//           (diagonal / coupling scalars of Hll^-1 for the preconditioner), Minv[C*36]
+//   edge classes: (information weight, Huber delta) pairs; at most 256 distinct pairs per edge family
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#define VDO_CHUNK 512
+
+namespace vdo {
+
+struct Chunk { int v, begin, end, pad; };
+
+struct BaDev {
+  int C = 0, P = 0, T = 0, Eobs = 0, Eter = 0, Ese = 0, n_obs_chunks = 0, n_ter_chunks = 0, n_nbr = 0;
+  double *se3 = 0, *pt = 0, *se3_bk = 0, *pt_bk = 0, *se3_init = 0, *pt_init = 0;
+  int* tk_begin = 0;
+  int* lm_obs_begin = 0; int* lm_cam = 0; double* lm_z = 0; uint8_t* lm_cls = 0; double* lm_omega = 0;
+  int* tk_h = 0; uint8_t* tk_cls = 0; double* tk_omega = 0;
+  int* vm_pt = 0; double* vm_z = 0; uint8_t* vm_cls = 0; double* vm_omega = 0; Chunk* obs_chunks = 0;
+  int* hm_p1 = 0; uint8_t* hm_cls = 0; double* hm_omega = 0; Chunk* ter_chunks = 0;
+  int *se_i = 0, *se_j = 0; double *se_Z = 0, *se_w = 0, *se_delta = 0, *se_Hoff = 0;
+  int *nbr_begin = 0, *nbr_edge = 0, *nbr_other = 0; uint8_t* nbr_tr = 0;
+  double *Hpp = 0, *bp = 0, *hll = 0, *bl = 0, *pt_s = 0, *Minv = 0;
+  double *pt_g = 0, *tk_gamma = 0;
+  // chain preconditioner (block-tridiagonal along the paths of the se3-se3 edge graph, solved by parallel cyclic reduction)
+  int n_paths = 0, pcr_levels = 0;
+  int* path_begin = 0;            // n_paths+1 ; se3 vertices are renumbered so that each path is a contiguous index range
+  int* path_of = 0;               // C : path id of each vertex
+  int* pcr_edge = 0; uint8_t* pcr_tr = 0;   // C : se3-se3 edge linking vertex v-1 and v (or -1), and whether M(v, v-1) = Hoff^T
+  double *pcr_D = 0, *pcr_L = 0, *pcr_Dinv = 0;   // 2*C*36 (double buffered), 2*C*36, C*36 scratch of the reduction
+  double *pcr_A = 0, *pcr_G = 0;  // pcr_levels * C * 36 : elimination operators per level
+  double *pcr_b = 0;              // 2 * C * 6 scratch of the solve   // per landmark: diagonal scalar of Hll^-1; per ternary edge: g_k + g_k+1 - 2 g_k,k+1
+  double *xp = 0, *r = 0, *z = 0, *p = 0, *Ap = 0, *rhs = 0; // 6C each
+  double *zl = 0, *xl = 0;                                    // 3P each
+  double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each
+  double* scal = 0;  // device scalars, see SC_* below
+};
+
+enum { SC_CHI2 = 0, SC_MAXDIAG = 1, SC_SCALE = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9, SC_N = 16 };
+
+// The backend: memory + one function per kernel.  Implemented for CUDA in ba_kernels.cu (the product) and, for the
+// CPU-only host-logic tests, as serial loops over the same per-thread bodies in tests/emul/ba_backend_emul.cpp.
+struct BaBackend {
+  virtual ~BaBackend() {}
+  virtual void* alloc(size_t bytes) = 0;            // zero-initialised
+  virtual void free_(void* p) = 0;
+  virtual void h2d(void* dst, const void* src, size_t bytes) = 0;
+  virtual void d2h(void* dst, const void* src, size_t bytes) = 0;   // synchronises the stream first
+  virtual void d2d(void* dst, const void* src, size_t bytes) = 0;
+  virtual void zero(void* dst, size_t bytes) = 0;
+  virtual void sync() = 0;
+  virtual int launches() const = 0;
+  virtual void* stream() const = 0;
+  virtual void timer_start(int slot) = 0;
+  virtual float timer_stop_ms(int slot) = 0;        // synchronises
+
+  // --- linearisation (buildSystem) ---
+  // landmark side: robust chi2 of all EdgeSE3PointXYZ + ternary edges into scal[SC_CHI2]; if write: lm_omega, tk_omega, hll, bl
+  virtual void lin_tracklets(BaDev& d, bool write) = 0;
+  // se3 side of EdgeSE3PointXYZ / ternary edges: Hpp += , bp += , vm_omega / hm_omega
+  virtual void lin_vertex_obs(BaDev& d) = 0;
+  virtual void lin_vertex_ter(BaDev& d) = 0;
+  // EdgeSE3 + EdgeSE3Prior: chi2 into scal[SC_CHI2]; if write: Hpp, bp, se_Hoff
+  virtual void lin_se3_edges(BaDev& d, bool write) = 0;
+  // scal[SC_MAXDIAG] = max |diagonal of H|
+  virtual void max_diagonal(BaDev& d) = 0;
+  // --- per-trial factorisation ---
+  virtual void factor_landmarks(BaDev& d, double lambda) = 0;   // pt_s
+  // Preconditioner M = Hpp(se3-se3 edges, incl. off-diagonal blocks) + lambda I + blockdiag(Hpp_landmark - Hpl Hll^-1 Hlp):
+  //   precond_begin: Minv = Hpp_vv + lambda I ; precond_vertex_*: Minv -= diagonal blocks of Hpl Hll^-1 Hlp ;
+  //   precond_factor: parallel-cyclic-reduction factorisation of the block-tridiagonal M along each path (pcr_A, pcr_G, Minv := D^-1);
+  //   scal[SC_BAD] counts blocks that were not SPD.
+  virtual void precond_begin(BaDev& d, double lambda) = 0;
+  virtual void precond_vertex_obs(BaDev& d) = 0;
+  virtual void precond_vertex_ter(BaDev& d) = 0;
+  virtual void precond_factor(BaDev& d, double lambda) = 0;
+  // --- Schur products ---
+  // mode 0: zl = Hll^-1 bl ; mode 1: zl = Hll^-1 (Hlp v) ; mode 2: xl = Hll^-1 (bl - Hlp v)
+  virtual void schur_landmarks(BaDev& d, int mode, const double* v) = 0;
+  // out[vertex] += sign * sum_edges Hpl_e * zl[landmark(e)]
+  virtual void schur_vertex_obs(BaDev& d, double sign, double* out) = 0;
+  virtual void schur_vertex_ter(BaDev& d, double sign, double* out) = 0;
+  // out = (Hpp + lambda I) v  (diagonal blocks and se3-se3 off-diagonal blocks)
+  virtual void hpp_mul(BaDev& d, double lambda, const double* v, double* out) = 0;
+  // --- PCG vector steps (device-side scalars; no host sync) ---
+  virtual void pcg_init(BaDev& d) = 0;     // r = rhs (x = 0), z = Minv r, p = z, rz = r.z, rz0 = rz, done = 0, iters = 0
+  virtual void pcg_dot_pAp(BaDev& d) = 0;  // scal[SC_PAP] = p.Ap
+  virtual void pcg_step(BaDev& d, double tol2) = 0;  // alpha, x, r, z, rz_new, beta, p; done=1 if rz_new <= tol2 * rz0, done=2 on breakdown
+  // --- update / acceptance ---
+  virtual void apply_update(BaDev& d, double lambda, bool reorthogonalize) = 0;  // oplus; scal[SC_SCALE] = sum x (lambda x + b)
+};
+
+// Product: CUDA implementation (ba_kernels.cu); returns nullptr and fills *err when no usable sm_100 device exists.
+BaBackend* make_backend(int device, char* err, size_t errlen);
+
+}  // namespace vdo
