@@ -179,6 +179,7 @@ struct EmulBackend : BaBackend {
       for (int i = 0; i < 6; ++i) out[6 * (size_t)ch.v + i] += sign * a[i];
     }
   }
+  void vertex_transform(BaDev& d, const double* v) override { ++n_launch; for (int c = 0; c < d.C; ++c) body_vertex_transform(d, c, v, d.vw); }
   void hpp_mul(BaDev& d, double lambda, const double* x, double* out) override {
     ++n_launch;
     for (int v = 0; v < d.C; ++v) body_hpp_mul(d, v, lambda, x, out);

@@ -98,6 +98,20 @@ VDO_HD void body_factor_tracklet(const BaDev& d, int t, double lambda) {
   }
 }
 
+// World-frame image of an se3 increment v = [vt, vr] of vertex c, so that the EdgeSE3PointXYZ product needs no pose:
+//   H_lp,e v_c = omega R_c J_c v_c = omega R_c(-vt + 2 Zc x vr) = omega (gamma + 2 p x beta),
+//   beta = R_c vr,  gamma = -R_c vt - 2 t_c x beta          (R (a x b) = (R a) x (R b), R Zc = p - t_c)
+VDO_HD void body_vertex_transform(const BaDev& d, int c, const double* __restrict__ v, double* __restrict__ vw) {
+  const double* T = d.se3 + 12 * (size_t)c;
+  double al[3], be[3], tb[3];
+  rot_apply(T, v + 6 * (size_t)c, al);
+  rot_apply(T, v + 6 * (size_t)c + 3, be);
+  cross3(T + 9, be, tb);
+  double* o = vw + 6 * (size_t)c;
+  o[0] = -al[0] - 2 * tb[0]; o[1] = -al[1] - 2 * tb[1]; o[2] = -al[2] - 2 * tb[2];
+  o[3] = be[0]; o[4] = be[1]; o[5] = be[2];
+}
+
 // mode 0: out = Hll^-1 bl ; mode 1: out = Hll^-1 (Hlp v) ; mode 2: out = Hll^-1 (bl - Hlp v)
 VDO_HD void body_schur_tracklet(const BaDev& d, int t, int mode, const double* __restrict__ v, double* __restrict__ out) {
   const int kb = d.tk_begin[t], ke = d.tk_begin[t + 1];
@@ -113,13 +127,10 @@ VDO_HD void body_schur_tracklet(const BaDev& d, int t, int mode, const double* _
     if (mode != 0) {
       const int eb = d.lm_obs_begin[k], ee = d.lm_obs_begin[k + 1];
       for (int e = eb; e < ee; ++e) {
-        const int c = d.lm_cam[e];
-        Iso T; iso_load(d.se3 + 12 * (size_t)c, T);
-        double Zc[3]; iso_inv_apply(T, p, Zc);
-        double a[3]; obs_Jc_mul(Zc, v + 6 * (size_t)c, a);
-        double Ra[3]; rot_apply(T.R, a, Ra);
+        const double* w = d.vw + 6 * (size_t)d.lm_cam[e];
+        double pxb[3]; cross3(p, w + 3, pxb);
         const double om = d.lm_omega[e];
-        u[0] += om * Ra[0]; u[1] += om * Ra[1]; u[2] += om * Ra[2];
+        u[0] += om * (w[0] + 2 * pxb[0]); u[1] += om * (w[1] + 2 * pxb[1]); u[2] += om * (w[2] + 2 * pxb[2]);
       }
     }
     if (h >= 0) {
@@ -143,6 +154,11 @@ VDO_HD void body_schur_tracklet(const BaDev& d, int t, int mode, const double* _
     if (k > kb) {   // y_k += (omega_{k-1}/s_{k-1}) R_{k-1} y_{k-1}
       double Ry[3]; rot_apply(Rprev, y_prev, Ry);
       y[0] += f_prev * Ry[0]; y[1] += f_prev * Ry[1]; y[2] += f_prev * Ry[2];
+    }
+    if (ke - kb == 1) {   // static point: no chain, z = y / s
+      const double is = 1.0 / d.pt_s[k];
+      out[3 * k] = y[0] * is; out[3 * k + 1] = y[1] * is; out[3 * k + 2] = y[2] * is;
+      return;
     }
     out[3 * k] = y[0]; out[3 * k + 1] = y[1]; out[3 * k + 2] = y[2];
     y_prev[0] = y[0]; y_prev[1] = y[1]; y_prev[2] = y[2];
@@ -294,6 +310,7 @@ VDO_HD void body_hpp_mul(const BaDev& d, int v, double lambda, const double* __r
   }
 #pragma unroll
   for (int r = 0; r < 6; ++r) out[6 * (size_t)v + r] = o[r];
+  body_vertex_transform(d, v, x, d.vw);
 }
 
 // Preconditioner pieces: diagonal block of Hpl Hll^-1 Hlp seen from the se3 vertex, per edge.
@@ -387,6 +404,19 @@ VDO_HD void body_pcr_apply(int v, int pb, int pe, int s, const double* A, const 
     for (int r = 0; r < 6; ++r) { double t = 0; for (int c = 0; c < 6; ++c) t += g[6 * r + c] * x[c]; o[r] += t; }
   }
   for (int i = 0; i < 6; ++i) bn[6 * (size_t)v + i] = o[i];
+}
+// same as body_pcr_apply for a single output row (6 work items per vertex: coalesced reads of A / G rows)
+VDO_HD double pcr_apply_row(int v, int row, int pb, int pe, int s, const double* A, const double* G, const double* b) {
+  double o = b[6 * (size_t)v + row];
+  if (v - s >= pb) {
+    const double* a = A + 36 * (size_t)v + 6 * row; const double* x = b + 6 * (size_t)(v - s);
+    o += a[0] * x[0] + a[1] * x[1] + a[2] * x[2] + a[3] * x[3] + a[4] * x[4] + a[5] * x[5];
+  }
+  if (v + s < pe) {
+    const double* g = G + 36 * (size_t)v + 6 * row; const double* x = b + 6 * (size_t)(v + s);
+    o += g[0] * x[0] + g[1] * x[1] + g[2] * x[2] + g[3] * x[3] + g[4] * x[4] + g[5] * x[5];
+  }
+  return o;
 }
 VDO_HD int pcr_num_levels(int m) { int l = 0; while ((1 << l) < m) ++l; return l; }
 VDO_HD void mul6(const double* M, const double* x, double* o) {

@@ -12,6 +12,7 @@
 namespace vdo {
 
 BaGraph::~BaGraph() {
+  if (finalized_) be_->release(d_);
   for (void* p : owned_) be_->free_(p);
 }
 
@@ -255,7 +256,7 @@ int BaGraph::finalize() {
   d.pcr_b = dalloc<double>(12 * (size_t)C);
   d.xp = dalloc<double>(6 * (size_t)C); d.r = dalloc<double>(6 * (size_t)C); d.z = dalloc<double>(6 * (size_t)C);
   d.p = dalloc<double>(6 * (size_t)C); d.Ap = dalloc<double>(6 * (size_t)C); d.rhs = dalloc<double>(6 * (size_t)C);
-  d.zl = dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P);
+  d.zl = dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P); d.vw = dalloc<double>(6 * (size_t)C);
   oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
   d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
   d.scal = dalloc<double>(SC_N);
@@ -337,14 +338,7 @@ bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   int it = 0;
   bool ok = true;
   while (it < opt.pcg_max_iterations) {
-    for (int b = 0; b < batch; ++b) {
-      be_->hpp_mul(d, lambda, d.p, d.Ap);
-      be_->schur_landmarks(d, 1, d.p);
-      be_->schur_vertex_obs(d, -1.0, d.Ap);
-      be_->schur_vertex_ter(d, -1.0, d.Ap);
-      be_->pcg_dot_pAp(d);
-      be_->pcg_step(d, tol2);
-    }
+    be_->pcg_iterate(d, lambda, tol2, batch);
     it += batch;
     be_->d2h(sc, d.scal, sizeof(sc));
     if (sc[SC_DONE] != 0.0) break;
@@ -352,6 +346,7 @@ bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   *pcg_iters = (int)sc[SC_ITERS];
   if (sc[SC_DONE] == 2.0 || !std::isfinite(sc[SC_RZ])) ok = false;   // breakdown (p.Ap <= 0 or NaN)
   // back substitution: xl = Hll^-1 (bl - Hlp xp)
+  be_->vertex_transform(d, d.xp);
   be_->schur_landmarks(d, 2, d.xp);
   return ok;
 }

@@ -9,13 +9,21 @@
 //                      the se3-se3 edge chains, solved by parallel cyclic reduction (one CTA per chain)
 // Kernel bodies live in ba_bodies.cuh (shared with the serial emulation under tests/emul).
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <cstdio>
 #include <cstring>
 
+#include <map>
+#include <utility>
+
 #include "ba_bodies.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace vdo {
+
+constexpr int PCR_CL = 8;   // CTAs per thread-block cluster working on one chain of the preconditioner
 
 #define CK(x)                                                                                       \
   do {                                                                                              \
@@ -164,71 +172,84 @@ __global__ void __launch_bounds__(128) k_precond_begin(BaDev d, double lambda) {
   if (i < d.C * 36) { const int k = i % 36; d.Minv[i] = d.Hpp[i] + ((k % 7) == 0 ? lambda : 0.0); }
 }
 
-__global__ void __launch_bounds__(128) k_hpp_mul(BaDev d, double lambda, const double* __restrict__ x, double* __restrict__ out) {
+__global__ void k_set_scalars(BaDev d, double lambda, double tol2) { d.scal[SC_LAMBDA] = lambda; d.scal[SC_TOL2] = tol2; }
+__global__ void __launch_bounds__(128) k_vertex_transform(BaDev d, const double* __restrict__ x) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < d.C) body_vertex_transform(d, v, x, d.vw);
+}
+__global__ void __launch_bounds__(128) k_hpp_mul(BaDev d, const double* __restrict__ x, double* __restrict__ out) {
   if (d.scal[SC_DONE] != 0.0) return;
+  const double lambda = d.scal[SC_LAMBDA];
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < d.C) body_hpp_mul(d, v, lambda, x, out);
 }
 
-// ---- parallel cyclic reduction, one CTA per path ----
-__global__ void __launch_bounds__(256) k_pcr_factor(BaDev d, double lambda) {
-  const int pb = d.path_begin[blockIdx.x], pe = d.path_begin[blockIdx.x + 1];
+// ---- parallel cyclic reduction: one thread-block CLUSTER (PCR_CL CTAs) per chain, cluster.sync() between levels ----
+__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcr_factor(BaDev d, double lambda) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int path = blockIdx.x / PCR_CL;
+  const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
   const int nl = pcr_num_levels(pe - pb);
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
   const size_t N36 = 36 * (size_t)d.C;
   int bad = 0, cur = 0;
-  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_setup(d, v, d.pcr_D, d.pcr_L);
-  __syncthreads();
+  for (int v = pb + tid; v < pe; v += nth) body_pcr_setup(d, v, d.pcr_D, d.pcr_L);
+  if (nl > 0) cl.sync();
   for (int l = 0; l < nl; ++l) {
     const double *D = d.pcr_D + cur * N36, *L = d.pcr_L + cur * N36;
     double *Dn = d.pcr_D + (1 - cur) * N36, *Ln = d.pcr_L + (1 - cur) * N36;
-    for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_invert(d, v, D, d.pcr_Dinv, lambda, &bad);
-    __syncthreads();
-    for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_reduce(v, pb, pe, 1 << l, D, L, d.pcr_Dinv, Dn, Ln, d.pcr_A + l * N36, d.pcr_G + l * N36);
-    __syncthreads();
+    for (int v = pb + tid; v < pe; v += nth) body_pcr_invert(d, v, D, d.pcr_Dinv, lambda, &bad);
+    cl.sync();
+    for (int v = pb + tid; v < pe; v += nth) body_pcr_reduce(v, pb, pe, 1 << l, D, L, d.pcr_Dinv, Dn, Ln, d.pcr_A + l * N36, d.pcr_G + l * N36);
+    cl.sync();
     cur = 1 - cur;
   }
-  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) body_pcr_invert(d, v, d.pcr_D + cur * N36, d.Minv, lambda, &bad);
+  for (int v = pb + tid; v < pe; v += nth) body_pcr_invert(d, v, d.pcr_D + cur * N36, d.Minv, lambda, &bad);
   if (bad) atomicAdd(d.scal + SC_BAD, 1.0);
 }
 
-// z = M^-1 r for the CTA's path (r must already be final for the whole path); returns this thread's share of r.z
-__device__ __forceinline__ double pcr_solve_path(const BaDev& d, int pb, int pe, const double* __restrict__ r, double* __restrict__ z) {
+// z = M^-1 r for the cluster's chain (r final for the whole chain on entry); returns this thread's share of r.z.
+// Work item = (vertex, row): 6 items per vertex so that A / G rows are read coalesced.
+__device__ __forceinline__ double pcr_solve_path(const BaDev& d, cg::cluster_group& cl, int pb, int pe, const double* __restrict__ r, double* __restrict__ z) {
   const int nl = pcr_num_levels(pe - pb);
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  const int n_items = 6 * (pe - pb);
   const size_t N6 = 6 * (size_t)d.C, N36 = 36 * (size_t)d.C;
+  const double* src = r;
   int cur = 0;
-  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) d.pcr_b[6 * (size_t)v + i] = r[6 * (size_t)v + i];
-  __syncthreads();
   for (int l = 0; l < nl; ++l) {
-    for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
-      body_pcr_apply(v, pb, pe, 1 << l, d.pcr_A + l * N36, d.pcr_G + l * N36, d.pcr_b + cur * N6, d.pcr_b + (1 - cur) * N6);
-    __syncthreads();
-    cur = 1 - cur;
+    double* dst = d.pcr_b + cur * N6;
+    for (int w = tid; w < n_items; w += nth) {
+      const int v = pb + w / 6, row = w % 6;
+      dst[6 * (size_t)v + row] = pcr_apply_row(v, row, pb, pe, 1 << l, d.pcr_A + l * N36, d.pcr_G + l * N36, src);
+    }
+    cl.sync();
+    src = dst; cur = 1 - cur;
   }
   double rz = 0.0;
-  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x) {
-    double zz[6];
-    mul6(d.Minv + 36 * (size_t)v, d.pcr_b + cur * N6 + 6 * (size_t)v, zz);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { z[6 * (size_t)v + i] = zz[i]; rz += zz[i] * r[6 * (size_t)v + i]; }
+  for (int w = tid; w < n_items; w += nth) {
+    const int v = pb + w / 6, row = w % 6;
+    const double* m = d.Minv + 36 * (size_t)v + 6 * row; const double* x = src + 6 * (size_t)v;
+    const double zz = m[0] * x[0] + m[1] * x[1] + m[2] * x[2] + m[3] * x[3] + m[4] * x[4] + m[5] * x[5];
+    z[6 * (size_t)v + row] = zz;
+    rz += zz * r[6 * (size_t)v + row];
   }
   return rz;
 }
 
-__global__ void __launch_bounds__(256) k_pcg_init(BaDev d) {
+__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_init(BaDev d) {
   __shared__ double red[32];
-  const int pb = d.path_begin[blockIdx.x], pe = d.path_begin[blockIdx.x + 1];
-  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { d.r[6 * (size_t)v + i] = d.rhs[6 * (size_t)v + i]; d.xp[6 * (size_t)v + i] = 0.0; }
-  __syncthreads();
-  double rz = pcr_solve_path(d, pb, pe, d.r, d.z);
-  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) d.p[6 * (size_t)v + i] = d.z[6 * (size_t)v + i];
+  cg::cluster_group cl = cg::this_cluster();
+  const int path = blockIdx.x / PCR_CL;
+  const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.r[q] = d.rhs[q]; d.xp[q] = 0.0; }
+  if (pe - pb > 1) cl.sync();
+  double rz = pcr_solve_path(d, cl, pb, pe, d.r, d.z);
+  // p = z: each thread copies exactly the items it produced in the last loop of pcr_solve_path
+  for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.p[q] = d.z[q]; }
   rz = block_sum(rz, red);
-  if (threadIdx.x == 0) atomicAdd(d.scal + SC_RZ, rz);
+  if (threadIdx.x == 0 && rz != 0.0) atomicAdd(d.scal + SC_RZ, rz);
 }
 __global__ void k_pcg_init_fin(BaDev d) {
   const double rz = d.scal[SC_RZ];
@@ -245,19 +266,20 @@ __global__ void __launch_bounds__(256) k_pcg_dot(BaDev d) {
   if (threadIdx.x == 0) atomicAdd(d.scal + SC_PAP, s);
 }
 // x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new += r.z
-__global__ void __launch_bounds__(256) k_pcg_step_a(BaDev d) {
+__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step_a(BaDev d) {
   __shared__ double red[32];
   if (d.scal[SC_DONE] != 0.0) return;
+  cg::cluster_group cl = cg::this_cluster();
   const double pap = d.scal[SC_PAP], rz = d.scal[SC_RZ];
   const double alpha = (pap > 0.0) ? rz / pap : 0.0;
-  const int pb = d.path_begin[blockIdx.x], pe = d.path_begin[blockIdx.x + 1];
-  for (int v = pb + threadIdx.x; v < pe; v += blockDim.x)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { const size_t q = 6 * (size_t)v + i; d.xp[q] += alpha * d.p[q]; d.r[q] -= alpha * d.Ap[q]; }
-  __syncthreads();
-  double rzn = pcr_solve_path(d, pb, pe, d.r, d.z);
+  const int path = blockIdx.x / PCR_CL;
+  const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.xp[q] += alpha * d.p[q]; d.r[q] -= alpha * d.Ap[q]; }
+  if (pe - pb > 1) cl.sync();
+  double rzn = pcr_solve_path(d, cl, pb, pe, d.r, d.z);
   rzn = block_sum(rzn, red);
-  if (threadIdx.x == 0) atomicAdd(d.scal + SC_RZ_NEW, rzn);
+  if (threadIdx.x == 0 && rzn != 0.0) atomicAdd(d.scal + SC_RZ_NEW, rzn);
 }
 __global__ void __launch_bounds__(256) k_pcg_step_b(BaDev d) {
   if (d.scal[SC_DONE] != 0.0) return;
@@ -265,8 +287,9 @@ __global__ void __launch_bounds__(256) k_pcg_step_b(BaDev d) {
   const int n = d.C * 6;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d.p[i] = d.z[i] + beta * d.p[i];
 }
-__global__ void k_pcg_scalars(BaDev d, double tol2) {
+__global__ void k_pcg_scalars(BaDev d) {
   if (d.scal[SC_DONE] != 0.0) return;
+  const double tol2 = d.scal[SC_TOL2];
   const double pap = d.scal[SC_PAP], rzn = d.scal[SC_RZ_NEW];
   if (!(pap > 0.0) || !isfinite(pap) || !isfinite(rzn)) { d.scal[SC_DONE] = 2.0; return; }
   d.scal[SC_RZ] = rzn; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] += 1.0;
@@ -328,7 +351,7 @@ struct CudaBackend : BaBackend {
   void precond_begin(BaDev& d, double lambda) override { LAUNCH(k_precond_begin, nblk(d.C * 36, 128), 128, d, lambda); }
   void precond_vertex_obs(BaDev& d) override { auto k = k_vertex_sym<1, true>; LAUNCH(k, d.n_obs_chunks, 128, d); }
   void precond_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
-  void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_paths, 256, d, lambda); }
+  void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_paths * PCR_CL, 256, d, lambda); }
   void schur_landmarks(BaDev& d, int mode, const double* v) override {
     const int g = nblk(d.T, 128);
     if (mode == 0) LAUNCH(k_schur_landmarks<0>, g, 128, d, v, d.zl);
@@ -337,17 +360,61 @@ struct CudaBackend : BaBackend {
   }
   void schur_vertex_obs(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
   void schur_vertex_ter(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<false>, d.n_ter_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
-  void hpp_mul(BaDev& d, double lambda, const double* x, double* out) override { LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, lambda, x, out); }
+  void set_scalars(BaDev& d, double lambda, double tol2) {
+    if (lambda != cur_lambda || tol2 != cur_tol2 || d.scal != cur_scal) { LAUNCH(k_set_scalars, 1, 1, d, lambda, tol2); cur_lambda = lambda; cur_tol2 = tol2; cur_scal = d.scal; }
+  }
+  double cur_lambda = -1, cur_tol2 = -1; double* cur_scal = nullptr;
+  void vertex_transform(BaDev& d, const double* v) override { LAUNCH(k_vertex_transform, nblk(d.C, 128), 128, d, v); }
+  void hpp_mul(BaDev& d, double lambda, const double* x, double* out) override { set_scalars(d, lambda, cur_tol2 < 0 ? 0.0 : cur_tol2); LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, x, out); }
   void pcg_init(BaDev& d) override {
     zero(d.scal + SC_PAP, 6 * sizeof(double));   // PAP, RZ, RZ_NEW, RZ0, DONE, ITERS
-    LAUNCH(k_pcg_init, d.n_paths, 256, d);
+    LAUNCH(k_pcg_init, d.n_paths * PCR_CL, 256, d);
     LAUNCH(k_pcg_init_fin, 1, 1, d);
   }
   void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, min(nblk(d.C * 6, 256), 148), 256, d); }
   void pcg_step(BaDev& d, double tol2) override {
-    LAUNCH(k_pcg_step_a, d.n_paths, 256, d);
+    set_scalars(d, cur_lambda, tol2);
+    LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
     LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
-    LAUNCH(k_pcg_scalars, 1, 1, d, tol2);
+    LAUNCH(k_pcg_scalars, 1, 1, d);
+  }
+  // n PCG iterations as ONE CUDA-graph launch (captured once per factor graph and batch size; lambda / tolerance travel
+  // through device scalars so the captured kernel arguments never change)
+  std::map<std::pair<const void*, int>, cudaGraphExec_t> graphs;
+  void pcg_iterate(BaDev& d, double lambda, double tol2, int n) override {
+    set_scalars(d, lambda, tol2);
+    auto key = std::make_pair((const void*)d.scal, n);
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+      const int before = n_launch;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (int b = 0; b < n; ++b) {
+        LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, (const double*)d.p, d.Ap);
+        schur_landmarks(d, 1, d.p);
+        schur_vertex_obs(d, -1.0, d.Ap);
+        schur_vertex_ter(d, -1.0, d.Ap);
+        pcg_dot_pAp(d);
+        LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
+        LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
+        LAUNCH(k_pcg_scalars, 1, 1, d);
+      }
+      CK(cudaStreamEndCapture(st, &g));
+      CK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      per_batch[key] = n_launch - before;
+      n_launch = before;
+      it = graphs.emplace(key, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second, st));
+    n_launch += per_batch[key];
+  }
+  std::map<std::pair<const void*, int>, int> per_batch;
+  void release(BaDev& d) override {
+    for (auto it = graphs.begin(); it != graphs.end();) {
+      if (it->first.first == (const void*)d.scal) { cudaGraphExecDestroy(it->second); per_batch.erase(it->first); it = graphs.erase(it); } else ++it;
+    }
+    if (cur_scal == d.scal) cur_scal = nullptr;
   }
   void apply_update(BaDev& d, double lambda, bool reortho) override { LAUNCH(k_apply_update, nblk(d.C + d.P, 128), 128, d, lambda, reortho ? 1 : 0); }
 };

@@ -52,11 +52,13 @@ struct BaDev {
   double *pcr_b = 0;              // 2 * C * 6 scratch of the solve   // per landmark: diagonal scalar of Hll^-1; per ternary edge: g_k + g_k+1 - 2 g_k,k+1
   double *xp = 0, *r = 0, *z = 0, *p = 0, *Ap = 0, *rhs = 0; // 6C each
   double *zl = 0, *xl = 0;                                    // 3P each
+  double *vw = 0;   // 6C: per-vertex world-frame image [gamma, beta] of the vector the landmark pass multiplies (see body_vertex_transform)
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each
   double* scal = 0;  // device scalars, see SC_* below
 };
 
-enum { SC_CHI2 = 0, SC_MAXDIAG = 1, SC_SCALE = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9, SC_N = 16 };
+enum { SC_CHI2 = 0, SC_MAXDIAG = 1, SC_SCALE = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9,
+       SC_LAMBDA = 10, SC_TOL2 = 11, SC_N = 16 };
 
 // The backend: memory + one function per kernel.  Implemented for CUDA in ba_kernels.cu (the product) and, for the
 // CPU-only host-logic tests, as serial loops over the same per-thread bodies in tests/emul/ba_backend_emul.cpp.
@@ -95,17 +97,33 @@ struct BaBackend {
   virtual void precond_vertex_ter(BaDev& d) = 0;
   virtual void precond_factor(BaDev& d, double lambda) = 0;
   // --- Schur products ---
-  // mode 0: zl = Hll^-1 bl ; mode 1: zl = Hll^-1 (Hlp v) ; mode 2: xl = Hll^-1 (bl - Hlp v)
+  // mode 0: zl = Hll^-1 bl ; mode 1: zl = Hll^-1 (Hlp v) ; mode 2: xl = Hll^-1 (bl - Hlp v).  Modes 1/2 read v through d.vw
+  // (vertex_transform / hpp_mul must have run on v) and, for ternary edges, v itself.
   virtual void schur_landmarks(BaDev& d, int mode, const double* v) = 0;
   // out[vertex] += sign * sum_edges Hpl_e * zl[landmark(e)]
   virtual void schur_vertex_obs(BaDev& d, double sign, double* out) = 0;
   virtual void schur_vertex_ter(BaDev& d, double sign, double* out) = 0;
-  // out = (Hpp + lambda I) v  (diagonal blocks and se3-se3 off-diagonal blocks)
+  // vw = world-frame image of v (needed by schur_landmarks modes 1 and 2)
+  virtual void vertex_transform(BaDev& d, const double* v) = 0;
+  // out = (Hpp + lambda I) v  (diagonal blocks and se3-se3 off-diagonal blocks); also performs vertex_transform(v)
   virtual void hpp_mul(BaDev& d, double lambda, const double* v, double* out) = 0;
   // --- PCG vector steps (device-side scalars; no host sync) ---
   virtual void pcg_init(BaDev& d) = 0;     // r = rhs (x = 0), z = Minv r, p = z, rz = r.z, rz0 = rz, done = 0, iters = 0
   virtual void pcg_dot_pAp(BaDev& d) = 0;  // scal[SC_PAP] = p.Ap
   virtual void pcg_step(BaDev& d, double tol2) = 0;  // alpha, x, r, z, rz_new, beta, p; done=1 if rz_new <= tol2 * rz0, done=2 on breakdown
+  // n PCG iterations (S*p, p.Ap, x/r/z update, beta, p update) without host involvement.  The default composes the
+  // primitives above; the CUDA backend replays a captured CUDA graph.
+  virtual void pcg_iterate(BaDev& d, double lambda, double tol2, int n) {
+    for (int b = 0; b < n; ++b) {
+      hpp_mul(d, lambda, d.p, d.Ap);
+      schur_landmarks(d, 1, d.p);
+      schur_vertex_obs(d, -1.0, d.Ap);
+      schur_vertex_ter(d, -1.0, d.Ap);
+      pcg_dot_pAp(d);
+      pcg_step(d, tol2);
+    }
+  }
+  virtual void release(BaDev& d) { (void)d; }   // drop anything cached for this graph (called before its buffers are freed)
   // --- update / acceptance ---
   virtual void apply_update(BaDev& d, double lambda, bool reorthogonalize) = 0;  // oplus; scal[SC_SCALE] = sum x (lambda x + b)
 };
