@@ -133,7 +133,8 @@ struct EmulBackend : BaBackend {
         const double *D = d.pcr_D + cur * N36, *L = d.pcr_L + cur * N36;
         double *Dn = d.pcr_D + (1 - cur) * N36, *Ln = d.pcr_L + (1 - cur) * N36;
         for (int v = pb; v < pe; ++v) { int bad = 0; body_pcr_invert(d, v, D, d.pcr_Dinv, lambda, &bad); d.scal[SC_BAD] += bad; }
-        for (int v = pb; v < pe; ++v) body_pcr_reduce(v, pb, pe, 1 << l, D, L, d.pcr_Dinv, Dn, Ln, d.pcr_A + l * N36, d.pcr_G + l * N36);
+        for (int v = pb; v < pe; ++v) for (int rc = 0; rc < 36; ++rc) body_pcr_AG(v, rc / 6, rc % 6, pb, pe, 1 << l, L, d.pcr_Dinv, d.pcr_A + l * N36, d.pcr_G + l * N36);
+        for (int v = pb; v < pe; ++v) for (int rc = 0; rc < 36; ++rc) body_pcr_DL(v, rc / 6, rc % 6, pb, pe, 1 << l, D, L, d.pcr_A + l * N36, d.pcr_G + l * N36, Dn, Ln);
         cur = 1 - cur;
       }
       for (int v = pb; v < pe; ++v) { int bad = 0; body_pcr_invert(d, v, d.pcr_D + cur * N36, d.Minv, lambda, &bad); d.scal[SC_BAD] += bad; }

@@ -362,34 +362,37 @@ VDO_HD void body_pcr_invert(const BaDev& d, int v, const double* D, double* Dinv
   }
   for (int i = 0; i < 36; ++i) Dinv[36 * (size_t)v + i] = M[i];
 }
-// one reduction step with stride s for vertex v of path [pb, pe): writes A, G (level operators) and the next-level D, L
-VDO_HD void body_pcr_reduce(int v, int pb, int pe, int s, const double* D, const double* L, const double* Dinv,
-                            double* Dn, double* Ln, double* A, double* G) {
-  double a[36], g[36], t[36];
-  double* Dv = Dn + 36 * (size_t)v;
-  for (int i = 0; i < 36; ++i) Dv[i] = D[36 * (size_t)v + i];
-  const bool has_m = v - s >= pb, has_p = v + s < pe;
-  if (has_m) {                       // A = -L_v Dinv_{v-s} ; D' += A L_v^T ; L' = A L_{v-s}
-    mat6_mul(L + 36 * (size_t)v, Dinv + 36 * (size_t)(v - s), a);
-    for (int i = 0; i < 36; ++i) a[i] = -a[i];
-    mat6_mul_nt(a, L + 36 * (size_t)v, t);
-    for (int i = 0; i < 36; ++i) Dv[i] += t[i];
-    if (v - 2 * s >= pb) mat6_mul(a, L + 36 * (size_t)(v - s), Ln + 36 * (size_t)v);
-    else for (int i = 0; i < 36; ++i) Ln[36 * (size_t)v + i] = 0;
-  } else {
-    for (int i = 0; i < 36; ++i) { a[i] = 0; Ln[36 * (size_t)v + i] = 0; }
+// One reduction step with stride s, split into two passes of (vertex, row, col) work items so that a whole cluster
+// can share a chain:  pass 1  A_v = -L_v Dinv_{v-s},  G_v = -L_{v+s}^T Dinv_{v+s}   (zero outside the chain)
+//                     pass 2  D'_v = D_v + A_v L_v^T + G_v L_{v+s},  L'_v = A_v L_{v-s}
+VDO_HD void body_pcr_AG(int v, int r, int c, int pb, int pe, int s, const double* L, const double* Dinv, double* A, double* G) {
+  double a = 0.0, g = 0.0;
+  if (v - s >= pb) {
+    const double* Lv = L + 36 * (size_t)v + 6 * r; const double* Di = Dinv + 36 * (size_t)(v - s) + c;
+    a = -(Lv[0] * Di[0] + Lv[1] * Di[6] + Lv[2] * Di[12] + Lv[3] * Di[18] + Lv[4] * Di[24] + Lv[5] * Di[30]);
   }
-  if (has_p) {                       // U_v = L_{v+s}^T ; G = -U_v Dinv_{v+s} ; D' += G U_v^T = G L_{v+s}
-    mat6_mul_tn(L + 36 * (size_t)(v + s), Dinv + 36 * (size_t)(v + s), g);
-    for (int i = 0; i < 36; ++i) g[i] = -g[i];
-    mat6_mul(g, L + 36 * (size_t)(v + s), t);
-    for (int i = 0; i < 36; ++i) Dv[i] += t[i];
-  } else {
-    for (int i = 0; i < 36; ++i) g[i] = 0;
+  if (v + s < pe) {
+    const double* Lp = L + 36 * (size_t)(v + s) + r; const double* Di = Dinv + 36 * (size_t)(v + s) + c;
+    g = -(Lp[0] * Di[0] + Lp[6] * Di[6] + Lp[12] * Di[12] + Lp[18] * Di[18] + Lp[24] * Di[24] + Lp[30] * Di[30]);
   }
-  // keep D' exactly symmetric
-  for (int r = 0; r < 6; ++r) for (int c = r + 1; c < 6; ++c) { double m = 0.5 * (Dv[6 * r + c] + Dv[6 * c + r]); Dv[6 * r + c] = Dv[6 * c + r] = m; }
-  for (int i = 0; i < 36; ++i) { A[36 * (size_t)v + i] = a[i]; G[36 * (size_t)v + i] = g[i]; }
+  A[36 * (size_t)v + 6 * r + c] = a; G[36 * (size_t)v + 6 * r + c] = g;
+}
+VDO_HD void body_pcr_DL(int v, int r, int c, int pb, int pe, int s, const double* D, const double* L, const double* A, const double* G,
+                        double* Dn, double* Ln) {
+  double dd = D[36 * (size_t)v + 6 * r + c], ll = 0.0;
+  if (v - s >= pb) {
+    const double* a = A + 36 * (size_t)v + 6 * r; const double* Lv = L + 36 * (size_t)v + 6 * c;
+    dd += a[0] * Lv[0] + a[1] * Lv[1] + a[2] * Lv[2] + a[3] * Lv[3] + a[4] * Lv[4] + a[5] * Lv[5];
+    if (v - 2 * s >= pb) {
+      const double* Lm = L + 36 * (size_t)(v - s) + c;
+      ll = a[0] * Lm[0] + a[1] * Lm[6] + a[2] * Lm[12] + a[3] * Lm[18] + a[4] * Lm[24] + a[5] * Lm[30];
+    }
+  }
+  if (v + s < pe) {
+    const double* g = G + 36 * (size_t)v + 6 * r; const double* Lp = L + 36 * (size_t)(v + s) + c;
+    dd += g[0] * Lp[0] + g[1] * Lp[6] + g[2] * Lp[12] + g[3] * Lp[18] + g[4] * Lp[24] + g[5] * Lp[30];
+  }
+  Dn[36 * (size_t)v + 6 * r + c] = dd; Ln[36 * (size_t)v + 6 * r + c] = ll;
 }
 // solve phase, one level: bn_v = b_v + A_v b_{v-s} + G_v b_{v+s}
 VDO_HD void body_pcr_apply(int v, int pb, int pe, int s, const double* A, const double* G, const double* b, double* bn) {

@@ -5,11 +5,20 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
 
 namespace vdo {
+
+namespace {
+struct Phase {
+  BaBackend* be; float* acc; bool on;
+  Phase(BaBackend* b, float* a, bool o) : be(b), acc(a), on(o) { if (on) be->timer_start(3); }
+  ~Phase() { if (on) *acc += be->timer_stop_ms(3); }
+};
+}  // namespace
 
 BaGraph::~BaGraph() {
   if (finalized_) be_->release(d_);
@@ -320,32 +329,43 @@ double BaGraph::robust_chi2() {
 // ---- one linear solve (H + lambda I) x = b by landmark elimination + PCG on the reduced se3 system ----
 bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   BaDev& d = d_;
+  const bool prof = prof_on_;
+  {
+  Phase ph(be_, &prof_ms_[0], prof);
   be_->factor_landmarks(d, lambda);
   be_->zero(d.scal + SC_BAD, sizeof(double));
   be_->precond_begin(d, lambda);
   be_->precond_vertex_obs(d);
   be_->precond_vertex_ter(d);
   be_->precond_factor(d, lambda);
+  }
+  {
+  Phase ph(be_, &prof_ms_[1], prof);
   // rhs = bp - Hpl Hll^-1 bl
   be_->schur_landmarks(d, 0, nullptr);
   be_->d2d(d.rhs, d.bp, 48 * (size_t)d.C);
   be_->schur_vertex_obs(d, -1.0, d.rhs);
   be_->schur_vertex_ter(d, -1.0, d.rhs);
   be_->pcg_init(d);
+  }
   const double tol2 = opt.pcg_rel_tol * opt.pcg_rel_tol;
   const int batch = 8;
   double sc[SC_N];
   int it = 0;
   bool ok = true;
+  {
+  Phase ph(be_, &prof_ms_[2], prof);
   while (it < opt.pcg_max_iterations) {
     be_->pcg_iterate(d, lambda, tol2, batch);
     it += batch;
     be_->d2h(sc, d.scal, sizeof(sc));
     if (sc[SC_DONE] != 0.0) break;
   }
+  }
   *pcg_iters = (int)sc[SC_ITERS];
   if (sc[SC_DONE] == 2.0 || !std::isfinite(sc[SC_RZ])) ok = false;   // breakdown (p.Ap <= 0 or NaN)
   // back substitution: xl = Hll^-1 (bl - Hlp xp)
+  Phase ph(be_, &prof_ms_[3], prof);
   be_->vertex_transform(d, d.xp);
   be_->schur_landmarks(d, 2, d.xp);
   return ok;
@@ -359,6 +379,8 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
   if (opt.pcg_max_iterations <= 0) opt.pcg_max_iterations = 2000;
   BaDev& d = d_;
   const int launches0 = be_->launches();
+  prof_on_ = std::getenv("VDO_PROFILE") != nullptr;
+  for (float& x : prof_ms_) x = 0;
   be_->timer_start(0);
   float ms_lin = 0, ms_solve = 0;
   double lambda = -1, ni = 2; int nbad = 0, trials = 0, pcg_total = 0;
@@ -386,6 +408,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
       int pit = 0;
       bool ok2 = solve(lambda, opt, &pit);
       pcg_total += pit;
+      Phase ph_u(be_, &prof_ms_[4], prof_on_);
       ++oplus_calls_;
       bool reortho = false;
       if (oplus_calls_ > 1000) { oplus_calls_ = 0; reortho = true; }   // vertex_se3.h:110-113
@@ -436,6 +459,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
     }
   }
   float ms_total = be_->timer_stop_ms(0);
+  if (prof_on_) std::fprintf(stderr, "[vdo_b200] phases (ms, synchronising timers): factor+precond %.2f | rhs+init %.2f | pcg %.2f | backsubst %.2f | update+chi2 %.2f | linearize %.2f | total %.2f (iters %d trials %d pcg %d)\n", prof_ms_[0], prof_ms_[1], prof_ms_[2], prof_ms_[3], prof_ms_[4], ms_lin, ms_total, iters_done, trials, pcg_total);
   if (stats) {
     stats->iterations = iters_done; stats->trials = trials; stats->pcg_iterations = pcg_total;
     stats->initial_chi2 = chi_init; stats->final_chi2 = chi_cur; stats->final_lambda = lambda;

@@ -41,6 +41,8 @@ class BaGraph {
   bool finalized_ = false;
   std::string err_;
   long oplus_calls_ = 0;
+  bool prof_on_ = false;
+  float prof_ms_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // host staging (until finalize)
   int n_se3_ = 0, n_pt_ = 0;
   std::vector<double> h_se3_, h_pt_;

@@ -198,9 +198,13 @@ __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcr_fact
   for (int l = 0; l < nl; ++l) {
     const double *D = d.pcr_D + cur * N36, *L = d.pcr_L + cur * N36;
     double *Dn = d.pcr_D + (1 - cur) * N36, *Ln = d.pcr_L + (1 - cur) * N36;
+    double *A = d.pcr_A + l * N36, *G = d.pcr_G + l * N36;
+    const int n_items = 36 * (pe - pb), s = 1 << l;
     for (int v = pb + tid; v < pe; v += nth) body_pcr_invert(d, v, D, d.pcr_Dinv, lambda, &bad);
     cl.sync();
-    for (int v = pb + tid; v < pe; v += nth) body_pcr_reduce(v, pb, pe, 1 << l, D, L, d.pcr_Dinv, Dn, Ln, d.pcr_A + l * N36, d.pcr_G + l * N36);
+    for (int w = tid; w < n_items; w += nth) { const int v = pb + w / 36, rc = w % 36; body_pcr_AG(v, rc / 6, rc % 6, pb, pe, s, L, d.pcr_Dinv, A, G); }
+    cl.sync();
+    for (int w = tid; w < n_items; w += nth) { const int v = pb + w / 36, rc = w % 36; body_pcr_DL(v, rc / 6, rc % 6, pb, pe, s, D, L, A, G, Dn, Ln); }
     cl.sync();
     cur = 1 - cur;
   }

@@ -333,34 +333,45 @@ VDO_HD void ter_JhT_mul(const double* q, const double* a, double* o) {  // [a ; 
 
 // in-place Cholesky inverse of a symmetric positive definite 6x6 (row-major full storage). Returns false if not SPD.
 VDO_HD bool spd6_inverse(double* M) {
-  double L[36];
-  for (int i = 0; i < 36; ++i) L[i] = 0;
+  double L[36], Li[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) { L[i] = 0; Li[i] = 0; }
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = M[7 * j];
+#pragma unroll
     for (int k = 0; k < j; ++k) d -= L[6 * j + k] * L[6 * j + k];
-    if (!(d > 0)) return false;
+    if (!(d > 0)) { ok = false; d = 1.0; }
     d = sqrt(d);
     L[7 * j] = d;
+    const double id = 1.0 / d;
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = M[6 * i + j];
+#pragma unroll
       for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k];
-      L[6 * i + j] = s / d;
+      L[6 * i + j] = s * id;
     }
   }
-  // invert L (lower) into Li
-  double Li[36];
-  for (int i = 0; i < 36; ++i) Li[i] = 0;
+  if (!ok) return false;
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     Li[7 * j] = 1.0 / L[7 * j];
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = 0;
+#pragma unroll
       for (int k = j; k < i; ++k) s -= L[6 * i + k] * Li[6 * k + j];
       Li[6 * i + j] = s / L[7 * i];
     }
   }
+#pragma unroll
   for (int i = 0; i < 6; ++i)
+#pragma unroll
     for (int j = 0; j <= i; ++j) {
       double s = 0;
+#pragma unroll
       for (int k = i; k < 6; ++k) s += Li[6 * k + i] * Li[6 * k + j];
       M[6 * i + j] = M[6 * j + i] = s;
     }
