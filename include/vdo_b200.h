@@ -115,6 +115,14 @@ int vdo_graph_info(const vdo_graph *g, int64_t out[8]);
  * diagonal blocks are that scalar times I3 for scalar information), bl: n_pt x 3, chi2: robust chi2. */
 int vdo_graph_debug_linearize(vdo_graph *g, double *Hpp_diag, double *bp, double *Hll_diag, double *bl, double *chi2);
 
+/* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
+ * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.
+ * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).
+ * names: "lin_tracklets" "chi2_tracklets" "lin_vertex_obs" "lin_vertex_ter" "lin_se3_edges" "linearize" (all four)
+ *        "factor_landmarks" "precond" (assembly + PCR factorisation) "schur_landmarks" "schur_vertex_obs"
+ *        "schur_vertex_ter" "hpp_mul" "pcg_dot" "pcg_step" "pcg_iterate8" (8 PCG iterations as launched in a solve) */
+int vdo_graph_time_kernel(vdo_graph *g, const char *name, int reps, float *ms_avg);
+
 #ifdef __cplusplus
 }
 #endif

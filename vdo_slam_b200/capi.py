@@ -150,6 +150,11 @@ class BatchGraph:
         self.ctx.check(self.ctx.L.vdo_graph_info(self.h, out), "vdo_graph_info")
         return dict(zip(["n_se3", "n_pt", "n_pointxyz_edges", "n_motion_edges", "n_se3_edges", "n_prior", "n_tracklets", "device_bytes"], list(out)))
 
+    def time_kernel(self, name: str, reps: int = 20) -> float:
+        ms = C.c_float(0)
+        self.ctx.check(self.ctx.L.vdo_graph_time_kernel(self.h, name.encode(), C.c_int(reps), C.byref(ms)), f"vdo_graph_time_kernel({name})")
+        return float(ms.value)
+
     def debug_linearize(self):
         Hpp = np.zeros((self.n_se3, 6, 6)); bp = np.zeros((self.n_se3, 6)); Hll = np.zeros(self.n_pt); bl = np.zeros((self.n_pt, 3))
         chi = C.c_double(0)

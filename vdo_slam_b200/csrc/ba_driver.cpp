@@ -436,6 +436,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
       ++qmax; ++trials;
     } while (rho < 0 && qmax < opt.max_trials && !stop_flag);
     ms_solve += be_->timer_stop_ms(2);
+    last_lambda_ = lambda;
     if (qmax == opt.max_trials || rho == 0) result_ok = false;
     else {
       if ((ini - current) * 1e3 < ini) nbad++; else nbad = 0;
@@ -466,6 +467,47 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
     stats->ms_linearize = ms_lin; stats->ms_solve = ms_solve; stats->ms_total = ms_total;
     stats->kernel_launches = be_->launches() - launches0;
   }
+  return VDO_OK;
+}
+
+int BaGraph::time_kernel(const char* name, int reps, float* ms_avg) {
+  if (!finalized_) return fail(VDO_ERR_STATE, "time_kernel before finalize");
+  if (!name || reps <= 0 || !ms_avg) return fail(VDO_ERR_ARG, "time_kernel: bad arguments");
+  BaDev& d = d_;
+  const std::string n(name);
+  const double lam = last_lambda_;
+  auto run = [&]() -> bool {
+    if (n == "lin_tracklets") be_->lin_tracklets(d, true);
+    else if (n == "chi2_tracklets") be_->lin_tracklets(d, false);
+    else if (n == "lin_vertex_obs") be_->lin_vertex_obs(d);
+    else if (n == "lin_vertex_ter") be_->lin_vertex_ter(d);
+    else if (n == "lin_se3_edges") be_->lin_se3_edges(d, true);
+    else if (n == "linearize") linearize();
+    else if (n == "factor_landmarks") be_->factor_landmarks(d, lam);
+    else if (n == "precond") { be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); be_->precond_factor(d, lam); }
+    else if (n == "schur_landmarks") be_->schur_landmarks(d, 1, d.p);
+    else if (n == "schur_vertex_obs") be_->schur_vertex_obs(d, -1.0, d.Ap);
+    else if (n == "schur_vertex_ter") be_->schur_vertex_ter(d, -1.0, d.Ap);
+    else if (n == "hpp_mul") be_->hpp_mul(d, lam, d.p, d.Ap);
+    else if (n == "pcg_dot") be_->pcg_dot_pAp(d);
+    else if (n == "pcg_step") be_->pcg_step(d, 0.0);
+    else if (n == "pcg_iterate8") be_->pcg_iterate(d, lam, 0.0, 8);
+    else return false;
+    return true;
+  };
+  // a valid, never-converging PCG state: linearise + factor at the last lambda, rhs, init
+  linearize();
+  be_->factor_landmarks(d, lam);
+  be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); be_->precond_factor(d, lam);
+  be_->schur_landmarks(d, 0, nullptr);
+  be_->d2d(d.rhs, d.bp, 48 * (size_t)d.C);
+  be_->schur_vertex_obs(d, -1.0, d.rhs); be_->schur_vertex_ter(d, -1.0, d.rhs);
+  be_->pcg_init(d);
+  if (!run()) return fail(VDO_ERR_ARG, "time_kernel: unknown kernel name");
+  be_->sync();
+  be_->timer_start(3);
+  for (int i = 0; i < reps; ++i) run();
+  *ms_avg = be_->timer_stop_ms(3) / reps;
   return VDO_OK;
 }
 

@@ -24,6 +24,7 @@ class BaGraph {
   int reset_vertices();
   int info(int64_t out[8]) const;
   int debug_linearize(double* Hpp, double* bp, double* Hll, double* bl, double* chi2);
+  int time_kernel(const char* name, int reps, float* ms_avg);
   const std::string& error() const { return err_; }
 
  private:
@@ -43,6 +44,7 @@ class BaGraph {
   long oplus_calls_ = 0;
   bool prof_on_ = false;
   float prof_ms_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double last_lambda_ = 1.0;
   // host staging (until finalize)
   int n_se3_ = 0, n_pt_ = 0;
   std::vector<double> h_se3_, h_pt_;
