@@ -79,7 +79,7 @@ typedef struct vdo_lm_options {
   int max_iterations;       /* optimizer.optimize(N): 300 full batch, 100 partial (src/Optimizer.cc:1935, :807) */
   double gain_threshold;    /* SparseOptimizerTerminateAction::setGainThreshold; <= 0: action not installed */
   int max_trials;           /* maxTrialsAfterFailure, g2o default 10 */
-  double pcg_rel_tol;       /* reduced-camera PCG: stop when sqrt(r.M^-1 r) <= tol * initial; default 1e-10 */
+  double pcg_rel_tol;       /* reduced-camera PCG: stop when sqrt(r.M^-1 r) <= tol * initial; default 1e-8 */
   int pcg_max_iterations;   /* default 2000 */
   int verbose;              /* per-iteration line on stderr, like optimizer.setVerbose(true) */
   int force_all_iterations; /* benchmarking: ignore every stop rule and run exactly max_iterations */

@@ -33,7 +33,8 @@ struct EmulBackend : BaBackend {
   void lin_tracklets(BaDev& d, bool write) override {
     ++n_launch;
     double chi = 0;
-    for (int t = 0; t < d.T; ++t) chi += body_lin_tracklet(d, t, write);
+    for (int t = 0; t < d.Tstat; ++t) chi += body_lin_static(d, t, write);
+    for (int t = d.Tstat; t < d.T; ++t) chi += body_lin_tracklet(d, t, write);
     d.scal[SC_CHI2] += chi;
   }
   static void add_sym(double* H36, const double* A21) {
@@ -92,7 +93,7 @@ struct EmulBackend : BaBackend {
     for (int k = 0; k < d.P; ++k) m = std::fmax(m, std::fabs(d.hll[k]));
     d.scal[SC_MAXDIAG] = m;
   }
-  void factor_landmarks(BaDev& d, double lambda) override { ++n_launch; for (int t = 0; t < d.T; ++t) body_factor_tracklet(d, t, lambda); }
+  void factor_landmarks(BaDev& d, double lambda) override { ++n_launch; for (int t = 0; t < d.Tstat; ++t) body_factor_static(d, t, lambda); for (int t = d.Tstat; t < d.T; ++t) body_factor_tracklet(d, t, lambda); }
   void precond_begin(BaDev& d, double lambda) override {
     ++n_launch;
     for (int v = 0; v < d.C; ++v) {
@@ -158,7 +159,8 @@ struct EmulBackend : BaBackend {
     ++n_launch;
     if (mode == 1 && d.scal[SC_DONE] != 0.0) return;
     double* out = mode == 2 ? d.xl : d.zl;
-    for (int t = 0; t < d.T; ++t) body_schur_tracklet(d, t, mode, v, out);
+    for (int t = 0; t < d.Tstat; ++t) body_schur_static(d, t, mode, out);
+    for (int t = d.Tstat; t < d.T; ++t) body_schur_tracklet(d, t, mode, v, out);
   }
   void schur_vertex_obs(BaDev& d, double sign, double* out) override {
     ++n_launch;

@@ -122,7 +122,7 @@ class BatchGraph:
             ctx.check(L.vdo_graph_add_edges_landmark_motion(self.h, len(w), _ip(pph), _dp(w), _dp(dl)), "add_edges_landmark_motion")
         ctx.check(L.vdo_graph_finalize(self.h), "vdo_graph_finalize")
 
-    def optimize(self, max_iterations=300, gain_threshold=1e-4, pcg_rel_tol=1e-10, pcg_max_iterations=2000,
+    def optimize(self, max_iterations=300, gain_threshold=1e-4, pcg_rel_tol=1e-8, pcg_max_iterations=2000,
                  verbose=False, force_all_iterations=False):
         o = LMOptions()
         self.ctx.L.vdo_lm_options_default(C.byref(o))

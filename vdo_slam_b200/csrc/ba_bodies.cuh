@@ -68,6 +68,86 @@ VDO_HD double body_lin_tracklet(const BaDev& d, int t, bool write) {
   return chi;
 }
 
+// ---- static landmarks (no ternary edges): one landmark per call, edge loop unrolled 2x/4x for memory-level parallelism ----
+VDO_HD double body_lin_static(const BaDev& d, int k, bool write) {
+  const double p[3] = {d.pt[3 * (size_t)k], d.pt[3 * (size_t)k + 1], d.pt[3 * (size_t)k + 2]};
+  const int eb = d.lm_obs_begin[k], ee = d.lm_obs_begin[k + 1];
+  double chi = 0.0, dsum = 0.0, b[3] = {0, 0, 0};
+  for (int e0 = eb; e0 < ee; e0 += 2) {
+    const bool two = e0 + 1 < ee;
+    const int e1 = two ? e0 + 1 : e0;
+    Iso T0, T1;
+    iso_load(d.se3 + 12 * (size_t)d.lm_cam[e0], T0);
+    iso_load(d.se3 + 12 * (size_t)d.lm_cam[e1], T1);
+    const double* z0 = d.lm_z + 3 * (size_t)e0; const double* z1 = d.lm_z + 3 * (size_t)e1;
+    const int c0 = d.lm_cls[e0], c1 = d.lm_cls[e1];
+    double Z0[3], Z1[3];
+    iso_inv_apply(T0, p, Z0); iso_inv_apply(T1, p, Z1);
+    const double r0[3] = {Z0[0] - z0[0], Z0[1] - z0[1], Z0[2] - z0[2]};
+    const double r1[3] = {Z1[0] - z1[0], Z1[1] - z1[1], Z1[2] - z1[2]};
+    const double w0 = d.obs_cls_w[c0], w1 = d.obs_cls_w[c1];
+    double rho0, h0, rho1, h1;
+    huber(w0 * (r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]), d.obs_cls_d[c0], rho0, h0);
+    huber(w1 * (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]), d.obs_cls_d[c1], rho1, h1);
+    chi += rho0;
+    if (two) chi += rho1;
+    if (write) {
+      const double o0 = w0 * h0, o1 = two ? w1 * h1 : 0.0;
+      d.lm_omega[e0] = o0;
+      if (two) d.lm_omega[e1] = o1;
+      double R0[3], R1[3];
+      rot_apply(T0.R, r0, R0); rot_apply(T1.R, r1, R1);
+      dsum += o0 + o1;
+      b[0] -= o0 * R0[0] + o1 * R1[0]; b[1] -= o0 * R0[1] + o1 * R1[1]; b[2] -= o0 * R0[2] + o1 * R1[2];
+    }
+  }
+  if (write) {
+    d.tk_omega[k] = 0.0;
+    d.hll[k] = dsum;
+    d.bl[3 * (size_t)k] = b[0]; d.bl[3 * (size_t)k + 1] = b[1]; d.bl[3 * (size_t)k + 2] = b[2];
+  }
+  return chi;
+}
+VDO_HD void body_factor_static(const BaDev& d, int k, double lambda) {
+  const double s = d.hll[k] + lambda;
+  d.pt_s[k] = s; d.pt_g[k] = 1.0 / s; d.tk_gamma[k] = 0.0;
+}
+// mode 0: out = bl / s ; mode 1: out = (Hlp v) / s ; mode 2: out = (bl - Hlp v) / s   (v enters through d.vw)
+VDO_HD void body_schur_static(const BaDev& d, int k, int mode, double* __restrict__ out) {
+  double u[3] = {0, 0, 0};
+  if (mode != 0) {
+    const double p[3] = {d.pt[3 * (size_t)k], d.pt[3 * (size_t)k + 1], d.pt[3 * (size_t)k + 2]};
+    const int eb = d.lm_obs_begin[k], ee = d.lm_obs_begin[k + 1];
+    for (int e0 = eb; e0 < ee; e0 += 4) {
+      int c[4]; double om[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in = e0 + j < ee;
+        c[j] = d.lm_cam[in ? e0 + j : e0];
+        om[j] = in ? d.lm_omega[e0 + j] : 0.0;
+      }
+      double w[4][6];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double* ww = d.vw + 6 * (size_t)c[j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[j][i] = ww[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double pxb[3]; cross3(p, &w[j][3], pxb);
+        u[0] += om[j] * (w[j][0] + 2 * pxb[0]); u[1] += om[j] * (w[j][1] + 2 * pxb[1]); u[2] += om[j] * (w[j][2] + 2 * pxb[2]);
+      }
+    }
+  }
+  double y[3];
+  if (mode == 0) { y[0] = d.bl[3 * (size_t)k]; y[1] = d.bl[3 * (size_t)k + 1]; y[2] = d.bl[3 * (size_t)k + 2]; }
+  else if (mode == 1) { y[0] = u[0]; y[1] = u[1]; y[2] = u[2]; }
+  else { y[0] = d.bl[3 * (size_t)k] - u[0]; y[1] = d.bl[3 * (size_t)k + 1] - u[1]; y[2] = d.bl[3 * (size_t)k + 2] - u[2]; }
+  const double is = 1.0 / d.pt_s[k];
+  out[3 * (size_t)k] = y[0] * is; out[3 * (size_t)k + 1] = y[1] * is; out[3 * (size_t)k + 2] = y[2] * is;
+}
+
 // Schur pivots of the tracklet's (H_ll + lambda I): with scalar diagonal blocks d_k I and off-diagonal blocks
 // -omega_k R_k^T, the block recursion S_{k+1} = d_{k+1} I - omega_k^2 R_k S_k^-1 R_k^T stays a scalar times I, i.e.
 // H_ll = Q (T (x) I3) Q^T with T the scalar tridiagonal (d_k, -omega_k) and Q block-diagonal orthogonal.

@@ -137,8 +137,15 @@ int BaGraph::finalize() {
   new_of_old_.assign(P, -1);
   std::vector<int> old_of_new(P), tk_begin;
   int cnt = 0;
+  // static landmarks (tracklets of one vertex) first, then the chains: the two groups run different kernels
   for (int p = 0; p < P; ++p) {
-    if (prev[p] != -1) continue;
+    if (prev[p] != -1 || next[p] != -1) continue;
+    tk_begin.push_back(cnt);
+    new_of_old_[p] = cnt; old_of_new[cnt++] = p;
+  }
+  const int Tstat = cnt;
+  for (int p = 0; p < P; ++p) {
+    if (prev[p] != -1 || next[p] == -1) continue;
     tk_begin.push_back(cnt);
     for (int q = p; q != -1; q = next[q]) { new_of_old_[q] = cnt; old_of_new[cnt++] = q; }
   }
@@ -243,7 +250,7 @@ int BaGraph::finalize() {
 
   // ---- upload ----
   BaDev& d = d_;
-  d.C = C; d.P = P; d.T = T; d.Eobs = Eo; d.Eter = Et; d.Ese = Ese;
+  d.C = C; d.P = P; d.T = T; d.Tstat = Tstat; d.Eobs = Eo; d.Eter = Et; d.Ese = Ese;
   d.n_obs_chunks = (int)obs_chunks.size(); d.n_ter_chunks = (int)ter_chunks.size(); d.n_nbr = (int)nbr_edge.size();
   d.se3 = upload(se3_int); d.pt = upload(pt_int);
   d.se3_init = upload(se3_int); d.pt_init = upload(pt_int);
@@ -375,7 +382,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
   if (!finalized_) return fail(VDO_ERR_STATE, "optimize before finalize");
   vdo_lm_options opt = o_in;
   if (opt.max_trials <= 0) opt.max_trials = 10;
-  if (opt.pcg_rel_tol <= 0) opt.pcg_rel_tol = 1e-10;
+  if (opt.pcg_rel_tol <= 0) opt.pcg_rel_tol = 1e-8;
   if (opt.pcg_max_iterations <= 0) opt.pcg_max_iterations = 2000;
   BaDev& d = d_;
   const int launches0 = be_->launches();

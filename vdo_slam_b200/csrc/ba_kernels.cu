@@ -52,9 +52,18 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
 template <bool WRITE>
 __global__ void __launch_bounds__(128) k_lin_tracklets(BaDev d) {
   __shared__ double red[32];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = d.Tstat + blockIdx.x * blockDim.x + threadIdx.x;
   double chi = 0.0;
   if (t < d.T) chi = body_lin_tracklet(d, t, WRITE);
+  chi = block_sum(chi, red);
+  if (threadIdx.x == 0 && chi != 0.0) atomicAdd(d.scal + SC_CHI2, chi);
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_lin_static(BaDev d) {
+  __shared__ double red[32];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double chi = 0.0;
+  if (k < d.Tstat) chi = body_lin_static(d, k, WRITE);
   chi = block_sum(chi, red);
   if (threadIdx.x == 0 && chi != 0.0) atomicAdd(d.scal + SC_CHI2, chi);
 }
@@ -157,14 +166,21 @@ __global__ void __launch_bounds__(256) k_max_diagonal(BaDev d) {
 
 __global__ void __launch_bounds__(128) k_factor_landmarks(BaDev d, double lambda) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < d.T) body_factor_tracklet(d, t, lambda);
+  if (t < d.Tstat) body_factor_static(d, t, lambda);
+  else if (t < d.T) body_factor_tracklet(d, t, lambda);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(128) k_schur_landmarks(BaDev d, const double* __restrict__ v, double* __restrict__ out) {
   if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = d.Tstat + blockIdx.x * blockDim.x + threadIdx.x;
   if (t < d.T) body_schur_tracklet(d, t, MODE, v, out);
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_schur_static(BaDev d, double* __restrict__ out) {
+  if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < d.Tstat) body_schur_static(d, k, MODE, out);
 }
 
 __global__ void __launch_bounds__(128) k_precond_begin(BaDev d, double lambda) {
@@ -339,7 +355,8 @@ struct CudaBackend : BaBackend {
   } while (0)
 
   void lin_tracklets(BaDev& d, bool write) override {
-    if (write) LAUNCH(k_lin_tracklets<true>, nblk(d.T, 128), 128, d); else LAUNCH(k_lin_tracklets<false>, nblk(d.T, 128), 128, d);
+    if (write) { LAUNCH(k_lin_static<true>, nblk(d.Tstat, 256), 256, d); LAUNCH(k_lin_tracklets<true>, nblk(d.T - d.Tstat, 128), 128, d); }
+    else { LAUNCH(k_lin_static<false>, nblk(d.Tstat, 256), 256, d); LAUNCH(k_lin_tracklets<false>, nblk(d.T - d.Tstat, 128), 128, d); }
   }
   void lin_vertex_obs(BaDev& d) override { auto k = k_vertex_sym<0, true>; LAUNCH(k, d.n_obs_chunks, 128, d); }
   void lin_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<0, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
@@ -357,10 +374,10 @@ struct CudaBackend : BaBackend {
   void precond_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
   void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_paths * PCR_CL, 256, d, lambda); }
   void schur_landmarks(BaDev& d, int mode, const double* v) override {
-    const int g = nblk(d.T, 128);
-    if (mode == 0) LAUNCH(k_schur_landmarks<0>, g, 128, d, v, d.zl);
-    else if (mode == 1) LAUNCH(k_schur_landmarks<1>, g, 128, d, v, d.zl);
-    else LAUNCH(k_schur_landmarks<2>, g, 128, d, v, d.xl);
+    const int g = nblk(d.T - d.Tstat, 128), gs = nblk(d.Tstat, 256);
+    if (mode == 0) { LAUNCH(k_schur_static<0>, gs, 256, d, d.zl); LAUNCH(k_schur_landmarks<0>, g, 128, d, v, d.zl); }
+    else if (mode == 1) { LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); LAUNCH(k_schur_landmarks<1>, g, 128, d, v, d.zl); }
+    else { LAUNCH(k_schur_static<2>, gs, 256, d, d.xl); LAUNCH(k_schur_landmarks<2>, g, 128, d, v, d.xl); }
   }
   void schur_vertex_obs(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
   void schur_vertex_ter(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<false>, d.n_ter_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }

@@ -31,6 +31,7 @@ namespace vdo {
 struct Chunk { int v, begin, end, pad; };
 
 struct BaDev {
+  int Tstat = 0;   // tracklets [0, Tstat) are static landmarks (tracklet t == landmark t); [Tstat, T) are chains
   int C = 0, P = 0, T = 0, Eobs = 0, Eter = 0, Ese = 0, n_obs_chunks = 0, n_ter_chunks = 0, n_nbr = 0;
   double *se3 = 0, *pt = 0, *se3_bk = 0, *pt_bk = 0, *se3_init = 0, *pt_init = 0;
   int* tk_begin = 0;

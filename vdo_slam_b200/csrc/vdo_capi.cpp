@@ -72,7 +72,7 @@ void vdo_lm_options_default(vdo_lm_options* o) {
   if (!o) return;
   std::memset(o, 0, sizeof *o);
   o->max_iterations = 300; o->gain_threshold = 1e-4; o->max_trials = 10;
-  o->pcg_rel_tol = 1e-10; o->pcg_max_iterations = 2000; o->verbose = 0; o->force_all_iterations = 0;
+  o->pcg_rel_tol = 1e-8; o->pcg_max_iterations = 2000; o->verbose = 0; o->force_all_iterations = 0;
 }
 int vdo_graph_optimize(vdo_graph* g, const vdo_lm_options* opt, vdo_lm_stats* stats, double* chi2_history) {
   vdo_lm_options o;
