@@ -75,17 +75,26 @@ def graph_h2d_bytes(g) -> int:
     return int(sum(v.nbytes for k, v in g.items() if isinstance(v, np.ndarray) and not k.endswith("_gt")))
 
 
-def my_algorithmic_bytes(sz) -> dict:
-    """Compulsory HBM bytes per launch of each linearisation kernel in THIS implementation's formulation (DESIGN.md
-    section 'Kernels'): inputs that must be read once + outputs that must be written once; se3 state gathers (<=1.3 MB,
-    L2 resident) are not counted."""
-    Ep, Et, P, C = sz["E_p"], sz["E_t"], sz["P"], sz["C"]
+def kernel_bytes(g) -> dict:
+    """Compulsory HBM bytes per launch of each hot kernel in THIS implementation's formulation (DESIGN.md section
+    "Kernels"): every input byte that must be read once + every output byte written once.  Gathers that re-read the
+    se3 state / per-vertex vectors (<= 1.3 MB, L2 resident) are not counted, landmark gathers (p, zl) are."""
+    P = len(g["pt"])
+    dyn = np.zeros(P, bool)
+    if len(g["ter_pph"]):
+        dyn[g["ter_pph"][:, 0]] = True; dyn[g["ter_pph"][:, 1]] = True
+    Pd = int(dyn.sum()); Ps = P - Pd
+    Epd = int(dyn[g["obs_cp"][:, 1]].sum()); Eps = len(g["obs_cp"]) - Epd
+    Ep, Et = len(g["obs_cp"]), len(g["ter_pph"])
     return {
-        "k_lin_tracklets": 37 * Ep + 73 * P,                 # edge: cam 4 + z 24 + cls 1 + omega 8 ; landmark: p 24 + begin 4 + h 4 + cls 1 + hll 8 + bl 24 + omega 8
-        "k_vertex_sym_obs": 61 * Ep + 16 * (Ep // 512 + C),   # edge: pt 4 + z 24 + cls 1 + p gather 24 + omega 8 ; chunk descriptor
-        "k_vertex_sym_ter": 61 * Et,                          # edge: p1 4 + cls 1 + two landmark gathers 48 + omega 8
-        "k_schur_landmarks": 12 * Ep + 64 * P,                # edge: cam 4 + omega 8 ; landmark: p 24 + begin 4 + h 4 + omega 8 + s 8 (+bl 24 in modes 0/2) ... + out 24 (x2: fwd+bwd)
-        "k_schur_vertex_obs": 60 * Ep,                        # edge: pt 4 + omega 8 + p 24 + zl 24
+        "lin_static": 37 * Eps + 68 * Ps,          # edge: cam 4 + z 24 + cls 1 + omega' 8 ; landmark: p 24 + begin 4 + hll 8 + bl 24 + omega 8
+        "lin_chains": 37 * Epd + 73 * Pd,          # + motion index 4 + class 1 per landmark
+        "lin_vertex_obs": 61 * Ep,                 # pt 4 + z 24 + cls 1 + landmark gather 24 + omega' 8
+        "lin_vertex_ter": 61 * Et,                 # p1 4 + cls 1 + two landmark gathers 48 + omega' 8
+        "schur_static": 12 * Eps + 60 * Ps,        # edge: cam 4 + omega 8 ; landmark: p 24 + begin 4 + pivot 8 + out 24
+        "schur_chains": 12 * Epd + 72 * Pd,        # + motion index 4 + omega 8
+        "schur_vertex_obs": 60 * Ep,               # pt 4 + omega 8 + landmark 24 + zl 24
+        "schur_vertex_ter": 84 * Et,               # p1 4 + omega 8 + p2 24 + zl 48
     }
 
 
@@ -161,7 +170,7 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([float(e_iters)], device="cuda"); dist.all_reduce(t); e_iters = float(t.item())
     e2e_val = e_iters / e2e_s
 
-    # ---- roofline of the linearisation (Jacobian assembly) kernels: CUDA events inside the library, on its stream ----
+    # ---- per-kernel CUDA-event timings (vdo_graph_time_kernel: back-to-back launches on the library's stream) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -169,14 +178,33 @@ def run_ours(args, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kb = kernel_bytes(g)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+    except Exception:
+        pass
+    pcg_per_it = pcg / max(iters, 1)
+    trials_per_it = 1.0
+    kernels = {}
+    for name, per_lm_iter in [("lin_static", 1 + trials_per_it), ("lin_chains", 1 + trials_per_it), ("lin_vertex_obs", 1), ("lin_vertex_ter", 1),
+                              ("schur_static", pcg_per_it), ("schur_chains", pcg_per_it), ("schur_vertex_obs", pcg_per_it),
+                              ("schur_vertex_ter", pcg_per_it)]:
+        ms_k = G.time_kernel(name, 20)
+        gbs = kb[name] / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+        kernels[name] = {"ms": ms_k, "algorithmic_bytes": kb[name], "GBps": gbs, "frac": gbs / peak,
+                         "launches_per_lm_iter": per_lm_iter, "ms_per_lm_iter": ms_k * per_lm_iter, "traffic": traffic.get(name)}
+    top = max(kernels, key=lambda k: kernels[k]["ms_per_lm_iter"])
+    roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[top]["frac"], "traffic": kernels[top]["traffic"], "peak_source": peak_src + " (burst figure: kernel timed alone)",
+                "algorithmic_bytes_per_launch": kernels[top]["algorithmic_bytes"], "ms_per_launch": kernels[top]["ms"],
+                "how": "vdo_graph_time_kernel: 20 back-to-back launches between CUDA events on the library stream"}
+    lin_names = ["lin_static", "lin_chains", "lin_vertex_obs", "lin_vertex_ter"]
+    lin_ms = sum(kernels[k]["ms"] for k in lin_names); lin_bytes = sum(kernels[k]["algorithmic_bytes"] for k in lin_names)
+    jac = {"kernels": lin_names, "ms": lin_ms, "algorithmic_bytes": lin_bytes, "GBps": lin_bytes / (lin_ms * 1e-3) / 1e9,
+           "frac": lin_bytes / (lin_ms * 1e-3) / 1e9 / peak, "survey_formula_bytes": algorithmic_bytes_per_iter(g),
+           "frac_with_survey_formula": algorithmic_bytes_per_iter(g) / (lin_ms * 1e-3) / 1e9 / peak}
     lin_ms_per_iter = ms_lin / max(iters, 1)
-    mine = my_algorithmic_bytes(sz)
-    lin_bytes = mine["k_lin_tracklets"] + mine["k_vertex_sym_obs"] + mine["k_vertex_sym_ter"]
-    achieved = lin_bytes / (lin_ms_per_iter * 1e-3) / 1e9 if lin_ms_per_iter > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "linearisation = k_lin_tracklets<1> + k_vertex_sym<0,obs> + k_vertex_sym<0,ter> + k_lin_se3_edges<1>",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": lin_bytes,
-                "survey_formula_bytes": algorithmic_bytes_per_iter(g), "ms_per_launch": lin_ms_per_iter}
 
     out = None
     if rank == 0:
@@ -193,7 +221,7 @@ def run_ours(args, rank, world, local_rank):
                "clocks": clocks, "gpu_launches": launches,
                "e2e": {"value": e2e_val, "unit": "LM iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "steps": e2e_steps, "note": "host numpy buffers -> vdo_graph_* C ABI (ingest + H2D + solve + D2H) each step"},
-               "roofline": roofline, "cpu_baseline": cpu}
+               "roofline": roofline, "jacobian_assembly": jac, "kernels": kernels, "cpu_baseline": cpu}
     if world > 1:
         dist.destroy_process_group()
     return out

@@ -120,7 +120,8 @@ int vdo_graph_debug_linearize(vdo_graph *g, double *Hpp_diag, double *bp, double
  * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).
  * names: "lin_tracklets" "chi2_tracklets" "lin_vertex_obs" "lin_vertex_ter" "lin_se3_edges" "linearize" (all four)
  *        "factor_landmarks" "precond" (assembly + PCR factorisation) "schur_landmarks" "schur_vertex_obs"
- *        "schur_vertex_ter" "hpp_mul" "pcg_dot" "pcg_step" "pcg_iterate8" (8 PCG iterations as launched in a solve) */
+ *        "schur_vertex_ter" "hpp_mul" "pcg_dot" "pcg_step" "pcg_iterate8" (8 PCG iterations as launched in a solve)
+ *        "schur_static" "schur_chains" "lin_static" "lin_chains" (the two halves of the landmark passes) "pcg_step_a" */
 int vdo_graph_time_kernel(vdo_graph *g, const char *name, int reps, float *ms_avg);
 
 #ifdef __cplusplus

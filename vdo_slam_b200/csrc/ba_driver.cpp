@@ -493,6 +493,11 @@ int BaGraph::time_kernel(const char* name, int reps, float* ms_avg) {
     else if (n == "factor_landmarks") be_->factor_landmarks(d, lam);
     else if (n == "precond") { be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); be_->precond_factor(d, lam); }
     else if (n == "schur_landmarks") be_->schur_landmarks(d, 1, d.p);
+    else if (n == "schur_static") be_->schur_landmarks_part(d, 1, d.p, 0);
+    else if (n == "schur_chains") be_->schur_landmarks_part(d, 1, d.p, 1);
+    else if (n == "lin_static") be_->lin_tracklets_part(d, true, 0);
+    else if (n == "lin_chains") be_->lin_tracklets_part(d, true, 1);
+    else if (n == "pcg_step_a") { be_->pcg_dot_pAp(d); be_->pcg_step(d, 0.0); }
     else if (n == "schur_vertex_obs") be_->schur_vertex_obs(d, -1.0, d.Ap);
     else if (n == "schur_vertex_ter") be_->schur_vertex_ter(d, -1.0, d.Ap);
     else if (n == "hpp_mul") be_->hpp_mul(d, lam, d.p, d.Ap);

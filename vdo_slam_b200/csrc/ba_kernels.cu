@@ -379,6 +379,15 @@ struct CudaBackend : BaBackend {
     else if (mode == 1) { LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); LAUNCH(k_schur_landmarks<1>, g, 128, d, v, d.zl); }
     else { LAUNCH(k_schur_static<2>, gs, 256, d, d.xl); LAUNCH(k_schur_landmarks<2>, g, 128, d, v, d.xl); }
   }
+  void schur_landmarks_part(BaDev& d, int mode, const double* v, int part) override {
+    const int g = nblk(d.T - d.Tstat, 128), gs = nblk(d.Tstat, 256);
+    if (part == 0) LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); else LAUNCH(k_schur_landmarks<1>, g, 128, d, v, d.zl);
+    (void)mode;
+  }
+  void lin_tracklets_part(BaDev& d, bool write, int part) override {
+    (void)write;
+    if (part == 0) LAUNCH(k_lin_static<true>, nblk(d.Tstat, 256), 256, d); else LAUNCH(k_lin_tracklets<true>, nblk(d.T - d.Tstat, 128), 128, d);
+  }
   void schur_vertex_obs(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
   void schur_vertex_ter(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<false>, d.n_ter_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
   void set_scalars(BaDev& d, double lambda, double tol2) {

@@ -101,6 +101,9 @@ struct BaBackend {
   // mode 0: zl = Hll^-1 bl ; mode 1: zl = Hll^-1 (Hlp v) ; mode 2: xl = Hll^-1 (bl - Hlp v).  Modes 1/2 read v through d.vw
   // (vertex_transform / hpp_mul must have run on v) and, for ternary edges, v itself.
   virtual void schur_landmarks(BaDev& d, int mode, const double* v) = 0;
+  // measurement only: part 0 = static landmarks, part 1 = chains
+  virtual void schur_landmarks_part(BaDev& d, int mode, const double* v, int part) { (void)part; schur_landmarks(d, mode, v); }
+  virtual void lin_tracklets_part(BaDev& d, bool write, int part) { (void)part; lin_tracklets(d, write); }
   // out[vertex] += sign * sum_edges Hpl_e * zl[landmark(e)]
   virtual void schur_vertex_obs(BaDev& d, double sign, double* out) = 0;
   virtual void schur_vertex_ter(BaDev& d, double sign, double* out) = 0;
