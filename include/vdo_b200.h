@@ -115,6 +115,39 @@ int vdo_graph_info(const vdo_graph *g, int64_t out[8]);
  * diagonal blocks are that scalar times I3 for scalar information), bl: n_pt x 3, chi2: robust chi2. */
 int vdo_graph_debug_linearize(vdo_graph *g, double *Hpp_diag, double *bp, double *Hll_diag, double *bl, double *chi2);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-frame joint optical-flow / SE(3) refinement.  Replaces Optimizer::PoseOptimizationFlow2 (object motion,
+ * src/Optimizer.cc:2755-2972: prior information 0.5*I2, optimize(200)) and Optimizer::PoseOptimizationFlow2Cam (camera
+ * pose, src/Optimizer.cc:2333-2542: prior 0.3*I2, optimize(100)), i.e. the g2o graph of one VertexSE3Expmap + n
+ * VertexSBAFlow with EdgeSE3ProjectFlow2 (information 0.1*I2, Huber sqrt(0.04)) and EdgeFlowPrior edges, solved by
+ * OptimizationAlgorithmLevenberg over BlockSolver_6_3 + LinearSolverDense.  The whole LM solve runs in one kernel.
+ *
+ *   mode       0 = camera (Flow2Cam), 1 = object (Flow2)
+ *   quirk      1 = reproduce the arithmetic of 2-D flow vertices inside BlockSolver_6_3's 3x3 blocks (SURVEY.md H1;
+ *              derived from source reading, the reference binary cannot be built here), 0 = intended 2x2 arithmetic
+ *   pts        n x 2 f32  pixel of each point in the LAST frame   (pLastFrame->mvObjKeys / mvStatKeys[...].pt)
+ *   depth      n     f32  its depth                               (mvObjDepth / mvStatDepth)
+ *   flow       n x 2 f32  measured optical flow                   (mvObjFlowNext / mvFlowNext)
+ *   K          4     f32  fx, fy, cx, cy                          (Frame::fx ...)
+ *   Tcw_last   4x4   f32  row-major, pLastFrame->mTcw             (Twl is formed from it as the reference does, in float)
+ *   T_init     4x4   f32  row-major, pCurFrame->mInitModel / mTcw
+ * outputs
+ *   T_out      4x4   f32  Converter::toCvMat(vSE3->estimate())
+ *   flow_out   n x 2 f64  refined flow of every point (the caller adds it to the last-frame pixel for inliers)
+ *   inlier     n     u8   1 if chi2 <= 0.04 (vIsOutlier[i] == false)
+ *   stats      8     f64  [0] LM iterations (-1: n < 3, nothing optimised, T_out = identity) [1] trials [2] robust chi2
+ *                         [3] lambda [4] inlier count
+ * The batch form runs nprob independent problems (all objects of a frame) in one launch: offset has nprob+1 entries
+ * into the concatenated pts / depth / flow / flow_out / inlier arrays; K, Tcw_last, T_init, T_out, stats are per problem. */
+int vdo_pose_opt_flow2(vdo_ctx *ctx, int mode, int quirk, int n, const float *pts, const float *depth, const float *flow,
+                       const float *K, const float *Tcw_last, const float *T_init, float *T_out, double *flow_out,
+                       unsigned char *inlier, double *stats);
+int vdo_pose_opt_flow2_batch(vdo_ctx *ctx, int quirk, int nprob, const int *mode, const int *offset, const float *pts,
+                             const float *depth, const float *flow, const float *K, const float *Tcw_last,
+                             const float *T_init, float *T_out, double *flow_out, unsigned char *inlier, double *stats);
+/* measurement: re-run the last uploaded batch `reps` times on the device (no host copies), average ms per launch */
+int vdo_pose_opt_flow2_time(vdo_ctx *ctx, int quirk, int nprob, int reps, float *ms_avg);
+
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
  * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.
  * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).

@@ -171,3 +171,33 @@ class BatchGraph:
             self.close()
         except Exception:
             pass
+
+
+def pose_opt_flow2(ctx: Context, problems, quirk: int = 1, modes=None):
+    """Optimizer::PoseOptimizationFlow2 / Flow2Cam for a list of problems (dicts shaped like synth.make_flow_problem);
+    all problems run in one kernel launch.  Returns a list of dict(T, flow, inlier, iters, trials, chi2, lam, n_inliers)."""
+    L = ctx.L
+    nprob = len(problems)
+    modes = np.asarray(modes if modes is not None else [1] * nprob, np.int32)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    off = np.zeros(nprob + 1, np.int32)
+    off[1:] = np.cumsum([len(p["depth"]) for p in problems])
+    cat = lambda k, shape: f32(np.concatenate([np.asarray(p[k], np.float32).reshape(shape) for p in problems], 0)) if off[-1] else np.zeros((0,) + shape[1:], np.float32)
+    pts, depth, flow = cat("pts", (-1, 2)), cat("depth", (-1,)), cat("flow", (-1, 2))
+    K = f32(np.stack([p["K"] for p in problems])); Tl = f32(np.stack([p["Tcw_last"] for p in problems])); Ti = f32(np.stack([p["T_init"] for p in problems]))
+    T_out = np.zeros((nprob, 4, 4), np.float32); flow_out = np.zeros((int(off[-1]), 2)); inl = np.zeros(int(off[-1]), np.uint8); stats = np.zeros((nprob, 8))
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    ctx.check(L.vdo_pose_opt_flow2_batch(ctx.h, C.c_int(quirk), C.c_int(nprob), _ip(modes), _ip(off), fp(pts), fp(depth), fp(flow), fp(K), fp(Tl), fp(Ti),
+                                         fp(T_out), _dp(flow_out), inl.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(stats)), "vdo_pose_opt_flow2_batch")
+    out = []
+    for i in range(nprob):
+        a, b = off[i], off[i + 1]
+        out.append(dict(T=T_out[i], flow=flow_out[a:b], inlier=inl[a:b].astype(bool), iters=int(stats[i, 0]), trials=int(stats[i, 1]),
+                        chi2=stats[i, 2], lam=stats[i, 3], n_inliers=int(stats[i, 4])))
+    return out
+
+
+def pose_opt_flow2_time(ctx: Context, nprob: int, quirk: int = 1, reps: int = 20) -> float:
+    ms = C.c_float(0)
+    ctx.check(ctx.L.vdo_pose_opt_flow2_time(ctx.h, C.c_int(quirk), C.c_int(nprob), C.c_int(reps), C.byref(ms)), "vdo_pose_opt_flow2_time")
+    return float(ms.value)
