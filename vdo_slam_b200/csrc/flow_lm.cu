@@ -42,6 +42,7 @@ struct FlowDev {
   unsigned char* inlier;             // total
   double* stats;                     // nprob x 8
   int quirk;
+  int debug;
 };
 constexpr int FL_PP = 28;  // Xw3 f2 fbk2 err2 J12 w h bl2 dl2 (=27) + pad
 enum { O_XW = 0, O_F = 3, O_FBK = 5, O_ERR = 7, O_J = 9, O_W = 21, O_H = 22, O_BL = 23, O_DL = 25 };
@@ -135,9 +136,9 @@ __device__ void se3_oplus(double* q, double* t, const double* u) {
   for (int i = 0; i < 4; ++i) q[i] = qn[i];
   quat_normalize_pos(q);
 }
-// Cholesky solve of the symmetric matrix given by the LOWER triangle of S (what Eigen's LDLT reads)
-__device__ bool solve6_lower(const double* S, const double* g, double* x) {
-  double L[36], y[6];
+// Cholesky solve of the symmetric matrix given by the LOWER triangle of S (what Eigen's LDLT reads).
+// L (36) and y (6) are caller-provided work arrays (shared memory).
+__device__ bool solve6_lower(const double* S, const double* g, double* x, double* L, double* y) {
   for (int i = 0; i < 36; ++i) L[i] = 0;
   for (int j = 0; j < 6; ++j) {
     double d = S[7 * j];
@@ -164,6 +165,7 @@ struct FlowShared {
   double q[4], t[3], R[9];
   double qbk[4], tbk[3];
   double xp[6], Hpp[36], bp[6];
+  double Sm[36], g[6], x[6], L[36], y[6];
   double lambda, ni, current, temp, rho, chi2_check, last_trial_chi;
   int nbad, qmax, ok, ok2, accept, iters, trials, stop_trials;
 };
@@ -336,14 +338,12 @@ __global__ void __launch_bounds__(FL_THREADS) k_flow2_lm(FlowDev d) {
       cta_reduce<42>(acc, red);
       if (tid == 0) {
         const double* r = red + FL_WARPS * FL_NV;
-        double Sm[36], g[6];
-        for (int k = 0; k < 36; ++k) Sm[k] = S.Hpp[k] - r[k];
-        for (int k = 0; k < 6; ++k) { Sm[7 * k] += lambda; g[k] = S.bp[k] - r[36 + k]; }
+        for (int k = 0; k < 36; ++k) S.Sm[k] = S.Hpp[k] - r[k];
+        for (int k = 0; k < 6; ++k) { S.Sm[7 * k] += lambda; S.g[k] = S.bp[k] - r[36 + k]; }
         for (int k = 0; k < 4; ++k) S.qbk[k] = S.q[k];
         for (int k = 0; k < 3; ++k) S.tbk[k] = S.t[k];
-        double x[6];
-        S.ok2 = solve6_lower(Sm, g, x) ? 1 : 0;
-        if (S.ok2) for (int k = 0; k < 6; ++k) S.xp[k] = x[k];      // a failed solve leaves the previous x in place
+        S.ok2 = solve6_lower(S.Sm, S.g, S.x, S.L, S.y) ? 1 : 0;
+        if (S.ok2) for (int k = 0; k < 6; ++k) S.xp[k] = S.x[k];      // a failed solve leaves the previous x in place
         se3_oplus(S.q, S.t, S.xp);
         quat_to_rot(S.q, S.R);
       }
@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_flow2_lm(FlowDev d) {
           for (int k = 0; k < 3; ++k) S.t[k] = S.tbk[k];
           quat_to_rot(S.q, S.R);
         }
+        if (d.debug) printf("[flow2 dbg] it %d trial %d lambda %.6g ok2 %d temp %.9g current %.9g scale %.6g rho %.6g xp %.3g %.3g %.3g %.3g %.3g %.3g\n", it, S.qmax, lambda, S.ok2, temp, S.current, sc_all, rho, S.xp[0], S.xp[1], S.xp[2], S.xp[3], S.xp[4], S.xp[5]);
         S.qmax++; S.trials++;
         S.stop_trials = !(rho < 0 && S.qmax < 10);
       }
@@ -474,7 +475,7 @@ extern "C" int vdo_pose_opt_flow2_batch(vdo_ctx* ctx, int quirk, int nprob, cons
     FCK(cudaMemcpyAsync(A.depth, depth, total * 4, cudaMemcpyHostToDevice, st));
     FCK(cudaMemcpyAsync(A.flow, flow, total * 8, cudaMemcpyHostToDevice, st));
   }
-  FlowDev d{A.prob, A.pts, A.depth, A.flow, A.scratch, A.T_out, A.flow_out, A.inlier, A.stats, quirk};
+  FlowDev d{A.prob, A.pts, A.depth, A.flow, A.scratch, A.T_out, A.flow_out, A.inlier, A.stats, quirk & 1, (quirk >> 1) & 1};
   k_flow2_lm<<<nprob, FL_THREADS, 0, st>>>(d);
   A.launches++;
   FCK(cudaGetLastError());
@@ -505,7 +506,7 @@ extern "C" int vdo_pose_opt_flow2_time(vdo_ctx* ctx, int quirk, int nprob, int r
   auto it = g_arenas.find((uint64_t)(uintptr_t)st);
   if (it == g_arenas.end() || (size_t)nprob > it->second.cap_prob) return VDO_ERR_STATE;
   FlowArena& A = it->second;
-  FlowDev d{A.prob, A.pts, A.depth, A.flow, A.scratch, A.T_out, A.flow_out, A.inlier, A.stats, quirk};
+  FlowDev d{A.prob, A.pts, A.depth, A.flow, A.scratch, A.T_out, A.flow_out, A.inlier, A.stats, quirk & 1, (quirk >> 1) & 1};
   cudaEvent_t e0, e1;
   FCK(cudaEventCreate(&e0)); FCK(cudaEventCreate(&e1));
   k_flow2_lm<<<nprob, FL_THREADS, 0, st>>>(d);
