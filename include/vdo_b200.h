@@ -40,6 +40,13 @@ const char *vdo_last_error(const vdo_ctx *ctx);
 /* cudaStream_t of the context as an integer handle (so torch / callers can order work against it) */
 uint64_t vdo_ctx_stream(const vdo_ctx *ctx);
 
+/* Multi-GPU (one process per GPU).  The batch graph shards by tracklet: after vdo_ctx_init_comm, vdo_graph_finalize keeps
+ * the tracklets of this rank only (round-robin), the se3 state is replicated, and partial se3-side sums are all-reduced
+ * over NCCL (H_pp/b_p once per linearisation, the 6C-vector S*p once per PCG iteration, chi2/scale once per LM trial).
+ * rank 0 calls vdo_nccl_unique_id and ships the 128 bytes to the other ranks (e.g. torch.distributed broadcast). */
+int vdo_nccl_unique_id(char *out128);
+int vdo_ctx_init_comm(vdo_ctx *ctx, int rank, int world, const char *id128);
+
 /* ------------------------------------------------------------------------------------------------
  * Batch factor-graph optimisation.  Replaces the g2o::SparseOptimizer + OptimizationAlgorithmLevenberg +
  * BlockSolverX + LinearSolverCSparse stack as driven by Optimizer::FullBatchOptimization

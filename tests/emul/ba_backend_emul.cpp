@@ -15,8 +15,12 @@
 
 namespace vdo {
 
+typedef void (*vdo_collective_fn)(double* buf, size_t n, int op, void* user);
 struct EmulBackend : BaBackend {
   int n_launch = 0;
+  vdo_collective_fn coll = nullptr; void* coll_user = nullptr;
+  void allreduce_sum(double* b, size_t n) override { if (world > 1 && coll) coll(b, n, 0, coll_user); }
+  void allreduce_max(double* b, size_t n) override { if (world > 1 && coll) coll(b, n, 1, coll_user); }
   std::chrono::steady_clock::time_point t0[4];
   void* alloc(size_t b) override { return std::calloc(1, b ? b : 1); }
   void free_(void* p) override { std::free(p); }
@@ -73,15 +77,17 @@ struct EmulBackend : BaBackend {
     for (int e = 0; e < d.Ese; ++e) {
       double chi, Hi[36], Hj[36], Ho[36], gi[6], gj[6];
       bool binary = body_se3_edge(d, e, write, chi, Hi, Hj, Ho, gi, gj);
-      chi_tot += chi;
+      if (d.own) chi_tot += chi;
       if (!write) continue;
       int i = d.se_i[e];
-      for (int k = 0; k < 36; ++k) d.Hpp[36 * (size_t)i + k] += Hi[k];
-      for (int k = 0; k < 6; ++k) d.bp[6 * (size_t)i + k] += gi[k];
+      if (d.own) {
+        for (int k = 0; k < 36; ++k) d.Hpp[36 * (size_t)i + k] += Hi[k];
+        for (int k = 0; k < 6; ++k) d.bp[6 * (size_t)i + k] += gi[k];
+      }
       if (binary) {
         int j = d.se_j[e];
-        for (int k = 0; k < 36; ++k) { d.Hpp[36 * (size_t)j + k] += Hj[k]; d.se_Hoff[36 * (size_t)e + k] = Ho[k]; }
-        for (int k = 0; k < 6; ++k) d.bp[6 * (size_t)j + k] += gj[k];
+        for (int k = 0; k < 36; ++k) { if (d.own) d.Hpp[36 * (size_t)j + k] += Hj[k]; d.se_Hoff[36 * (size_t)e + k] = Ho[k]; }
+        if (d.own) for (int k = 0; k < 6; ++k) d.bp[6 * (size_t)j + k] += gj[k];
       }
     }
     d.scal[SC_CHI2] += chi_tot;
@@ -97,8 +103,8 @@ struct EmulBackend : BaBackend {
   void precond_begin(BaDev& d, double lambda) override {
     ++n_launch;
     for (int v = 0; v < d.C; ++v) {
-      for (int i = 0; i < 36; ++i) d.Minv[36 * (size_t)v + i] = d.Hpp[36 * (size_t)v + i];
-      for (int i = 0; i < 6; ++i) d.Minv[36 * (size_t)v + 7 * i] += lambda;
+      for (int i = 0; i < 36; ++i) d.Minv[36 * (size_t)v + i] = d.own ? d.Hpp[36 * (size_t)v + i] : 0.0;
+      if (d.own) for (int i = 0; i < 6; ++i) d.Minv[36 * (size_t)v + 7 * i] += lambda;
     }
   }
   void precond_vertex_obs(BaDev& d) override {
@@ -228,5 +234,20 @@ struct EmulBackend : BaBackend {
 };
 
 BaBackend* make_backend(int, char*, size_t) { return new EmulBackend; }
+// test-only: attach a host collective (e.g. torch.distributed over gloo) to the emulated backend
+void emul_set_collective(BaBackend* be, int rank, int world, vdo_collective_fn fn, void* user) {
+  EmulBackend* e = static_cast<EmulBackend*>(be);
+  e->rank = rank; e->world = world; e->coll = fn; e->coll_user = user;
+}
 
 }  // namespace vdo
+
+// ---- test-only C entry point: attach a host collective to an emulated context ----
+struct vdo_ctx;
+namespace vdo { BaBackend* ctx_backend(vdo_ctx* c); }
+extern "C" int vdo_emul_set_collective(vdo_ctx* ctx, int rank, int world, vdo::vdo_collective_fn fn, void* user) {
+  vdo::BaBackend* be = vdo::ctx_backend(ctx);
+  if (!be || world < 1 || rank < 0 || rank >= world) return -2;
+  vdo::emul_set_collective(be, rank, world, fn, user);
+  return 0;
+}

@@ -98,3 +98,21 @@ def test_rejects_branching_landmark_motion_graph(ctx):
     g["ter_pph"] = t
     with pytest.raises(capi.VdoError):
         capi.BatchGraph(ctx, g)
+
+
+def test_two_gpu_sharded_solve_matches_oracle(tmp_path):
+    import os, socket, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "r0.npz")
+    procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "_dist_worker_gpu.py"), str(r), "2", str(port), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    d = np.load(out)
+    g = make_batch_graph(n_frames=30, n_objects=2, n_static=1500, n_dynamic=300, seed=1)
+    ro = po.ba_optimize(g)
+    assert int(d["iters"]) == ro["iters"]
+    assert np.abs(d["se3"] - ro["se3"]).max() < 1e-6 and np.abs(d["pt"] - ro["pt"]).max() < 1e-6

@@ -85,6 +85,38 @@ class Context:
     def stream(self) -> int:
         return int(self.L.vdo_ctx_stream(self.h))
 
+    rank, world = 0, 1
+
+    def init_comm(self, rank: int, world: int, dist=None):
+        """Multi-GPU: create the NCCL communicator of this context (id from rank 0, broadcast through torch.distributed)."""
+        self.rank, self.world = rank, world
+        if world <= 1:
+            return
+        import torch
+        dist = dist or torch.distributed
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            self.check(self.L.vdo_nccl_unique_id(buf), "vdo_nccl_unique_id")
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(dev)
+        dist.broadcast(t, src=0)
+        idb = bytes(t.cpu().numpy().tobytes())
+        self.check(self.L.vdo_ctx_init_comm(self.h, C.c_int(rank), C.c_int(world), C.c_char_p(idb)), "vdo_ctx_init_comm")
+
+    def set_collective_emul(self, rank: int, world: int, dist):
+        """TEST ONLY (tests/emul/libvdo_emul.so): all-reduce of the emulated backend through torch.distributed (gloo)."""
+        import torch
+        self.rank, self.world = rank, world
+        CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_size_t, C.c_int, C.c_void_p)
+
+        def _cb(ptr, n, op, user):
+            a = np.ctypeslib.as_array(ptr, shape=(n,))
+            t = torch.from_numpy(a)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)
+
+        self._cb = CB(_cb)
+        self.check(self.L.vdo_emul_set_collective(self.h, C.c_int(rank), C.c_int(world), self._cb, None), "vdo_emul_set_collective")
+
     def close(self):
         if self.h:
             self.L.vdo_ctx_destroy(self.h)
@@ -141,6 +173,21 @@ class BatchGraph:
         pt = np.zeros((self.n_pt, 3))
         self.ctx.check(self.ctx.L.vdo_graph_get_vertices(self.h, _dp(se3), _dp(pt)), "vdo_graph_get_vertices")
         return se3, pt
+
+    def vertices_gathered(self, dist):
+        """Sharded graphs: every rank gets all landmark estimates (each rank holds only its own after optimize())."""
+        import torch
+        se3 = np.zeros((self.n_se3, 12))
+        pt = np.full((self.n_pt, 3), np.nan)
+        self.ctx.check(self.ctx.L.vdo_graph_get_vertices(self.h, _dp(se3), _dp(pt)), "vdo_graph_get_vertices")
+        own = ~np.isnan(pt[:, 0])
+        t = torch.from_numpy(np.where(own[:, None], pt, 0.0).copy())
+        c = torch.from_numpy(own.astype(np.float64))
+        if dist.get_backend() == "nccl":
+            t, c = t.cuda(), c.cuda()
+        dist.all_reduce(t); dist.all_reduce(c)
+        assert bool((c.cpu() == 1).all()), "every landmark must be owned by exactly one rank"
+        return se3, t.cpu().numpy()
 
     def reset(self):
         self.ctx.check(self.ctx.L.vdo_graph_reset_vertices(self.h), "vdo_graph_reset_vertices")

@@ -389,7 +389,7 @@ VDO_HD void body_hpp_mul(const BaDev& d, int v, double lambda, const double* __r
     }
   }
 #pragma unroll
-  for (int r = 0; r < 6; ++r) out[6 * (size_t)v + r] = o[r];
+  for (int r = 0; r < 6; ++r) out[6 * (size_t)v + r] = d.own ? o[r] : 0.0;   // sharded graphs: rank 0 contributes H_pp p, every rank its landmark terms
   body_vertex_transform(d, v, x, d.vw);
 }
 
@@ -523,7 +523,7 @@ VDO_HD double body_update_se3(const BaDev& d, int v, double lambda, bool reortho
   double s = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) s += x[i] * (lambda * x[i] + b[i]);
-  return s;
+  return d.own ? s : 0.0;
 }
 VDO_HD double body_update_pt(const BaDev& d, int k, double lambda) {
   double s = 0;

@@ -85,8 +85,8 @@ void make_chunks(const std::vector<int>& begin, std::vector<Chunk>& out) {
 
 int BaGraph::finalize() {
   if (finalized_) return fail(VDO_ERR_STATE, "finalize called twice");
-  const int C = n_se3_, P = n_pt_;
-  const int Eo = (int)ob_w_.size(), Et = (int)te_w_.size(), Es = (int)se_w_.size(), Ep = (int)pr_w_.size();
+  const int C = n_se3_; int P = n_pt_;
+  const int Eo_all = (int)ob_w_.size(), Et_all = (int)te_w_.size(), Es = (int)se_w_.size(), Ep = (int)pr_w_.size();
   // ---- se3 vertices: renumber so that every path of the se3-se3 edge graph (camera odometry chain, per-object
   //      motion-smoothness chains) is a contiguous, ordered index range; other vertices become singleton paths ----
   std::vector<int> path_begin;
@@ -127,8 +127,9 @@ int BaGraph::finalize() {
   }
   auto S3 = [&](int old_id) { return new_se3_of_old_[old_id]; };
   // ---- tracklets: chains of landmarks linked by ternary edges ----
+  (void)0;
   std::vector<int> next(P, -1), prev(P, -1), ter_of(P, -1);
-  for (int e = 0; e < Et; ++e) {
+  for (int e = 0; e < Et_all; ++e) {
     int p1 = te_pph_[3 * e], p2 = te_pph_[3 * e + 1];
     if (p1 == p2 || next[p1] != -1 || prev[p2] != -1)
       return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges must form simple chains (one predecessor / successor per landmark)");
@@ -137,33 +138,49 @@ int BaGraph::finalize() {
   new_of_old_.assign(P, -1);
   std::vector<int> old_of_new(P), tk_begin;
   int cnt = 0;
-  // static landmarks (tracklets of one vertex) first, then the chains: the two groups run different kernels
+  // static landmarks (tracklets of one vertex) first, then the chains: the two groups run different kernels.
+  // Multi-GPU: tracklets are dealt round-robin to the ranks (each group separately); a rank keeps only its own
+  // landmarks and their edges, the se3 state is replicated.
+  const int rank = be_->rank, world = be_->world;
+  int n_seen = 0, t_idx = 0;
   for (int p = 0; p < P; ++p) {
     if (prev[p] != -1 || next[p] != -1) continue;
+    ++n_seen;
+    if ((t_idx++ % world) != rank) continue;
     tk_begin.push_back(cnt);
     new_of_old_[p] = cnt; old_of_new[cnt++] = p;
   }
   const int Tstat = cnt;
+  t_idx = 0;
   for (int p = 0; p < P; ++p) {
     if (prev[p] != -1 || next[p] == -1) continue;
+    const bool mine = (t_idx++ % world) == rank;
+    for (int q = p; q != -1; q = next[q]) ++n_seen;
+    if (!mine) continue;
     tk_begin.push_back(cnt);
     for (int q = p; q != -1; q = next[q]) { new_of_old_[q] = cnt; old_of_new[cnt++] = q; }
   }
-  if (cnt != P) return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges contain a cycle");
+  if (n_seen != P) return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges contain a cycle");
+  const int P_all = P;
+  P = cnt;                      // from here on P = landmarks owned by this rank
+  old_of_new.resize(P);
   tk_begin.push_back(cnt);
   const int T = (int)tk_begin.size() - 1;
 
   ClassTable oc, tc;
   // ---- landmark-major pointxyz stream ----
   std::vector<int> lm_begin(P + 1, 0);
-  for (int e = 0; e < Eo; ++e) lm_begin[new_of_old_[ob_cp_[2 * e + 1]] + 1]++;
+  int Eo = 0;
+  for (int e = 0; e < Eo_all; ++e) { int k = new_of_old_[ob_cp_[2 * e + 1]]; if (k >= 0) { lm_begin[k + 1]++; ++Eo; } }
   for (int k = 0; k < P; ++k) lm_begin[k + 1] += lm_begin[k];
-  std::vector<int> fill(lm_begin.begin(), lm_begin.end() - 1), lm_cam(Eo), lm_pos(Eo);
+  std::vector<int> fill(lm_begin.begin(), lm_begin.end() - 1), lm_cam(Eo);
   std::vector<double> lm_z(3 * (size_t)Eo);
   std::vector<uint8_t> lm_cls(Eo);
-  for (int e = 0; e < Eo; ++e) {
-    int k = new_of_old_[ob_cp_[2 * e + 1]], pos = fill[k]++;
-    lm_pos[e] = pos; lm_cam[pos] = S3(ob_cp_[2 * e]);
+  for (int e = 0; e < Eo_all; ++e) {
+    int k = new_of_old_[ob_cp_[2 * e + 1]];
+    if (k < 0) continue;
+    int pos = fill[k]++;
+    lm_cam[pos] = S3(ob_cp_[2 * e]);
     for (int i = 0; i < 3; ++i) lm_z[3 * (size_t)pos + i] = ob_z_[3 * (size_t)e + i];
     int cls = oc.get(ob_w_[e], ob_d_[e]);
     if (cls > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on pointxyz edges");
@@ -190,8 +207,11 @@ int BaGraph::finalize() {
   std::vector<int> tk_h(P, -1);
   std::vector<uint8_t> tk_cls(P, 0);
   std::vector<int> hm_begin(C + 1, 0);
-  for (int e = 0; e < Et; ++e) {
+  int Et = 0;
+  for (int e = 0; e < Et_all; ++e) {
     int k = new_of_old_[te_pph_[3 * e]];
+    if (k < 0) continue;
+    ++Et;
     tk_h[k] = S3(te_pph_[3 * e + 2]);
     int cls = tc.get(te_w_[e], te_d_[e]);
     if (cls > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on landmark-motion edges");
@@ -250,7 +270,8 @@ int BaGraph::finalize() {
 
   // ---- upload ----
   BaDev& d = d_;
-  d.C = C; d.P = P; d.T = T; d.Tstat = Tstat; d.Eobs = Eo; d.Eter = Et; d.Ese = Ese;
+  d.C = C; d.P = P; d.T = T; d.Tstat = Tstat; d.own = (rank == 0) ? 1 : 0;
+  P_all_ = P_all; d.Eobs = Eo; d.Eter = Et; d.Ese = Ese;
   d.n_obs_chunks = (int)obs_chunks.size(); d.n_ter_chunks = (int)ter_chunks.size(); d.n_nbr = (int)nbr_edge.size();
   d.se3 = upload(se3_int); d.pt = upload(pt_int);
   d.se3_init = upload(se3_int); d.pt_init = upload(pt_int);
@@ -262,7 +283,7 @@ int BaGraph::finalize() {
   d.hm_p1 = upload(hm_p1); d.hm_cls = upload(hm_cls); d.hm_omega = dalloc<double>(Et); d.ter_chunks = upload(ter_chunks);
   d.se_i = upload(se_i); d.se_j = upload(se_j); d.se_Z = upload(se_Z); d.se_w = upload(se_w); d.se_delta = upload(se_d); d.se_Hoff = dalloc<double>(36 * (size_t)Ese);
   d.nbr_begin = upload(nbr_begin); d.nbr_edge = upload(nbr_edge); d.nbr_other = upload(nbr_other); d.nbr_tr = upload(nbr_tr);
-  d.Hpp = dalloc<double>(36 * (size_t)C); d.bp = dalloc<double>(6 * (size_t)C); d.hll = dalloc<double>(P); d.bl = dalloc<double>(3 * (size_t)P);
+  d.Hpp = dalloc<double>(42 * (size_t)C); d.bp = d.Hpp + 36 * (size_t)C; d.hll = dalloc<double>(P); d.bl = dalloc<double>(3 * (size_t)P);
   d.pt_s = dalloc<double>(P); d.Minv = dalloc<double>(36 * (size_t)C);
   d.pt_g = dalloc<double>(P); d.tk_gamma = dalloc<double>(P);
   d.n_paths = n_paths; d.pcr_levels = pcr_levels;
@@ -296,8 +317,9 @@ int BaGraph::get_vertices(double* se3, double* pt) {
   if (pt) {
     std::vector<double> tmp(3 * (size_t)d_.P);
     be_->d2h(tmp.data(), d_.pt, 24 * (size_t)d_.P);
-    for (int o = 0; o < d_.P; ++o) {
+    for (int o = 0; o < P_all_; ++o) {      // landmarks owned by other ranks are left untouched in the caller's buffer
       int k = new_of_old_[o];
+      if (k < 0) continue;
       pt[3 * (size_t)o] = tmp[3 * (size_t)k]; pt[3 * (size_t)o + 1] = tmp[3 * (size_t)k + 1]; pt[3 * (size_t)o + 2] = tmp[3 * (size_t)k + 2];
     }
   }
@@ -317,18 +339,20 @@ int BaGraph::info(int64_t out[8]) const {
 
 // ---- buildSystem (g2o/core/block_solver.hpp:501-560) ----
 void BaGraph::linearize() {
-  be_->zero(d_.Hpp, 288 * (size_t)d_.C);
-  be_->zero(d_.bp, 48 * (size_t)d_.C);
+  be_->zero(d_.Hpp, 336 * (size_t)d_.C);          // H_pp diagonal blocks and b_p are one buffer (one all-reduce)
   be_->zero(d_.scal, sizeof(double) * SC_N);
   be_->lin_tracklets(d_, true);
   be_->lin_vertex_obs(d_);
   be_->lin_vertex_ter(d_);
   be_->lin_se3_edges(d_, true);
+  be_->allreduce_sum(d_.Hpp, 42 * (size_t)d_.C);
+  be_->allreduce_sum(d_.scal + SC_CHI2, 1);
 }
 double BaGraph::robust_chi2() {
   be_->zero(d_.scal + SC_CHI2, sizeof(double));
   be_->lin_tracklets(d_, false);
   be_->lin_se3_edges(d_, false);
+  be_->allreduce_sum(d_.scal + SC_CHI2, 1);
   double c; be_->d2h(&c, d_.scal + SC_CHI2, sizeof(double));
   return c;
 }
@@ -344,15 +368,17 @@ bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   be_->precond_begin(d, lambda);
   be_->precond_vertex_obs(d);
   be_->precond_vertex_ter(d);
+  be_->allreduce_sum(d.Minv, 36 * (size_t)d.C);
   be_->precond_factor(d, lambda);
   }
   {
   Phase ph(be_, &prof_ms_[1], prof);
   // rhs = bp - Hpl Hll^-1 bl
   be_->schur_landmarks(d, 0, nullptr);
-  be_->d2d(d.rhs, d.bp, 48 * (size_t)d.C);
+  if (d.own) be_->d2d(d.rhs, d.bp, 48 * (size_t)d.C); else be_->zero(d.rhs, 48 * (size_t)d.C);
   be_->schur_vertex_obs(d, -1.0, d.rhs);
   be_->schur_vertex_ter(d, -1.0, d.rhs);
+  be_->allreduce_sum(d.rhs, 6 * (size_t)d.C);
   be_->pcg_init(d);
   }
   const double tol2 = opt.pcg_rel_tol * opt.pcg_rel_tol;
@@ -403,6 +429,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
     linearize();
     if (it == 0) {
       be_->max_diagonal(d);
+      be_->allreduce_max(d.scal + SC_MAXDIAG, 1);
       double md; be_->d2h(&md, d.scal + SC_MAXDIAG, sizeof(double));
       lambda = 1e-5 * md; ni = 2; nbad = 0;
     }
@@ -424,6 +451,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
       be_->zero(d.scal + SC_CHI2, sizeof(double));
       be_->lin_tracklets(d, false);
       be_->lin_se3_edges(d, false);
+      be_->allreduce_sum(d.scal + SC_CHI2, 2);      // chi2 and scale are adjacent
       double sc[SC_N]; be_->d2h(sc, d.scal, sizeof(sc));
       temp = sc[SC_CHI2];
       if (!ok2) temp = DBL_MAX;
@@ -510,10 +538,11 @@ int BaGraph::time_kernel(const char* name, int reps, float* ms_avg) {
   // a valid, never-converging PCG state: linearise + factor at the last lambda, rhs, init
   linearize();
   be_->factor_landmarks(d, lam);
-  be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); be_->precond_factor(d, lam);
+  be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); be_->allreduce_sum(d.Minv, 36 * (size_t)d.C); be_->precond_factor(d, lam);
   be_->schur_landmarks(d, 0, nullptr);
   be_->d2d(d.rhs, d.bp, 48 * (size_t)d.C);
   be_->schur_vertex_obs(d, -1.0, d.rhs); be_->schur_vertex_ter(d, -1.0, d.rhs);
+  be_->allreduce_sum(d.rhs, 6 * (size_t)d.C);
   be_->pcg_init(d);
   if (!run()) return fail(VDO_ERR_ARG, "time_kernel: unknown kernel name");
   be_->sync();
@@ -539,8 +568,9 @@ int BaGraph::debug_linearize(double* Hpp, double* bp, double* Hll, double* bl, d
   std::vector<double> th(d_.P), tb(3 * (size_t)d_.P);
   be_->d2h(th.data(), d_.hll, 8 * (size_t)d_.P);
   be_->d2h(tb.data(), d_.bl, 24 * (size_t)d_.P);
-  for (int o = 0; o < d_.P; ++o) {
+  for (int o = 0; o < P_all_; ++o) {
     int k = new_of_old_[o];
+    if (k < 0) continue;
     if (Hll) Hll[o] = th[k];
     if (bl) for (int i = 0; i < 3; ++i) bl[3 * (size_t)o + i] = tb[3 * (size_t)k + i];
   }

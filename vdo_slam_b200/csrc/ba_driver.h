@@ -46,7 +46,7 @@ class BaGraph {
   float prof_ms_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double last_lambda_ = 1.0;
   // host staging (until finalize)
-  int n_se3_ = 0, n_pt_ = 0;
+  int n_se3_ = 0, n_pt_ = 0, P_all_ = 0;
   std::vector<double> h_se3_, h_pt_;
   std::vector<int> pr_v_; std::vector<double> pr_Z_, pr_w_;
   std::vector<int> se_ij_; std::vector<double> se_Z_, se_w_, se_d_;

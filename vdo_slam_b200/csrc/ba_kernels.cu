@@ -14,6 +14,9 @@
 #include <cstdio>
 #include <cstring>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <map>
 #include <utility>
 
@@ -132,14 +135,17 @@ __global__ void __launch_bounds__(64) k_lin_se3_edges(BaDev d) {
   if (e < d.Ese) {
     double Hi[36], Hj[36], Ho[36], gi[6], gj[6];
     const bool binary = body_se3_edge(d, e, WRITE, chi, Hi, Hj, Ho, gi, gj);
+    if (!d.own) chi = 0.0;      // sharded graphs: the se3-se3 edges are accumulated by rank 0 only (every rank keeps J_i^T W J_j)
     if (WRITE) {
       const int i = d.se_i[e];
-      for (int k = 0; k < 36; ++k) atomicAdd(d.Hpp + 36 * (size_t)i + k, Hi[k]);
-      for (int k = 0; k < 6; ++k) atomicAdd(d.bp + 6 * (size_t)i + k, gi[k]);
+      if (d.own) {
+        for (int k = 0; k < 36; ++k) atomicAdd(d.Hpp + 36 * (size_t)i + k, Hi[k]);
+        for (int k = 0; k < 6; ++k) atomicAdd(d.bp + 6 * (size_t)i + k, gi[k]);
+      }
       if (binary) {
         const int j = d.se_j[e];
-        for (int k = 0; k < 36; ++k) { atomicAdd(d.Hpp + 36 * (size_t)j + k, Hj[k]); d.se_Hoff[36 * (size_t)e + k] = Ho[k]; }
-        for (int k = 0; k < 6; ++k) atomicAdd(d.bp + 6 * (size_t)j + k, gj[k]);
+        for (int k = 0; k < 36; ++k) { if (d.own) atomicAdd(d.Hpp + 36 * (size_t)j + k, Hj[k]); d.se_Hoff[36 * (size_t)e + k] = Ho[k]; }
+        if (d.own) for (int k = 0; k < 6; ++k) atomicAdd(d.bp + 6 * (size_t)j + k, gj[k]);
       }
     }
   }
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(256) k_schur_static(BaDev d, double* __restric
 
 __global__ void __launch_bounds__(128) k_precond_begin(BaDev d, double lambda) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < d.C * 36) { const int k = i % 36; d.Minv[i] = d.Hpp[i] + ((k % 7) == 0 ? lambda : 0.0); }
+  if (i < d.C * 36) { const int k = i % 36; d.Minv[i] = d.own ? d.Hpp[i] + ((k % 7) == 0 ? lambda : 0.0) : 0.0; }
 }
 
 __global__ void k_set_scalars(BaDev d, double lambda, double tol2) { d.scal[SC_LAMBDA] = lambda; d.scal[SC_TOL2] = tol2; }
@@ -327,13 +333,51 @@ __global__ void __launch_bounds__(128) k_apply_update(BaDev d, double lambda, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// NCCL is resolved at run time (dlopen) so that the library links without it and picks up the copy torch already loaded
+struct NcclApi {
+  void* h = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+  }
+};
+static NcclApi g_nccl;
+
 struct CudaBackend : BaBackend {
   int dev = 0;
+  ncclComm_t comm = nullptr;
+  void allreduce_sum(double* b, size_t n) override {
+    if (world <= 1 || n == 0) return;
+    ncclResult_t r = g_nccl.AllReduce(b, b, n, ncclDouble, ncclSum, comm, st);
+    if (r != ncclSuccess) std::fprintf(stderr, "[vdo_b200] ncclAllReduce failed: %s\n", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    ++n_coll;
+  }
+  void allreduce_max(double* b, size_t n) override {
+    if (world <= 1 || n == 0) return;
+    ncclResult_t r = g_nccl.AllReduce(b, b, n, ncclDouble, ncclMax, comm, st);
+    if (r != ncclSuccess) std::fprintf(stderr, "[vdo_b200] ncclAllReduce failed: %s\n", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    ++n_coll;
+  }
+  int n_coll = 0;
   cudaStream_t st = nullptr;
   int n_launch = 0;
   cudaEvent_t ev0[4], ev1[4];
   ~CudaBackend() override {
     for (int i = 0; i < 4; ++i) { cudaEventDestroy(ev0[i]); cudaEventDestroy(ev1[i]); }
+    if (comm) g_nccl.CommDestroy(comm);
     if (st) cudaStreamDestroy(st);
   }
   void* alloc(size_t b) override { void* p = nullptr; CK(cudaMalloc(&p, b ? b : 8)); CK(cudaMemsetAsync(p, 0, b ? b : 8, st)); return p; }
@@ -424,6 +468,7 @@ struct CudaBackend : BaBackend {
         schur_landmarks(d, 1, d.p);
         schur_vertex_obs(d, -1.0, d.Ap);
         schur_vertex_ter(d, -1.0, d.Ap);
+        allreduce_sum(d.Ap, 6 * (size_t)d.C);      // NCCL all-reduce captured into the graph (no-op on one GPU)
         pcg_dot_pAp(d);
         LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
         LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
@@ -466,3 +511,28 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
 }
 
 }  // namespace vdo
+
+// ---- multi-GPU bootstrap (C ABI, declared in include/vdo_b200.h) ----
+struct vdo_ctx;
+namespace vdo { BaBackend* ctx_backend(vdo_ctx* c); }
+extern "C" int vdo_nccl_unique_id(char* out128) {
+  if (!out128) return -2;
+  if (!vdo::g_nccl.load()) return -5;
+  ncclUniqueId id;
+  if (vdo::g_nccl.GetUniqueId(&id) != ncclSuccess) return -5;
+  std::memcpy(out128, &id, sizeof id);
+  return 0;
+}
+extern "C" int vdo_ctx_init_comm(vdo_ctx* ctx, int rank, int world, const char* id128) {
+  vdo::CudaBackend* be = static_cast<vdo::CudaBackend*>(vdo::ctx_backend(ctx));
+  if (!be || !id128 || world < 1 || rank < 0 || rank >= world) return -2;
+  if (world == 1) { be->rank = 0; be->world = 1; return 0; }
+  if (!vdo::g_nccl.load()) return -5;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  cudaSetDevice(be->dev);
+  ncclResult_t r = vdo::g_nccl.CommInitRank(&be->comm, world, id, rank);
+  if (r != ncclSuccess) { std::fprintf(stderr, "[vdo_b200] ncclCommInitRank failed: %s\n", vdo::g_nccl.GetErrorString ? vdo::g_nccl.GetErrorString(r) : "?"); return -5; }
+  be->rank = rank; be->world = world;
+  return 0;
+}

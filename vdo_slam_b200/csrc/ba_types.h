@@ -31,6 +31,7 @@ namespace vdo {
 struct Chunk { int v, begin, end, pad; };
 
 struct BaDev {
+  int own = 1;     // 1 on the rank that accumulates the se3-se3 edges / se3 parts of scalar sums (rank 0), 0 elsewhere
   int Tstat = 0;   // tracklets [0, Tstat) are static landmarks (tracklet t == landmark t); [Tstat, T) are chains
   int C = 0, P = 0, T = 0, Eobs = 0, Eter = 0, Ese = 0, n_obs_chunks = 0, n_ter_chunks = 0, n_nbr = 0;
   double *se3 = 0, *pt = 0, *se3_bk = 0, *pt_bk = 0, *se3_init = 0, *pt_init = 0;
@@ -58,13 +59,17 @@ struct BaDev {
   double* scal = 0;  // device scalars, see SC_* below
 };
 
-enum { SC_CHI2 = 0, SC_MAXDIAG = 1, SC_SCALE = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9,
+enum { SC_CHI2 = 0, SC_SCALE = 1, SC_MAXDIAG = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9,
        SC_LAMBDA = 10, SC_TOL2 = 11, SC_N = 16 };
 
 // The backend: memory + one function per kernel.  Implemented for CUDA in ba_kernels.cu (the product) and, for the
 // CPU-only host-logic tests, as serial loops over the same per-thread bodies in tests/emul/ba_backend_emul.cpp.
 struct BaBackend {
   virtual ~BaBackend() {}
+  // multi-GPU: landmark-sharded graphs sum their partial se3-side quantities across ranks (NCCL in the CUDA backend)
+  int rank = 0, world = 1;
+  virtual void allreduce_sum(double* buf, size_t n) { (void)buf; (void)n; }
+  virtual void allreduce_max(double* buf, size_t n) { (void)buf; (void)n; }
   virtual void* alloc(size_t bytes) = 0;            // zero-initialised
   virtual void free_(void* p) = 0;
   virtual void h2d(void* dst, const void* src, size_t bytes) = 0;
@@ -123,6 +128,7 @@ struct BaBackend {
       schur_landmarks(d, 1, d.p);
       schur_vertex_obs(d, -1.0, d.Ap);
       schur_vertex_ter(d, -1.0, d.Ap);
+      allreduce_sum(d.Ap, 6 * (size_t)d.C);
       pcg_dot_pAp(d);
       pcg_step(d, tol2);
     }

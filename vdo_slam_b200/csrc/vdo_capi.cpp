@@ -16,6 +16,8 @@ struct vdo_graph {
   vdo::BaGraph* g;
 };
 
+namespace vdo { BaBackend* ctx_backend(vdo_ctx* c) { return c ? c->be : nullptr; } }
+
 extern "C" {
 
 int vdo_ctx_create(int device, vdo_ctx** out) {
