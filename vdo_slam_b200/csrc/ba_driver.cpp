@@ -297,6 +297,8 @@ int BaGraph::finalize() {
   oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
   d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
   d.scal = dalloc<double>(SC_N);
+  d.n_part_pap = 148; d.n_part_rz = std::max(1, n_paths) * 8;
+  d.part_pap = dalloc<double>(d.n_part_pap); d.part_rz = dalloc<double>(d.n_part_rz);
   be_->sync();
   // host staging is no longer needed (keep the landmark map for read-back)
   std::vector<double>().swap(ob_z_); std::vector<double>().swap(ob_w_); std::vector<double>().swap(ob_d_); std::vector<int>().swap(ob_cp_);

@@ -51,6 +51,17 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
   return v;
 }
 
+// deterministic sum of a[0..n) by one CTA (fixed per-thread strides, fixed tree): same inputs => same bits on every rank.
+// All threads receive the result.  smem must hold >= 33 doubles.
+__device__ __forceinline__ double det_sum(const double* __restrict__ a, int n, double* smem) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += a[i];
+  v = block_sum(v, smem);
+  if (threadIdx.x == 0) smem[32] = v;
+  __syncthreads();
+  return smem[32];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 template <bool WRITE>
 __global__ void __launch_bounds__(128) k_lin_tracklets(BaDev d) {
@@ -275,11 +286,13 @@ __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_init
   // p = z: each thread copies exactly the items it produced in the last loop of pcr_solve_path
   for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.p[q] = d.z[q]; }
   rz = block_sum(rz, red);
-  if (threadIdx.x == 0 && rz != 0.0) atomicAdd(d.scal + SC_RZ, rz);
+  if (threadIdx.x == 0) d.part_rz[blockIdx.x] = rz;
 }
-__global__ void k_pcg_init_fin(BaDev d) {
-  const double rz = d.scal[SC_RZ];
-  d.scal[SC_RZ0] = rz; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] = 0.0;
+__global__ void __launch_bounds__(256) k_pcg_init_fin(BaDev d) {
+  __shared__ double red[33];
+  const double rz = det_sum(d.part_rz, d.n_paths * PCR_CL, red);
+  if (threadIdx.x != 0) return;
+  d.scal[SC_RZ] = rz; d.scal[SC_RZ0] = rz; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] = 0.0;
   d.scal[SC_DONE] = (rz > 0.0) ? 0.0 : 1.0;
 }
 __global__ void __launch_bounds__(256) k_pcg_dot(BaDev d) {
@@ -289,14 +302,14 @@ __global__ void __launch_bounds__(256) k_pcg_dot(BaDev d) {
   double s = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += d.p[i] * d.Ap[i];
   s = block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(d.scal + SC_PAP, s);
+  if (threadIdx.x == 0) d.part_pap[blockIdx.x] = s;
 }
 // x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new += r.z
 __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step_a(BaDev d) {
-  __shared__ double red[32];
+  __shared__ double red[33];
   if (d.scal[SC_DONE] != 0.0) return;
   cg::cluster_group cl = cg::this_cluster();
-  const double pap = d.scal[SC_PAP], rz = d.scal[SC_RZ];
+  const double pap = det_sum(d.part_pap, d.n_part_pap, red), rz = d.scal[SC_RZ];
   const double alpha = (pap > 0.0) ? rz / pap : 0.0;
   const int path = blockIdx.x / PCR_CL;
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
@@ -305,18 +318,22 @@ __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step
   if (pe - pb > 1) cl.sync();
   double rzn = pcr_solve_path(d, cl, pb, pe, d.r, d.z);
   rzn = block_sum(rzn, red);
-  if (threadIdx.x == 0 && rzn != 0.0) atomicAdd(d.scal + SC_RZ_NEW, rzn);
+  if (threadIdx.x == 0) d.part_rz[blockIdx.x] = rzn;
 }
 __global__ void __launch_bounds__(256) k_pcg_step_b(BaDev d) {
+  __shared__ double red[33];
   if (d.scal[SC_DONE] != 0.0) return;
-  const double beta = d.scal[SC_RZ_NEW] / d.scal[SC_RZ];
+  const double beta = det_sum(d.part_rz, d.n_paths * PCR_CL, red) / d.scal[SC_RZ];
   const int n = d.C * 6;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d.p[i] = d.z[i] + beta * d.p[i];
 }
-__global__ void k_pcg_scalars(BaDev d) {
+__global__ void __launch_bounds__(256) k_pcg_scalars(BaDev d) {
+  __shared__ double red[33];
   if (d.scal[SC_DONE] != 0.0) return;
   const double tol2 = d.scal[SC_TOL2];
-  const double pap = d.scal[SC_PAP], rzn = d.scal[SC_RZ_NEW];
+  const double pap = det_sum(d.part_pap, d.n_part_pap, red);
+  const double rzn = det_sum(d.part_rz, d.n_paths * PCR_CL, red);
+  if (threadIdx.x != 0) return;
   if (!(pap > 0.0) || !isfinite(pap) || !isfinite(rzn)) { d.scal[SC_DONE] = 2.0; return; }
   d.scal[SC_RZ] = rzn; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] += 1.0;
   if (rzn <= tol2 * d.scal[SC_RZ0]) d.scal[SC_DONE] = 1.0;
@@ -443,19 +460,20 @@ struct CudaBackend : BaBackend {
   void pcg_init(BaDev& d) override {
     zero(d.scal + SC_PAP, 6 * sizeof(double));   // PAP, RZ, RZ_NEW, RZ0, DONE, ITERS
     LAUNCH(k_pcg_init, d.n_paths * PCR_CL, 256, d);
-    LAUNCH(k_pcg_init_fin, 1, 1, d);
+    LAUNCH(k_pcg_init_fin, 1, 256, d);
   }
-  void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, min(nblk(d.C * 6, 256), 148), 256, d); }
+  void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, 148, 256, d); }   // always 148 CTAs: part_pap has exactly 148 slots
   void pcg_step(BaDev& d, double tol2) override {
     set_scalars(d, cur_lambda, tol2);
     LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
     LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
-    LAUNCH(k_pcg_scalars, 1, 1, d);
+    LAUNCH(k_pcg_scalars, 1, 256, d);
   }
   // n PCG iterations as ONE CUDA-graph launch (captured once per factor graph and batch size; lambda / tolerance travel
   // through device scalars so the captured kernel arguments never change)
   std::map<std::pair<const void*, int>, cudaGraphExec_t> graphs;
   void pcg_iterate(BaDev& d, double lambda, double tol2, int n) override {
+    if (world > 1) { BaBackend::pcg_iterate(d, lambda, tol2, n); return; }   // sharded: plain launches + NCCL between them
     set_scalars(d, lambda, tol2);
     auto key = std::make_pair((const void*)d.scal, n);
     auto it = graphs.find(key);
@@ -469,10 +487,10 @@ struct CudaBackend : BaBackend {
         schur_vertex_obs(d, -1.0, d.Ap);
         schur_vertex_ter(d, -1.0, d.Ap);
         allreduce_sum(d.Ap, 6 * (size_t)d.C);      // NCCL all-reduce captured into the graph (no-op on one GPU)
-        pcg_dot_pAp(d);
+        LAUNCH(k_pcg_dot, 148, 256, d);
         LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
         LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
-        LAUNCH(k_pcg_scalars, 1, 1, d);
+        LAUNCH(k_pcg_scalars, 1, 256, d);
       }
       CK(cudaStreamEndCapture(st, &g));
       CK(cudaGraphInstantiate(&ge, g, 0));

@@ -57,6 +57,9 @@ struct BaDev {
   double *vw = 0;   // 6C: per-vertex world-frame image [gamma, beta] of the vector the landmark pass multiplies (see body_vertex_transform)
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each
   double* scal = 0;  // device scalars, see SC_* below
+  double *part_pap = 0, *part_rz = 0;   // per-CTA partial sums of p.Ap (<= 148) and r.z (n_paths * 8): summed in a FIXED order so that
+                                        // every rank of a sharded solve computes bit-identical PCG scalars (and convergence flags)
+  int n_part_pap = 0, n_part_rz = 0;
 };
 
 enum { SC_CHI2 = 0, SC_SCALE = 1, SC_MAXDIAG = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9,
