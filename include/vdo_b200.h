@@ -155,6 +155,41 @@ int vdo_pose_opt_flow2_batch(vdo_ctx *ctx, int quirk, int nprob, const int *mode
 /* measurement: re-run the last uploaded batch `reps` times on the device (no host copies), average ms per launch */
 int vdo_pose_opt_flow2_time(vdo_ctx *ctx, int quirk, int nprob, int reps, float *ms_avg);
 
+/* ------------------------------------------------------------------------------------------------
+ * Image side of the per-frame path.  A vdo_frame keeps one frame's images resident in HBM: gray (u8), depth (f32),
+ * optical flow (f32 x2, interleaved like CV_32FC2) and semantic mask (i32), all row-major width x height with no padding.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct vdo_frame vdo_frame;
+int vdo_frame_create(vdo_ctx *ctx, int width, int height, vdo_frame **out);
+void vdo_frame_destroy(vdo_frame *f);
+/* H2D of the images TrackRGBD receives (include/System.h:49-51); any pointer may be NULL to keep what is resident */
+int vdo_frame_upload(vdo_frame *f, const unsigned char *gray, const float *depth, const float *flow, const int *mask);
+/* Tracking::GrabImageRGBD depth pre-processing (src/Tracking.cc:180-204): d < 0 -> 0, else bf / (d / factor), in place on the
+ * resident depth; depth_out (may be NULL) receives the result so the caller's cv::Mat can be mutated like the reference does */
+int vdo_frame_depth_prep(vdo_frame *f, float bf, float factor, float *depth_out);
+/* ORBextractor::operator() (include/ORBextractor.h:47-49, src/ORBextractor.cc:1035-1110) on the resident gray image:
+ * pyramid (cv::resize INTER_LINEAR chain), FAST-9/16 per 30-px cell with threshold fallback, octree distribution, IC_Angle.
+ * Outputs are in the reference's keypoint order (level-major); max_out bounds the arrays; n_candidates (nlevels, may be NULL)
+ * receives the per-level FAST candidate counts.  Descriptors are not produced (dead code in the reference, ORBextractor.cc:1091). */
+int vdo_orb_extract(vdo_frame *f, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int max_out, float *x,
+                    float *y, int *octave, float *response, float *angle, int *size, int *n_out, int *n_candidates);
+/* Frame::Frame static candidates (src/Frame.cc:100-129, 181-194): keep ORB keypoints with mask == 0, 0 < depth <= th_depth,
+ * non-zero flow whose target stays inside the image.  keep_idx = indices into the input, in order. */
+int vdo_frame_filter_static(vdo_frame *f, int n, const float *kx, const float *ky, float th_depth, int *keep_idx, float *cx,
+                            float *cy, float *fu, float *fv, float *depth, int *n_out);
+/* Frame::Frame semi-dense object sampling (src/Frame.cc:200-228): raster scan with the given stride, mask != 0,
+ * 0 < depth < th_depth_obj, flow target inside the image; outputs in raster (push_back) order */
+int vdo_frame_sample_objects(vdo_frame *f, float th_depth_obj, int step, int max_out, int *x, int *y, float *cx, float *cy,
+                             float *fx, float *fy, float *depth, int *label, int *n_out);
+/* Tracking::GetSceneFlowObj with Frame::UnprojectStereoObject (src/Tracking.cc:1278-1364, src/Frame.cc:521-555):
+ * flow3d[i] = X_w(cur, i) - X_w(prev, i) in float; valid[i] = both labels > 0 (otherwise the reference sets vObjLabel = -1).
+ * Tcw_* are 4x4 row-major f32 (Frame::mTcw); Xw_prev (n x 3, may be NULL) returns the previous-frame world points. */
+int vdo_scene_flow(vdo_ctx *ctx, int n, const float *u_prev, const float *v_prev, const float *z_prev, const float *Tcw_prev,
+                   const float *u_cur, const float *v_cur, const float *z_cur, const float *Tcw_cur, const float *K,
+                   const int *label_prev, const int *label_cur, float *flow3d, float *Xw_prev, unsigned char *valid);
+/* measurement: device time of the ORB front end (pyramid + FAST score maps) on the resident image */
+int vdo_orb_time(vdo_frame *f, int reps, float *ms_avg);
+
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
  * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.
  * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).

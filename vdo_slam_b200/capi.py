@@ -248,3 +248,84 @@ def pose_opt_flow2_time(ctx: Context, nprob: int, quirk: int = 1, reps: int = 20
     ms = C.c_float(0)
     ctx.check(ctx.L.vdo_pose_opt_flow2_time(ctx.h, C.c_int(quirk), C.c_int(nprob), C.c_int(reps), C.byref(ms)), "vdo_pose_opt_flow2_time")
     return float(ms.value)
+
+
+class Frame:
+    """vdo_frame: one RGB-D frame resident on the device (gray u8, depth f32, flow f32x2, mask i32)."""
+
+    def __init__(self, ctx: Context, width: int, height: int):
+        self.ctx, self.w, self.h = ctx, width, height
+        self.h_ = C.c_void_p()
+        ctx.check(ctx.L.vdo_frame_create(ctx.h, C.c_int(width), C.c_int(height), C.byref(self.h_)), "vdo_frame_create")
+
+    def upload(self, gray=None, depth=None, flow=None, mask=None):
+        self._keep = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in ((gray, np.uint8), (depth, np.float32), (flow, np.float32), (mask, np.int32))]
+        ptr = lambda a, ty: None if a is None else a.ctypes.data_as(C.POINTER(ty))
+        g, d, f, m = self._keep
+        self.ctx.check(self.ctx.L.vdo_frame_upload(self.h_, ptr(g, C.c_ubyte), ptr(d, C.c_float), ptr(f, C.c_float), ptr(m, C.c_int)), "vdo_frame_upload")
+
+    def depth_prep(self, bf, factor):
+        out = np.zeros((self.h, self.w), np.float32)
+        self.ctx.check(self.ctx.L.vdo_frame_depth_prep(self.h_, C.c_float(bf), C.c_float(factor), out.ctypes.data_as(C.POINTER(C.c_float))), "vdo_frame_depth_prep")
+        return out
+
+    def orb_extract(self, nfeatures=2500, scale=1.2, nlevels=8, ini_th=20, min_th=7, max_out=20000):
+        f32 = lambda n: np.zeros(n, np.float32); i32 = lambda n: np.zeros(n, np.int32)
+        x, y, resp, ang = f32(max_out), f32(max_out), f32(max_out), f32(max_out)
+        octv, size, ncand = i32(max_out), i32(max_out), i32(nlevels)
+        n = C.c_int(0)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float)); ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self.ctx.check(self.ctx.L.vdo_orb_extract(self.h_, C.c_int(nfeatures), C.c_float(scale), C.c_int(nlevels), C.c_int(ini_th), C.c_int(min_th), C.c_int(max_out),
+                                                  fp(x), fp(y), ip(octv), fp(resp), fp(ang), ip(size), C.byref(n), ip(ncand)), "vdo_orb_extract")
+        k = n.value
+        return dict(x=x[:k], y=y[:k], octave=octv[:k], response=resp[:k], angle=ang[:k], size=size[:k], n_candidates=ncand.tolist())
+
+    def filter_static(self, kx, ky, th_depth):
+        n = len(kx)
+        kx, ky = np.ascontiguousarray(kx, np.float32), np.ascontiguousarray(ky, np.float32)
+        idx = np.zeros(n, np.int32); out = [np.zeros(n, np.float32) for _ in range(5)]
+        m = C.c_int(0)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        self.ctx.check(self.ctx.L.vdo_frame_filter_static(self.h_, C.c_int(n), fp(kx), fp(ky), C.c_float(th_depth), idx.ctypes.data_as(C.POINTER(C.c_int)),
+                                                          *[fp(a) for a in out], C.byref(m)), "vdo_frame_filter_static")
+        k = m.value
+        return (idx[:k],) + tuple(a[:k] for a in out)
+
+    def sample_objects(self, th_depth_obj, step=4, max_out=None):
+        max_out = max_out or ((self.w + step - 1) // step) * ((self.h + step - 1) // step)
+        x, y, lab = (np.zeros(max_out, np.int32) for _ in range(3))
+        cx, cy, fx, fy, dep = (np.zeros(max_out, np.float32) for _ in range(5))
+        n = C.c_int(0)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float)); ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self.ctx.check(self.ctx.L.vdo_frame_sample_objects(self.h_, C.c_float(th_depth_obj), C.c_int(step), C.c_int(max_out), ip(x), ip(y), fp(cx), fp(cy), fp(fx), fp(fy),
+                                                           fp(dep), ip(lab), C.byref(n)), "vdo_frame_sample_objects")
+        k = n.value
+        return dict(x=x[:k], y=y[:k], cx=cx[:k], cy=cy[:k], fx=fx[:k], fy=fy[:k], depth=dep[:k], label=lab[:k])
+
+    def orb_time(self, reps=20):
+        ms = C.c_float(0)
+        self.ctx.check(self.ctx.L.vdo_orb_time(self.h_, C.c_int(reps), C.byref(ms)), "vdo_orb_time")
+        return float(ms.value)
+
+    def close(self):
+        if self.h_:
+            self.ctx.L.vdo_frame_destroy(self.h_)
+            self.h_ = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scene_flow(ctx: Context, u_prev, v_prev, z_prev, Tcw_prev, u_cur, v_cur, z_cur, Tcw_cur, K, lab_prev, lab_cur):
+    n = len(u_prev)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32); i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    arrs = [f32(a) for a in (u_prev, v_prev, z_prev)] + [f32(Tcw_prev)] + [f32(a) for a in (u_cur, v_cur, z_cur)] + [f32(Tcw_cur), f32(K)]
+    lp, lc = i32(lab_prev), i32(lab_cur)
+    flow3d = np.zeros((n, 3), np.float32); Xp = np.zeros((n, 3), np.float32); valid = np.zeros(n, np.uint8)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    ctx.check(ctx.L.vdo_scene_flow(ctx.h, C.c_int(n), *[fp(a) for a in arrs], lp.ctypes.data_as(C.POINTER(C.c_int)), lc.ctypes.data_as(C.POINTER(C.c_int)),
+                                   fp(flow3d), fp(Xp), valid.ctypes.data_as(C.POINTER(C.c_uint8))), "vdo_scene_flow")
+    return flow3d, Xp, valid.astype(bool)

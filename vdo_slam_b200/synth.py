@@ -246,3 +246,36 @@ def make_flow_problem(n=2000, seed=1234, outlier_frac=0.10, flow_sigma=0.3, widt
     T_init = T_true @ dT
     return dict(pts=pts.astype(np.float32), depth=depth.astype(np.float32), flow=flow.astype(np.float32), K=KITTI_K.copy(),
                 Tcw_last=np.eye(4, dtype=np.float32), T_init=T_init.astype(np.float32), T_true=T_true, outlier=out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Config 3 building block: one synthetic KITTI-shaped RGB-D frame (gray, raw depth, optical flow, semantic mask)
+# ---------------------------------------------------------------------------------------------------------------------
+KITTI_BF, KITTI_DEPTH_FACTOR = np.float32(387.5744), np.float32(256.0)
+
+
+def make_frame(seed=0, width=1242, height=375, n_rect=3500, n_obj=4):
+    """gray u8 (H,W): blocky texture so FAST fires a few thousand times; depth_raw f32 (H,W): disparity*256 as
+    example/vdo_slam.cc feeds it (negative = invalid); flow f32 (H,W,2); mask i32 (H,W) with objects labelled 1..n_obj."""
+    rng = np.random.default_rng(seed)
+    gray = np.full((height, width), 110, np.uint8)
+    x0 = rng.integers(0, width - 8, n_rect); y0 = rng.integers(0, height - 8, n_rect)
+    ww = rng.integers(6, 60, n_rect); hh = rng.integers(6, 40, n_rect); val = rng.integers(20, 236, n_rect)
+    for i in range(n_rect):
+        gray[y0[i]:y0[i] + hh[i], x0[i]:x0[i] + ww[i]] = val[i]
+    gray = np.clip(gray.astype(np.int16) + rng.integers(-3, 4, gray.shape), 0, 255).astype(np.uint8)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    z = (6.0 + 50.0 * (1.0 - yy / height) + 2.0 * np.sin(xx / 90.0)).astype(np.float32)     # far at the top, near at the bottom
+    mask = np.zeros((height, width), np.int32)
+    flow = np.stack([-(xx - width / 2) * 0.01 - 0.3, (yy - height / 2) * 0.012 + 0.2], -1).astype(np.float32)
+    for o in range(n_obj):
+        ow, oh = int(rng.integers(60, 200)), int(rng.integers(40, 110))
+        ox, oy = int(rng.integers(20, width - ow - 20)), int(rng.integers(height // 3, height - oh - 10))
+        mask[oy:oy + oh, ox:ox + ow] = o + 1
+        z[oy:oy + oh, ox:ox + ow] = np.float32(rng.uniform(6, 22))
+        flow[oy:oy + oh, ox:ox + ow] = np.array([rng.uniform(-6, 6), rng.uniform(-1.5, 1.5)], np.float32)
+    depth_raw = (KITTI_BF * KITTI_DEPTH_FACTOR / z).astype(np.float32)
+    bad = rng.random((height, width)) < 0.01
+    depth_raw[bad] = -1.0                                        # invalid disparities
+    flow[rng.random((height, width)) < 0.01] = 0.0               # exact zeros exercise the flow != 0 test
+    return dict(gray=gray, depth_raw=depth_raw, flow=flow, mask=mask)
