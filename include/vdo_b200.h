@@ -187,6 +187,8 @@ int vdo_frame_sample_objects(vdo_frame *f, float th_depth_obj, int step, int max
 int vdo_scene_flow(vdo_ctx *ctx, int n, const float *u_prev, const float *v_prev, const float *z_prev, const float *Tcw_prev,
                    const float *u_cur, const float *v_cur, const float *z_cur, const float *Tcw_cur, const float *K,
                    const int *label_prev, const int *label_cur, float *flow3d, float *Xw_prev, unsigned char *valid);
+/* test hook: pyramid level and FAST score map (u8, cv::cornerScore clipped at 0) of the last vdo_orb_extract call */
+int vdo_frame_debug_level(vdo_frame *f, int level, unsigned char *img_out, unsigned char *score_out, int *w_out, int *h_out);
 /* measurement: device time of the ORB front end (pyramid + FAST score maps) on the resident image */
 int vdo_orb_time(vdo_frame *f, int reps, float *ms_avg);
 

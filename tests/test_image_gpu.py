@@ -16,6 +16,19 @@ def ctx():
     return capi.Context(0)
 
 
+def test_pyramid_and_fast_score_maps_match_cv2(ctx):
+    from tests.test_image_oracle import _fast_score
+    f = make_frame(0)
+    F = capi.Frame(ctx, 1242, 375)
+    F.upload(gray=f["gray"])
+    F.orb_extract()
+    levels = io.compute_pyramid(f["gray"], io.OrbParams())
+    for lv in range(8):
+        img, sc = F.debug_level(lv)
+        assert img.shape == levels[lv].shape and np.array_equal(img, levels[lv]), f"pyramid level {lv}"     # cv2.resize chain, bit exact
+        assert np.array_equal(sc.astype(np.int32), np.minimum(_fast_score(levels[lv]), 255)), f"score level {lv}"
+
+
 @pytest.mark.parametrize("seed,shape", [(0, (375, 1242)), (5, (375, 1242)), (2, (480, 640))])
 def test_orb_extract_matches_oracle_exactly(ctx, seed, shape):
     f = make_frame(seed, width=shape[1], height=shape[0])

@@ -302,6 +302,14 @@ class Frame:
         k = n.value
         return dict(x=x[:k], y=y[:k], cx=cx[:k], cy=cy[:k], fx=fx[:k], fy=fy[:k], depth=dep[:k], label=lab[:k])
 
+    def debug_level(self, level: int):
+        w, h = C.c_int(0), C.c_int(0)
+        self.ctx.check(self.ctx.L.vdo_frame_debug_level(self.h_, C.c_int(level), None, None, C.byref(w), C.byref(h)), "vdo_frame_debug_level")
+        img = np.zeros((h.value, w.value), np.uint8); sc = np.zeros((h.value, w.value), np.uint8)
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_ubyte))
+        self.ctx.check(self.ctx.L.vdo_frame_debug_level(self.h_, C.c_int(level), up(img), up(sc), None, None), "vdo_frame_debug_level")
+        return img, sc
+
     def orb_time(self, reps=20):
         ms = C.c_float(0)
         self.ctx.check(self.ctx.L.vdo_orb_time(self.h_, C.c_int(reps), C.byref(ms)), "vdo_orb_time")

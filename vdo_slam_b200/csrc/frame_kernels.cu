@@ -59,32 +59,49 @@ __global__ void k_resize_u8(const unsigned char* __restrict__ src, int sw, int s
   const int h0 = src[(size_t)y0 * sw + x0] * ax0 + src[(size_t)y0 * sw + x1] * ax1;
   const int h1 = src[(size_t)y1 * sw + x0] * ax0 + src[(size_t)y1 * sw + x1] * ax1;
   int v = (((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2;
-  dst[(size_t)y * dw + x] = (unsigned char)min(max(v, 0), 255);
+  dst[(size_t)y * dw + x] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
 // ------------------------------------------------------------------------------------------------ FAST score
 // score(p) = max over the 16 arcs of 9 contiguous circle pixels of min(|I_p - I_k| signed consistently) - 1
 // (== cv::cornerScore<16>); a pixel is a FAST-9/16 corner at threshold t iff score >= t.
-__constant__ int c_off_x[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__constant__ int c_off_y[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 __global__ void k_fast_score(const unsigned char* __restrict__ img, int w, int h, unsigned char* __restrict__ score) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
   int out = 0;
   if (x >= 3 && y >= 3 && x < w - 3 && y < h - 3) {
-    const int v = img[(size_t)y * w + x];
+    const unsigned char* p = img + (size_t)y * w + x;
+    const int v = p[0];
+    // Bresenham circle of radius 3, clockwise from (0,+3); signed differences centre - neighbour
     int d[16];
+    d[0] = v - p[3 * w];      d[1] = v - p[3 * w + 1];  d[2] = v - p[2 * w + 2];  d[3] = v - p[w + 3];
+    d[4] = v - p[3];          d[5] = v - p[-w + 3];     d[6] = v - p[-2 * w + 2]; d[7] = v - p[-3 * w + 1];
+    d[8] = v - p[-3 * w];     d[9] = v - p[-3 * w - 1]; d[10] = v - p[-2 * w - 2]; d[11] = v - p[-w - 3];
+    d[12] = v - p[-3];        d[13] = v - p[w - 3];     d[14] = v - p[2 * w - 2]; d[15] = v - p[3 * w - 1];
+    // cornerScore = (largest t such that 9 contiguous circle pixels are all > v + t or all < v - t), found by bisection on t with
+    // 16-bit circle masks.  (A first version used min/max chains; ptxas fuses those into VIMNMX3 on sm_100a and the result came
+    // out wrong on the B200 although the PTX was correct -- see profiles/r1_notes.md -- so this kernel avoids integer min/max.)
+    auto is_corner = [&](int t) -> bool {
+      unsigned br = 0, dk = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = v - (int)img[(size_t)(y + c_off_y[k]) * w + (x + c_off_x[k])];
-    int best = -1000;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      int mn = d[k], mx = -d[k];
-#pragma unroll
-      for (int j = 1; j < 9; ++j) { const int e = d[(k + j) & 15]; mn = min(mn, e); mx = min(mx, -e); }
-      best = max(best, max(mn, mx));
+      for (int k = 0; k < 16; ++k) { br |= (unsigned)(d[k] > t) << k; dk |= (unsigned)(d[k] < -t) << k; }
+      auto nine = [](unsigned m) -> bool {
+        m |= m << 16;                                   // unroll the circle
+        unsigned a = m & (m >> 1);                      // 2 contiguous
+        a &= a >> 2;                                    // 4
+        a &= a >> 4;                                    // 8
+        a &= m >> 8;                                    // 9
+        return (a & 0xffffu) != 0u;
+      };
+      return nine(br) || nine(dk);
+    };
+    int lo = -1, hi = 255;                              // invariant: corner at lo (t = -1 is always true), not a corner at hi
+#pragma unroll 1
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (is_corner(mid)) lo = mid; else hi = mid;
     }
-    out = max(best - 1, 0);
+    out = lo < 0 ? 0 : lo;
   }
   score[(size_t)y * w + x] = (unsigned char)out;
 }
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const unsigned char* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ IC_Angle
-__constant__ int c_umax[16];
+struct UmaxArg { int v[16]; };
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {   // cv::fastAtan2 (scalar path), no FMA contraction
   const float s = (float)(180.0 / 3.14159265358979323846);
   const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
@@ -190,13 +207,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {   // cv::fas
 }
 struct KpLvl { float x, y; int level; };
 struct LevelDesc { const unsigned char* img; int w, h; };
-__constant__ LevelDesc c_levels[MAX_LEVELS];
+struct LevelsArg { LevelDesc L[MAX_LEVELS]; };
 // one warp per keypoint: lanes stride over the rows v = 0..15 of the circular patch
-__global__ void k_ic_angle(const KpLvl* __restrict__ kps, int n, float* __restrict__ angle) {
+__global__ void k_ic_angle(const KpLvl* __restrict__ kps, int n, float* __restrict__ angle, LevelsArg levels, UmaxArg umax) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= n) return;
   const KpLvl k = kps[wid];
-  const LevelDesc L = c_levels[k.level];
+  const LevelDesc L = levels.L[k.level];
   const int cx = __float2int_rn(k.x), cy = __float2int_rn(k.y);
   int m01 = 0, m10 = 0;
   if (lane <= HALF_PATCH) {
@@ -205,7 +222,7 @@ __global__ void k_ic_angle(const KpLvl* __restrict__ kps, int n, float* __restri
       const unsigned char* r = L.img + (size_t)cy * L.w + cx;
       for (int u = -HALF_PATCH; u <= HALF_PATCH; ++u) m10 += u * (int)r[u];
     } else {
-      const int d = c_umax[v];
+      const int d = umax.v[v];
       const unsigned char* rp = L.img + (size_t)(cy + v) * L.w + cx;
       const unsigned char* rm = L.img + (size_t)(cy - v) * L.w + cx;
       int vs = 0;
@@ -496,13 +513,13 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
   if (!f || nlevels < 1 || nlevels > MAX_LEVELS || !x || !y || !n_out) return VDO_ERR_ARG;
   if (!f->orb_ready || f->orb.nfeatures != nfeatures || f->orb.nlevels != nlevels || f->orb.ini_th != ini_th || f->orb.min_th != min_th) {
     f->orb.init(nfeatures, scale_factor, nlevels, ini_th, min_th);
-    FRK(cudaMemcpyToSymbol(c_umax, f->orb.umax, sizeof(int) * 16));
     f->orb_ready = true;
   }
   const OrbSetup& P = f->orb;
   // ---- pyramid + score maps ----
   f->pyr[0] = f->gray; f->lw[0] = f->w; f->lh[0] = f->h;
-  LevelDesc lv[MAX_LEVELS];
+  LevelsArg lva; std::memset(&lva, 0, sizeof lva);
+  LevelDesc* lv = lva.L;
   for (int l = 0; l < nlevels; ++l) {
     if (l > 0) {
       f->lw[l] = (int)std::lrint((float)f->w * P.inv_scale[l]); f->lh[l] = (int)std::lrint((float)f->h * P.inv_scale[l]);
@@ -515,7 +532,6 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
     k_fast_score<<<g, b, 0, f->st>>>(f->pyr[l], f->lw[l], f->lh[l], f->score[l]); f->launches++;
     lv[l] = LevelDesc{f->pyr[l], f->lw[l], f->lh[l]};
   }
-  FRK(cudaMemcpyToSymbolAsync(c_levels, lv, sizeof(LevelDesc) * nlevels, 0, cudaMemcpyHostToDevice, f->st));
   // ---- cell grids of all levels (ComputeKeyPointsOctTree geometry) ----
   std::vector<Cell> cells; std::vector<int> cell_begin(nlevels + 1, 0);
   int bord[MAX_LEVELS][4];
@@ -573,7 +589,8 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
   std::vector<float> h_ang(n, -1.f);
   if (angle) {
     FRK(cudaMemcpyAsync(f->kps, sel.data(), sizeof(KpLvl) * n, cudaMemcpyHostToDevice, f->st));
-    k_ic_angle<<<(n * 32 + 255) / 256, 256, 0, f->st>>>(f->kps, n, f->ang); f->launches++;
+    UmaxArg ua; for (int i = 0; i < 16; ++i) ua.v[i] = P.umax[i];
+    k_ic_angle<<<(n * 32 + 255) / 256, 256, 0, f->st>>>(f->kps, n, f->ang, lva, ua); f->launches++;
     FRK(cudaMemcpyAsync(h_ang.data(), f->ang, sizeof(float) * n, cudaMemcpyDeviceToHost, f->st));
     FRK(cudaStreamSynchronize(f->st));
   }
@@ -651,6 +668,18 @@ extern "C" int vdo_scene_flow(vdo_ctx* ctx, int n, const float* u_prev, const fl
   if (valid) FRK(cudaMemcpyAsync(valid, dv, fl, cudaMemcpyDeviceToHost, st));
   FRK(cudaStreamSynchronize(st));
   cudaFree(d);
+  return VDO_OK;
+}
+
+// test hook: download pyramid level `level` (and its FAST score map) computed by the last vdo_orb_extract; sizes via w_out/h_out
+extern "C" int vdo_frame_debug_level(vdo_frame* f, int level, unsigned char* img_out, unsigned char* score_out, int* w_out, int* h_out) {
+  if (!f || !f->orb_ready || level < 0 || level >= f->orb.nlevels) return VDO_ERR_ARG;
+  if (w_out) *w_out = f->lw[level];
+  if (h_out) *h_out = f->lh[level];
+  const size_t n = (size_t)f->lw[level] * f->lh[level];
+  if (img_out) FRK(cudaMemcpyAsync(img_out, f->pyr[level], n, cudaMemcpyDeviceToHost, f->st));
+  if (score_out) FRK(cudaMemcpyAsync(score_out, f->score[level], n, cudaMemcpyDeviceToHost, f->st));
+  FRK(cudaStreamSynchronize(f->st));
   return VDO_OK;
 }
 
