@@ -230,6 +230,44 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:  # pragma: no cover
             flow2 = {"error": repr(e)}
 
+    # ---- image side of one KITTI-shaped frame (upload + depth prep + ORB + static filter + object sampling), host buffers ----
+    image_side = None
+    if rank == 0:
+        try:
+            import cv2
+            from vdo_slam_b200.synth import make_frame
+            from oracle import image_ops as io
+            fr = make_frame(0)
+            Hh, Ww = fr["gray"].shape
+            F = capi.Frame(ctx, Ww, Hh)
+
+            def one_frame():
+                F.upload(gray=fr["gray"], depth=fr["depth_raw"], flow=fr["flow"], mask=fr["mask"])
+                F.depth_prep(387.5744, 256.0)
+                kp = F.orb_extract()
+                F.filter_static(kp["x"], kp["y"], 40.0)
+                F.sample_objects(25.0)
+                return kp
+            kp = one_frame()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                one_frame()
+            gpu_ms = (time.perf_counter() - t0) / 10 * 1e3
+            front_ms = F.orb_time(20)
+            prm = io.OrbParams()
+            t0 = time.perf_counter()
+            lv = io.compute_pyramid(fr["gray"], prm)
+            for im in lv:
+                io.fast_candidates(im, prm)
+            cv_ms = (time.perf_counter() - t0) * 1e3
+            image_side = {"workload": "1242x375 synthetic frame, 2500 ORB features, 8 levels", "n_keypoints": int(len(kp["x"])),
+                          "e2e_ms_per_frame": gpu_ms, "frames_per_s_image_side": 1e3 / gpu_ms, "h2d_bytes_per_frame": int(Hh * Ww * (1 + 4 + 8 + 4)),
+                          "device_ms_pyramid_plus_fast_score": front_ms,
+                          "cpu_cv2_ms_pyramid_plus_fast_cells": cv_ms, "cpu_note": "cv2 4.13 resize chain + ~1.4k cv2.FAST ROI calls from Python, 1 thread; octree/IC_Angle/sampling not included",
+                          "note": "latency-bound (9 MB of inputs per frame); octree distribution runs on the host between two kernels"}
+        except Exception as e:  # pragma: no cover
+            image_side = {"error": repr(e)}
+
     out = None
     if rank == 0:
         cpu = cpu_baseline(args)
@@ -245,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
                "clocks": clocks, "gpu_launches": launches,
                "e2e": {"value": e2e_val, "unit": "LM iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "steps": e2e_steps, "note": "host numpy buffers -> vdo_graph_* C ABI (ingest + H2D + solve + D2H) each step"},
-               "roofline": roofline, "jacobian_assembly": jac, "kernels": kernels, "per_frame_flow2": flow2, "cpu_baseline": cpu}
+               "roofline": roofline, "jacobian_assembly": jac, "kernels": kernels, "per_frame_flow2": flow2, "per_frame_image_side": image_side, "cpu_baseline": cpu}
     if world > 1:
         dist.destroy_process_group()
     return out
