@@ -193,6 +193,126 @@ __global__ void __launch_bounds__(128) k_schur_landmarks(BaDev d, const double* 
   const int t = d.Tstat + blockIdx.x * blockDim.x + threadIdx.x;
   if (t < d.T) body_schur_tracklet(d, t, MODE, v, out);
 }
+// Chains (dynamic tracklets): 8 lanes cooperate on one tracklet.  Each lane owns one landmark of the current 8-landmark
+// segment and does that landmark's gathers (pointxyz edges through the per-vertex world-frame vectors, its ternary edge through the
+// motion pose) in parallel with its neighbours; only the 3-vector recursions y_k = u_k + f_{k-1} R_{k-1} y_{k-1} (forward) and
+// z_k = (y_k + omega_k R_k^T z_{k+1}) / s_k (backward) walk the lanes, one shuffle of 3 doubles per step.
+// mode 0: out = Hll^-1 bl ; mode 1: out = Hll^-1 (Hlp v) ; mode 2: out = Hll^-1 (bl - Hlp v)
+template <int MODE>
+__global__ void __launch_bounds__(128) k_schur_chains8(BaDev d, const double* __restrict__ v, double* __restrict__ out) {
+  if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
+  const int lane8 = threadIdx.x & 7;
+  const int t = d.Tstat + ((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+  const bool live = t < d.T;
+  const int kb = live ? d.tk_begin[t] : 0, ke = live ? d.tk_begin[t + 1] : 0;
+  const unsigned FULL = 0xffffffffu;
+  double seg_w[3] = {0, 0, 0};       // f_{k-1} R_{k-1} y_{k-1} entering the segment
+  double seg_c[3] = {0, 0, 0};       // ternary contribution of edge (k-1, k) to u_k entering the segment
+  // ---------------- forward ----------------
+  for (int base = kb; __any_sync(FULL, base < ke); base += 8) {
+    const int k = base + lane8;
+    const bool valid = k < ke;
+    double u[3] = {0, 0, 0}, cn[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double f = 0.0;
+    if (valid) {
+      const int h = d.tk_h[k];
+      const double om = d.tk_omega[k];
+      f = om / d.pt_s[k];
+      if (MODE != 0) {
+        const double p[3] = {d.pt[3 * (size_t)k], d.pt[3 * (size_t)k + 1], d.pt[3 * (size_t)k + 2]};
+        for (int e = d.lm_obs_begin[k]; e < d.lm_obs_begin[k + 1]; ++e) {
+          const double* w = d.vw + 6 * (size_t)d.lm_cam[e];
+          double pxb[3]; cross3(p, w + 3, pxb);
+          const double oe = d.lm_omega[e];
+          u[0] += oe * (w[0] + 2 * pxb[0]); u[1] += oe * (w[1] + 2 * pxb[1]); u[2] += oe * (w[2] + 2 * pxb[2]);
+        }
+      }
+      if (h >= 0) {
+        Iso H; iso_load(d.se3 + 12 * (size_t)h, H);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = H.R[i];
+        if (MODE != 0) {
+          const double pn[3] = {d.pt[3 * (size_t)(k + 1)], d.pt[3 * (size_t)(k + 1) + 1], d.pt[3 * (size_t)(k + 1) + 2]};
+          double q[3]; iso_inv_apply(H, pn, q);
+          double a[3]; ter_Jh_mul(q, v + 6 * (size_t)h, a);
+          u[0] += om * a[0]; u[1] += om * a[1]; u[2] += om * a[2];
+          double Ra[3]; rot_apply(H.R, a, Ra);
+          cn[0] = -om * Ra[0]; cn[1] = -om * Ra[1]; cn[2] = -om * Ra[2];
+        }
+      }
+    }
+    // ternary contribution from the previous landmark's edge
+    double cp[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { cp[i] = __shfl_up_sync(FULL, cn[i], 1, 8); if (lane8 == 0) cp[i] = seg_c[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { u[i] += cp[i]; seg_c[i] = __shfl_sync(FULL, cn[i], 7, 8); }
+    double y[3];
+    if (valid) {
+      if (MODE == 0) { y[0] = d.bl[3 * (size_t)k]; y[1] = d.bl[3 * (size_t)k + 1]; y[2] = d.bl[3 * (size_t)k + 2]; }
+      else if (MODE == 1) { y[0] = u[0]; y[1] = u[1]; y[2] = u[2]; }
+      else { y[0] = d.bl[3 * (size_t)k] - u[0]; y[1] = d.bl[3 * (size_t)k + 1] - u[1]; y[2] = d.bl[3 * (size_t)k + 2] - u[2]; }
+    } else { y[0] = y[1] = y[2] = 0; }
+    double wout[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double win[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) win[i] = __shfl_up_sync(FULL, wout[i], 1, 8);
+      if (lane8 == j) {
+        if (j == 0) { win[0] = seg_w[0]; win[1] = seg_w[1]; win[2] = seg_w[2]; }
+        y[0] += win[0]; y[1] += win[1]; y[2] += win[2];
+        double Ry[3]; rot_apply(R, y, Ry);
+        wout[0] = f * Ry[0]; wout[1] = f * Ry[1]; wout[2] = f * Ry[2];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) seg_w[i] = __shfl_sync(FULL, wout[i], 7, 8);
+    if (valid) { out[3 * (size_t)k] = y[0]; out[3 * (size_t)k + 1] = y[1]; out[3 * (size_t)k + 2] = y[2]; }
+  }
+  // ---------------- backward ----------------
+  double seg_z[3] = {0, 0, 0};       // z of the first landmark of the following segment
+  const int nseg = (ke - kb + 7) >> 3;
+  int max_seg = nseg;
+  { const int a = __shfl_xor_sync(FULL, max_seg, 8); if (a > max_seg) max_seg = a; }      // uniform trip count per warp (4 groups of 8 lanes)
+  { const int a = __shfl_xor_sync(FULL, max_seg, 16); if (a > max_seg) max_seg = a; }
+  for (int sgi = max_seg - 1; sgi >= 0; --sgi) {
+    const int k = kb + 8 * sgi + lane8;
+    const bool valid = sgi < nseg && k < ke;
+    double y[3] = {0, 0, 0}, Rt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, om = 0.0, is = 0.0;
+    bool last = true;
+    if (valid) {
+      y[0] = out[3 * (size_t)k]; y[1] = out[3 * (size_t)k + 1]; y[2] = out[3 * (size_t)k + 2];
+      is = 1.0 / d.pt_s[k];
+      const int h = d.tk_h[k];
+      if (h >= 0 && k + 1 < ke) {
+        last = false; om = d.tk_omega[k];
+        const double* Rp = d.se3 + 12 * (size_t)h;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rt[i] = Rp[i];
+      }
+    }
+    double z[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      double zn[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) zn[i] = __shfl_down_sync(FULL, z[i], 1, 8);
+      if (lane8 == j && valid) {
+        if (j == 7) { zn[0] = seg_z[0]; zn[1] = seg_z[1]; zn[2] = seg_z[2]; }
+        if (!last) {
+          double t3[3]; rot_t_apply(Rt, zn, t3);
+          y[0] += om * t3[0]; y[1] += om * t3[1]; y[2] += om * t3[2];
+        }
+        z[0] = y[0] * is; z[1] = y[1] * is; z[2] = y[2] * is;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) seg_z[i] = __shfl_sync(FULL, z[i], 0, 8);
+    if (valid) { out[3 * (size_t)k] = z[0]; out[3 * (size_t)k + 1] = z[1]; out[3 * (size_t)k + 2] = z[2]; }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_schur_static(BaDev d, double* __restrict__ out) {
   if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
@@ -389,12 +509,16 @@ struct CudaBackend : BaBackend {
     ++n_coll;
   }
   int n_coll = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, st2 = nullptr;   // st2: second branch inside the captured PCG graph
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_launch = 0;
   cudaEvent_t ev0[4], ev1[4];
   ~CudaBackend() override {
     for (int i = 0; i < 4; ++i) { cudaEventDestroy(ev0[i]); cudaEventDestroy(ev1[i]); }
     if (comm) g_nccl.CommDestroy(comm);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
   }
   void* alloc(size_t b) override { void* p = nullptr; CK(cudaMalloc(&p, b ? b : 8)); CK(cudaMemsetAsync(p, 0, b ? b : 8, st)); return p; }
@@ -435,14 +559,14 @@ struct CudaBackend : BaBackend {
   void precond_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
   void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_paths * PCR_CL, 256, d, lambda); }
   void schur_landmarks(BaDev& d, int mode, const double* v) override {
-    const int g = nblk(d.T - d.Tstat, 128), gs = nblk(d.Tstat, 256);
-    if (mode == 0) { LAUNCH(k_schur_static<0>, gs, 256, d, d.zl); LAUNCH(k_schur_landmarks<0>, g, 128, d, v, d.zl); }
-    else if (mode == 1) { LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); LAUNCH(k_schur_landmarks<1>, g, 128, d, v, d.zl); }
-    else { LAUNCH(k_schur_static<2>, gs, 256, d, d.xl); LAUNCH(k_schur_landmarks<2>, g, 128, d, v, d.xl); }
+    const int g = nblk((d.T - d.Tstat) * 8, 128), gs = nblk(d.Tstat, 256);
+    if (mode == 0) { LAUNCH(k_schur_static<0>, gs, 256, d, d.zl); LAUNCH(k_schur_chains8<0>, g, 128, d, v, d.zl); }
+    else if (mode == 1) { LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); LAUNCH(k_schur_chains8<1>, g, 128, d, v, d.zl); }
+    else { LAUNCH(k_schur_static<2>, gs, 256, d, d.xl); LAUNCH(k_schur_chains8<2>, g, 128, d, v, d.xl); }
   }
   void schur_landmarks_part(BaDev& d, int mode, const double* v, int part) override {
-    const int g = nblk(d.T - d.Tstat, 128), gs = nblk(d.Tstat, 256);
-    if (part == 0) LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); else LAUNCH(k_schur_landmarks<1>, g, 128, d, v, d.zl);
+    const int g = nblk((d.T - d.Tstat) * 8, 128), gs = nblk(d.Tstat, 256);
+    if (part == 0) LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); else LAUNCH(k_schur_chains8<1>, g, 128, d, v, d.zl);
     (void)mode;
   }
   void lin_tracklets_part(BaDev& d, bool write, int part) override {
@@ -481,12 +605,19 @@ struct CudaBackend : BaBackend {
       cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
       const int before = n_launch;
       CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int gch = nblk((d.T - d.Tstat) * 8, 128), gst = nblk(d.Tstat, 256);
       for (int b = 0; b < n; ++b) {
         LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, (const double*)d.p, d.Ap);
-        schur_landmarks(d, 1, d.p);
+        // fork: static landmarks on st, chains on st2 (independent landmark sets; the chain kernel is latency-bound)
+        CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
+        LAUNCH(k_schur_static<1>, gst, 256, d, d.zl);
+        if (gch > 0) { k_schur_chains8<1><<<gch, 128, 0, st2>>>(d, (const double*)d.p, d.zl); ++n_launch; }
+        CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
+        // fork: the two vertex-major passes add into Ap with atomics and are independent of each other
+        CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
         schur_vertex_obs(d, -1.0, d.Ap);
-        schur_vertex_ter(d, -1.0, d.Ap);
-        allreduce_sum(d.Ap, 6 * (size_t)d.C);      // NCCL all-reduce captured into the graph (no-op on one GPU)
+        if (d.n_ter_chunks > 0) { k_schur_vertex<false><<<d.n_ter_chunks, 128, 0, st2>>>(d, -1.0, d.Ap, 1); ++n_launch; }
+        CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
         LAUNCH(k_pcg_dot, 148, 256, d);
         LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
         LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
@@ -525,6 +656,9 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
   b->dev = device;
   if ((e = cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking)) != cudaSuccess) { std::snprintf(err, errlen, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete b; return nullptr; }
   for (int i = 0; i < 4; ++i) { cudaEventCreate(&b->ev0[i]); cudaEventCreate(&b->ev1[i]); }
+  cudaStreamCreateWithFlags(&b->st2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming);
   return b;
 }
 
