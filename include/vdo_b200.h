@@ -192,6 +192,34 @@ int vdo_frame_debug_level(vdo_frame *f, int level, unsigned char *img_out, unsig
 /* measurement: device time of the ORB front end (pyramid + FAST score maps) on the resident image */
 int vdo_orb_time(vdo_frame *f, int reps, float *ms_avg);
 
+/* ---- tracking bookkeeping -----------------------------------------------------------
+ * vdo_tracklets_build  <- Tracking::GetStaticTrack / GetDynamicTrackNew (src/Tracking.cc:2201-2307, 2309-2421).
+ *   Row i (0-based, i = frame pair id) holds row_begin[i+1]-row_begin[i] features of frame i+1; assoc[k] is the index of the
+ *   same feature in frame i's row (Map::vnAssoSta / vnAssoDyn), -1 = no correspondence; labels (NULL for the static map) is
+ *   Map::vnFeatLabel (the dynamic-object id of the feature).  Tracklets come out in the reference's creation order as CSR:
+ *   entry e of tracklet t is (trk_frame[e], trk_feat[e]) = TrackLets[t][.] = (frame id, feature id); obj_id[t] = ObjLab[t].
+ *   Host-only (no device work).  Returns VDO_ERR_ARG (with *n_trk set) when max_tracklets / max_entries are too small. */
+int vdo_tracklets_build(int n_rows, const int *row_begin, const int *assoc, const int *labels, int max_tracklets, int max_entries,
+                        int *n_trk, int *trk_begin, int *trk_frame, int *trk_feat, int *obj_id);
+/* vdo_update_mask  <- Tracking::UpdateMask (src/Tracking.cc:2997-3110).  cur / last are resident frames (mask of both, flow of
+ *   last).  sem_label_last / corres_x / corres_y are the last frame's vSemObjLabel and mvObjCorres (n object points).  The
+ *   current mask is updated in place on the device; mask_out (h*w int, may be NULL) receives it (the caller's mSegMap);
+ *   warped_labels (may be NULL, sized for the number of distinct labels) lists the objects whose mask was recovered. */
+int vdo_update_mask(vdo_frame *cur, vdo_frame *last, int n, const int *sem_label_last, const float *corres_x, const float *corres_y,
+                    int *mask_out, int *n_warped, int *warped_labels);
+/* vdo_dyn_obj_tracking  <- Tracking::DynObjTracking (src/Tracking.cc:1366-1612; ground-truth bookkeeping :1531-1544 excluded).
+ *   n object points of the current frame: sem_label (vSemObjLabel), obj_label (vObjLabel, in/out), kx/ky (mvObjKeys),
+ *   depth (mvObjDepth), flow3d (vFlow_3d, n x 3), sem_label_last (mLastFrame.vSemObjLabel); the last frame's object table
+ *   (nSemPosition, bObjStat, nModLabel); rows/cols of the image, shrink_row/col (25/50 for KITTI, 0 otherwise),
+ *   sf_mg_thres / sf_ds_thres / th_depth_obj (fSFMgThres, fSFDsThres, mThDepthObj), f_id and max_id (in/out).
+ *   Outputs: the kept objects as CSR over point indices (return value ObjIdNew), mod_label (nModLabel), sem_position
+ *   (nSemPosition). */
+int vdo_dyn_obj_tracking(vdo_ctx *ctx, int n, const int *sem_label, int *obj_label, const float *kx, const float *ky, const float *depth,
+                         const float *flow3d, const int *sem_label_last, int n_last_obj, const int *last_sem_position,
+                         const unsigned char *last_obj_stat, const int *last_mod_label, int rows, int cols, int shrink_row, int shrink_col,
+                         float sf_mg_thres, float sf_ds_thres, float th_depth_obj, int f_id, int *max_id, int max_objects,
+                         int *n_objects, int *obj_begin, int *obj_idx, int *mod_label, int *sem_position);
+
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
  * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.
  * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).

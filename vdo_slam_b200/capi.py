@@ -337,3 +337,65 @@ def scene_flow(ctx: Context, u_prev, v_prev, z_prev, Tcw_prev, u_cur, v_cur, z_c
     ctx.check(ctx.L.vdo_scene_flow(ctx.h, C.c_int(n), *[fp(a) for a in arrs], lp.ctypes.data_as(C.POINTER(C.c_int)), lc.ctypes.data_as(C.POINTER(C.c_int)),
                                    fp(flow3d), fp(Xp), valid.ctypes.data_as(C.POINTER(C.c_uint8))), "vdo_scene_flow")
     return flow3d, Xp, valid.astype(bool)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def tracklets_build(assoc_rows, label_rows=None, lib_path: str | None = None):
+    """vdo_tracklets_build (host-only): Tracking::GetStaticTrack / GetDynamicTrackNew.  Returns (tracklets, obj_ids)."""
+    L = load(lib_path)
+    rb = np.zeros(len(assoc_rows) + 1, np.int32)
+    rb[1:] = np.cumsum([len(r) for r in assoc_rows])
+    flat = _i32(np.concatenate([np.asarray(r, np.int32) for r in assoc_rows])) if len(assoc_rows) and rb[-1] else np.zeros(0, np.int32)
+    lab = None
+    if label_rows is not None:
+        lab = _i32(np.concatenate([np.asarray(r, np.int32) for r in label_rows])) if rb[-1] else np.zeros(0, np.int32)
+    max_t = int(np.count_nonzero(flat != -1)) + 1
+    max_e = 2 * max_t
+    tb, tf, tk, oid = np.zeros(max_t + 1, np.int32), np.zeros(max_e, np.int32), np.zeros(max_e, np.int32), np.zeros(max_t, np.int32)
+    nt = C.c_int(0)
+    rc = L.vdo_tracklets_build(C.c_int(len(assoc_rows)), _ip(rb), _ip(flat), None if lab is None else _ip(lab), C.c_int(max_t), C.c_int(max_e),
+                               C.byref(nt), _ip(tb), _ip(tf), _ip(tk), _ip(oid))
+    if rc != 0:
+        raise VdoError(f"vdo_tracklets_build failed ({rc})")
+    n = nt.value
+    trk = [list(zip(tf[tb[t]:tb[t + 1]].tolist(), tk[tb[t]:tb[t + 1]].tolist())) for t in range(n)]
+    return trk, (oid[:n].tolist() if label_rows is not None else [])
+
+
+def update_mask(cur: "Frame", last: "Frame", sem_label_last, corres):
+    """vdo_update_mask: Tracking::UpdateMask on two resident frames.  Returns (updated mask, recovered labels)."""
+    ctx = cur.ctx
+    sl = _i32(sem_label_last)
+    n = len(sl)
+    corres = np.asarray(corres, np.float32).reshape(-1, 2)
+    cx, cy = np.ascontiguousarray(corres[:, 0]), np.ascontiguousarray(corres[:, 1])
+    out = np.zeros((cur.h, cur.w), np.int32)
+    wl = np.zeros(max(1, len(set(sl.tolist()))), np.int32)
+    nw = C.c_int(0)
+    ctx.check(ctx.L.vdo_update_mask(cur.h_, last.h_, C.c_int(n), _ip(sl), _fp(cx), _fp(cy), _ip(out), C.byref(nw), _ip(wl)), "vdo_update_mask")
+    return out, wl[:nw.value].tolist()
+
+
+def dyn_obj_tracking(ctx: Context, sem_label, obj_label, keys, depth, flow3d, sem_label_last, last_sem_position, last_obj_stat, last_mod_label,
+                     rows, cols, shrink_row, shrink_col, sf_mg_thres, sf_ds_thres, th_depth_obj, f_id, max_id, max_objects=256):
+    """vdo_dyn_obj_tracking: Tracking::DynObjTracking.  Returns (obj_label', objects, mod_label, sem_position, max_id')."""
+    sl, ol, sll = _i32(sem_label), _i32(obj_label).copy(), _i32(sem_label_last)
+    n = len(sl)
+    keys = np.asarray(keys, np.float32).reshape(-1, 2)
+    kx, ky = np.ascontiguousarray(keys[:, 0]), np.ascontiguousarray(keys[:, 1])
+    dp, f3 = np.ascontiguousarray(depth, np.float32), np.ascontiguousarray(flow3d, np.float32)
+    lsp, lml = _i32(last_sem_position), _i32(last_mod_label)
+    los = np.ascontiguousarray(last_obj_stat, np.uint8)
+    mid, no = C.c_int(max_id), C.c_int(0)
+    ob, oi = np.zeros(max_objects + 1, np.int32), np.zeros(max(n, 1), np.int32)
+    ml, sp = np.zeros(max_objects, np.int32), np.zeros(max_objects, np.int32)
+    ctx.check(ctx.L.vdo_dyn_obj_tracking(ctx.h, C.c_int(n), _ip(sl), _ip(ol), _fp(kx), _fp(ky), _fp(dp), _fp(f3), _ip(sll), C.c_int(len(lsp)), _ip(lsp),
+                                         los.ctypes.data_as(C.POINTER(C.c_ubyte)), _ip(lml), C.c_int(rows), C.c_int(cols), C.c_int(shrink_row), C.c_int(shrink_col),
+                                         C.c_float(sf_mg_thres), C.c_float(sf_ds_thres), C.c_float(th_depth_obj), C.c_int(f_id), C.byref(mid), C.c_int(max_objects),
+                                         C.byref(no), _ip(ob), _ip(oi), _ip(ml), _ip(sp)), "vdo_dyn_obj_tracking")
+    k = no.value
+    objs = [oi[ob[t]:ob[t + 1]].tolist() for t in range(k)]
+    return ol, objs, ml[:k].tolist(), sp[:k].tolist(), mid.value

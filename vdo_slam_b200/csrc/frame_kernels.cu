@@ -490,6 +490,13 @@ extern "C" void vdo_frame_destroy(vdo_frame* f) {
   cudaFree(f->cells); cudaFree(f->cell_out); cudaFree(f->cell_cnt); cudaFree(f->kps); cudaFree(f->ang); cudaFree(f->scratch);
   delete f;
 }
+// internal: device pointers of a resident frame for the other translation units (tracking_ops.cu)
+extern "C" int vdo_frame_device_ptrs(vdo_frame* f, unsigned char** gray, float** depth, float** flow, int** mask, int* w, int* h, void** stream) {
+  if (!f) return VDO_ERR_ARG;
+  if (gray) *gray = f->gray; if (depth) *depth = f->depth; if (flow) *flow = f->flow; if (mask) *mask = f->mask;
+  if (w) *w = f->w; if (h) *h = f->h; if (stream) *stream = (void*)f->st;
+  return VDO_OK;
+}
 // any of the four pointers may be NULL (keep what is resident)
 extern "C" int vdo_frame_upload(vdo_frame* f, const unsigned char* gray, const float* depth, const float* flow, const int* mask) {
   if (!f) return VDO_ERR_ARG;
