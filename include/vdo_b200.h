@@ -192,6 +192,22 @@ int vdo_frame_debug_level(vdo_frame *f, int level, unsigned char *img_out, unsig
 /* measurement: device time of the ORB front end (pyramid + FAST score maps) on the resident image */
 int vdo_orb_time(vdo_frame *f, int reps, float *ms_avg);
 
+/* ---- initial model ------------------------------------------------------------------
+ * vdo_init_model_batch  <- Tracking::GetInitModelCam / GetInitModelObj (src/Tracking.cc:1614-1715, 1717-1849), including the
+ *   cv::solvePnPRansac(pre_3d, cur_2d, K, 0, rvec, tvec, false, iters=500, thr=0.4, conf=0.98, inliers, SOLVEPNP_AP3P) call
+ *   (OpenCV 3.4; engine restated in oracle/pnp_ransac.c).  One problem per camera / object: points offsets[p]..offsets[p+1] of
+ *   obj3d (pre_3d, n x 3 f32, world) and img2d (cur_2d, n x 2 f32).  K4 = fx, fy, cx, cy (Frame::fx.. / mK).  T_mm (nprob x 16,
+ *   4x4 row-major f32) is the constant-motion model (mVelocity*mLastFrame.mTcw, or mTcw*vObjMod[PreObjID]); has_mm[p] = 0 for an
+ *   object with no previous motion (PreObjID == -1).  Outputs: T_init (nprob x 16: `output`), n_sub[p] and sub_idx (the chosen
+ *   inlier subset as ascending LOCAL indices, stored from offsets[p]); info (nprob x 8 ints: inliers.rows, MM_inlier.size(),
+ *   motion model used, n_sub, RANSAC iterations run, winning iteration, valid minimal solves, 0); Rt_refit / Rt_hyp
+ *   (nprob x 12 f64 [R row-major | t], may be NULL): refitted model and winning hypothesis (test hooks). */
+int vdo_init_model_batch(vdo_ctx *ctx, int nprob, const int *offsets, const float *obj3d, const float *img2d, const float *K4, int iters,
+                         double thr, double conf, const float *T_mm, const unsigned char *has_mm, float *T_init, int *n_sub, int *sub_idx,
+                         int *info, double *Rt_refit, double *Rt_hyp);
+/* kernels launched so far by vdo_init_model_batch on this context (bench accounting) */
+int vdo_init_model_launches(vdo_ctx *ctx);
+
 /* ---- tracking bookkeeping -----------------------------------------------------------
  * vdo_tracklets_build  <- Tracking::GetStaticTrack / GetDynamicTrackNew (src/Tracking.cc:2201-2307, 2309-2421).
  *   Row i (0-based, i = frame pair id) holds row_begin[i+1]-row_begin[i] features of frame i+1; assoc[k] is the index of the

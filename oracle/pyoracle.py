@@ -95,3 +95,36 @@ def flow2(p, mode=1, quirk=1):
                             fp(T_out), _p(flow_out, C.c_double), inl.ctypes.data_as(C.POINTER(C.c_uint8)), _p(stats, C.c_double))
     return dict(T=T_out, flow=flow_out, inlier=inl.astype(bool), iters=it, trials=int(stats[1]), chi2=stats[2], lam=stats[3],
                 n_inliers=int(stats[4]), q=stats[5:9].copy(), t=stats[9:12].copy())
+
+
+def pnp_ransac(obj, img, K4, max_iters=500, thr=0.4, conf=0.98):
+    """oracle/pnp_ransac.c.  obj (n,3) f32 world points, img (n,2) f32 pixels, K4 = (fx, fy, cx, cy).
+    Returns dict(Rt (12,) [R row-major | t], inliers (ascending), stats, Rt_hyp) or None when RANSAC fails."""
+    L = lib()
+    obj = np.ascontiguousarray(obj, np.float32); img = np.ascontiguousarray(img, np.float32)
+    K = np.ascontiguousarray(K4, np.float64)
+    n = len(obj)
+    Rt, Rh = np.zeros(12), np.zeros(12)
+    inl = np.zeros(max(n, 1), np.int32); stats = np.zeros(3, np.int32)
+    L.vdo_oracle_pnp_ransac.restype = C.c_int
+    m = L.vdo_oracle_pnp_ransac(C.c_int(n), _p(obj, C.c_float), _p(img, C.c_float), _p(K, C.c_double), C.c_int(max_iters), C.c_double(thr),
+                                C.c_double(conf), _p(Rt, C.c_double), _p(inl, C.c_int), _p(stats, C.c_int), _p(Rh, C.c_double))
+    if m <= 0:
+        return None
+    return dict(Rt=Rt, inliers=inl[:m].copy(), stats=stats.tolist(), Rt_hyp=Rh)
+
+
+def ransac_samples(n, iters=500):
+    L = lib()
+    idx = np.zeros((iters, 4), np.int32)
+    L.vdo_oracle_ransac_samples(C.c_int(n), C.c_int(iters), _p(idx, C.c_int))
+    return idx
+
+
+def p3p4(P, uv, K4):
+    L = lib()
+    P = np.ascontiguousarray(P, np.float64); uv = np.ascontiguousarray(uv, np.float64); K = np.ascontiguousarray(K4, np.float64)
+    Rt = np.zeros(12)
+    L.vdo_oracle_p3p4.restype = C.c_int
+    ok = L.vdo_oracle_p3p4(_p(P, C.c_double), _p(uv, C.c_double), _p(K, C.c_double), _p(Rt, C.c_double))
+    return Rt if ok else None

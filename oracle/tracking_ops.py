@@ -133,3 +133,38 @@ def dyn_obj_tracking(sem_label, obj_label, keys, depth, flow3d, sem_label_last, 
         obj_label[p] = ident
         lab_id.append(ident)
     return obj_label, objs, lab_id, sems, max_id
+
+
+def motion_model_inliers(obj, img, T_mm, K4, thr=0.4):
+    """Tracking.cc:1676-1691 / 1783-1798: reprojection test of the constant-motion model in float arithmetic
+    (cv::Mat float gemm = double accumulation rounded once; 1.0/z in double rounded to float)."""
+    f32 = np.float32
+    obj = np.asarray(obj, f32); img = np.asarray(img, f32); T = np.asarray(T_mm, f32).reshape(4, 4); K = np.asarray(K4, f32)
+    Xc = (obj.astype(np.float64) @ T[:3, :3].astype(np.float64).T + T[:3, 3].astype(np.float64)).astype(f32)
+    invz = (1.0 / Xc[:, 2].astype(np.float64)).astype(f32)
+    u = (K[0] * Xc[:, 0]) * invz + K[2]
+    v = (K[1] * Xc[:, 1]) * invz + K[3]
+    u_, v_ = img[:, 0] - u, img[:, 1] - v
+    rpe = np.sqrt(u_ * u_ + v_ * v_, dtype=f32)
+    return np.nonzero(rpe.astype(np.float64) < thr)[0].astype(np.int32)
+
+
+def init_model(obj, img, K4, T_mm=None, iters=500, thr=0.4, conf=0.98):
+    """GetInitModelCam / GetInitModelObj (Tracking.cc:1614-1715, 1717-1849): RANSAC model vs constant-motion model.
+    Returns (T_init 4x4 f32, chosen local inlier indices, info dict)."""
+    from . import pyoracle as po
+    r = po.pnp_ransac(obj, img, np.asarray(K4, np.float32).astype(np.float64), iters, thr, conf)
+    Mod = np.eye(4, dtype=np.float32)
+    inl = np.zeros(0, np.int32)
+    if r is not None:
+        Mod[:3, :3] = r["Rt"][:9].reshape(3, 3).astype(np.float32)
+        Mod[:3, 3] = r["Rt"][9:].astype(np.float32)
+        inl = r["inliers"]
+    info = dict(n_ransac=len(inl), n_mm=0, used_mm=False, ransac=r)
+    if T_mm is not None:
+        mm = motion_model_inliers(obj, img, T_mm, K4, thr)
+        info["n_mm"] = len(mm)
+        if not (len(inl) > len(mm)):
+            info["used_mm"] = True
+            return np.asarray(T_mm, np.float32).reshape(4, 4).copy(), mm, info
+    return Mod, inl, info

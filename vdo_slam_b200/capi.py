@@ -399,3 +399,28 @@ def dyn_obj_tracking(ctx: Context, sem_label, obj_label, keys, depth, flow3d, se
     k = no.value
     objs = [oi[ob[t]:ob[t + 1]].tolist() for t in range(k)]
     return ol, objs, ml[:k].tolist(), sp[:k].tolist(), mid.value
+
+
+def init_model_batch(ctx: Context, problems, K4, iters=500, thr=0.4, conf=0.98):
+    """vdo_init_model_batch: GetInitModelCam/Obj for a batch.  problems: list of dict(obj (n,3), img (n,2), T_mm (4,4) or None).
+    Returns list of dict(T, sub (local indices), n_ransac, n_mm, used_mm, iters_run, best_it, n_valid, Rt, Rt_hyp)."""
+    npb = len(problems)
+    off = np.zeros(npb + 1, np.int32)
+    off[1:] = np.cumsum([len(p["obj"]) for p in problems])
+    tot = int(off[-1])
+    obj = np.ascontiguousarray(np.concatenate([np.asarray(p["obj"], np.float32).reshape(-1, 3) for p in problems]) if tot else np.zeros((0, 3), np.float32))
+    img = np.ascontiguousarray(np.concatenate([np.asarray(p["img"], np.float32).reshape(-1, 2) for p in problems]) if tot else np.zeros((0, 2), np.float32))
+    Tmm = np.zeros((npb, 16), np.float32); has = np.zeros(npb, np.uint8)
+    for i, p in enumerate(problems):
+        if p.get("T_mm") is not None:
+            Tmm[i] = np.asarray(p["T_mm"], np.float32).reshape(16); has[i] = 1
+    K = np.ascontiguousarray(K4, np.float32)
+    T = np.zeros((npb, 16), np.float32); nsub = np.zeros(npb, np.int32); sub = np.zeros(max(tot, 1), np.int32)
+    info = np.zeros((npb, 8), np.int32); Rt = np.zeros((npb, 12)); Rh = np.zeros((npb, 12))
+    ctx.check(ctx.L.vdo_init_model_batch(ctx.h, C.c_int(npb), _ip(off), _fp(obj), _fp(img), _fp(K), C.c_int(iters), C.c_double(thr), C.c_double(conf),
+                                         _fp(Tmm), has.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(T), _ip(nsub), _ip(sub), _ip(info), _dp(Rt), _dp(Rh)), "vdo_init_model_batch")
+    out = []
+    for i in range(npb):
+        out.append(dict(T=T[i].reshape(4, 4).copy(), sub=sub[off[i]:off[i] + nsub[i]].copy(), n_ransac=int(info[i, 0]), n_mm=int(info[i, 1]), used_mm=bool(info[i, 2]),
+                        iters_run=int(info[i, 4]), best_it=int(info[i, 5]), n_valid=int(info[i, 6]), Rt=Rt[i].copy(), Rt_hyp=Rh[i].copy()))
+    return out
