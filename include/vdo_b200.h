@@ -236,6 +236,24 @@ int vdo_dyn_obj_tracking(vdo_ctx *ctx, int n, const int *sem_label, int *obj_lab
                          float sf_mg_thres, float sf_ds_thres, float th_depth_obj, int f_id, int *max_id, int max_objects,
                          int *n_objects, int *obj_begin, int *obj_idx, int *mod_label, int *sem_position);
 
+/* vdo_renew_frame_info  <- Tracking::RenewFrameInfo (src/Tracking.cc:2660-2995).  `cur` holds the current images (prepared depth,
+ *   updated mask, flow).  Static part: tm_sta (TM_sta = TemperalMatch_subset after Flow2Cam, -1 = outlier) indexes stat_keys
+ *   (mCurrentFrame.mvStatKeys, n_stat x 2); samp_keys (n_samp x 2) is mvKeys (ORB) or mvStatKeysTmp (nUseSampleFea == 1);
+ *   max_num_sta = nMaxTrackPointBG.  Object part: inl_begin / inl_idx = vnObjInlierID (CSR over n_obj objects), obj_stat =
+ *   bObjStat, sem_position = nSemPosition, mod_label = nModLabel, obj_keys / obj_label = mvObjKeys / vObjLabel (n_objkeys),
+ *   tmp_* = this frame's fresh semi-dense samples (mvTmpObjKeys, mvTmpObjDepth, mvTmpSemObjLabel, mvTmpObjFlowNext, mvTmpObjCorres;
+ *   n_tmp), max_num_obj = nMaxTrackPointOBJ.  K4 = fx, fy, cx, cy; Twc = Converter::toInvMatrix(mTcw), 4x4 row-major f32.
+ *   Outputs (caller-allocated, capacities cap_sta / cap_obj): static mvStatKeysTmp, mvCorres, mvFlowNext, nStaInlierID,
+ *   mvStatDepthTmp, mvStat3DPointTmp; objects mvObjKeys, mvObjDepth, mvObjCorres, mvObjFlowNext, vSemObjLabel, nDynInlierID,
+ *   vObjLabel, mvObj3DPoint.  The depth limits 40 / 25 are hard-coded like in the reference (:2691, :2849). */
+int vdo_renew_frame_info(vdo_frame *cur, int n_tm, const int *tm_sta, int n_stat, const float *stat_keys, int n_samp, const float *samp_keys,
+                         int max_num_sta, int n_obj, const int *inl_begin, const int *inl_idx, const unsigned char *obj_stat,
+                         const int *sem_position, const int *mod_label, int n_objkeys, const float *obj_keys, const int *obj_label, int n_tmp,
+                         const float *tmp_keys, const float *tmp_depth, const int *tmp_sem, const float *tmp_flow, const float *tmp_corres,
+                         int max_num_obj, const float *K4, const float *Twc, int cap_sta, int *n_sta_out, float *sta_keys, float *sta_corres,
+                         float *sta_flow, int *sta_inlier_id, float *sta_depth, float *sta_3d, int cap_obj, int *n_obj_out, float *o_keys,
+                         float *o_depth, float *o_corres, float *o_flow, int *o_sem, int *o_inlier_id, int *o_label, float *o_3d);
+
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
  * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.
  * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).

@@ -168,3 +168,127 @@ def init_model(obj, img, K4, T_mm=None, iters=500, thr=0.4, conf=0.98):
             info["used_mm"] = True
             return np.asarray(T_mm, np.float32).reshape(4, 4).copy(), mm, info
     return Mod, inl, info
+
+
+def get3d_world(key, depth, K4, Twc):
+    """Optimizer::Get3DinWorld (src/Optimizer.cc:2974-2993): float back-projection, Rwc*x + twc as a float gemm."""
+    f32 = np.float32
+    K = np.asarray(K4, f32); T = np.asarray(Twc, f32).reshape(4, 4)
+    invfx, invfy = f32(1.0) / K[0], f32(1.0) / K[1]
+    z = f32(depth)
+    x = f32(f32(f32(key[0]) - K[2]) * z) * invfx
+    y = f32(f32(f32(key[1]) - K[3]) * z) * invfy
+    v = np.array([x, y, z], np.float64)
+    return (T[:3, :3].astype(np.float64) @ v + T[:3, 3].astype(np.float64)).astype(f32)
+
+
+def renew_frame_info(mask, depth, flow, tm_sta, stat_keys, samp_keys, max_num_sta, obj_inliers, obj_stat, sem_position, mod_label,
+                     obj_keys, obj_label, tmp_keys, tmp_depth, tmp_sem, tmp_flow, tmp_corres, max_num_obj, K4, Twc):
+    """Tracking::RenewFrameInfo (src/Tracking.cc:2660-2995), statement by statement.  Images: mask (h,w) i32, depth (h,w) f32, flow (h,w,2) f32."""
+    f32 = np.float32
+    h, w = mask.shape
+    stat_keys = np.asarray(stat_keys, f32).reshape(-1, 2); samp_keys = np.asarray(samp_keys, f32).reshape(-1, 2)
+    obj_keys = np.asarray(obj_keys, f32).reshape(-1, 2); tmp_keys = np.asarray(tmp_keys, f32).reshape(-1, 2)
+    tmp_flow = np.asarray(tmp_flow, f32).reshape(-1, 2); tmp_corres = np.asarray(tmp_corres, f32).reshape(-1, 2)
+    S = dict(keys=[], corres=[], flow=[], inlier_id=[], depth=[])
+
+    def try_static(k, ident):
+        x, y = int(k[0]), int(k[1])                                      # :2684-2685 truncation
+        if x >= w or y >= h or x <= 0 or y <= 0:
+            return False
+        if mask[y, x] != 0:
+            return False
+        d = depth[y, x]
+        if d > 40 or d <= 0:
+            return False
+        fx, fy = flow[y, x, 0], flow[y, x, 1]
+        if fx != 0 and fy != 0:
+            cx, cy = f32(k[0] + fx), f32(k[1] + fy)
+            if cx < w and cy < h and cx > 0 and cy > 0:
+                S["keys"].append((k[0], k[1])); S["corres"].append((cx, cy)); S["flow"].append((fx, fy)); S["inlier_id"].append(ident); S["depth"].append(d)
+                return True
+        return False
+
+    for t in tm_sta:                                                      # (1) :2677-2708
+        if t == -1:
+            continue
+        try_static(stat_keys[t], int(t))
+        if len(S["keys"]) > max_num_sta:
+            break
+    check = np.array(S["keys"], f32).reshape(-1, 2)                       # snapshot :2714
+    tot, start_id, step = len(S["keys"]), 0, 20
+    while tot < max_num_sta:                                              # (2) :2719-2790
+        if start_id == step:
+            break
+        for i in range(start_id, len(samp_keys), step):
+            k = samp_keys[i]
+            if len(check):
+                dx, dy = check[:, 0] - k[0], check[:, 1] - k[1]
+                if (np.sqrt(dx * dx + dy * dy, dtype=f32) < f32(1.0)).any():
+                    continue
+            if try_static(k, -1):
+                tot += 1
+            if tot >= max_num_sta:
+                break
+        start_id += 1
+    S["p3d"] = [get3d_world(k, d, K4, Twc) for k, d in zip(S["keys"], S["depth"])]
+
+    O = dict(keys=[], depth=[], corres=[], flow=[], sem=[], inlier_id=[], label=[])
+    n_obj = len(obj_inliers)
+    fea = [0] * n_obj
+    for i in range(n_obj):                                                # (1) :2831-2869
+        if not obj_stat[i]:
+            fea[i] = -1
+            continue
+        cnt = 0
+        for idx in obj_inliers[i]:
+            x, y = int(obj_keys[idx][0]), int(obj_keys[idx][1])
+            if x >= w or y >= h or x <= 0 or y <= 0:
+                continue
+            if mask[y, x] != 0 and depth[y, x] < 25 and depth[y, x] > 0:
+                fx, fy = flow[y, x, 0], flow[y, x, 1]
+                cx, cy = f32(f32(x) + fx), f32(f32(y) + fy)
+                if cx < w and cy < h and cx > 0 and cy > 0:
+                    O["keys"].append((f32(x), f32(y))); O["depth"].append(depth[y, x]); O["sem"].append(int(mask[y, x])); O["flow"].append((fx, fy))
+                    O["corres"].append((cx, cy)); O["inlier_id"].append(int(idx)); O["label"].append(int(obj_label[idx]))
+                    cnt += 1
+        fea[i] = cnt
+    check = np.array(O["keys"], f32).reshape(-1, 2)                       # snapshot :2874
+
+    def push_tmp(j, lab):
+        O["keys"].append(tuple(tmp_keys[j])); O["depth"].append(tmp_depth[j]); O["sem"].append(int(tmp_sem[j])); O["flow"].append(tuple(tmp_flow[j]))
+        O["corres"].append(tuple(tmp_corres[j])); O["inlier_id"].append(-1); O["label"].append(lab)
+
+    for i in range(n_obj):                                                # (2) :2875-2927
+        if not obj_stat[i]:
+            continue
+        sem, tot, start_id, step = sem_position[i], fea[i], 0, 15
+        while tot < max_num_obj:
+            if start_id == step:
+                break
+            for j in range(start_id, len(tmp_sem), step):
+                if tmp_sem[j] != sem:
+                    continue
+                if len(check):
+                    dx, dy = check[:, 0] - tmp_keys[j][0], check[:, 1] - tmp_keys[j][1]
+                    if (np.sqrt(dx * dx + dy * dy, dtype=f32) < f32(1.0)).any():
+                        continue
+                push_tmp(j, int(mod_label[i]))
+                tot += 1
+                if tot >= max_num_obj:
+                    break
+            start_id += 1
+    uni = sorted(set(int(x) for x in tmp_sem))                            # (3) :2929-2972
+    known = [any(sem_position[i] == u and obj_stat[i] for i in range(n_obj)) for u in uni]
+    for u, kn in zip(uni, known):
+        if kn:
+            continue
+        for j in range(len(tmp_sem)):
+            if tmp_sem[j] == u:
+                push_tmp(j, -2)
+    O["p3d"] = [get3d_world(k, d, K4, Twc) for k, d in zip(O["keys"], O["depth"])]
+    A = lambda l, dt, sh: np.array(l, dt).reshape(sh)
+    return (dict(keys=A(S["keys"], f32, (-1, 2)), corres=A(S["corres"], f32, (-1, 2)), flow=A(S["flow"], f32, (-1, 2)), inlier_id=A(S["inlier_id"], np.int32, -1),
+                 depth=A(S["depth"], f32, -1), p3d=A(S["p3d"], f32, (-1, 3))),
+            dict(keys=A(O["keys"], f32, (-1, 2)), depth=A(O["depth"], f32, -1), corres=A(O["corres"], f32, (-1, 2)), flow=A(O["flow"], f32, (-1, 2)),
+                 sem=A(O["sem"], np.int32, -1), inlier_id=A(O["inlier_id"], np.int32, -1), label=A(O["label"], np.int32, -1), p3d=A(O["p3d"], f32, (-1, 3))))

@@ -142,3 +142,71 @@ def test_dyn_obj_tracking_gpu(seed, f_id):
     got = capi.dyn_obj_tracking(ctx, sem, lab, keys, depth, f3, seml, *last, 375, 1242, 25, 50, 0.12, 0.7, 40.0, f_id, 12)
     assert np.array_equal(got[0], ref[0])
     assert got[1] == ref[1] and got[2] == ref[2] and got[3] == ref[3] and got[4] == ref[4]
+
+
+def _renew_case(rng, w=640, h=240, n_obj=3, max_sta=300, max_obj=200):
+    mask = np.zeros((h, w), np.int32)
+    boxes = []
+    for o in range(1, n_obj + 2):                 # one more semantic region than tracked objects: a brand-new object
+        x0, y0 = 40 + (o - 1) * 140, int(rng.integers(40, h - 110))
+        mask[y0:y0 + 70, x0:x0 + 110] = o; boxes.append((x0, y0))
+    depth = rng.uniform(3, 60, (h, w)).astype(np.float32)
+    depth[mask > 0] = rng.uniform(5, 30, int((mask > 0).sum())).astype(np.float32)
+    depth[rng.random((h, w)) < 0.02] = 0
+    flow = rng.normal(0, 2, (h, w, 2)).astype(np.float32)
+    flow[rng.random((h, w)) < 0.03] = 0
+    n_stat = 400
+    stat_keys = np.stack([rng.uniform(-5, w + 5, n_stat), rng.uniform(-5, h + 5, n_stat)], 1).astype(np.float32)
+    tm = rng.permutation(n_stat)[:330].astype(np.int32); tm[rng.random(330) < 0.2] = -1
+    samp = np.stack([rng.uniform(0, w, 900), rng.uniform(0, h, 900)], 1).astype(np.float32)
+    samp[:40] = stat_keys[tm[tm >= 0][:40]] + 0.3                      # near-duplicates of inliers
+    # object side: previous object keys (float, propagated), inlier lists, fresh raster samples
+    obj_keys, obj_label, inl = [], [], []
+    for o in range(1, n_obj + 1):
+        x0, y0 = boxes[o - 1]; n = 260
+        k = np.stack([rng.uniform(x0 - 8, x0 + 118, n), rng.uniform(y0 - 8, y0 + 78, n)], 1)
+        base = sum(len(x) for x in obj_keys)
+        obj_keys.append(k); obj_label += [10 + o] * n
+        inl.append((base + rng.permutation(n)[:int(rng.integers(60, 230))]).astype(np.int32))
+    obj_keys = np.concatenate(obj_keys).astype(np.float32)
+    ys, xs = np.mgrid[0:h:4, 0:w:4]
+    ys, xs = ys.ravel(), xs.ravel()
+    sel = mask[ys, xs] > 0
+    ys, xs = ys[sel], xs[sel]
+    tmp_keys = np.stack([xs, ys], 1).astype(np.float32); tmp_depth = depth[ys, xs]; tmp_sem = mask[ys, xs]
+    tmp_flow = flow[ys, xs]; tmp_corres = tmp_keys + tmp_flow
+    obj_stat = np.ones(n_obj, np.uint8); obj_stat[n_obj - 1] = 0          # one failed object: re-enters as new with label -2
+    sem_pos = np.arange(1, n_obj + 1, dtype=np.int32); mod_lab = (10 + sem_pos).astype(np.int32)
+    K4 = np.array([721.5377, 721.5377, 320.0, 120.0], np.float32)
+    Twc = np.eye(4, dtype=np.float32); Twc[:3, 3] = [0.3, -0.1, 2.0]; Twc[0, 1] = 0.01; Twc[1, 0] = -0.01
+    return dict(mask=mask, depth=depth, flow=flow, tm_sta=tm, stat_keys=stat_keys, samp_keys=samp, max_num_sta=max_sta, obj_inliers=inl, obj_stat=obj_stat,
+                sem_position=sem_pos, mod_label=mod_lab, obj_keys=obj_keys, obj_label=np.array(obj_label, np.int32), tmp_keys=tmp_keys, tmp_depth=tmp_depth,
+                tmp_sem=tmp_sem, tmp_flow=tmp_flow, tmp_corres=tmp_corres, max_num_obj=max_obj, K4=K4, Twc=Twc)
+
+
+def test_oracle_renew_frame_info_quotas():
+    c = _renew_case(np.random.default_rng(11))
+    S, O = T.renew_frame_info(**c)
+    assert len(S["keys"]) == c["max_num_sta"]                           # enough ORB candidates to fill the quota exactly
+    n_inl = int((S["inlier_id"] >= 0).sum())
+    assert 0 < n_inl < c["max_num_sta"] and (S["inlier_id"][n_inl:] == -1).all()
+    assert (O["label"] == -2).sum() > 0                                 # failed + brand-new object re-enter with label -2
+    for lab in (11, 12):
+        assert (O["label"] == lab).sum() <= c["max_num_obj"] + 230
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,max_sta,max_obj", [(11, 300, 200), (12, 100, 50), (13, 2000, 5000)])
+def test_renew_frame_info_gpu(seed, max_sta, max_obj):
+    c = _renew_case(np.random.default_rng(seed), max_sta=max_sta, max_obj=max_obj)
+    S_ref, O_ref = T.renew_frame_info(**c)
+    ctx = capi.Context()
+    h, w = c["mask"].shape
+    fr = capi.Frame(ctx, w, h)
+    fr.upload(depth=c["depth"], flow=c["flow"], mask=c["mask"])
+    args = {k: v for k, v in c.items() if k not in ("mask", "depth", "flow")}
+    S, O = capi.renew_frame_info(fr, **args)
+    for k in S_ref:
+        assert np.array_equal(S[k], S_ref[k]), k
+    for k in O_ref:
+        assert np.array_equal(O[k], O_ref[k]), k

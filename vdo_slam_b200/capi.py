@@ -424,3 +424,33 @@ def init_model_batch(ctx: Context, problems, K4, iters=500, thr=0.4, conf=0.98):
         out.append(dict(T=T[i].reshape(4, 4).copy(), sub=sub[off[i]:off[i] + nsub[i]].copy(), n_ransac=int(info[i, 0]), n_mm=int(info[i, 1]), used_mm=bool(info[i, 2]),
                         iters_run=int(info[i, 4]), best_it=int(info[i, 5]), n_valid=int(info[i, 6]), Rt=Rt[i].copy(), Rt_hyp=Rh[i].copy()))
     return out
+
+
+def renew_frame_info(cur: "Frame", tm_sta, stat_keys, samp_keys, max_num_sta, obj_inliers, obj_stat, sem_position, mod_label, obj_keys, obj_label,
+                     tmp_keys, tmp_depth, tmp_sem, tmp_flow, tmp_corres, max_num_obj, K4, Twc):
+    """vdo_renew_frame_info: Tracking::RenewFrameInfo on a resident frame.  Returns (static dict, object dict)."""
+    ctx = cur.ctx
+    f2 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1, 2))
+    tm = _i32(tm_sta); sk = f2(stat_keys); sp = f2(samp_keys); ok = f2(obj_keys); ol = _i32(obj_label)
+    n_obj = len(obj_inliers)
+    ib = np.zeros(n_obj + 1, np.int32); ib[1:] = np.cumsum([len(x) for x in obj_inliers])
+    ii = _i32(np.concatenate([np.asarray(x, np.int32) for x in obj_inliers])) if n_obj and ib[-1] else np.zeros(0, np.int32)
+    st = np.ascontiguousarray(obj_stat, np.uint8); sem = _i32(sem_position); ml = _i32(mod_label)
+    tk = f2(tmp_keys); td = np.ascontiguousarray(tmp_depth, np.float32); ts = _i32(tmp_sem); tf = f2(tmp_flow); tc = f2(tmp_corres)
+    K = np.ascontiguousarray(K4, np.float32); T = np.ascontiguousarray(Twc, np.float32).reshape(16)
+    cap_s = len(tm) + len(sp) + 8; cap_o = int(ib[-1]) + (n_obj + 1) * len(tk) + 8
+    z2 = lambda n: np.zeros((n, 2), np.float32)
+    s_keys, s_cor, s_flow, s_id, s_dep, s_3d = z2(cap_s), z2(cap_s), z2(cap_s), np.zeros(cap_s, np.int32), np.zeros(cap_s, np.float32), np.zeros((cap_s, 3), np.float32)
+    o_keys, o_dep, o_cor, o_flow = z2(cap_o), np.zeros(cap_o, np.float32), z2(cap_o), z2(cap_o)
+    o_sem, o_id, o_lab, o_3d = np.zeros(cap_o, np.int32), np.zeros(cap_o, np.int32), np.zeros(cap_o, np.int32), np.zeros((cap_o, 3), np.float32)
+    ns, no = C.c_int(0), C.c_int(0)
+    ub = lambda a: a.ctypes.data_as(C.POINTER(C.c_ubyte))
+    ctx.check(ctx.L.vdo_renew_frame_info(cur.h_, C.c_int(len(tm)), _ip(tm), C.c_int(len(sk)), _fp(sk), C.c_int(len(sp)), _fp(sp), C.c_int(max_num_sta),
+                                         C.c_int(n_obj), _ip(ib), _ip(ii), ub(st), _ip(sem), _ip(ml), C.c_int(len(ok)), _fp(ok), _ip(ol), C.c_int(len(tk)),
+                                         _fp(tk), _fp(td), _ip(ts), _fp(tf), _fp(tc), C.c_int(max_num_obj), _fp(K), _fp(T),
+                                         C.c_int(cap_s), C.byref(ns), _fp(s_keys), _fp(s_cor), _fp(s_flow), _ip(s_id), _fp(s_dep), _fp(s_3d),
+                                         C.c_int(cap_o), C.byref(no), _fp(o_keys), _fp(o_dep), _fp(o_cor), _fp(o_flow), _ip(o_sem), _ip(o_id), _ip(o_lab), _fp(o_3d)),
+              "vdo_renew_frame_info")
+    a, b = ns.value, no.value
+    return (dict(keys=s_keys[:a], corres=s_cor[:a], flow=s_flow[:a], inlier_id=s_id[:a], depth=s_dep[:a], p3d=s_3d[:a]),
+            dict(keys=o_keys[:b], depth=o_dep[:b], corres=o_cor[:b], flow=o_flow[:b], sem=o_sem[:b], inlier_id=o_id[:b], label=o_lab[:b], p3d=o_3d[:b]))

@@ -230,3 +230,233 @@ extern "C" int vdo_dyn_obj_tracking(vdo_ctx* ctx, int n, const int* sem_label, i
   *n_objects = (int)obj_new.size();
   return VDO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ A14
+// Tracking::RenewFrameInfo (src/Tracking.cc:2660-2995).  The reference walks candidates sequentially, but every accept / reject
+// test depends only on the candidate, the current images and a SNAPSHOT of the inlier set taken before the top-up starts
+// (mvKeysTmpCheck / mvObjKeysTmpCheck), so the tests run as two kernel launches (inliers of static + objects; then top-up
+// candidates against the snapshots) and only the ordered "take until the quota is met" selection stays on the host.
+namespace {
+struct RenewCand { float fx, fy, depth; int flag, x, y, sem; };
+// static inlier / ORB candidate test (:2680-2704, :2750-2777): pixel truncated, mask == 0, 0 < depth <= 40, both flow components non-zero,
+// float key + flow strictly inside the image
+__device__ __forceinline__ void test_static(float kx, float ky, const int* mask, const float* depth, const float* flow, int w, int h, RenewCand& c) {
+  c.flag = 0; c.fx = c.fy = c.depth = 0.f; c.sem = 0;
+  const int x = (int)kx, y = (int)ky;
+  c.x = x; c.y = y;
+  if (x >= w || y >= h || x <= 0 || y <= 0) return;
+  const size_t p = (size_t)y * w + x;
+  if (mask[p] != 0) return;
+  const float d = depth[p];
+  if (d > 40.f || d <= 0.f) return;
+  const float fx = flow[2 * p], fy = flow[2 * p + 1];
+  if (fx != 0.f && fy != 0.f) {
+    const float cx = __fadd_rn(kx, fx), cy = __fadd_rn(ky, fy);
+    if (cx < (float)w && cy < (float)h && cx > 0.f && cy > 0.f) { c.flag = 1; c.fx = fx; c.fy = fy; c.depth = d; }
+  }
+}
+__global__ void k_renew_inliers(int n_tm, const int* __restrict__ tm, const float* __restrict__ stat_keys, int n_oinl, const int* __restrict__ oinl,
+                                const float* __restrict__ obj_keys, const int* __restrict__ mask, const float* __restrict__ depth,
+                                const float* __restrict__ flow, int w, int h, RenewCand* __restrict__ sta, RenewCand* __restrict__ obj) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tm) {
+    RenewCand c; c.flag = 0; c.fx = c.fy = c.depth = 0.f; c.x = c.y = c.sem = 0;
+    const int t = tm[i];
+    if (t != -1) test_static(stat_keys[2 * t], stat_keys[2 * t + 1], mask, depth, flow, w, h, c);
+    sta[i] = c;
+  } else if (i < n_tm + n_oinl) {
+    // object inlier (:2841-2866): integer pixel, mask != 0, 0 < depth < 25, integer pixel + flow strictly inside
+    const int q = i - n_tm, idx = oinl[q];
+    RenewCand c; c.flag = 0; c.fx = c.fy = c.depth = 0.f; c.sem = 0;
+    const int x = (int)obj_keys[2 * idx], y = (int)obj_keys[2 * idx + 1];
+    c.x = x; c.y = y;
+    if (!(x >= w || y >= h || x <= 0 || y <= 0)) {
+      const size_t p = (size_t)y * w + x;
+      const float d = depth[p];
+      if (mask[p] != 0 && d < 25.f && d > 0.f) {
+        const float fx = flow[2 * p], fy = flow[2 * p + 1];
+        const float cx = __fadd_rn((float)x, fx), cy = __fadd_rn((float)y, fy);
+        if (cx < (float)w && cy < (float)h && cx > 0.f && cy > 0.f) { c.flag = 1; c.fx = fx; c.fy = fy; c.depth = d; c.sem = mask[p]; }
+      }
+    }
+    obj[q] = c;
+  }
+}
+// "already used" test of the top-up loops (:2735-2748, :2893-2907): any snapshot key closer than 1 px (float sqrt of float squares)
+__device__ __forceinline__ bool near_any(float kx, float ky, const float* __restrict__ snap, int n) {
+  for (int j = 0; j < n; ++j) {
+    const float dx = __fsub_rn(snap[2 * j], kx), dy = __fsub_rn(snap[2 * j + 1], ky);
+    if (sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) < 1.0f) return true;
+  }
+  return false;
+}
+__global__ void k_renew_candidates(int n_samp, const float* __restrict__ samp, int n_snap_s, const float* __restrict__ snap_s, int n_tmp,
+                                   const float* __restrict__ tmp_keys, int n_snap_o, const float* __restrict__ snap_o, const int* __restrict__ mask,
+                                   const float* __restrict__ depth, const float* __restrict__ flow, int w, int h, RenewCand* __restrict__ sta,
+                                   unsigned char* __restrict__ tmp_used) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_samp) {
+    RenewCand c; c.flag = 0; c.fx = c.fy = c.depth = 0.f; c.x = c.y = c.sem = 0;
+    const float kx = samp[2 * i], ky = samp[2 * i + 1];
+    if (!near_any(kx, ky, snap_s, n_snap_s)) test_static(kx, ky, mask, depth, flow, w, h, c);
+    sta[i] = c;
+  } else if (i < n_samp + n_tmp) {
+    const int j = i - n_samp;
+    tmp_used[j] = near_any(tmp_keys[2 * j], tmp_keys[2 * j + 1], snap_o, n_snap_o) ? 1 : 0;
+  }
+}
+// Optimizer::Get3DinWorld (src/Optimizer.cc:2974-2993): float back-projection, then Rwc*x + twc as a float gemm
+inline void get3d_world(float u, float v, float z, const float* K4, const float* Twc, float* X) {
+  const float invfx = 1.0f / K4[0], invfy = 1.0f / K4[1];
+  const float x = (u - K4[2]) * z * invfx, y = (v - K4[3]) * z * invfy;
+  for (int r = 0; r < 3; ++r)
+    X[r] = (float)((double)Twc[4 * r] * (double)x + (double)Twc[4 * r + 1] * (double)y + (double)Twc[4 * r + 2] * (double)z + (double)Twc[4 * r + 3]);
+}
+struct DevBuf {            // grow-only scratch of one call
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  template <class T> T* as() { return (T*)p; }
+};
+}  // namespace
+
+extern "C" int vdo_renew_frame_info(vdo_frame* cur, int n_tm, const int* tm_sta, int n_stat, const float* stat_keys, int n_samp, const float* samp_keys,
+                                    int max_num_sta, int n_obj, const int* inl_begin, const int* inl_idx, const unsigned char* obj_stat,
+                                    const int* sem_position, const int* mod_label, int n_objkeys, const float* obj_keys, const int* obj_label, int n_tmp,
+                                    const float* tmp_keys, const float* tmp_depth, const int* tmp_sem, const float* tmp_flow, const float* tmp_corres,
+                                    int max_num_obj, const float* K4, const float* Twc, int cap_sta, int* n_sta_out, float* sta_keys, float* sta_corres,
+                                    float* sta_flow, int* sta_inlier_id, float* sta_depth, float* sta_3d, int cap_obj, int* n_obj_out, float* o_keys,
+                                    float* o_depth, float* o_corres, float* o_flow, int* o_sem, int* o_inlier_id, int* o_label, float* o_3d) {
+  if (!cur || n_tm < 0 || n_stat < 0 || n_samp < 0 || n_obj < 0 || n_tmp < 0 || !K4 || !Twc || !n_sta_out || !n_obj_out) return VDO_ERR_ARG;
+  int *mask, w, h; float *depth, *flow; void* stv;
+  if (vdo_frame_device_ptrs(cur, nullptr, &depth, &flow, &mask, &w, &h, &stv)) return VDO_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stv;
+  for (int i = 0; i < n_tm; ++i) if (tm_sta[i] < -1 || tm_sta[i] >= n_stat) return VDO_ERR_ARG;
+  // object inlier entries of the objects that are still alive (:2833-2838)
+  std::vector<int> oinl; std::vector<int> oinl_begin(n_obj + 1, 0);
+  for (int i = 0; i < n_obj; ++i) {
+    oinl_begin[i] = (int)oinl.size();
+    if (obj_stat[i]) for (int q = inl_begin[i]; q < inl_begin[i + 1]; ++q) { if (inl_idx[q] < 0 || inl_idx[q] >= n_objkeys) return VDO_ERR_ARG; oinl.push_back(inl_idx[q]); }
+  }
+  oinl_begin[n_obj] = (int)oinl.size();
+  const int n_oinl = (int)oinl.size();
+  DevBuf b_tm, b_sk, b_oi, b_ok, b_cs, b_co, b_samp, b_tmp, b_snap_s, b_snap_o, b_cc, b_used;
+  TRK(b_tm.alloc(sizeof(int) * n_tm)); TRK(b_sk.alloc(sizeof(float) * 2 * n_stat)); TRK(b_oi.alloc(sizeof(int) * n_oinl)); TRK(b_ok.alloc(sizeof(float) * 2 * n_objkeys));
+  TRK(b_cs.alloc(sizeof(RenewCand) * n_tm)); TRK(b_co.alloc(sizeof(RenewCand) * n_oinl));
+  TRK(b_samp.alloc(sizeof(float) * 2 * n_samp)); TRK(b_tmp.alloc(sizeof(float) * 2 * n_tmp));
+  if (n_tm) TRK(cudaMemcpyAsync(b_tm.p, tm_sta, sizeof(int) * n_tm, cudaMemcpyHostToDevice, st));
+  if (n_stat) TRK(cudaMemcpyAsync(b_sk.p, stat_keys, sizeof(float) * 2 * n_stat, cudaMemcpyHostToDevice, st));
+  if (n_oinl) TRK(cudaMemcpyAsync(b_oi.p, oinl.data(), sizeof(int) * n_oinl, cudaMemcpyHostToDevice, st));
+  if (n_objkeys) TRK(cudaMemcpyAsync(b_ok.p, obj_keys, sizeof(float) * 2 * n_objkeys, cudaMemcpyHostToDevice, st));
+  if (n_samp) TRK(cudaMemcpyAsync(b_samp.p, samp_keys, sizeof(float) * 2 * n_samp, cudaMemcpyHostToDevice, st));
+  if (n_tmp) TRK(cudaMemcpyAsync(b_tmp.p, tmp_keys, sizeof(float) * 2 * n_tmp, cudaMemcpyHostToDevice, st));
+  std::vector<RenewCand> cs(n_tm), co(n_oinl);
+  if (n_tm + n_oinl > 0) {
+    k_renew_inliers<<<(n_tm + n_oinl + 127) / 128, 128, 0, st>>>(n_tm, b_tm.as<int>(), b_sk.as<float>(), n_oinl, b_oi.as<int>(), b_ok.as<float>(), mask, depth, flow, w, h,
+                                                                  b_cs.as<RenewCand>(), b_co.as<RenewCand>());
+    if (n_tm) TRK(cudaMemcpyAsync(cs.data(), b_cs.p, sizeof(RenewCand) * n_tm, cudaMemcpyDeviceToHost, st));
+    if (n_oinl) TRK(cudaMemcpyAsync(co.data(), b_co.p, sizeof(RenewCand) * n_oinl, cudaMemcpyDeviceToHost, st));
+  }
+  TRK(cudaStreamSynchronize(st));
+  // ---- static (1): inliers in TM order; the size test comes after the push and uses '>' (:2706-2707) ----
+  int ns = 0; bool overflow = false;
+  auto push_sta = [&](float kx, float ky, const RenewCand& c, int id) {
+    if (ns >= cap_sta) { overflow = true; return; }
+    sta_keys[2 * ns] = kx; sta_keys[2 * ns + 1] = ky; sta_corres[2 * ns] = kx + c.fx; sta_corres[2 * ns + 1] = ky + c.fy;
+    sta_flow[2 * ns] = c.fx; sta_flow[2 * ns + 1] = c.fy; sta_inlier_id[ns] = id; sta_depth[ns] = c.depth;
+    get3d_world(kx, ky, c.depth, K4, Twc, sta_3d + 3 * ns);
+    ++ns;
+  };
+  for (int i = 0; i < n_tm; ++i) {
+    if (tm_sta[i] == -1) continue;
+    if (cs[i].flag) push_sta(stat_keys[2 * tm_sta[i]], stat_keys[2 * tm_sta[i] + 1], cs[i], tm_sta[i]);
+    if (ns > max_num_sta) break;
+  }
+  const int n_snap_s = ns;
+  // ---- objects (1): inliers of each live object in order (:2839-2869) ----
+  int no = 0;
+  std::vector<int> fea_count(n_obj, -1);
+  auto push_obj = [&](float kx, float ky, float d, float cx, float cy, float fx, float fy, int sem, int inl, int lab) {
+    if (no >= cap_obj) { overflow = true; return; }
+    o_keys[2 * no] = kx; o_keys[2 * no + 1] = ky; o_depth[no] = d; o_corres[2 * no] = cx; o_corres[2 * no + 1] = cy; o_flow[2 * no] = fx; o_flow[2 * no + 1] = fy;
+    o_sem[no] = sem; o_inlier_id[no] = inl; o_label[no] = lab;
+    get3d_world(kx, ky, d, K4, Twc, o_3d + 3 * no);
+    ++no;
+  };
+  for (int i = 0; i < n_obj; ++i) {
+    if (!obj_stat[i]) continue;
+    int count = 0;
+    for (int q = oinl_begin[i]; q < oinl_begin[i + 1]; ++q) {
+      const RenewCand& c = co[q];
+      if (!c.flag) continue;
+      push_obj((float)c.x, (float)c.y, c.depth, (float)c.x + c.fx, (float)c.y + c.fy, c.fx, c.fy, c.sem, oinl[q], obj_label[oinl[q]]);
+      ++count;
+    }
+    fea_count[i] = count;
+  }
+  const int n_snap_o = no;
+  // ---- (2) top-up candidates against the two snapshots ----
+  std::vector<RenewCand> cc(n_samp); std::vector<unsigned char> used(n_tmp, 0);
+  const bool need_sta = ns < max_num_sta && n_samp > 0;
+  bool need_obj = false;
+  for (int i = 0; i < n_obj; ++i) if (obj_stat[i] && fea_count[i] < max_num_obj) need_obj = true;
+  need_obj = need_obj && n_tmp > 0;
+  if (need_sta || need_obj) {
+    TRK(b_snap_s.alloc(sizeof(float) * 2 * n_snap_s)); TRK(b_snap_o.alloc(sizeof(float) * 2 * n_snap_o));
+    TRK(b_cc.alloc(sizeof(RenewCand) * n_samp)); TRK(b_used.alloc(n_tmp));
+    if (n_snap_s) TRK(cudaMemcpyAsync(b_snap_s.p, sta_keys, sizeof(float) * 2 * n_snap_s, cudaMemcpyHostToDevice, st));
+    if (n_snap_o) TRK(cudaMemcpyAsync(b_snap_o.p, o_keys, sizeof(float) * 2 * n_snap_o, cudaMemcpyHostToDevice, st));
+    const int ns_k = need_sta ? n_samp : 0, nt_k = need_obj ? n_tmp : 0;
+    k_renew_candidates<<<(ns_k + nt_k + 127) / 128, 128, 0, st>>>(ns_k, b_samp.as<float>(), n_snap_s, b_snap_s.as<float>(), nt_k, b_tmp.as<float>(), n_snap_o,
+                                                                  b_snap_o.as<float>(), mask, depth, flow, w, h, b_cc.as<RenewCand>(), b_used.as<unsigned char>());
+    if (ns_k) TRK(cudaMemcpyAsync(cc.data(), b_cc.p, sizeof(RenewCand) * n_samp, cudaMemcpyDeviceToHost, st));
+    if (nt_k) TRK(cudaMemcpyAsync(used.data(), b_used.p, n_tmp, cudaMemcpyDeviceToHost, st));
+    TRK(cudaStreamSynchronize(st));
+  }
+  {   // static top-up: passes start_id = 0..19 with stride 20 (:2719-2790)
+    int tot = ns, start_id = 0; const int step = 20;
+    while (tot < max_num_sta) {
+      if (start_id == step) break;
+      for (int i = start_id; i < n_samp; i += step) {
+        if (cc[i].flag) { push_sta(samp_keys[2 * i], samp_keys[2 * i + 1], cc[i], -1); ++tot; }
+        if (tot >= max_num_sta) break;
+      }
+      ++start_id;
+    }
+  }
+  // object top-up: per live object, stride-15 passes over this frame's fresh samples with the same semantic label (:2873-2927)
+  for (int i = 0; i < n_obj; ++i) {
+    if (!obj_stat[i]) continue;
+    const int sem = sem_position[i];
+    int tot = fea_count[i], start_id = 0; const int step = 15;
+    while (tot < max_num_obj) {
+      if (start_id == step) break;
+      for (int j = start_id; j < n_tmp; j += step) {
+        if (tmp_sem[j] != sem) continue;
+        if (used[j]) continue;
+        push_obj(tmp_keys[2 * j], tmp_keys[2 * j + 1], tmp_depth[j], tmp_corres[2 * j], tmp_corres[2 * j + 1], tmp_flow[2 * j], tmp_flow[2 * j + 1], tmp_sem[j], -1, mod_label[i]);
+        ++tot;
+        if (tot >= max_num_obj) break;
+      }
+      ++start_id;
+    }
+  }
+  // (3) objects that appear for the first time (or failed this frame): all their samples, label -2 (:2929-2972)
+  {
+    std::vector<int> uni(tmp_sem, tmp_sem + n_tmp);
+    std::sort(uni.begin(), uni.end());
+    uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+    std::vector<char> known(uni.size(), 0);
+    for (int i = 0; i < n_obj; ++i)
+      for (size_t j = 0; j < uni.size(); ++j)
+        if (uni[j] == sem_position[i] && obj_stat[i]) { known[j] = 1; break; }
+    for (size_t i = 0; i < uni.size(); ++i) {
+      if (known[i]) continue;
+      for (int j = 0; j < n_tmp; ++j)
+        if (uni[i] == tmp_sem[j])
+          push_obj(tmp_keys[2 * j], tmp_keys[2 * j + 1], tmp_depth[j], tmp_corres[2 * j], tmp_corres[2 * j + 1], tmp_flow[2 * j], tmp_flow[2 * j + 1], tmp_sem[j], -1, -2);
+    }
+  }
+  *n_sta_out = ns; *n_obj_out = no;
+  return overflow ? VDO_ERR_ARG : VDO_OK;
+}

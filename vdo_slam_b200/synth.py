@@ -279,3 +279,69 @@ def make_frame(seed=0, width=1242, height=375, n_rect=3500, n_obj=4):
     depth_raw[bad] = -1.0                                        # invalid disparities
     flow[rng.random((height, width)) < 0.01] = 0.0               # exact zeros exercise the flow != 0 test
     return dict(gray=gray, depth_raw=depth_raw, flow=flow, mask=mask)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Config 3: synthetic KITTI-shape RGB-D sequence with geometry-consistent depth / flow / masks.
+# A corridor (ground plane, two side walls, far wall) seen from a camera on a gentle arc, plus rigid fronto-parallel boxes that
+# translate with constant velocity.  Depth is rendered by ray casting, flow is the exact projection of each pixel's world point
+# (moved with its object) into the next camera plus N(0, flow_sigma^2); the gray image only has to make FAST fire (the pipeline
+# never matches appearance, it follows the flow).
+# ---------------------------------------------------------------------------------------------------------------------
+def _cam_pose(t, speed=0.8, yaw_rate=0.002):
+    """camera-to-world (Twc) at frame t: forward motion on a gentle arc (y down, z forward)."""
+    yaw = yaw_rate * t
+    c, s = np.cos(yaw), np.sin(yaw)
+    R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+    # integrate the arc in closed form for small yaw_rate
+    pos = np.array([speed * (1 - np.cos(yaw)) / yaw_rate, 0.0, speed * np.sin(yaw) / yaw_rate]) if yaw_rate else np.array([0, 0, speed * t])
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = pos
+    return T
+
+
+def make_sequence_frame(t, seed=0, width=1242, height=375, n_obj=3, flow_sigma=0.2, K=None, cam_h=1.65, half_w=7.0):
+    """Frame t of the sequence `seed`.  Returns dict(gray, depth_raw (disparity*256, f32), flow (H,W,2 to frame t+1), mask,
+    Twc (4x4 f64 ground truth), obj_ids (semantic ids visible), K)."""
+    K = KITTI_K if K is None else K
+    fx, fy, cx, cy = [float(v) for v in K]
+    rng_o = np.random.default_rng(1000 + seed)
+    objs = []
+    for o in range(n_obj):
+        objs.append(dict(id=o + 1, x=float(rng_o.uniform(-4.0, 4.0)), z0=float(rng_o.uniform(9.0, 18.0)) + 2.0 * o,
+                         vz=float(rng_o.uniform(0.55, 1.0)), vx=float(rng_o.uniform(-0.02, 0.02)), w=float(rng_o.uniform(1.6, 2.4)), h=float(rng_o.uniform(1.3, 1.8))))
+    T0, T1 = _cam_pose(t), _cam_pose(t + 1)
+    vv, uu = np.mgrid[0:height, 0:width].astype(np.float64)
+    d_cam = np.stack([(uu - cx) / fx, (vv - cy) / fy, np.ones_like(uu)], -1)
+    d_w = d_cam @ T0[:3, :3].T
+    c_w = T0[:3, 3]
+    big = 1e9
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lam = np.full(uu.shape, big)
+        # ground y = cam_h, walls x = +-half_w, far wall z = c_z + 400
+        for axis, val in ((1, cam_h), (0, half_w), (0, -half_w), (2, c_w[2] + 400.0)):
+            l = (val - c_w[axis]) / d_w[..., axis]
+            l = np.where((l > 0) & np.isfinite(l), l, big)
+            lam = np.minimum(lam, l)
+        mask = np.zeros(uu.shape, np.int32)
+        vel = np.zeros(uu.shape + (3,))
+        for ob in objs:
+            zc = ob["z0"] + ob["vz"] * t; xc = ob["x"] + ob["vx"] * t
+            l = (zc - c_w[2]) / d_w[..., 2]
+            P = c_w + l[..., None] * d_w
+            hit = (l > 0) & (l < lam) & (np.abs(P[..., 0] - xc) < ob["w"] / 2) & (P[..., 1] < cam_h) & (P[..., 1] > cam_h - ob["h"])
+            lam = np.where(hit, l, lam); mask[hit] = ob["id"]; vel[hit] = [ob["vx"], 0.0, ob["vz"]]
+    Pw = c_w + lam[..., None] * d_w
+    z = lam.copy()                                  # d_cam has unit z: lambda is the camera-frame depth
+    Pn = Pw + vel
+    Pc1 = (Pn - T1[:3, 3]) @ T1[:3, :3]             # R^T (P - c)
+    u1 = fx * Pc1[..., 0] / Pc1[..., 2] + cx; v1 = fy * Pc1[..., 1] / Pc1[..., 2] + cy
+    rng = np.random.default_rng(7919 * seed + t)
+    flow = np.stack([u1 - uu, v1 - vv], -1) + rng.normal(0, flow_sigma, uu.shape + (2,))
+    flow = flow.astype(np.float32)
+    flow[rng.random(uu.shape) < 0.005] = 0.0
+    disp = np.round(KITTI_BF * KITTI_DEPTH_FACTOR / np.maximum(z, 0.5))
+    depth_raw = disp.astype(np.float32)
+    depth_raw[rng.random(uu.shape) < 0.005] = -1.0
+    gray = make_frame(seed=31 * seed + t, width=width, height=height, n_obj=0)["gray"]
+    ids = [ob["id"] for ob in objs if (mask == ob["id"]).any()]
+    return dict(gray=gray, depth_raw=depth_raw, flow=flow, mask=mask, Twc=T0, obj_ids=ids, K=np.asarray(K, np.float32))
