@@ -254,6 +254,47 @@ int vdo_renew_frame_info(vdo_frame *cur, int n_tm, const int *tm_sta, int n_stat
                          float *sta_flow, int *sta_inlier_id, float *sta_depth, float *sta_3d, int cap_obj, int *n_obj_out, float *o_keys,
                          float *o_depth, float *o_corres, float *o_flow, int *o_sem, int *o_inlier_id, int *o_label, float *o_3d);
 
+/* depth and mask label at the truncated pixel of each key (x, y interleaved, n x 2 f32); 0 / 0 outside the image.  The
+ * "update current frame from last" look-ups of Tracking::GrabImageRGBD (src/Tracking.cc:262-312). */
+int vdo_frame_gather(vdo_frame *f, int n, const float *keys, float *depth_out, int *mask_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole per-frame path: System::TrackRGBD -> Tracking::GrabImageRGBD -> Tracking::Track (include/System.h:49-51,
+ * src/Tracking.cc:164-648, 650-1212) sequenced over the stages above, with the per-frame state of `Frame` and the slice of `Map`
+ * the batch optimisers read kept inside the tracker.  Settings mirror the YAML keys Tracking::Tracking reads
+ * (src/Tracking.cc:57-162; defaults = example/kitti-0000-0013.yaml).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct vdo_tracker vdo_tracker;
+typedef struct vdo_tracker_params {
+  int width, height;                 /* Camera.width / Camera.height */
+  float fx, fy, cx, cy;              /* Camera.fx .. */
+  float bf, depth_factor;            /* Camera.bf, DepthMapFactor */
+  float th_depth_bg, th_depth_obj;   /* ThDepthBG, ThDepthOBJ */
+  int max_track_bg, max_track_obj;   /* MaxTrackPointBG, MaxTrackPointOBJ */
+  float sf_mg_thres, sf_ds_thres;    /* SFMgThres, SFDsThres */
+  int n_features; float scale_factor; int n_levels, ini_th_fast, min_th_fast;   /* ORBextractor.* */
+  int is_kitti;                      /* mTestData == KITTI: boundary shrink 25 / 50 px (src/Tracking.cc:1405-1409) */
+  int quirk;                         /* see vdo_pose_opt_flow2 */
+  int window_size, overlap_size;     /* WINDOW_SIZE, OVERLAP_SIZE (recorded; the windowed BA is driven by the caller) */
+  int reserved[4];
+} vdo_tracker_params;
+void vdo_tracker_params_default(vdo_tracker_params *p);
+int vdo_tracker_create(vdo_ctx *ctx, const vdo_tracker_params *params, vdo_tracker **out);
+void vdo_tracker_destroy(vdo_tracker *t);
+const char *vdo_tracker_last_error(const vdo_tracker *t);
+/* One frame.  gray: h x w u8; depth: h x w f32 raw disparity*factor as example/vdo_slam.cc passes it -- when writeback != 0 it is
+ * overwritten with metric depth like the reference does to the caller's cv::Mat (src/Tracking.cc:180-204); flow: h x w x 2 f32;
+ * mask: h x w i32 -- when writeback != 0 it receives the propagated labels (UpdateMask, :3062).  gt_sem_ids: semantic ids that have a
+ * ground-truth object pose in this frame (vObjPose_gt[i][1]); the reference only estimates motion for objects present in the
+ * ground truth of both frames (:767-810).  Tcw_out: 4x4 row-major f32 = the returned mCurrentFrame.mTcw. */
+int vdo_tracker_track(vdo_tracker *t, const unsigned char *gray, float *depth, const float *flow, int *mask, int n_gt,
+                      const int *gt_sem_ids, int writeback, float *Tcw_out);
+/* Named read-back of the frame state after the last call ('f' arrays are f32, the others i32; out may be NULL to query the size):
+ * Tcw mVelocity mvKeys mvStatKeysTmp mvStatDepthTmp mvCorres mvFlowNext mvStat3DPointTmp nStaInlierID mvObjKeys mvObjDepth
+ * mvObjCorres mvObjFlowNext mvObj3DPoint vSemObjLabel vObjLabel nDynInlierID vFlow_3d nModLabel nSemPosition bObjStat vObjMod
+ * TemperalMatch_subset max_id f_id */
+int vdo_tracker_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
+
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
  * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.
  * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).

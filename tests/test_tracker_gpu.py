@@ -1,0 +1,71 @@
+"""Whole per-frame path (config 3 shape): vdo_tracker on the GPU against the Python/C oracle pipeline on a synthetic,
+geometry-consistent RGB-D sequence.  Track IDs / labels / index sets exact; poses and motions <= 1e-4."""
+import numpy as np
+import pytest
+
+from oracle.tracking_pipeline import OracleTracker
+from vdo_slam_b200 import capi
+from vdo_slam_b200.synth import make_sequence_frame
+
+
+def _compare(tr, orc, t):
+    C = orc.cur
+    assert np.abs(tr.get("Tcw").reshape(4, 4) - C.Tcw).max() <= 1e-4, f"frame {t}: camera pose"
+    for name, ref in (("nModLabel", C.nModLabel), ("nSemPosition", C.nSemPosition), ("bObjStat", [int(b) for b in C.bObjStat])):
+        assert tr.get(name).tolist() == [int(v) for v in ref], f"frame {t}: {name}"
+    assert np.array_equal(tr.get("vObjLabel"), C.objLabel), f"frame {t}: vObjLabel"
+    assert np.array_equal(tr.get("vSemObjLabel"), C.semObjLabel), f"frame {t}: vSemObjLabel"
+    assert int(tr.get("max_id")[0]) == orc.max_id
+    if t > 0:
+        assert np.array_equal(tr.get("nStaInlierID"), C.staInlierID), f"frame {t}: nStaInlierID"
+        assert np.array_equal(tr.get("nDynInlierID"), C.dynInlierID), f"frame {t}: nDynInlierID"
+        assert np.array_equal(tr.get("TemperalMatch_subset"), orc.tm_sub), f"frame {t}: TemperalMatch_subset"
+        mods = tr.get("vObjMod").reshape(-1, 4, 4)
+        assert len(mods) == len(C.vObjMod)
+        for a, b in zip(mods, C.vObjMod):
+            assert np.abs(a - b).max() <= 1e-4, f"frame {t}: object motion"
+    for name, ref in (("mvStatKeysTmp", C.statKeysTmp), ("mvCorres", C.corres), ("mvFlowNext", C.flowNext), ("mvObjKeys", C.objKeys), ("mvObjCorres", C.objCorres)):
+        got = tr.get(name).reshape(-1, 2)
+        assert got.shape == np.asarray(ref).reshape(-1, 2).shape, f"frame {t}: {name} count"
+        assert np.abs(got - np.asarray(ref).reshape(-1, 2)).max() <= 1e-3, f"frame {t}: {name}"
+    assert np.abs(tr.get("mvObjDepth") - C.objDepth).max() <= 1e-5 if len(C.objDepth) else True
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n_frames,size", [(0, 6, (1242, 375)), (1, 5, (640, 240))])
+def test_tracker_matches_oracle_pipeline(seed, n_frames, size):
+    w, h = size
+    K = np.array([721.5377, 721.5377, w * 0.49, h * 0.46], np.float32)
+    ctx = capi.Context()
+    tr = capi.Tracker(ctx, width=w, height=h, cx=float(K[2]), cy=float(K[3]))
+    orc = OracleTracker(width=w, height=h, K4=K)
+    for t in range(n_frames):
+        f = make_sequence_frame(t, seed=seed, width=w, height=h, K=K)
+        ids = f["obj_ids"] if t != 3 else f["obj_ids"][:1]          # frame 3: one object has no ground truth -> its motion is not estimated
+        T_ref = orc.track(f["gray"], f["depth_raw"], f["flow"], f["mask"], ids)
+        d, m = f["depth_raw"].copy(), f["mask"].copy()
+        T = tr.track(f["gray"], d, f["flow"], m, ids, writeback=True)
+        assert np.abs(T - T_ref).max() <= 1e-4
+        assert np.array_equal(m, orc.mask), f"frame {t}: propagated mask"
+        assert np.array_equal(d, orc.depth), f"frame {t}: prepared depth"
+        _compare(tr, orc, t)
+    # the estimated camera motion is close to the ground truth of the generator (sanity of the whole chain, not a parity claim)
+    T_gt = np.linalg.inv(f["Twc"]) @ make_sequence_frame(0, seed=seed, width=w, height=h, K=K)["Twc"]
+    assert np.abs(T[:3, 3] - T_gt[:3, 3]).max() < 0.1
+
+
+@pytest.mark.gpu
+def test_tracker_degenerate_frames():
+    """empty masks (no objects), zero flow (no static candidates): the tracker must not fail and must keep identity / last pose."""
+    w, h = 400, 240          # the smallest pyramid level must still hold one 30-px FAST cell (the reference divides by zero below that)
+    ctx = capi.Context()
+    tr = capi.Tracker(ctx, width=w, height=h, cx=200.0, cy=110.0)
+    orc = OracleTracker(width=w, height=h, K4=np.array([721.5377, 721.5377, 200.0, 110.0], np.float32))
+    rng = np.random.default_rng(0)
+    for t in range(3):
+        gray = rng.integers(0, 255, (h, w)).astype(np.uint8)
+        depth = np.full((h, w), 9000.0, np.float32); flow = np.zeros((h, w, 2), np.float32); mask = np.zeros((h, w), np.int32)
+        T_ref = orc.track(gray, depth, flow, mask, [])
+        T = tr.track(gray, depth.copy(), flow, mask.copy(), [])
+        assert np.abs(T - T_ref).max() <= 1e-6
+        assert len(tr.get("mvStatKeysTmp")) == 2 * len(orc.cur.statKeysTmp)

@@ -454,3 +454,56 @@ def renew_frame_info(cur: "Frame", tm_sta, stat_keys, samp_keys, max_num_sta, ob
     a, b = ns.value, no.value
     return (dict(keys=s_keys[:a], corres=s_cor[:a], flow=s_flow[:a], inlier_id=s_id[:a], depth=s_dep[:a], p3d=s_3d[:a]),
             dict(keys=o_keys[:b], depth=o_dep[:b], corres=o_cor[:b], flow=o_flow[:b], sem=o_sem[:b], inlier_id=o_id[:b], label=o_lab[:b], p3d=o_3d[:b]))
+
+
+class TrackerParams(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("depth_factor", C.c_float), ("th_depth_bg", C.c_float), ("th_depth_obj", C.c_float), ("max_track_bg", C.c_int), ("max_track_obj", C.c_int),
+                ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float), ("n_features", C.c_int), ("scale_factor", C.c_float), ("n_levels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int), ("is_kitti", C.c_int), ("quirk", C.c_int), ("window_size", C.c_int),
+                ("overlap_size", C.c_int), ("reserved", C.c_int * 4)]
+
+
+class Tracker:
+    """vdo_tracker: System::TrackRGBD -> Tracking::GrabImageRGBD -> Tracking::Track on the device stages."""
+    _INT = {"nStaInlierID", "vSemObjLabel", "vObjLabel", "nDynInlierID", "nModLabel", "nSemPosition", "bObjStat", "TemperalMatch_subset", "max_id", "f_id"}
+
+    def __init__(self, ctx: Context, **overrides):
+        self.ctx = ctx
+        self.params = TrackerParams()
+        ctx.L.vdo_tracker_params_default(C.byref(self.params))
+        for k, v in overrides.items():
+            setattr(self.params, k, v)
+        self.h_ = C.c_void_p()
+        ctx.check(ctx.L.vdo_tracker_create(ctx.h, C.byref(self.params), C.byref(self.h_)), "vdo_tracker_create")
+        ctx.L.vdo_tracker_last_error.restype = C.c_char_p
+
+    def track(self, gray, depth, flow, mask, gt_ids, writeback=True):
+        """depth (f32 h x w) and mask (i32 h x w) must be C-contiguous arrays; with writeback they are mutated like the reference's cv::Mat."""
+        assert depth.dtype == np.float32 and depth.flags.c_contiguous and mask.dtype == np.int32 and mask.flags.c_contiguous
+        g = np.ascontiguousarray(gray, np.uint8); f = np.ascontiguousarray(flow, np.float32)
+        ids = _i32(gt_ids)
+        T = np.zeros((4, 4), np.float32)
+        rc = self.ctx.L.vdo_tracker_track(self.h_, g.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(depth), _fp(f), _ip(mask), C.c_int(len(ids)), _ip(ids),
+                                          C.c_int(int(writeback)), _fp(T))
+        if rc != 0:
+            raise VdoError(f"vdo_tracker_track failed ({rc}): {self.ctx.L.vdo_tracker_last_error(self.h_).decode()}")
+        return T
+
+    def get(self, name: str):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.L.vdo_tracker_get(self.h_, name.encode(), None, C.c_int(0), C.byref(n)), "vdo_tracker_get")
+        out = np.zeros(max(n.value, 1), np.int32 if name in self._INT else np.float32)
+        self.ctx.check(self.ctx.L.vdo_tracker_get(self.h_, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_int(len(out)), C.byref(n)), "vdo_tracker_get")
+        return out[:n.value]
+
+    def close(self):
+        if getattr(self, "h_", None):
+            self.ctx.L.vdo_tracker_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -114,7 +114,7 @@ struct KpOut { float x, y, resp; };
 // first threshold thr_hi, and if the cell stays empty thr_lo.  Output row-major, like cv::FAST.
 __global__ void __launch_bounds__(256) k_fast_cells(const unsigned char* __restrict__ score, int w, const Cell* __restrict__ cells,
                                                     int thr_hi, int thr_lo, KpOut* __restrict__ out, int* __restrict__ count) {
-  __shared__ unsigned char s[48 * 48];
+  __shared__ unsigned char s[64 * 64];     // cell <= 60 px on a side (width / floor(width / 30) < 60) plus the zero halo
   __shared__ int wsum[8];
   __shared__ int total;
   const Cell c = cells[blockIdx.x];
@@ -549,7 +549,7 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
     const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
     if (nCols < 1 || nRows < 1) { cell_begin[l + 1] = (int)cells.size(); continue; }
     const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
-    if (wCell + 6 - 6 + 2 > 46 || hCell + 2 > 46) return VDO_ERR_UNSUPPORTED;
+    if (wCell + 2 > 64 || hCell + 2 > 64) return VDO_ERR_UNSUPPORTED;
     for (int i = 0; i < nRows; ++i) {
       const int iniY = minB + i * hCell; int maxY = iniY + hCell + 6;
       if (iniY >= maxBY - 3) continue;

@@ -460,3 +460,33 @@ extern "C" int vdo_renew_frame_info(vdo_frame* cur, int n_tm, const int* tm_sta,
   *n_sta_out = ns; *n_obj_out = no;
   return overflow ? VDO_ERR_ARG : VDO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ point look-ups
+namespace {
+__global__ void k_gather_points(int n, const float* __restrict__ keys, const float* __restrict__ depth, const int* __restrict__ mask, int w, int h,
+                                float* __restrict__ d_out, int* __restrict__ m_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int u = (int)keys[2 * i], v = (int)keys[2 * i + 1];
+  const bool in = u >= 0 && u < w && v >= 0 && v < h;
+  d_out[i] = in ? depth[(size_t)v * w + u] : 0.f;
+  m_out[i] = in ? mask[(size_t)v * w + u] : 0;
+}
+}  // namespace
+// depth and mask label at the truncated pixel of each key (x, y interleaved); 0 / 0 outside the image.
+// Used for the "update current frame from last" look-ups of Tracking::GrabImageRGBD (src/Tracking.cc:262-312).
+extern "C" int vdo_frame_gather(vdo_frame* f, int n, const float* keys, float* depth_out, int* mask_out) {
+  if (!f || n < 0 || (n && (!keys || !depth_out || !mask_out))) return VDO_ERR_ARG;
+  if (n == 0) return VDO_OK;
+  int *mask, w, h; float* depth; void* stv;
+  if (vdo_frame_device_ptrs(f, nullptr, &depth, nullptr, &mask, &w, &h, &stv)) return VDO_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stv;
+  DevBuf bk, bd, bm;
+  TRK(bk.alloc(sizeof(float) * 2 * n)); TRK(bd.alloc(sizeof(float) * n)); TRK(bm.alloc(sizeof(int) * n));
+  TRK(cudaMemcpyAsync(bk.p, keys, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, st));
+  k_gather_points<<<(n + 255) / 256, 256, 0, st>>>(n, bk.as<float>(), depth, mask, w, h, bd.as<float>(), bm.as<int>());
+  TRK(cudaMemcpyAsync(depth_out, bd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  TRK(cudaMemcpyAsync(mask_out, bm.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  TRK(cudaStreamSynchronize(st));
+  return VDO_OK;
+}
