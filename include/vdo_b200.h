@@ -292,7 +292,8 @@ int vdo_tracker_track(vdo_tracker *t, const unsigned char *gray, float *depth, c
 /* Named read-back of the frame state after the last call ('f' arrays are f32, the others i32; out may be NULL to query the size):
  * Tcw mVelocity mvKeys mvStatKeysTmp mvStatDepthTmp mvCorres mvFlowNext mvStat3DPointTmp nStaInlierID mvObjKeys mvObjDepth
  * mvObjCorres mvObjFlowNext mvObj3DPoint vSemObjLabel vObjLabel nDynInlierID vFlow_3d nModLabel nSemPosition bObjStat vObjMod
- * TemperalMatch_subset max_id f_id */
+ * TemperalMatch_subset max_id f_id; stage_ms (8 x f32, accumulated host wall-clock per stage since creation: upload+depth, mask,
+ * frame build (ORB + static filter + object samples), look-ups, initial camera model, camera LM, objects, renewal) */
 int vdo_tracker_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
 
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back

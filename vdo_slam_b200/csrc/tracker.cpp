@@ -9,6 +9,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -91,6 +92,11 @@ struct vdo_tracker {
 };
 
 namespace {
+struct StageTimer {
+  double* acc; std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~StageTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 #define TK(call) do { int rc_ = (call); if (rc_ != VDO_OK) { t->err = std::string(#call) + " failed"; return rc_; } } while (0)
 
 void get3d_camera(float u, float v, float z, const vdo_tracker_params& p, float* X) {      // Optimizer::Get3DinCamera (src/Optimizer.cc:2995-3013)
@@ -179,6 +185,7 @@ int track_frame(vdo_tracker* t, FrameState& C, FrameState& L) {
   t->temperalMatch.resize(Ns);
   for (int i = 0; i < Ns; ++i) t->temperalMatch[i] = i;
   {   // GetInitModelCam (:1614-1715)
+    StageTimer stage_timer_4(&t->stage_ms[4]);
     std::vector<float> obj3(3 * (size_t)Ns + 3), img2(2 * (size_t)Ns + 2);
     for (int i = 0; i < Ns; ++i) {
       img2[2 * i] = C.statKeys[2 * i]; img2[2 * i + 1] = C.statKeys[2 * i + 1];
@@ -192,6 +199,7 @@ int track_frame(vdo_tracker* t, FrameState& C, FrameState& L) {
     C.Tcw = T0;
   }
   {   // PoseOptimizationFlow2Cam (src/Optimizer.cc:2333-2542)
+    StageTimer stage_timer_5(&t->stage_ms[5]);
     std::vector<FlowJob> jobs{{0, &t->temperalMatchSubset, C.Tcw}};
     std::vector<M4> To; std::vector<double> fo, st; std::vector<unsigned char> inl; std::vector<int> offs;
     if ((int)t->temperalMatchSubset.size() >= 3) {
@@ -210,6 +218,8 @@ int track_frame(vdo_tracker* t, FrameState& C, FrameState& L) {
   // ---------------- objects (:735-1003) ----------------
   const int No = (int)C.objKeys.size() / 2;
   C.flow3d.assign(3 * (size_t)No, 0.f);
+  StageTimer* st_obj = new StageTimer(&t->stage_ms[6]);
+  struct Guard { StageTimer*& p; ~Guard() { delete p; p = nullptr; } } guard{st_obj};
   if (No > 0) {   // GetSceneFlowObj (:1278-1364)
     std::vector<float> up(No), vp(No), uc(No), vc(No); std::vector<unsigned char> valid(No);
     for (int i = 0; i < No; ++i) { up[i] = L.objKeys[2 * i]; vp[i] = L.objKeys[2 * i + 1]; uc[i] = C.objKeys[2 * i]; vc[i] = C.objKeys[2 * i + 1]; }
@@ -297,8 +307,10 @@ int track_frame(vdo_tracker* t, FrameState& C, FrameState& L) {
       }
     }
   }
+  delete st_obj; st_obj = nullptr;
   // ---------------- RenewFrameInfo (:2660-2995) ----------------
   {
+    StageTimer stage_timer_7(&t->stage_ms[7]);
     const M4 Twc = inv4(C.Tcw);
     std::vector<int> ib(nobj + 1, 0), ii;
     for (int i = 0; i < nobj; ++i) { ii.insert(ii.end(), C.vnObjInlierID[i].begin(), C.vnObjInlierID[i].end()); ib[i + 1] = (int)ii.size(); }
@@ -384,17 +396,25 @@ extern "C" int vdo_tracker_track(vdo_tracker* t, const unsigned char* gray, floa
   vdo_frame* img = C.img;
   C.clear_dynamic(); C.img = img; C.Tcw = eye4();
   if (t->first) t->f_id = 0;
-  TK(vdo_frame_upload(C.img, gray, depth, flow, mask));
-  TK(vdo_frame_depth_prep(C.img, p.bf, p.depth_factor, writeback ? depth : nullptr));        // :180-204, in place on the caller's Mat
+  {
+    StageTimer stage_timer_0(&t->stage_ms[0]);
+    TK(vdo_frame_upload(C.img, gray, depth, flow, mask));
+    TK(vdo_frame_depth_prep(C.img, p.bf, p.depth_factor, writeback ? depth : nullptr));      // :180-204, in place on the caller's Mat
+  }
   if (!t->first) {                                                                            // UpdateMask (:2997-3110)
     const int n = (int)L.semObjLabel.size();
     std::vector<float> cx(n + 1), cy(n + 1);
     for (int i = 0; i < n; ++i) { cx[i] = L.objCorres[2 * i]; cy[i] = L.objCorres[2 * i + 1]; }
     int nw = 0;
+    StageTimer stage_timer_1(&t->stage_ms[1]);
     TK(vdo_update_mask(C.img, L.img, n, L.semObjLabel.data(), cx.data(), cy.data(), writeback ? mask : nullptr, &nw, nullptr));
   }
-  TK(build_frame(t, C));
+  {
+    StageTimer stage_timer_2(&t->stage_ms[2]);
+    TK(build_frame(t, C));
+  }
   if (!t->first) {                                                                            // :254-312
+    StageTimer stage_timer_3(&t->stage_ms[3]);
     C.statKeys = L.corres;
     std::vector<int> mk;
     TK(lookup_points(t, C, C.statKeys, C.statDepth, mk));
@@ -472,5 +492,6 @@ extern "C" int vdo_tracker_get(const vdo_tracker* t, const char* name, void* out
   if (s == "vObjMod") { std::vector<float> v; for (auto& m : C.vObjMod) v.insert(v.end(), m.begin(), m.end()); return put_f(v.data(), v.size()); }
   if (s == "max_id") return put_i(&t->max_id, 1);
   if (s == "f_id") return put_i(&t->f_id, 1);
+  if (s == "stage_ms") { float v[8]; for (int i = 0; i < 8; ++i) v[i] = (float)t->stage_ms[i]; return put_f(v, 8); }
   return VDO_ERR_ARG;
 }
