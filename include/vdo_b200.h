@@ -296,6 +296,18 @@ int vdo_tracker_track(vdo_tracker *t, const unsigned char *gray, float *depth, c
  * frame build (ORB + static filter + object samples), look-ups, initial camera model, camera LM, objects, renewal) */
 int vdo_tracker_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
 
+/* Map -> factor graph -> optimise -> write back: mode 0 = Optimizer::PartialBatchOptimization(pMap, K, WINDOW_SIZE)
+ * (src/Optimizer.cc:42-1230) over the last window_size frames, mode 1 = Optimizer::FullBatchOptimization(pMap, K) (:1232-2175),
+ * on the map the tracker accumulated (Tracking.cc:1016-1070).  opt may be NULL (the reference's optimize(100 | 300) and gain
+ * thresholds 1e-3 | 1e-4).  info (may be NULL, 6 ints): vertices se3 / point, edges prior / se3 / point-observation / landmark-motion. */
+int vdo_tracker_batch_optimize(vdo_tracker *t, int mode, const vdo_lm_options *opt, vdo_lm_stats *stats, int *info);
+/* test hook: the arrays the builder passes to vdo_graph_* for a mode.  f64 names: se3 pt prior_Z prior_w se3e_Z se3e_w se3e_delta
+ * obs_z obs_w obs_delta ter_w ter_delta; i32 names: prior_v se3e_ij obs_cp ter_pph.  out may be NULL to query the element count. */
+int vdo_tracker_graph_export(vdo_tracker *t, int mode, const char *name, void *out, int cap_elems, int *n_elems);
+/* map read-back: vmCameraPose (n_frames x 16 f32), vmRigidMotion (every frame's motions concatenated, 16 f32 each, entry 0 = camera
+ * motion), vnRMLabel (i32, same order), n_frames (i32) */
+int vdo_tracker_map_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
+
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
  * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.
  * The graph must have been optimised at least once (buffers hold a valid linearisation / factorisation).

@@ -46,7 +46,8 @@ class OracleTracker:
         self.velocity = None
         self.last = None
         self.cur = None
-        self.map = dict(cameraPose=[], assoSta=[], assoDyn=[], featLabel=[], featSta=[], featDyn=[], rigidMotion=[], rmLabel=[])
+        self.map = dict(cameraPose=[], assoSta=[], assoDyn=[], featLabel=[], featSta=[], depSta=[], p3dSta=[], featDyn=[], depDyn=[], p3dDyn=[],
+                        rigidMotion=[], rmLabel=[])
 
     # ---- Frame::Frame (src/Frame.cc:61-260) ----
     def _build_frame(self, gray, depth, flow, mask):
@@ -103,11 +104,15 @@ class OracleTracker:
         C.objLabel = np.full(len(C.objKeys), -2, np.int32)
         if self.first:                                                                 # Initialization (:1215-1276)
             C.Tcw = np.eye(4, dtype=f32)
+            C.stat3DTmp = np.array([to.get3d_world(k, d, self.K4, np.eye(4, dtype=f32)) for k, d in zip(C.statKeysTmp, C.statDepthTmp)], f32).reshape(-1, 3)
+            C.obj3D = np.array([to.get3d_world(k, d, self.K4, np.eye(4, dtype=f32)) for k, d in zip(C.objKeys, C.objDepth)], f32).reshape(-1, 3)
             self.map["cameraPose"].append(np.eye(4, dtype=f32))
             self.first = False
         else:
             self._track(C, L, depth, flow, mask)
         self.map["featSta"].append(C.statKeysTmp.copy()); self.map["featDyn"].append(C.objKeys.copy())
+        self.map["depSta"].append(C.statDepthTmp.copy()); self.map["depDyn"].append(C.objDepth.copy())
+        self.map["p3dSta"].append(np.asarray(C.stat3DTmp, f32).reshape(-1, 3).copy()); self.map["p3dDyn"].append(np.asarray(C.obj3D, f32).reshape(-1, 3).copy())
         C.statKeys = C.statKeysTmp; C.statDepth = C.statDepthTmp                      # :1006-1014
         self.last, self.cur = C, C
         self.mask_last, self.flow_last, self.depth, self.mask = mask, flow, depth, mask

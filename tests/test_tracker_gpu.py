@@ -69,3 +69,48 @@ def test_tracker_degenerate_frames():
         T = tr.track(gray, depth.copy(), flow, mask.copy(), [])
         assert np.abs(T - T_ref).max() <= 1e-6
         assert len(tr.get("mvStatKeysTmp")) == 2 * len(orc.cur.statKeysTmp)
+
+
+@pytest.mark.gpu
+def test_map_graph_builder_and_batch_optimisation():
+    """Map -> graph builder (PartialBatchOptimization / FullBatchOptimization construction) against the Python restatement on the
+    oracle pipeline's map: identical arrays; then the optimised camera poses against the CPU oracle LM."""
+    from oracle import map_graph as mg
+    from oracle import pyoracle as po
+    w, h, n = 1242, 375, 9
+    ctx = capi.Context()
+    tr = capi.Tracker(ctx, window_size=8)
+    orc = OracleTracker(width=w, height=h)
+    for t in range(n):
+        f = make_sequence_frame(t, seed=3)
+        orc.track(f["gray"], f["depth_raw"], f["flow"], f["mask"], f["obj_ids"])
+        tr.track(f["gray"], f["depth_raw"].copy(), f["flow"], f["mask"].copy(), f["obj_ids"])
+    metas = {}
+    for mode, name in ((1, "full"), (0, "partial")):
+        g_ref, metas[name] = mg.build_graph(orc.map, orc.K4, name, window=8)
+        g = tr.graph_export(mode)
+        for k in g_ref:
+            assert g[k].shape == g_ref[k].shape, (name, k, g[k].shape, g_ref[k].shape)
+            assert np.array_equal(g[k], g_ref[k]), (name, k)          # both maps hold the same f32 values, the conversions are deterministic
+    assert len(g_ref["prior_v"]) == 0 and len(g_ref["ter_pph"]) == 0   # partial: static only, no prior unless N == WINDOW (src/Optimizer.cc:240)
+
+    def check(mode, name):
+        g_in = tr.graph_export(mode)                                   # the builder's arrays at the map's current state
+        meta = metas[name]
+        r_ref = po.ba_optimize(g_in, max_iters=100 if mode == 0 else 300, gain_threshold=1e-3 if mode == 0 else 1e-4)
+        before = tr.map_get("vmCameraPose").reshape(-1, 4, 4).copy()
+        r = tr.batch_optimize(mode)
+        assert r["iterations"] == r_ref["iters"], (name, r["iterations"], r_ref["iters"])
+        assert r["sizes"]["n_se3"] == len(g_in["se3"]) and r["sizes"]["n_obs"] == len(g_in["obs_w"])
+        poses = tr.map_get("vmCameraPose").reshape(-1, 4, 4)
+        for i, v in enumerate(meta["cam_vid"]):
+            if v == -1:
+                assert np.array_equal(poses[i], before[i]), (name, i)
+                continue
+            iso = r_ref["se3"][v]
+            assert np.abs(poses[i][:3, :3] - iso[:9].reshape(3, 3)).max() <= 1e-4 and np.abs(poses[i][:3, 3] - iso[9:]).max() <= 1e-4, (name, i)
+        return r
+
+    r0 = check(0, "partial")          # Tracking.cc:1150-1160: the windowed pass runs first, on the live map
+    r1 = check(1, "full")             # :1162-1176: the full batch runs on the map the windowed pass refined
+    assert r1["sizes"]["n_ternary"] > 0 and r1["final_chi2"] <= r1["initial_chi2"]

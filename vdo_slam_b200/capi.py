@@ -497,6 +497,43 @@ class Tracker:
         self.ctx.check(self.ctx.L.vdo_tracker_get(self.h_, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_int(len(out)), C.byref(n)), "vdo_tracker_get")
         return out[:n.value]
 
+    _GI = {"prior_v", "se3e_ij", "obs_cp", "ter_pph"}
+
+    def graph_export(self, mode: int):
+        """arrays the Map->graph builder hands to vdo_graph_* (mode 0 partial window, 1 full batch), in make_batch_graph layout"""
+        g = {}
+        shapes = dict(se3=(-1, 12), pt=(-1, 3), prior_Z=(-1, 12), se3e_Z=(-1, 12), obs_z=(-1, 3), se3e_ij=(-1, 2), obs_cp=(-1, 2), ter_pph=(-1, 3))
+        for name in ("se3", "pt", "prior_v", "prior_Z", "prior_w", "se3e_ij", "se3e_Z", "se3e_w", "se3e_delta", "obs_cp", "obs_z", "obs_w", "obs_delta", "ter_pph",
+                     "ter_w", "ter_delta"):
+            n = C.c_int(0)
+            self.ctx.check(self.ctx.L.vdo_tracker_graph_export(self.h_, C.c_int(mode), name.encode(), None, C.c_int(0), C.byref(n)), "vdo_tracker_graph_export")
+            out = np.zeros(max(n.value, 1), np.int32 if name in self._GI else np.float64)
+            self.ctx.check(self.ctx.L.vdo_tracker_graph_export(self.h_, C.c_int(mode), name.encode(), out.ctypes.data_as(C.c_void_p), C.c_int(len(out)), C.byref(n)),
+                           "vdo_tracker_graph_export")
+            g[name] = out[:n.value].reshape(shapes.get(name, -1))
+        return g
+
+    def batch_optimize(self, mode: int, **opt):
+        o = LMOptions(); self.ctx.L.vdo_lm_options_default(C.byref(o))
+        st = LMStats(); info = np.zeros(6, np.int32)
+        po = None
+        if opt:
+            for k, v in opt.items():
+                setattr(o, k, v)
+            po = C.byref(o)
+        rc = self.ctx.L.vdo_tracker_batch_optimize(self.h_, C.c_int(mode), po, C.byref(st), _ip(info))
+        if rc != 0:
+            raise VdoError(f"vdo_tracker_batch_optimize failed ({rc}): {self.ctx.L.vdo_tracker_last_error(self.h_).decode()}")
+        r = st.asdict(); r["sizes"] = dict(zip(["n_se3", "n_pt", "n_prior", "n_se3_edges", "n_obs", "n_ternary"], info.tolist()))
+        return r
+
+    def map_get(self, name: str):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.L.vdo_tracker_map_get(self.h_, name.encode(), None, C.c_int(0), C.byref(n)), "vdo_tracker_map_get")
+        out = np.zeros(max(n.value, 1), np.int32 if name in ("vnRMLabel", "n_frames") else np.float32)
+        self.ctx.check(self.ctx.L.vdo_tracker_map_get(self.h_, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_int(len(out)), C.byref(n)), "vdo_tracker_map_get")
+        return out[:n.value]
+
     def close(self):
         if getattr(self, "h_", None):
             self.ctx.L.vdo_tracker_destroy(self.h_)

@@ -495,3 +495,245 @@ extern "C" int vdo_tracker_get(const vdo_tracker* t, const char* name, void* out
   if (s == "stage_ms") { float v[8]; for (int i = 0; i < 8; ++i) v[i] = (float)t->stage_ms[i]; return put_f(v, 8); }
   return VDO_ERR_ARG;
 }
+
+// ------------------------------------------------------------------------------------------------ Map -> factor graph
+// Graph construction of Optimizer::FullBatchOptimization (src/Optimizer.cc:1232-1767) and Optimizer::PartialBatchOptimization
+// (:42-805) from the tracker's map, emitted as the arrays of the vdo_graph_* calls; refined camera poses, object motions and
+// points are written back like :2094-2172 / :983-1050.  Where the reference would dereference a null vertex (a track whose
+// previous position never received a vertex) the edge is skipped.
+#include "ba_math.cuh"
+
+namespace {
+struct GraphArrays {
+  std::vector<double> se3, pt, prior_Z, prior_w, se3e_Z, se3e_w, se3e_delta, obs_z, obs_w, obs_delta, ter_w, ter_delta;
+  std::vector<int> prior_v, se3e_ij, obs_cp, ter_pph;
+  std::vector<int> cam_vid;                       // per frame: se3 index of the camera vertex (-1 outside the window)
+  std::vector<std::vector<int>> mot_vid;          // per frame pair: se3 index of each rigid-motion vertex (entry 0 unused)
+  std::vector<std::vector<int>> makS, makD;       // per frame, per feature: point index (-1 = not in the graph)
+  int max_iters = 300; double gain = 1e-4;
+};
+struct BatchConsts { float sigma2_cam, sigma2_3d_sta, sigma2_obj_smo, sigma2_obj, sigma2_3d_dyn; double prior_w; bool static_only; int max_iters; double gain; };
+const BatchConsts kFull{0.001f, 80.f, 0.001f, 100.f, 80.f, 100000.0, false, 300, 1e-4};                 // src/Optimizer.cc:1330-1335
+const BatchConsts kPartial{0.0001f, 16.f, 0.1f, 20.f, 16.f, 1.0 / 0.0000001, true, 100, 1e-3};          // :190-195, :230
+
+// Converter::toSE3Quat (src/Converter.cc:25-35) + SE3Quat -> Isometry3d (se3quat.h): rotation re-normalised through the quaternion
+void to_iso(const M4& T, double* out) {
+  double R[9], q[4];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[3 * i + j] = (double)T[4 * i + j];
+  vdo::quat_from_rot(R, q);
+  if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int k = 0; k < 4; ++k) q[k] /= n;
+  vdo::rot_from_quat(q, out);
+  out[9] = (double)T[3]; out[10] = (double)T[7]; out[11] = (double)T[11];
+}
+// getEstimateData -> Quaterniond -> rotation matrix -> Converter::toCvSE3 (src/Optimizer.cc:2094-2110)
+M4 from_iso(const double* T) {
+  double q[4], R[9];
+  vdo::quat_from_rot(T, q);
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int k = 0; k < 4; ++k) q[k] /= n;
+  vdo::rot_from_quat(q, R);
+  M4 m = eye4();
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) m[4 * i + j] = (float)R[3 * i + j]; m[4 * i + 3] = (float)T[9 + i]; }
+  return m;
+}
+
+int build_tracklets(const std::vector<std::vector<int>>& asso, const std::vector<std::vector<int>>* labels, std::vector<std::vector<std::pair<int, int>>>& tracks,
+                    std::vector<int>& obj_id) {
+  const int n_rows = (int)asso.size();
+  std::vector<int> rb(n_rows + 1, 0), flat, lab;
+  for (int i = 0; i < n_rows; ++i) {
+    flat.insert(flat.end(), asso[i].begin(), asso[i].end());
+    if (labels) lab.insert(lab.end(), (*labels)[i].begin(), (*labels)[i].end());
+    rb[i + 1] = (int)flat.size();
+  }
+  int cnt = 0;
+  for (int v : flat) cnt += v != -1;
+  const int max_t = cnt + 1, max_e = 2 * cnt + 2;
+  std::vector<int> tb(max_t + 1), tf(max_e), tk(max_e), oid(max_t);
+  int nt = 0;
+  const int rc = vdo_tracklets_build(n_rows, rb.data(), flat.data(), labels ? lab.data() : nullptr, max_t, max_e, &nt, tb.data(), tf.data(), tk.data(), oid.data());
+  if (rc != VDO_OK) return rc;
+  tracks.assign(nt, {});
+  for (int t = 0; t < nt; ++t) for (int e = tb[t]; e < tb[t + 1]; ++e) tracks[t].push_back({tf[e], tk[e]});
+  obj_id.assign(oid.begin(), oid.begin() + nt);
+  return VDO_OK;
+}
+
+int build_graph(vdo_tracker* t, bool full, GraphArrays& G) {
+  const MapSlice& m = t->map;
+  const BatchConsts& c = full ? kFull : kPartial;
+  const int N = (int)m.featSta.size(), window = t->p.window_size;
+  if (N < 2 || (!full && (window < 2 || N < window))) return VDO_ERR_STATE;
+  std::vector<std::vector<std::pair<int, int>>> staT, dynT; std::vector<int> objId, dummy;
+  TK(build_tracklets(m.assoSta, nullptr, staT, dummy));
+  TK(build_tracklets(m.assoDyn, &m.featLabel, dynT, objId));
+  std::vector<std::vector<int>> labS(N), labD(N);
+  G = GraphArrays();
+  G.makS.resize(N); G.makD.resize(N); G.cam_vid.assign(N, -1); G.mot_vid.resize(N - 1);
+  for (int i = 0; i < N; ++i) {
+    labS[i].assign(m.featSta[i].size() / 2, -1); G.makS[i].assign(m.featSta[i].size() / 2, -1);
+    labD[i].assign(m.featDyn[i].size() / 2, -1); G.makD[i].assign(m.featDyn[i].size() / 2, -1);
+    if (i < N - 1) G.mot_vid[i].assign(m.rmLabel[i].size(), -1);
+  }
+  for (size_t k = 0; k < staT.size(); ++k) if (staT[k].size() >= 3) for (auto& pr : staT[k]) labS[pr.first][pr.second] = (int)k;
+  for (size_t k = 0; k < dynT.size(); ++k) if (dynT[k].size() >= 3) for (auto& pr : dynT[k]) labD[pr.first][pr.second] = (int)k;
+  G.max_iters = c.max_iters; G.gain = c.gain;
+  const double huber = (double)0.0001f;
+  const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  auto n_se3 = [&]() { return (int)G.se3.size() / 12; };
+  auto n_pt = [&]() { return (int)G.pt.size() / 3; };
+  auto add_obs = [&](int cam, int p, const float* key, float dep, double w) {
+    G.obs_cp.push_back(cam); G.obs_cp.push_back(p);
+    float X[3]; get3d_camera(key[0], key[1], dep, t->p, X);
+    for (int k = 0; k < 3; ++k) G.obs_z.push_back((double)X[k]);
+    G.obs_w.push_back(w); G.obs_delta.push_back(huber);
+  };
+  auto add_pt = [&](const float* X) { for (int k = 0; k < 3; ++k) G.pt.push_back((double)X[k]); return n_pt() - 1; };
+  auto find_pos = [](const std::vector<std::pair<int, int>>& tr, int f, int j) { for (size_t k = 0; k < tr.size(); ++k) if (tr[k].first == f && tr[k].second == j) return (int)k; return -1; };
+  const int start = full ? 0 : N - window;
+  int pre = -1;
+  for (int i = start; i < N; ++i) {
+    const int cur = n_se3();
+    double iso[12]; to_iso(m.cameraPose[i], iso);
+    G.se3.insert(G.se3.end(), iso, iso + 12); G.cam_vid[i] = cur;
+    if (cur == 0 && (full || N == window)) { G.prior_v.push_back(cur); G.prior_Z.insert(G.prior_Z.end(), iso, iso + 12); G.prior_w.push_back(c.prior_w); }
+    if (i != start) {
+      double z[12]; to_iso(m.rigidMotion[i - 1][0], z);
+      G.se3e_ij.push_back(pre); G.se3e_ij.push_back(cur); G.se3e_Z.insert(G.se3e_Z.end(), z, z + 12);
+      G.se3e_w.push_back(1.0 / (double)c.sigma2_cam); G.se3e_delta.push_back(huber);
+    }
+    for (size_t j = 0; j < labS[i].size(); ++j) {                       // static points (:1402-1516 / :254-349)
+      const int tid = labS[i][j];
+      if (tid == -1) continue;
+      const int pos = find_pos(staT[tid], i, (int)j);
+      if (pos == -1) continue;
+      const double w = 1.0 / (double)c.sigma2_3d_sta;
+      int p;
+      if (pos == 0) p = add_pt(&m.p3dSta[i][3 * j]);
+      else { p = G.makS[staT[tid][pos - 1].first][staT[tid][pos - 1].second]; if (p == -1) continue; }
+      add_obs(cur, p, &m.featSta[i][2 * j], m.depSta[i][j], w);
+      G.makS[i][j] = p;
+    }
+    if (!c.static_only && i == 0) {                                    // :1521-1549
+      for (size_t j = 0; j < labD[i].size(); ++j) {
+        if (labD[i][j] == -1) continue;
+        const int p = add_pt(&m.p3dDyn[i][3 * j]);
+        add_obs(cur, p, &m.featDyn[i][2 * j], m.depDyn[i][j], 1.0 / (double)c.sigma2_3d_dyn);
+        G.makD[i][j] = p;
+      }
+    } else if (!c.static_only) {                                       // :1551-1762
+      std::vector<int> objUid;
+      for (size_t j = 1; j < m.rigidMotion[i - 1].size(); ++j) {
+        const int v = n_se3();
+        G.se3.insert(G.se3.end(), ident, ident + 12);
+        if (i > 2) {
+          int trace = -1;
+          for (size_t k = 0; k < m.rmLabel[i - 2].size(); ++k) if (m.rmLabel[i - 2][k] == m.rmLabel[i - 1][j]) { trace = (int)k; break; }
+          if (trace != -1 && G.mot_vid[i - 2][trace] != -1) {
+            G.se3e_ij.push_back(G.mot_vid[i - 2][trace]); G.se3e_ij.push_back(v); G.se3e_Z.insert(G.se3e_Z.end(), ident, ident + 12);
+            G.se3e_w.push_back(1.0 / (double)c.sigma2_obj_smo); G.se3e_delta.push_back(huber);
+          }
+        }
+        objUid.push_back(v); G.mot_vid[i - 1][j] = v;
+      }
+      for (size_t j = 0; j < labD[i].size(); ++j) {
+        const int tid = labD[i][j];
+        if (tid == -1) continue;
+        const int pos = find_pos(dynT[tid], i, (int)j);
+        if (pos == -1) continue;
+        int objv = -1;
+        for (size_t k = 1; k < m.rmLabel[i - 1].size(); ++k) if (m.rmLabel[i - 1][k] == objId[tid]) { objv = objUid[k - 1]; break; }
+        if (objv == -1 && pos != 0) continue;
+        const int p = add_pt(&m.p3dDyn[i][3 * j]);
+        add_obs(cur, p, &m.featDyn[i][2 * j], m.depDyn[i][j], 1.0 / (double)c.sigma2_3d_dyn);
+        if (pos != 0) {
+          const int q = G.makD[dynT[tid][pos - 1].first][dynT[tid][pos - 1].second];
+          if (q != -1) { G.ter_pph.push_back(q); G.ter_pph.push_back(p); G.ter_pph.push_back(objv); G.ter_w.push_back(1.0 / (double)c.sigma2_obj); G.ter_delta.push_back(huber); }
+        }
+        G.makD[i][j] = p;
+      }
+    }
+    pre = cur;
+  }
+  return VDO_OK;
+}
+}  // namespace
+
+// mode 0 = PartialBatchOptimization over the last window_size frames, 1 = FullBatchOptimization.  Builds the graph from the map,
+// runs vdo_graph_optimize (opt may be NULL: the reference's iteration cap and gain threshold) and writes the refined camera poses,
+// motions and points back into the map.  info (may be NULL): n_se3, n_pt, n_prior, n_se3_edges, n_obs, n_ternary.
+extern "C" int vdo_tracker_batch_optimize(vdo_tracker* t, int mode, const vdo_lm_options* opt, vdo_lm_stats* stats, int* info) {
+  if (!t || (mode != 0 && mode != 1)) return VDO_ERR_ARG;
+  GraphArrays G;
+  TK(build_graph(t, mode == 1, G));
+  const int ns = (int)G.se3.size() / 12, np = (int)G.pt.size() / 3;
+  if (info) { info[0] = ns; info[1] = np; info[2] = (int)G.prior_v.size(); info[3] = (int)G.se3e_w.size(); info[4] = (int)G.obs_w.size(); info[5] = (int)G.ter_w.size(); }
+  vdo_graph* g = nullptr;
+  TK(vdo_graph_create(t->ctx, &g));
+  int rc = vdo_graph_set_vertices(g, ns, G.se3.data(), np, G.pt.data());
+  if (rc == VDO_OK && !G.prior_v.empty()) rc = vdo_graph_add_edges_se3_prior(g, (int)G.prior_v.size(), G.prior_v.data(), G.prior_Z.data(), G.prior_w.data());
+  if (rc == VDO_OK && !G.se3e_w.empty()) rc = vdo_graph_add_edges_se3(g, (int)G.se3e_w.size(), G.se3e_ij.data(), G.se3e_Z.data(), G.se3e_w.data(), G.se3e_delta.data());
+  if (rc == VDO_OK && !G.obs_w.empty()) rc = vdo_graph_add_edges_se3_pointxyz(g, (int)G.obs_w.size(), G.obs_cp.data(), G.obs_z.data(), G.obs_w.data(), G.obs_delta.data());
+  if (rc == VDO_OK && !G.ter_w.empty()) rc = vdo_graph_add_edges_landmark_motion(g, (int)G.ter_w.size(), G.ter_pph.data(), G.ter_w.data(), G.ter_delta.data());
+  if (rc == VDO_OK) rc = vdo_graph_finalize(g);
+  vdo_lm_options o;
+  if (opt) o = *opt; else { vdo_lm_options_default(&o); o.max_iterations = G.max_iters; o.gain_threshold = G.gain; }
+  if (rc == VDO_OK) rc = vdo_graph_optimize(g, &o, stats, nullptr);
+  std::vector<double> se3(12 * (size_t)ns + 12), pt(3 * (size_t)np + 3);
+  if (rc == VDO_OK) rc = vdo_graph_get_vertices(g, se3.data(), pt.data());
+  vdo_graph_destroy(g);
+  if (rc != VDO_OK) { t->err = std::string("batch optimisation failed: ") + vdo_last_error(t->ctx); return rc; }
+  MapSlice& m = t->map;
+  const int N = (int)m.featSta.size();
+  for (int i = 0; i < N; ++i) {                                                    // :2094-2172 / :983-1050
+    if (G.cam_vid[i] != -1) m.cameraPose[i] = from_iso(&se3[12 * (size_t)G.cam_vid[i]]);
+    for (size_t j = 0; j < G.makS[i].size(); ++j) if (G.makS[i][j] != -1) for (int k = 0; k < 3; ++k) m.p3dSta[i][3 * j + k] = (float)pt[3 * (size_t)G.makS[i][j] + k];
+    for (size_t j = 0; j < G.makD[i].size(); ++j) if (G.makD[i][j] != -1) for (int k = 0; k < 3; ++k) m.p3dDyn[i][3 * j + k] = (float)pt[3 * (size_t)G.makD[i][j] + k];
+  }
+  for (int i = 0; i + 1 < N; ++i) {
+    if (mode == 0) { if (G.cam_vid[i] != -1 && G.cam_vid[i + 1] != -1) m.rigidMotion[i][0] = mul4(inv4(m.cameraPose[i]), m.cameraPose[i + 1]); }   // :1001
+    for (size_t j = 1; j < G.mot_vid[i].size(); ++j) if (G.mot_vid[i][j] != -1) m.rigidMotion[i][j] = from_iso(&se3[12 * (size_t)G.mot_vid[i][j]]);
+  }
+  return VDO_OK;
+}
+
+// graph arrays of the last build for a mode (parity tests): name in {se3, pt, prior_Z, prior_w, se3e_Z, se3e_w, se3e_delta, obs_z, obs_w, obs_delta, ter_w,
+// ter_delta} (f64) or {prior_v, se3e_ij, obs_cp, ter_pph} (i32; out is then an int buffer)
+extern "C" int vdo_tracker_graph_export(vdo_tracker* t, int mode, const char* name, void* out, int cap_elems, int* n_elems) {
+  if (!t || !name || !n_elems) return VDO_ERR_ARG;
+  GraphArrays G;
+  TK(build_graph(t, mode == 1, G));
+  const std::string s(name);
+  const std::vector<double>* d = nullptr; const std::vector<int>* iv = nullptr;
+  if (s == "se3") d = &G.se3; else if (s == "pt") d = &G.pt; else if (s == "prior_Z") d = &G.prior_Z; else if (s == "prior_w") d = &G.prior_w;
+  else if (s == "se3e_Z") d = &G.se3e_Z; else if (s == "se3e_w") d = &G.se3e_w; else if (s == "se3e_delta") d = &G.se3e_delta; else if (s == "obs_z") d = &G.obs_z;
+  else if (s == "obs_w") d = &G.obs_w; else if (s == "obs_delta") d = &G.obs_delta; else if (s == "ter_w") d = &G.ter_w; else if (s == "ter_delta") d = &G.ter_delta;
+  else if (s == "prior_v") iv = &G.prior_v; else if (s == "se3e_ij") iv = &G.se3e_ij; else if (s == "obs_cp") iv = &G.obs_cp; else if (s == "ter_pph") iv = &G.ter_pph;
+  else return VDO_ERR_ARG;
+  const size_t n = d ? d->size() : iv->size();
+  *n_elems = (int)n;
+  if (!out) return VDO_OK;
+  if ((int)n > cap_elems) return VDO_ERR_ARG;
+  if (n) std::memcpy(out, d ? (const void*)d->data() : (const void*)iv->data(), n * (d ? 8 : 4));
+  return VDO_OK;
+}
+
+// map read-back: "vmCameraPose" (N x 16 f32), "vmRigidMotion" (all frames concatenated, 16 f32 each), "vnRMLabel" (i32, same order), "n_frames"
+extern "C" int vdo_tracker_map_get(const vdo_tracker* t, const char* name, void* out, int cap_elems, int* n_elems) {
+  if (!t || !name || !n_elems) return VDO_ERR_ARG;
+  const std::string s(name);
+  std::vector<float> f; std::vector<int> iv; bool is_f = true;
+  if (s == "vmCameraPose") for (auto& T : t->map.cameraPose) f.insert(f.end(), T.begin(), T.end());
+  else if (s == "vmRigidMotion") { for (auto& fr : t->map.rigidMotion) for (auto& T : fr) f.insert(f.end(), T.begin(), T.end()); }
+  else if (s == "vnRMLabel") { is_f = false; for (auto& fr : t->map.rmLabel) iv.insert(iv.end(), fr.begin(), fr.end()); }
+  else if (s == "n_frames") { is_f = false; iv.push_back((int)t->map.featSta.size()); }
+  else return VDO_ERR_ARG;
+  const size_t n = is_f ? f.size() : iv.size();
+  *n_elems = (int)n;
+  if (!out) return VDO_OK;
+  if ((int)n > cap_elems) return VDO_ERR_ARG;
+  if (n) std::memcpy(out, is_f ? (const void*)f.data() : (const void*)iv.data(), n * 4);
+  return VDO_OK;
+}
