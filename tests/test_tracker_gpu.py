@@ -91,7 +91,10 @@ def test_map_graph_builder_and_batch_optimisation():
         g = tr.graph_export(mode)
         for k in g_ref:
             assert g[k].shape == g_ref[k].shape, (name, k, g[k].shape, g_ref[k].shape)
-            assert np.array_equal(g[k], g_ref[k]), (name, k)          # both maps hold the same f32 values, the conversions are deterministic
+            if g_ref[k].dtype == np.int32:
+                assert np.array_equal(g[k], g_ref[k]), (name, k)
+            elif g_ref[k].size:                                        # both maps hold the same f32 values; the quaternion round trip differs in the last bits
+                assert np.abs(g[k] - g_ref[k]).max() <= 1e-12, (name, k)
     assert len(g_ref["prior_v"]) == 0 and len(g_ref["ter_pph"]) == 0   # partial: static only, no prior unless N == WINDOW (src/Optimizer.cc:240)
 
     def check(mode, name):

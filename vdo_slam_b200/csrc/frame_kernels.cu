@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstring>
 #include <list>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/vdo_b200.h"
@@ -308,6 +310,37 @@ __global__ void __launch_bounds__(1024) k_filter_static(const float* __restrict_
   if (threadIdx.x == 0) *n_out = base;
 }
 
+// Dense packing of the per-cell candidate lists (cell-major, row-major inside a cell = the order the host octree expects):
+// k_cell_offsets: exclusive scan of the cell counts by one CTA; k_cell_gather: one CTA per cell copies its entries.
+// Only count + offsets (a few KB) and the packed candidates (~0.3 MB) cross PCIe instead of ncell * CELL_CAP slots (~8 MB).
+__global__ void __launch_bounds__(1024) k_cell_offsets(const int* __restrict__ count, int n, int* __restrict__ offset) {
+  __shared__ int s[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? count[i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) offset[i] = carry + s[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += s[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offset[n] = carry;
+}
+__global__ void k_cell_gather(const KpOut* __restrict__ cell_out, const int* __restrict__ count, const int* __restrict__ offset, KpOut* __restrict__ dense) {
+  const int c = blockIdx.x, n = count[c], o = offset[c];
+  for (int k = threadIdx.x; k < n; k += blockDim.x) dense[o + k] = cell_out[(size_t)c * CELL_CAP + k];
+}
+
 // ------------------------------------------------------------------------------------------------ back-projection / scene flow
 struct Pose32 { float R[9], t[3]; };   // Tcw rows
 // X_w = Rwl * x3Dc + twl as a cv::Mat float gemm: products accumulated in double, one rounding to float (twl itself is float)
@@ -457,6 +490,7 @@ struct vdo_frame {
   unsigned char* gray = nullptr; float* depth = nullptr; float* flow = nullptr; int* mask = nullptr;
   unsigned char* pyr[MAX_LEVELS] = {nullptr}; unsigned char* score[MAX_LEVELS] = {nullptr}; int lw[MAX_LEVELS], lh[MAX_LEVELS];
   Cell* cells = nullptr; KpOut* cell_out = nullptr; int* cell_cnt = nullptr; int cells_cap = 0;
+  int* cell_off = nullptr; KpOut* cell_dense = nullptr; int* h_cnt_off = nullptr; KpOut* h_dense = nullptr; size_t h_dense_cap = 0;   // packed candidates (pinned host side)
   KpLvl* kps = nullptr; float* ang = nullptr; int kp_cap = 0;
   void* scratch = nullptr; size_t scratch_cap = 0; int* d_count = nullptr;
   std::vector<KpOut> h_cell_out; std::vector<int> h_cell_cnt;
@@ -488,6 +522,7 @@ extern "C" void vdo_frame_destroy(vdo_frame* f) {
   for (int l = 1; l < MAX_LEVELS; ++l) cudaFree(f->pyr[l]);
   for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(f->score[l]);
   cudaFree(f->cells); cudaFree(f->cell_out); cudaFree(f->cell_cnt); cudaFree(f->kps); cudaFree(f->ang); cudaFree(f->scratch);
+  cudaFree(f->cell_off); cudaFree(f->cell_dense); cudaFreeHost(f->h_cnt_off); cudaFreeHost(f->h_dense);
   delete f;
 }
 // internal: device pointers of a resident frame for the other translation units (tracking_ops.cu)
@@ -567,7 +602,10 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
   if (ncell > f->cells_cap) {
     cudaFree(f->cells); cudaFree(f->cell_out); cudaFree(f->cell_cnt);
     FRK(cudaMalloc(&f->cells, sizeof(Cell) * ncell)); FRK(cudaMalloc(&f->cell_out, sizeof(KpOut) * (size_t)ncell * CELL_CAP)); FRK(cudaMalloc(&f->cell_cnt, sizeof(int) * ncell));
-    f->cells_cap = ncell; f->h_cell_out.resize((size_t)ncell * CELL_CAP); f->h_cell_cnt.resize(ncell);
+    f->cells_cap = ncell; f->h_cell_cnt.resize(ncell);
+    cudaFree(f->cell_off); cudaFree(f->cell_dense); cudaFreeHost(f->h_cnt_off);
+    FRK(cudaMalloc(&f->cell_off, sizeof(int) * (ncell + 1))); FRK(cudaMalloc(&f->cell_dense, sizeof(KpOut) * (size_t)ncell * CELL_CAP));
+    FRK(cudaMallocHost(&f->h_cnt_off, sizeof(int) * (2 * ncell + 1)));
   }
   FRK(cudaMemcpyAsync(f->cells, cells.data(), sizeof(Cell) * ncell, cudaMemcpyHostToDevice, f->st));
   for (int l = 0; l < nlevels; ++l) {
@@ -576,15 +614,21 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
     k_fast_cells<<<nc, 256, 0, f->st>>>(f->score[l], f->lw[l], f->cells + cell_begin[l], ini_th, min_th, f->cell_out + (size_t)cell_begin[l] * CELL_CAP, f->cell_cnt + cell_begin[l]);
     f->launches++;
   }
-  FRK(cudaMemcpyAsync(f->h_cell_cnt.data(), f->cell_cnt, sizeof(int) * ncell, cudaMemcpyDeviceToHost, f->st));
-  FRK(cudaMemcpyAsync(f->h_cell_out.data(), f->cell_out, sizeof(KpOut) * (size_t)ncell * CELL_CAP, cudaMemcpyDeviceToHost, f->st));
+  k_cell_offsets<<<1, 1024, 0, f->st>>>(f->cell_cnt, ncell, f->cell_off); f->launches++;
+  k_cell_gather<<<ncell, 64, 0, f->st>>>(f->cell_out, f->cell_cnt, f->cell_off, f->cell_dense); f->launches++;
+  FRK(cudaMemcpyAsync(f->h_cnt_off, f->cell_cnt, sizeof(int) * ncell, cudaMemcpyDeviceToHost, f->st));
+  FRK(cudaMemcpyAsync(f->h_cnt_off + ncell, f->cell_off, sizeof(int) * (ncell + 1), cudaMemcpyDeviceToHost, f->st));
   FRK(cudaStreamSynchronize(f->st));
+  const int* h_cnt = f->h_cnt_off; const int* h_off = f->h_cnt_off + ncell;
+  const size_t n_dense = (size_t)h_off[ncell];
+  if (n_dense > f->h_dense_cap) { cudaFreeHost(f->h_dense); FRK(cudaMallocHost(&f->h_dense, sizeof(KpOut) * n_dense * 2)); f->h_dense_cap = n_dense * 2; }
+  if (n_dense) { FRK(cudaMemcpyAsync(f->h_dense, f->cell_dense, sizeof(KpOut) * n_dense, cudaMemcpyDeviceToHost, f->st)); FRK(cudaStreamSynchronize(f->st)); }
   // ---- octree distribution per level (host) ----
   std::vector<KpLvl> sel; std::vector<float> resp; std::vector<int> lvl_of;
   for (int l = 0; l < nlevels; ++l) {
     std::vector<OKey> cand;
     for (int c = cell_begin[l]; c < cell_begin[l + 1]; ++c)
-      for (int k = 0; k < f->h_cell_cnt[c]; ++k) { const KpOut& o = f->h_cell_out[(size_t)c * CELL_CAP + k]; cand.push_back(OKey{o.x, o.y, o.resp}); }
+      for (int k = 0; k < h_cnt[c]; ++k) { const KpOut& o = f->h_dense[(size_t)h_off[c] + k]; cand.push_back(OKey{o.x, o.y, o.resp}); }
     if (n_candidates) n_candidates[l] = (int)cand.size();
     std::vector<OKey> kept = distribute_octtree(cand, bord[l][0], bord[l][1], bord[l][2], bord[l][3], P.per_level[l]);
     for (const OKey& k : kept) { sel.push_back(KpLvl{k.x + (float)bord[l][0], k.y + (float)bord[l][2], l}); resp.push_back(k.r); }
@@ -656,9 +700,13 @@ extern "C" int vdo_scene_flow(vdo_ctx* ctx, int n, const float* u_prev, const fl
   if (!ctx || n < 0) return VDO_ERR_ARG;
   if (n == 0) return VDO_OK;
   cudaStream_t st = (cudaStream_t)(uintptr_t)vdo_ctx_stream(ctx);
-  float* d = nullptr;
   const size_t fl = (size_t)n;
-  FRK(cudaMalloc(&d, fl * 4 * (6 + 2 + 3 + 3) + fl));
+  static std::mutex mu; static std::map<cudaStream_t, std::pair<float*, size_t>> pool;      // grow-only scratch per stream (the call is synchronous)
+  std::lock_guard<std::mutex> lk(mu);
+  auto& slot = pool[st];
+  const size_t need = fl * 4 * (6 + 2 + 3 + 3) + fl;
+  if (need > slot.second) { cudaFree(slot.first); slot.first = nullptr; FRK(cudaMalloc(&slot.first, need * 2)); slot.second = need * 2; }
+  float* d = slot.first;
   float *up = d, *vp = up + fl, *zp = vp + fl, *uc = zp + fl, *vc = uc + fl, *zc = vc + fl;
   int *lp = (int*)(zc + fl), *lc = lp + fl;
   float *df = (float*)(lc + fl), *dx = df + 3 * fl;
@@ -674,7 +722,6 @@ extern "C" int vdo_scene_flow(vdo_ctx* ctx, int n, const float* u_prev, const fl
   if (Xw_prev) FRK(cudaMemcpyAsync(Xw_prev, dx, fl * 12, cudaMemcpyDeviceToHost, st));
   if (valid) FRK(cudaMemcpyAsync(valid, dv, fl, cudaMemcpyDeviceToHost, st));
   FRK(cudaStreamSynchronize(st));
-  cudaFree(d);
   return VDO_OK;
 }
 

@@ -15,12 +15,54 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/vdo_b200.h"
 
 namespace {
 #define TRK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "[vdo_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return VDO_ERR_CUDA; } } while (0)
+
+// Per-stream scratch arena: every entry point of this file is synchronous on the context stream, so the scratch of one call can be
+// recycled by the next.  Chunks are only added during a call; at the start of the next call several chunks are merged into one.
+// (cudaMalloc / cudaFree per call cost tens of microseconds each and cudaFree synchronises the device.)
+struct Arena {
+  struct Chunk { char* p; size_t cap, off; };
+  std::vector<Chunk> chunks;
+  void reset() {
+    if (chunks.size() > 1) {
+      size_t tot = 0;
+      for (auto& c : chunks) { tot += c.cap; cudaFree(c.p); }
+      chunks.clear();
+      char* p = nullptr;
+      if (cudaMalloc(&p, tot) == cudaSuccess) chunks.push_back({p, tot, 0});
+    }
+    for (auto& c : chunks) c.off = 0;
+  }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    for (auto& c : chunks) if (c.off + bytes <= c.cap) { void* r = c.p + c.off; c.off += bytes; return r; }
+    const size_t cap = std::max(bytes, (size_t)1 << 20);
+    char* p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+    chunks.push_back({p, cap, bytes});
+    return p;
+  }
+};
+std::mutex g_arena_mu;
+std::map<cudaStream_t, Arena> g_arena;
+Arena& arena_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  Arena& a = g_arena[st];
+  a.reset();
+  return a;
+}
+struct DevBuf {
+  void* p = nullptr;
+  cudaError_t alloc(Arena& a, size_t bytes) { p = a.alloc(bytes); return p ? cudaSuccess : cudaErrorMemoryAllocation; }
+  template <class T> T* as() { return (T*)p; }
+};
 
 // label of the current mask at the (truncated) flow target of every last-frame object point; -1 = outside (u>0, v>0 strict)
 __global__ void k_gather_mask(const int* __restrict__ mask, int w, int h, const float* __restrict__ cx, const float* __restrict__ cy, int n, int* __restrict__ out) {
@@ -126,8 +168,11 @@ extern "C" int vdo_update_mask(vdo_frame* cur, vdo_frame* last, int n, const int
   std::sort(uni.begin(), uni.end());
   uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
   float *d_cx = nullptr, *d_cy = nullptr; int* d_lab = nullptr;
+  Arena& A = arena_begin(st);
   if (n > 0) {
-    TRK(cudaMalloc(&d_cx, sizeof(float) * n)); TRK(cudaMalloc(&d_cy, sizeof(float) * n)); TRK(cudaMalloc(&d_lab, sizeof(int) * n));
+    DevBuf b1, b2, b3;
+    TRK(b1.alloc(A, sizeof(float) * n)); TRK(b2.alloc(A, sizeof(float) * n)); TRK(b3.alloc(A, sizeof(int) * n));
+    d_cx = b1.as<float>(); d_cy = b2.as<float>(); d_lab = b3.as<int>();
     TRK(cudaMemcpyAsync(d_cx, corres_x, sizeof(float) * n, cudaMemcpyHostToDevice, st));
     TRK(cudaMemcpyAsync(d_cy, corres_y, sizeof(float) * n, cudaMemcpyHostToDevice, st));
   }
@@ -152,7 +197,6 @@ extern "C" int vdo_update_mask(vdo_frame* cur, vdo_frame* last, int n, const int
   }
   if (mask_out) TRK(cudaMemcpyAsync(mask_out, mcur, sizeof(int) * (size_t)w * h, cudaMemcpyDeviceToHost, st));
   TRK(cudaStreamSynchronize(st));
-  cudaFree(d_cx); cudaFree(d_cy); cudaFree(d_lab);
   return VDO_OK;
 }
 
@@ -184,10 +228,13 @@ extern "C" int vdo_dyn_obj_tracking(vdo_ctx* ctx, int n, const int* sem_label, i
   const int no = (int)posi.size();
   std::vector<ObjStat> stats(no);
   if (no > 0 && !oidx.empty()) {
-    int *d_ob, *d_oi; float *d_kx, *d_ky, *d_dp, *d_f3; ObjStat* d_st;
-    TRK(cudaMalloc(&d_ob, sizeof(int) * (no + 1))); TRK(cudaMalloc(&d_oi, sizeof(int) * oidx.size()));
-    TRK(cudaMalloc(&d_kx, sizeof(float) * n)); TRK(cudaMalloc(&d_ky, sizeof(float) * n)); TRK(cudaMalloc(&d_dp, sizeof(float) * n)); TRK(cudaMalloc(&d_f3, sizeof(float) * 3 * n));
-    TRK(cudaMalloc(&d_st, sizeof(ObjStat) * no));
+    Arena& A = arena_begin(st);
+    DevBuf c1, c2, c3, c4, c5, c6, c7;
+    TRK(c1.alloc(A, sizeof(int) * (no + 1))); TRK(c2.alloc(A, sizeof(int) * oidx.size()));
+    TRK(c3.alloc(A, sizeof(float) * n)); TRK(c4.alloc(A, sizeof(float) * n)); TRK(c5.alloc(A, sizeof(float) * n)); TRK(c6.alloc(A, sizeof(float) * 3 * n));
+    TRK(c7.alloc(A, sizeof(ObjStat) * no));
+    int *d_ob = c1.as<int>(), *d_oi = c2.as<int>(); float *d_kx = c3.as<float>(), *d_ky = c4.as<float>(), *d_dp = c5.as<float>(), *d_f3 = c6.as<float>();
+    ObjStat* d_st = c7.as<ObjStat>();
     TRK(cudaMemcpyAsync(d_ob, ob.data(), sizeof(int) * (no + 1), cudaMemcpyHostToDevice, st));
     TRK(cudaMemcpyAsync(d_oi, oidx.data(), sizeof(int) * oidx.size(), cudaMemcpyHostToDevice, st));
     TRK(cudaMemcpyAsync(d_kx, kx, sizeof(float) * n, cudaMemcpyHostToDevice, st)); TRK(cudaMemcpyAsync(d_ky, ky, sizeof(float) * n, cudaMemcpyHostToDevice, st));
@@ -195,7 +242,6 @@ extern "C" int vdo_dyn_obj_tracking(vdo_ctx* ctx, int n, const int* sem_label, i
     k_obj_stats<<<(no + 31) / 32, 32, 0, st>>>(d_ob, d_oi, no, d_kx, d_ky, d_dp, d_f3, rows, cols, shrink_row, shrink_col, sf_mg_thres, d_st);
     TRK(cudaMemcpyAsync(stats.data(), d_st, sizeof(ObjStat) * no, cudaMemcpyDeviceToHost, st));
     TRK(cudaStreamSynchronize(st));
-    cudaFree(d_ob); cudaFree(d_oi); cudaFree(d_kx); cudaFree(d_ky); cudaFree(d_dp); cudaFree(d_f3); cudaFree(d_st);
   }
   // ---- decisions, in label order like the reference ----
   std::vector<std::vector<int>> obj_new; std::vector<int> sem_new;
@@ -312,12 +358,6 @@ inline void get3d_world(float u, float v, float z, const float* K4, const float*
   for (int r = 0; r < 3; ++r)
     X[r] = (float)((double)Twc[4 * r] * (double)x + (double)Twc[4 * r + 1] * (double)y + (double)Twc[4 * r + 2] * (double)z + (double)Twc[4 * r + 3]);
 }
-struct DevBuf {            // grow-only scratch of one call
-  void* p = nullptr;
-  ~DevBuf() { cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-  template <class T> T* as() { return (T*)p; }
-};
 }  // namespace
 
 extern "C" int vdo_renew_frame_info(vdo_frame* cur, int n_tm, const int* tm_sta, int n_stat, const float* stat_keys, int n_samp, const float* samp_keys,
@@ -340,10 +380,11 @@ extern "C" int vdo_renew_frame_info(vdo_frame* cur, int n_tm, const int* tm_sta,
   }
   oinl_begin[n_obj] = (int)oinl.size();
   const int n_oinl = (int)oinl.size();
+  Arena& A = arena_begin(st);
   DevBuf b_tm, b_sk, b_oi, b_ok, b_cs, b_co, b_samp, b_tmp, b_snap_s, b_snap_o, b_cc, b_used;
-  TRK(b_tm.alloc(sizeof(int) * n_tm)); TRK(b_sk.alloc(sizeof(float) * 2 * n_stat)); TRK(b_oi.alloc(sizeof(int) * n_oinl)); TRK(b_ok.alloc(sizeof(float) * 2 * n_objkeys));
-  TRK(b_cs.alloc(sizeof(RenewCand) * n_tm)); TRK(b_co.alloc(sizeof(RenewCand) * n_oinl));
-  TRK(b_samp.alloc(sizeof(float) * 2 * n_samp)); TRK(b_tmp.alloc(sizeof(float) * 2 * n_tmp));
+  TRK(b_tm.alloc(A, sizeof(int) * n_tm)); TRK(b_sk.alloc(A, sizeof(float) * 2 * n_stat)); TRK(b_oi.alloc(A, sizeof(int) * n_oinl)); TRK(b_ok.alloc(A, sizeof(float) * 2 * n_objkeys));
+  TRK(b_cs.alloc(A, sizeof(RenewCand) * n_tm)); TRK(b_co.alloc(A, sizeof(RenewCand) * n_oinl));
+  TRK(b_samp.alloc(A, sizeof(float) * 2 * n_samp)); TRK(b_tmp.alloc(A, sizeof(float) * 2 * n_tmp));
   if (n_tm) TRK(cudaMemcpyAsync(b_tm.p, tm_sta, sizeof(int) * n_tm, cudaMemcpyHostToDevice, st));
   if (n_stat) TRK(cudaMemcpyAsync(b_sk.p, stat_keys, sizeof(float) * 2 * n_stat, cudaMemcpyHostToDevice, st));
   if (n_oinl) TRK(cudaMemcpyAsync(b_oi.p, oinl.data(), sizeof(int) * n_oinl, cudaMemcpyHostToDevice, st));
@@ -402,8 +443,8 @@ extern "C" int vdo_renew_frame_info(vdo_frame* cur, int n_tm, const int* tm_sta,
   for (int i = 0; i < n_obj; ++i) if (obj_stat[i] && fea_count[i] < max_num_obj) need_obj = true;
   need_obj = need_obj && n_tmp > 0;
   if (need_sta || need_obj) {
-    TRK(b_snap_s.alloc(sizeof(float) * 2 * n_snap_s)); TRK(b_snap_o.alloc(sizeof(float) * 2 * n_snap_o));
-    TRK(b_cc.alloc(sizeof(RenewCand) * n_samp)); TRK(b_used.alloc(n_tmp));
+    TRK(b_snap_s.alloc(A, sizeof(float) * 2 * n_snap_s)); TRK(b_snap_o.alloc(A, sizeof(float) * 2 * n_snap_o));
+    TRK(b_cc.alloc(A, sizeof(RenewCand) * n_samp)); TRK(b_used.alloc(A, n_tmp));
     if (n_snap_s) TRK(cudaMemcpyAsync(b_snap_s.p, sta_keys, sizeof(float) * 2 * n_snap_s, cudaMemcpyHostToDevice, st));
     if (n_snap_o) TRK(cudaMemcpyAsync(b_snap_o.p, o_keys, sizeof(float) * 2 * n_snap_o, cudaMemcpyHostToDevice, st));
     const int ns_k = need_sta ? n_samp : 0, nt_k = need_obj ? n_tmp : 0;
@@ -481,8 +522,9 @@ extern "C" int vdo_frame_gather(vdo_frame* f, int n, const float* keys, float* d
   int *mask, w, h; float* depth; void* stv;
   if (vdo_frame_device_ptrs(f, nullptr, &depth, nullptr, &mask, &w, &h, &stv)) return VDO_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stv;
+  Arena& A = arena_begin(st);
   DevBuf bk, bd, bm;
-  TRK(bk.alloc(sizeof(float) * 2 * n)); TRK(bd.alloc(sizeof(float) * n)); TRK(bm.alloc(sizeof(int) * n));
+  TRK(bk.alloc(A, sizeof(float) * 2 * n)); TRK(bd.alloc(A, sizeof(float) * n)); TRK(bm.alloc(A, sizeof(int) * n));
   TRK(cudaMemcpyAsync(bk.p, keys, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, st));
   k_gather_points<<<(n + 255) / 256, 256, 0, st>>>(n, bk.as<float>(), depth, mask, w, h, bd.as<float>(), bm.as<int>());
   TRK(cudaMemcpyAsync(depth_out, bd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
