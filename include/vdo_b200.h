@@ -275,8 +275,10 @@ typedef struct vdo_tracker_params {
   int n_features; float scale_factor; int n_levels, ini_th_fast, min_th_fast;   /* ORBextractor.* */
   int is_kitti;                      /* mTestData == KITTI: boundary shrink 25 / 50 px (src/Tracking.cc:1405-1409) */
   int quirk;                         /* see vdo_pose_opt_flow2 */
-  int window_size, overlap_size;     /* WINDOW_SIZE, OVERLAP_SIZE (recorded; the windowed BA is driven by the caller) */
-  int reserved[4];
+  int window_size, overlap_size;     /* WINDOW_SIZE, OVERLAP_SIZE */
+  int local_batch;                   /* bLocalBatch: run PartialBatchOptimization inside vdo_tracker_track on the reference's schedule
+                                        ((f_id - OVERLAP + 1) % (WINDOW - OVERLAP) == 0 && f_id >= WINDOW - 1, src/Tracking.cc:1150-1160) */
+  int reserved[3];
 } vdo_tracker_params;
 void vdo_tracker_params_default(vdo_tracker_params *p);
 int vdo_tracker_create(vdo_ctx *ctx, const vdo_tracker_params *params, vdo_tracker **out);
@@ -292,8 +294,9 @@ int vdo_tracker_track(vdo_tracker *t, const unsigned char *gray, float *depth, c
 /* Named read-back of the frame state after the last call ('f' arrays are f32, the others i32; out may be NULL to query the size):
  * Tcw mVelocity mvKeys mvStatKeysTmp mvStatDepthTmp mvCorres mvFlowNext mvStat3DPointTmp nStaInlierID mvObjKeys mvObjDepth
  * mvObjCorres mvObjFlowNext mvObj3DPoint vSemObjLabel vObjLabel nDynInlierID vFlow_3d nModLabel nSemPosition bObjStat vObjMod
- * TemperalMatch_subset max_id f_id; stage_ms (8 x f32, accumulated host wall-clock per stage since creation: upload+depth, mask,
- * frame build (ORB + static filter + object samples), look-ups, initial camera model, camera LM, objects, renewal) */
+ * TemperalMatch_subset max_id f_id; stage_ms (9 x f32, accumulated host wall-clock per stage since creation: upload+depth, mask,
+ * frame build (ORB + static filter + object samples), look-ups, initial camera model, camera LM, objects, renewal, windowed BA);
+ * local_ba (2 x i32: windowed optimisations run, their LM iterations) */
 int vdo_tracker_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
 
 /* Map -> factor graph -> optimise -> write back: mode 0 = Optimizer::PartialBatchOptimization(pMap, K, WINDOW_SIZE)

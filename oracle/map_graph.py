@@ -28,6 +28,16 @@ def to_iso(T):
     return out
 
 
+def to_iso_matrix(T12):
+    """getEstimateData -> Quaterniond -> rotation matrix (src/Optimizer.cc:2094-2110): rotation part re-normalised through the quaternion."""
+    import ctypes as C
+    T12 = np.ascontiguousarray(T12, np.float64)
+    out = np.zeros(12)
+    R = np.ascontiguousarray(T12[:9]); t = np.ascontiguousarray(T12[9:])
+    po.lib().vdo_oracle_iso_from_Rt_via_quat(R.ctypes.data_as(C.POINTER(C.c_double)), t.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
 def get3d_camera(key, depth, K4):
     f32 = np.float32
     K = np.asarray(K4, f32)

@@ -32,7 +32,7 @@ class Frame:
 class OracleTracker:
     def __init__(self, width=1242, height=375, K4=(721.5377, 721.5377, 609.5593, 172.8540), bf=387.5744, depth_factor=256.0, th_depth_bg=40.0,
                  th_depth_obj=25.0, max_track_bg=1200, max_track_obj=800, sf_mg_thres=0.12, sf_ds_thres=0.3, n_features=2500, scale_factor=1.2, n_levels=8,
-                 ini_th_fast=20, min_th_fast=7, is_kitti=True, quirk=1):
+                 ini_th_fast=20, min_th_fast=7, is_kitti=True, quirk=1, window_size=20, overlap_size=4, local_batch=True):
         self.w, self.h = width, height
         self.K4 = np.asarray(K4, f32)
         self.bf, self.factor = f32(bf), f32(depth_factor)
@@ -41,6 +41,8 @@ class OracleTracker:
         self.sf_mg, self.sf_ds = f32(sf_mg_thres), f32(sf_ds_thres)
         self.orb = io.OrbParams(n_features, scale_factor, n_levels, ini_th_fast, min_th_fast)
         self.kitti, self.quirk = is_kitti, quirk
+        self.window, self.overlap, self.local_batch = window_size, overlap_size, local_batch
+        self.local_ba = []
         self.first = True
         self.f_id, self.max_id = 0, 1
         self.velocity = None
@@ -116,6 +118,9 @@ class OracleTracker:
         C.statKeys = C.statKeysTmp; C.statDepth = C.statDepthTmp                      # :1006-1014
         self.last, self.cur = C, C
         self.mask_last, self.flow_last, self.depth, self.mask = mask, flow, depth, mask
+        if (self.local_batch and self.window > self.overlap and (self.f_id - self.overlap + 1) % (self.window - self.overlap) == 0
+                and self.f_id >= self.window - 1):                                   # Tracking.cc:1150-1160
+            self.batch_optimize("partial")
         self.f_id += 1
         return C.Tcw.copy()
 
@@ -190,3 +195,33 @@ class OracleTracker:
         self.map["featLabel"].append(C.objLabel.copy())
         self.map["rigidMotion"].append([inv4(self.velocity)] + [C.vObjMod[i] for i in range(nobj) if C.bObjStat[i]])
         self.map["rmLabel"].append([0] + [C.nModLabel[i] for i in range(nobj) if C.bObjStat[i]])
+
+    def batch_optimize(self, mode):
+        """PartialBatchOptimization / FullBatchOptimization on the map, with the write-back of src/Optimizer.cc:983-1050 / :2094-2172."""
+        from . import map_graph as mg
+        g, meta = mg.build_graph(self.map, self.K4, mode, self.window)
+        r = po.ba_optimize(g, max_iters=meta["max_iters"], gain_threshold=meta["gain"])
+        m = self.map
+
+        def from_iso(T):
+            out = np.eye(4, dtype=f32)
+            out[:3, :3] = mg.to_iso_matrix(T)[:9].reshape(3, 3).astype(f32); out[:3, 3] = T[9:].astype(f32)
+            return out
+        for i, v in enumerate(meta["cam_vid"]):
+            if v != -1:
+                m["cameraPose"][i] = from_iso(r["se3"][v])
+        for i in range(len(m["p3dSta"])):
+            for j, pidx in enumerate(meta["makS"][i]):
+                if pidx != -1:
+                    m["p3dSta"][i][j] = r["pt"][pidx].astype(f32)
+            for j, pidx in enumerate(meta["makD"][i]):
+                if pidx != -1:
+                    m["p3dDyn"][i][j] = r["pt"][pidx].astype(f32)
+        for i in range(len(m["cameraPose"]) - 1):
+            if mode == "partial" and meta["cam_vid"][i] != -1 and meta["cam_vid"][i + 1] != -1:
+                m["rigidMotion"][i][0] = mul4(inv4(m["cameraPose"][i]), m["cameraPose"][i + 1])
+            for j in range(1, len(meta["mot_vid"][i])):
+                if meta["mot_vid"][i][j] != -1:
+                    m["rigidMotion"][i][j] = from_iso(r["se3"][meta["mot_vid"][i][j]])
+        self.local_ba.append(r["iters"])
+        return r

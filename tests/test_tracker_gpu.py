@@ -79,8 +79,8 @@ def test_map_graph_builder_and_batch_optimisation():
     from oracle import pyoracle as po
     w, h, n = 1242, 375, 9
     ctx = capi.Context()
-    tr = capi.Tracker(ctx, window_size=8)
-    orc = OracleTracker(width=w, height=h)
+    tr = capi.Tracker(ctx, window_size=8, overlap_size=4)
+    orc = OracleTracker(width=w, height=h, window_size=8, overlap_size=4)      # both run the windowed pass at f_id = 7
     for t in range(n):
         f = make_sequence_frame(t, seed=3)
         orc.track(f["gray"], f["depth_raw"], f["flow"], f["mask"], f["obj_ids"])
@@ -117,3 +117,29 @@ def test_map_graph_builder_and_batch_optimisation():
     r0 = check(0, "partial")          # Tracking.cc:1150-1160: the windowed pass runs first, on the live map
     r1 = check(1, "full")             # :1162-1176: the full batch runs on the map the windowed pass refined
     assert r1["sizes"]["n_ternary"] > 0 and r1["final_chi2"] <= r1["initial_chi2"]
+
+
+@pytest.mark.gpu
+def test_windowed_and_full_batch_inside_the_pipeline():
+    """bLocalBatch schedule inside vdo_tracker_track (Tracking.cc:1150-1160) and the final FullBatchOptimization: same number of
+    runs / LM iterations as the oracle pipeline, refined map poses <= 1e-4."""
+    ctx = capi.Context()
+    tr = capi.Tracker(ctx, window_size=6, overlap_size=2)
+    orc = OracleTracker(window_size=6, overlap_size=2)
+    for t in range(11):
+        f = make_sequence_frame(t, seed=0)
+        orc.track(f["gray"], f["depth_raw"], f["flow"], f["mask"], f["obj_ids"])
+        tr.track(f["gray"], f["depth_raw"].copy(), f["flow"], f["mask"].copy(), f["obj_ids"])
+    runs, iters = tr.get("local_ba").tolist()
+    assert runs == len(orc.local_ba) == 2 and iters == sum(orc.local_ba)
+    P = tr.map_get("vmCameraPose").reshape(-1, 4, 4)
+    assert np.abs(P - np.array(orc.map["cameraPose"])).max() <= 1e-4
+    r_ref = orc.batch_optimize("full")
+    r = tr.batch_optimize(1)
+    assert r["iterations"] == r_ref["iters"]
+    P = tr.map_get("vmCameraPose").reshape(-1, 4, 4)
+    assert np.abs(P - np.array(orc.map["cameraPose"])).max() <= 1e-4
+    M = tr.map_get("vmRigidMotion").reshape(-1, 4, 4)
+    M_ref = np.array([T for fr in orc.map["rigidMotion"] for T in fr])
+    assert M.shape == M_ref.shape and np.abs(M - M_ref).max() <= 1e-4
+    assert tr.map_get("vnRMLabel").tolist() == [int(l) for fr in orc.map["rmLabel"] for l in fr]

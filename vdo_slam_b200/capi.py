@@ -461,12 +461,12 @@ class TrackerParams(C.Structure):
                 ("depth_factor", C.c_float), ("th_depth_bg", C.c_float), ("th_depth_obj", C.c_float), ("max_track_bg", C.c_int), ("max_track_obj", C.c_int),
                 ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float), ("n_features", C.c_int), ("scale_factor", C.c_float), ("n_levels", C.c_int),
                 ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int), ("is_kitti", C.c_int), ("quirk", C.c_int), ("window_size", C.c_int),
-                ("overlap_size", C.c_int), ("reserved", C.c_int * 4)]
+                ("overlap_size", C.c_int), ("local_batch", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class Tracker:
     """vdo_tracker: System::TrackRGBD -> Tracking::GrabImageRGBD -> Tracking::Track on the device stages."""
-    _INT = {"nStaInlierID", "vSemObjLabel", "vObjLabel", "nDynInlierID", "nModLabel", "nSemPosition", "bObjStat", "TemperalMatch_subset", "max_id", "f_id"}
+    _INT = {"nStaInlierID", "vSemObjLabel", "vObjLabel", "nDynInlierID", "nModLabel", "nSemPosition", "bObjStat", "TemperalMatch_subset", "max_id", "f_id", "local_ba"}
 
     def __init__(self, ctx: Context, **overrides):
         self.ctx = ctx

@@ -85,8 +85,8 @@ struct vdo_tracker {
   std::vector<int> temperalMatch, temperalMatchSubset;
   MapSlice map;
   std::string err;
-  double stage_ms[8] = {0};
-  int frames = 0;
+  double stage_ms[9] = {0};
+  int frames = 0, local_ba_runs = 0, local_ba_iters = 0;
   // scratch
   std::vector<float> s_f[12]; std::vector<int> s_i[8]; std::vector<unsigned char> s_b[2]; std::vector<double> s_d[2];
 };
@@ -367,7 +367,7 @@ extern "C" void vdo_tracker_params_default(vdo_tracker_params* p) {       // exa
   p->width = 1242; p->height = 375; p->fx = 721.5377f; p->fy = 721.5377f; p->cx = 609.5593f; p->cy = 172.8540f; p->bf = 387.5744f; p->depth_factor = 256.f;
   p->th_depth_bg = 40.f; p->th_depth_obj = 25.f; p->max_track_bg = 1200; p->max_track_obj = 800; p->sf_mg_thres = 0.12f; p->sf_ds_thres = 0.3f;
   p->n_features = 2500; p->scale_factor = 1.2f; p->n_levels = 8; p->ini_th_fast = 20; p->min_th_fast = 7; p->is_kitti = 1; p->quirk = 1;
-  p->window_size = 20; p->overlap_size = 4;
+  p->window_size = 20; p->overlap_size = 4; p->local_batch = 1;
 }
 
 extern "C" int vdo_tracker_create(vdo_ctx* ctx, const vdo_tracker_params* params, vdo_tracker** out) {
@@ -452,6 +452,14 @@ extern "C" int vdo_tracker_track(vdo_tracker* t, const unsigned char* gray, floa
   }
   // mLastFrame = Frame(mCurrentFrame) with the "new added" overrides (:1006-1014): the next call reads this frame through L
   C.statKeys = C.statKeysTmp; C.statDepth = C.statDepthTmp;
+  // windowed optimisation on the reference's schedule (src/Tracking.cc:1150-1160)
+  if (p.local_batch && p.window_size > p.overlap_size && p.overlap_size >= 0 && (t->f_id - p.overlap_size + 1) % (p.window_size - p.overlap_size) == 0 &&
+      t->f_id >= p.window_size - 1) {
+    StageTimer stage_timer_ba(&t->stage_ms[8]);
+    vdo_lm_stats st;
+    TK(vdo_tracker_batch_optimize(t, 0, nullptr, &st, nullptr));
+    t->local_ba_runs += 1; t->local_ba_iters += st.iterations;
+  }
   t->f_id += 1; t->frames += 1;
   if (Tcw_out) std::memcpy(Tcw_out, C.Tcw.data(), 64);
   return VDO_OK;
@@ -492,7 +500,8 @@ extern "C" int vdo_tracker_get(const vdo_tracker* t, const char* name, void* out
   if (s == "vObjMod") { std::vector<float> v; for (auto& m : C.vObjMod) v.insert(v.end(), m.begin(), m.end()); return put_f(v.data(), v.size()); }
   if (s == "max_id") return put_i(&t->max_id, 1);
   if (s == "f_id") return put_i(&t->f_id, 1);
-  if (s == "stage_ms") { float v[8]; for (int i = 0; i < 8; ++i) v[i] = (float)t->stage_ms[i]; return put_f(v, 8); }
+  if (s == "stage_ms") { float v[9]; for (int i = 0; i < 9; ++i) v[i] = (float)t->stage_ms[i]; return put_f(v, 9); }
+  if (s == "local_ba") { const int v[2] = {t->local_ba_runs, t->local_ba_iters}; return put_i(v, 2); }
   return VDO_ERR_ARG;
 }
 

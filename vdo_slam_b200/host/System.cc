@@ -58,6 +58,7 @@ System::System(const string &strSettingsFile, const eSensor sensor) : mSensor(se
   p.is_kitti = ((int)get(kv, "ChooseData") == 2) ? 1 : 0;
   p.window_size = (int)get(kv, "WINDOW_SIZE"); p.overlap_size = (int)get(kv, "OVERLAP_SIZE");
   mbRGB = (int)get(kv, "Camera.RGB") != 0;
+  mbKitti = p.is_kitti != 0;
   if ((int)get(kv, "UseSampleFeature") == 1) {
     cerr << "UseSampleFeature: 1 draws its samples from cv::RNG(time(NULL)) in the reference and is not reproducible; not supported." << endl;
     exit(-1);
@@ -78,7 +79,7 @@ System::~System() {
 }
 
 cv::Mat System::TrackRGBD(const cv::Mat &im, cv::Mat &depthmap, const cv::Mat &flowmap, const cv::Mat &masksem, const cv::Mat &, const vector<vector<float> > &vObjPose_gt,
-                          const double &, cv::Mat &, const int &) {
+                          const double &, cv::Mat &, const int &nImage) {
   if (mSensor != RGBD) {
     cerr << "ERROR: you called TrackRGBD but input sensor was not set to RGBD." << endl;
     exit(-1);
@@ -117,6 +118,12 @@ cv::Mat System::TrackRGBD(const cv::Mat &im, cv::Mat &depthmap, const cv::Mat &f
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) Tcw.at<float>(i, j) = T[4 * i + j];
   mTrajectory.push_back(vector<float>(T, T + 16));
+  // StopFrame = nImage - 1: whole-sequence optimisation after the last frame (src/Tracking.cc:168, 1162-1176; KITTI only)
+  if ((int)mTrajectory.size() == nImage && mbKitti && nImage > 2) {
+    vdo_lm_stats st;
+    if (vdo_tracker_batch_optimize(mpTracker, 1, nullptr, &st, nullptr) != VDO_OK)
+      cerr << "vdo_b200: FullBatchOptimization failed: " << vdo_tracker_last_error(mpTracker) << endl;
+  }
   return Tcw;
 }
 
@@ -125,6 +132,15 @@ void System::SaveResults(const string &filename) {
   f.precision(9);
   for (size_t k = 0; k < mTrajectory.size(); ++k) {
     for (int i = 0; i < 16; ++i) f << mTrajectory[k][i] << (i == 15 ? "\n" : " ");
+  }
+  // camera poses Twc of the map after the windowed / full batch optimisations (Map::vmCameraPose)
+  int n = 0;
+  if (vdo_tracker_map_get(mpTracker, "vmCameraPose", nullptr, 0, &n) == VDO_OK && n > 0) {
+    vector<float> P(n);
+    vdo_tracker_map_get(mpTracker, "vmCameraPose", P.data(), n, &n);
+    f << "# refined Twc" << "\n";
+    for (int k = 0; k < n / 16; ++k)
+      for (int i = 0; i < 16; ++i) f << P[16 * k + i] << (i == 15 ? "\n" : " ");
   }
 }
 

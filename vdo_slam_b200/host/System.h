@@ -42,7 +42,7 @@ class System {
   eSensor mSensor;
   vdo_ctx *mpCtx;
   vdo_tracker *mpTracker;
-  bool mbRGB;
+  bool mbRGB, mbKitti;
   vector<unsigned char> mGray;
   vector<vector<float> > mTrajectory;
 };
