@@ -11,7 +11,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <vector>
+
 #include "../../vdo_slam_b200/csrc/ba_bodies.cuh"
+#include "../../vdo_slam_b200/csrc/ba_tiles.cuh"
 
 namespace vdo {
 
@@ -34,8 +37,107 @@ struct EmulBackend : BaBackend {
   void timer_start(int s) override { t0[s] = std::chrono::steady_clock::now(); }
   float timer_stop_ms(int s) override { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0[s]).count(); }
 
+
+  // ---- tiled layout: the phases of ba_tile_kernels.cuh as serial loops (segments summed lane by lane) ----
+  struct SmBuf {
+    std::vector<double> P, OM, EW, Z, IS, F, OMT, Y, QS, TC, E2; std::vector<int> HH; std::vector<uint8_t> LML;
+    TileSm sm;
+    SmBuf() : P(3 * VDO_TILE_L), OM(VDO_TILE_E), EW(3 * VDO_TILE_E), Z(3 * VDO_TILE_L), IS(VDO_TILE_L), F(VDO_TILE_L), OMT(VDO_TILE_L), Y(3 * VDO_TILE_L),
+              QS(9 * VDO_TILE_L), TC(4 * VDO_TILE_L), E2(3 * VDO_TILE_L), HH(VDO_TILE_L), LML(VDO_TILE_E) {
+      sm.P = P.data(); sm.OM = OM.data(); sm.EW = EW.data(); sm.Z = Z.data(); sm.IS = IS.data(); sm.F = F.data(); sm.OMT = OMT.data(); sm.Y = Y.data();
+      sm.QS = QS.data(); sm.TC = TC.data(); sm.E2 = E2.data(); sm.HH = HH.data(); sm.LML = LML.data();
+    }
+  } sb;
+  template <int N, typename F> static void seg_loop(const BaDev& d, const Seg* segs, int s0, int s1, double* dst_base, int stride, int nused, F item) {
+    for (int s = s0; s < s1; ++s) {
+      const Seg sg = segs[s];
+      const double* T = d.se3 + 12 * (size_t)sg.v;
+      const double t[3] = {T[9], T[10], T[11]};
+      double acc[N] = {0};
+      for (int l = 0; l < sg.n; ++l) item(sg, l, t, acc);
+      for (int i = 0; i < nused; ++i) dst_base[(size_t)stride * sg.v + i] += acc[i];
+    }
+  }
+  void tile_lin(BaDev& d, bool write) {
+    TileSm& sm = sb.sm;
+    double chi = 0;
+    for (int ti = 0; ti < d.n_tiles; ++ti) {
+      const Tile tl = d.tiles[ti];
+      const bool chains = ti >= d.n_tiles_stat;
+      const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
+      for (int j = 0; j < nl; ++j) tile_stage_p(d, tl, j, sm);
+      if (!chains) {
+        for (int i = 0; i < ne; ++i) chi += write ? tile_lin_edge<true>(d, tl, i, d.lm_lml[tl.e0 + i], sm) : tile_lin_edge<false>(d, tl, i, d.lm_lml[tl.e0 + i], sm);
+        if (write) for (int j = 0; j < nl; ++j) {
+          double dsum = 0, b[3] = {0, 0, 0};
+          tile_lin_landmark_obs(d, tl, j, sm, dsum, b);
+          const size_t k = (size_t)tl.k0 + j;
+          d.tk_omega[k] = 0; d.hll[k] = dsum; d.bl[3 * k] = b[0]; d.bl[3 * k + 1] = b[1]; d.bl[3 * k + 2] = b[2];
+        }
+      } else {
+        std::vector<double> ds(nl, 0.0), bb(3 * (size_t)nl, 0.0);
+        for (int j = 0; j < nl; ++j) {
+          const int k = tl.k0 + j;
+          for (int i = d.lm_obs_begin[k] - tl.e0; i < d.lm_obs_begin[k + 1] - tl.e0; ++i) chi += write ? tile_lin_edge<true>(d, tl, i, j, sm) : tile_lin_edge<false>(d, tl, i, j, sm);
+          if (write) tile_lin_landmark_obs(d, tl, j, sm, ds[j], &bb[3 * j]);
+          chi += write ? tile_lin_ternary<true>(d, tl, j, sm, ds[j], &bb[3 * j]) : tile_lin_ternary<false>(d, tl, j, sm, ds[j], &bb[3 * j]);
+        }
+        if (write) {
+          for (int j = 0; j < nl; ++j) {
+            if (j > 0) { ds[j] += sm.TC[4 * j - 4]; bb[3 * j] += sm.TC[4 * j - 3]; bb[3 * j + 1] += sm.TC[4 * j - 2]; bb[3 * j + 2] += sm.TC[4 * j - 1]; }
+            const size_t k = (size_t)tl.k0 + j;
+            d.hll[k] = ds[j]; d.bl[3 * k] = bb[3 * j]; d.bl[3 * k + 1] = bb[3 * j + 1]; d.bl[3 * k + 2] = bb[3 * j + 2];
+          }
+          for (int jt = 0; jt < tl.t1 - tl.t0; ++jt) tile_chain_Q(d, tl, jt);
+        }
+      }
+      if (write) {
+        seg_loop<16>(d, d.osegs, tl.os0, tl.os1, d.accO, 16, 16, [&](const Seg& sg, int l, const double* t, double* acc) { tile_lin_oseg_item(d, tl, sg, l, sm, t, acc); });
+        if (chains) seg_loop<16>(d, d.tsegs, tl.ts0, tl.ts1, d.accT, 16, 16, [&](const Seg& sg, int l, const double* t, double* acc) { tile_lin_tseg_item(d, tl, sg, l, sm, t, acc); });
+      }
+    }
+    d.scal[SC_CHI2] += chi;
+  }
+  void tile_precond(BaDev& d) {
+    TileSm& sm = sb.sm;
+    for (int ti = 0; ti < d.n_tiles; ++ti) {
+      const Tile tl = d.tiles[ti];
+      const bool chains = ti >= d.n_tiles_stat;
+      for (int j = 0; j < tl.k1 - tl.k0; ++j) {
+        tile_stage_p(d, tl, j, sm);
+        sm.IS[j] = d.pt_g[tl.k0 + j];
+        if (chains) { sm.F[j] = d.tk_gamma[tl.k0 + j]; sm.OMT[j] = d.tk_omega[tl.k0 + j]; }
+      }
+      seg_loop<16>(d, d.osegs, tl.os0, tl.os1, d.accO, 16, 10, [&](const Seg& sg, int l, const double* t, double* acc) { tile_pre_oseg_item(d, tl, sg, l, sm, t, acc); });
+      if (chains) seg_loop<16>(d, d.tsegs, tl.ts0, tl.ts1, d.accT, 16, 10, [&](const Seg& sg, int l, const double* t, double* acc) { tile_pre_tseg_item(d, tl, sg, l, sm, t, acc); });
+    }
+    for (int v = 0; v < d.C; ++v) tile_finalize_precond(d, v);
+  }
+  template <int MODE> void tile_schur(BaDev& d) {
+    TileSm& sm = sb.sm;
+    for (int ti = 0; ti < d.n_tiles; ++ti) {
+      const Tile tl = d.tiles[ti];
+      const bool chains = ti >= d.n_tiles_stat;
+      const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
+      if (!chains) {
+        for (int j = 0; j < nl; ++j) tile_stage_p(d, tl, j, sm);
+        for (int i = 0; i < ne; ++i) tile_schur_edge<MODE>(d, tl, i, d.lm_lml[tl.e0 + i], sm);
+        for (int j = 0; j < nl; ++j) tile_schur_static_landmark<MODE>(d, tl, j, sm);
+      } else {
+        for (int j = 0; j < nl; ++j) tile_schur_chain_stage(d, tl, j, sm);
+        for (int j = 0; j < nl; ++j) tile_schur_chain_u<MODE>(d, tl, j, sm);
+        for (int j = 0; j < nl; ++j) tile_schur_chain_y<MODE>(d, tl, j, sm);
+        for (int jt = 0; jt < tl.t1 - tl.t0; ++jt) tile_schur_chain_walk(d, tl, jt, sm);
+        for (int j = 0; j < nl; ++j) tile_schur_chain_z<MODE>(d, tl, j, sm);
+      }
+      if (MODE == 2) continue;
+      seg_loop<8>(d, d.osegs, tl.os0, tl.os1, d.acc6, 6, 6, [&](const Seg& sg, int l, const double* t, double* acc) { tile_schur_oseg_item(d, tl, sg, l, sm, t, acc); });
+      if (chains) seg_loop<8>(d, d.tsegs, tl.ts0, tl.ts1, d.acc6, 6, 6, [&](const Seg& sg, int l, const double* t, double* acc) { tile_schur_tseg_item(d, tl, sg, l, sm, t, acc); });
+    }
+  }
   void lin_tracklets(BaDev& d, bool write) override {
     ++n_launch;
+    if (d.tiled) { tile_lin(d, write); return; }
     double chi = 0;
     for (int t = 0; t < d.Tstat; ++t) chi += body_lin_static(d, t, write);
     for (int t = d.Tstat; t < d.T; ++t) chi += body_lin_tracklet(d, t, write);
@@ -51,6 +153,7 @@ struct EmulBackend : BaBackend {
   }
   void lin_vertex_obs(BaDev& d) override {
     ++n_launch;
+    if (d.tiled) { for (int v = 0; v < d.C; ++v) tile_finalize_lin(d, v); return; }
     for (int ci = 0; ci < d.n_obs_chunks; ++ci) {
       Chunk ch = d.obs_chunks[ci];
       Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
@@ -61,6 +164,7 @@ struct EmulBackend : BaBackend {
     }
   }
   void lin_vertex_ter(BaDev& d) override {
+    if (d.tiled) return;
     ++n_launch;
     for (int ci = 0; ci < d.n_ter_chunks; ++ci) {
       Chunk ch = d.ter_chunks[ci];
@@ -109,6 +213,7 @@ struct EmulBackend : BaBackend {
   }
   void precond_vertex_obs(BaDev& d) override {
     ++n_launch;
+    if (d.tiled) { tile_precond(d); return; }
     for (int ci = 0; ci < d.n_obs_chunks; ++ci) {
       Chunk ch = d.obs_chunks[ci];
       Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
@@ -119,6 +224,7 @@ struct EmulBackend : BaBackend {
     }
   }
   void precond_vertex_ter(BaDev& d) override {
+    if (d.tiled) return;
     ++n_launch;
     for (int ci = 0; ci < d.n_ter_chunks; ++ci) {
       Chunk ch = d.ter_chunks[ci];
@@ -164,12 +270,14 @@ struct EmulBackend : BaBackend {
   void schur_landmarks(BaDev& d, int mode, const double* v) override {
     ++n_launch;
     if (mode == 1 && d.scal[SC_DONE] != 0.0) return;
+    if (d.tiled) { if (mode == 0) tile_schur<0>(d); else if (mode == 1) tile_schur<1>(d); else tile_schur<2>(d); return; }
     double* out = mode == 2 ? d.xl : d.zl;
     for (int t = 0; t < d.Tstat; ++t) body_schur_static(d, t, mode, out);
     for (int t = d.Tstat; t < d.T; ++t) body_schur_tracklet(d, t, mode, v, out);
   }
   void schur_vertex_obs(BaDev& d, double sign, double* out) override {
     ++n_launch;
+    if (d.tiled) { if (out == d.Ap && d.scal[SC_DONE] != 0.0) return; for (int v = 0; v < d.C; ++v) tile_finalize_schur(d, v, sign, out); return; }
     for (int ci = 0; ci < d.n_obs_chunks; ++ci) {
       Chunk ch = d.obs_chunks[ci];
       Iso T; iso_load(d.se3 + 12 * (size_t)ch.v, T);
@@ -179,6 +287,7 @@ struct EmulBackend : BaBackend {
     }
   }
   void schur_vertex_ter(BaDev& d, double sign, double* out) override {
+    if (d.tiled) return;
     ++n_launch;
     for (int ci = 0; ci < d.n_ter_chunks; ++ci) {
       Chunk ch = d.ter_chunks[ci];

@@ -190,6 +190,10 @@ VDO_HD void body_vertex_transform(const BaDev& d, int c, const double* __restric
   double* o = vw + 6 * (size_t)c;
   o[0] = -al[0] - 2 * tb[0]; o[1] = -al[1] - 2 * tb[1]; o[2] = -al[2] - 2 * tb[2];
   o[3] = be[0]; o[4] = be[1]; o[5] = be[2];
+  if (d.vh) {   // tiled layout: image seen by the ternary edges, R_H (J_H v) = gamma' - p2 x beta with gamma' = R vt + t x beta
+    double* oh = d.vh + 6 * (size_t)c;
+    oh[0] = al[0] + tb[0]; oh[1] = al[1] + tb[1]; oh[2] = al[2] + tb[2]; oh[3] = be[0]; oh[4] = be[1]; oh[5] = be[2];
+  }
 }
 
 // mode 0: out = Hll^-1 bl ; mode 1: out = Hll^-1 (Hlp v) ; mode 2: out = Hll^-1 (bl - Hlp v)

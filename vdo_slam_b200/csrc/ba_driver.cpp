@@ -9,6 +9,8 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <chrono>
+#include <thread>
 
 namespace vdo {
 
@@ -77,6 +79,23 @@ struct ClassTable {
     return id;
   }
 };
+// Host-side worker threads of finalize() (graph ingestion is memory-latency-bound scatter work; the reference's own
+// graph construction is single-threaded, src/Optimizer.cc:1232-1930).  VDO_HOST_THREADS overrides the default.
+int host_threads() {
+  static int n = [] {
+    const char* e = std::getenv("VDO_HOST_THREADS");
+    int v = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    return std::max(1, std::min(v, 64));
+  }();
+  return n;
+}
+template <typename F> void parallel_for(int nthreads, F fn) {   // fn(thread index, thread count)
+  if (nthreads <= 1) { fn(0, 1); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back([=] { fn(t, nthreads); });
+  fn(0, nthreads);
+  for (auto& x : th) x.join();
+}
 void make_chunks(const std::vector<int>& begin, std::vector<Chunk>& out) {
   for (int v = 0; v + 1 < (int)begin.size(); ++v)
     for (int b = begin[v]; b < begin[v + 1]; b += VDO_CHUNK) out.push_back(Chunk{v, b, std::min(b + VDO_CHUNK, begin[v + 1]), 0});
@@ -85,6 +104,14 @@ void make_chunks(const std::vector<int>& begin, std::vector<Chunk>& out) {
 
 int BaGraph::finalize() {
   if (finalized_) return fail(VDO_ERR_STATE, "finalize called twice");
+  const bool prof_fin = std::getenv("VDO_PROFILE") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof_fin) return;
+    auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[vdo_b200] finalize: %-28s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+    tp0 = t;
+  };
   const int C = n_se3_; int P = n_pt_;
   const int Eo_all = (int)ob_w_.size(), Et_all = (int)te_w_.size(), Es = (int)se_w_.size(), Ep = (int)pr_w_.size();
   // ---- se3 vertices: renumber so that every path of the se3-se3 edge graph (camera odometry chain, per-object
@@ -126,6 +153,7 @@ int BaGraph::finalize() {
     path_begin.push_back(cnt);
   }
   auto S3 = [&](int old_id) { return new_se3_of_old_[old_id]; };
+  lap("se3 paths");
   // ---- tracklets: chains of landmarks linked by ternary edges ----
   (void)0;
   std::vector<int> next(P, -1), prev(P, -1), ter_of(P, -1);
@@ -138,25 +166,45 @@ int BaGraph::finalize() {
   new_of_old_.assign(P, -1);
   std::vector<int> old_of_new(P), tk_begin;
   int cnt = 0;
-  // static landmarks (tracklets of one vertex) first, then the chains: the two groups run different kernels.
-  // Multi-GPU: tracklets are dealt round-robin to the ranks (each group separately); a rank keeps only its own
-  // landmarks and their edges, the se3 state is replicated.
+  // Tracklet order.  Static landmarks (tracklets of one vertex) first, then the chains: the two groups run different
+  // kernels.  Inside each group tracklets are ordered by the first se3 vertex that observes them (chains: by the motion
+  // vertex of their first ternary edge, then by the first observing camera), so that the landmarks of one tile meet only
+  // a few se3 vertices and the per-tile vertex-sorted segments stay long.  Counting sorts: O(P + C).
+  // Multi-GPU: tracklets are dealt round-robin to the ranks (each group separately, in this order); a rank keeps only its
+  // own landmarks and their edges, the se3 state is replicated.
   const int rank = be_->rank, world = be_->world;
-  int n_seen = 0, t_idx = 0;
+  std::vector<int> first_cam(P, C);
+  for (int e = 0; e < Eo_all; ++e) { int& f = first_cam[ob_cp_[2 * e + 1]]; f = std::min(f, S3(ob_cp_[2 * e])); }
+  auto counting_sort = [&](std::vector<int>& ids, const std::vector<int>& key_of_id, int nkeys) {   // stable
+    std::vector<int> cntk(nkeys + 1, 0), out(ids.size());
+    for (int id : ids) cntk[key_of_id[id] + 1]++;
+    for (int k = 0; k < nkeys; ++k) cntk[k + 1] += cntk[k];
+    for (int id : ids) out[cntk[key_of_id[id]]++] = id;
+    ids.swap(out);
+  };
+  std::vector<int> stat_ids, chain_heads;
+  int n_seen = 0;
   for (int p = 0; p < P; ++p) {
-    if (prev[p] != -1 || next[p] != -1) continue;
-    ++n_seen;
+    if (prev[p] == -1 && next[p] == -1) { stat_ids.push_back(p); ++n_seen; }
+    else if (prev[p] == -1) { chain_heads.push_back(p); for (int q = p; q != -1; q = next[q]) ++n_seen; }
+  }
+  counting_sort(stat_ids, first_cam, C + 1);
+  {
+    std::vector<int> first_h(P, 0);
+    for (int p : chain_heads) first_h[p] = S3(te_pph_[3 * ter_of[p] + 2]);
+    counting_sort(chain_heads, first_cam, C + 1);
+    counting_sort(chain_heads, first_h, C + 1);
+  }
+  int t_idx = 0;
+  for (int p : stat_ids) {
     if ((t_idx++ % world) != rank) continue;
     tk_begin.push_back(cnt);
     new_of_old_[p] = cnt; old_of_new[cnt++] = p;
   }
   const int Tstat = cnt;
   t_idx = 0;
-  for (int p = 0; p < P; ++p) {
-    if (prev[p] != -1 || next[p] == -1) continue;
-    const bool mine = (t_idx++ % world) == rank;
-    for (int q = p; q != -1; q = next[q]) ++n_seen;
-    if (!mine) continue;
+  for (int p : chain_heads) {
+    if ((t_idx++ % world) != rank) continue;
     tk_begin.push_back(cnt);
     for (int q = p; q != -1; q = next[q]) { new_of_old_[q] = cnt; old_of_new[cnt++] = q; }
   }
@@ -167,32 +215,86 @@ int BaGraph::finalize() {
   tk_begin.push_back(cnt);
   const int T = (int)tk_begin.size() - 1;
 
+  lap("tracklet order");
   ClassTable oc, tc;
   // ---- landmark-major pointxyz stream ----
+  // Edge classes first (sequential; consecutive edges almost always share their (information, delta) pair), then the scatter
+  // into landmark order by worker threads that each own a contiguous landmark range and scan the edge list in order, so the
+  // order of a landmark's edges is the caller's order whatever the thread count.
+  const int NT = host_threads();
+  std::vector<uint8_t> ecls(Eo_all);
+  {
+    double lw = 0, ld = 0; int lc = -1;
+    for (int e = 0; e < Eo_all; ++e) {
+      if (lc < 0 || ob_w_[e] != lw || ob_d_[e] != ld) {
+        lc = oc.get(ob_w_[e], ob_d_[e]); lw = ob_w_[e]; ld = ob_d_[e];
+        if (lc > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on pointxyz edges");
+      }
+      ecls[e] = (uint8_t)lc;
+    }
+  }
+  lap("  edge classes");
+  std::vector<int> kof(Eo_all);
+  parallel_for(NT, [&](int t, int n) {
+    const int a = (int)((int64_t)Eo_all * t / n), b = (int)((int64_t)Eo_all * (t + 1) / n);
+    for (int e = a; e < b; ++e) kof[e] = new_of_old_[ob_cp_[2 * e + 1]];
+  });
+  lap("  kof");
   std::vector<int> lm_begin(P + 1, 0);
-  int Eo = 0;
-  for (int e = 0; e < Eo_all; ++e) { int k = new_of_old_[ob_cp_[2 * e + 1]]; if (k >= 0) { lm_begin[k + 1]++; ++Eo; } }
+  parallel_for(NT, [&](int t, int n) {
+    const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
+    for (int e = 0; e < Eo_all; ++e) { const int k = kof[e]; if (k >= lo && k < hi) lm_begin[k + 1]++; }
+  });
+  lap("  count");
   for (int k = 0; k < P; ++k) lm_begin[k + 1] += lm_begin[k];
+  const int Eo = lm_begin[P];
   std::vector<int> fill(lm_begin.begin(), lm_begin.end() - 1), lm_cam(Eo);
   std::vector<double> lm_z(3 * (size_t)Eo);
   std::vector<uint8_t> lm_cls(Eo);
-  for (int e = 0; e < Eo_all; ++e) {
-    int k = new_of_old_[ob_cp_[2 * e + 1]];
-    if (k < 0) continue;
-    int pos = fill[k]++;
-    lm_cam[pos] = S3(ob_cp_[2 * e]);
-    for (int i = 0; i < 3; ++i) lm_z[3 * (size_t)pos + i] = ob_z_[3 * (size_t)e + i];
-    int cls = oc.get(ob_w_[e], ob_d_[e]);
-    if (cls > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on pointxyz edges");
-    lm_cls[pos] = (uint8_t)cls;
+  lap("  prefix + alloc");
+  parallel_for(NT, [&](int t, int n) {
+    const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
+    for (int e = 0; e < Eo_all; ++e) {
+      const int k = kof[e];
+      if (k < lo || k >= hi) continue;
+      const int pos = fill[k]++;
+      lm_cam[pos] = new_se3_of_old_[ob_cp_[2 * e]];
+      lm_z[3 * (size_t)pos] = ob_z_[3 * (size_t)e]; lm_z[3 * (size_t)pos + 1] = ob_z_[3 * (size_t)e + 1]; lm_z[3 * (size_t)pos + 2] = ob_z_[3 * (size_t)e + 2];
+      lm_cls[pos] = ecls[e];
+    }
+  });
+  std::vector<int>().swap(kof);
+  lap("landmark-major stream");
+  // ---- layout choice: tiles of whole tracklets (default) or, when a tracklet is too large for a tile (more than
+  //      VDO_TILE_L landmarks or VDO_TILE_E pointxyz edges) or VDO_BA_LAYOUT=chunked is set, the chunked vertex-major layout ----
+  std::vector<Tile> tiles;
+  int n_tiles_stat = 0;
+  bool tiled = true;
+  {
+    const char* env = std::getenv("VDO_BA_LAYOUT");
+    if (env && std::string(env) == "chunked") tiled = false;
+    Tile cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto close = [&](int t) { if (cur.t1 > cur.t0) tiles.push_back(cur); cur.t0 = cur.t1 = t; cur.k0 = cur.k1 = tk_begin[t]; cur.e0 = cur.e1 = lm_begin[tk_begin[t]]; };
+    for (int t = 0; t < T && tiled; ++t) {
+      if (t == Tstat) { close(t); n_tiles_stat = (int)tiles.size(); }
+      const int nl = tk_begin[t + 1] - tk_begin[t], ne = lm_begin[tk_begin[t + 1]] - lm_begin[tk_begin[t]];
+      if (nl > VDO_TILE_L || ne > VDO_TILE_E) { tiled = false; break; }
+      if ((cur.k1 - cur.k0) + nl > VDO_TILE_L || (cur.e1 - cur.e0) + ne > VDO_TILE_E) close(t);
+      cur.t1 = t + 1; cur.k1 = tk_begin[t + 1]; cur.e1 = lm_begin[tk_begin[t + 1]];
+    }
+    if (tiled) { if (cur.t1 > cur.t0) tiles.push_back(cur); if (Tstat == T) n_tiles_stat = (int)tiles.size(); }
+    else tiles.clear();
   }
+  std::vector<int> vm_begin(C + 1, 0), vm_pt;
+  std::vector<double> vm_z;
+  std::vector<uint8_t> vm_cls;
+  std::vector<Chunk> obs_chunks;
+  if (!tiled) {
   // ---- vertex-major pointxyz stream: walk the landmark-major stream so each vertex's edges stay landmark-sorted ----
-  std::vector<int> vm_begin(C + 1, 0);
   for (int pos = 0; pos < Eo; ++pos) vm_begin[lm_cam[pos] + 1]++;
   for (int v = 0; v < C; ++v) vm_begin[v + 1] += vm_begin[v];
-  std::vector<int> vfill(vm_begin.begin(), vm_begin.end() - 1), vm_pt(Eo);
-  std::vector<double> vm_z(3 * (size_t)Eo);
-  std::vector<uint8_t> vm_cls(Eo);
+  std::vector<int> vfill(vm_begin.begin(), vm_begin.end() - 1);
+  vm_pt.resize(Eo); vm_z.resize(3 * (size_t)Eo); vm_cls.resize(Eo);
   {
     int k = 0;
     for (int pos = 0; pos < Eo; ++pos) {
@@ -202,7 +304,8 @@ int BaGraph::finalize() {
       for (int i = 0; i < 3; ++i) vm_z[3 * (size_t)q + i] = lm_z[3 * (size_t)pos + i];
     }
   }
-  std::vector<Chunk> obs_chunks; make_chunks(vm_begin, obs_chunks);
+  make_chunks(vm_begin, obs_chunks);
+  }
   // ---- ternary edges: per landmark (as p1) and motion-vertex-major ----
   std::vector<int> tk_h(P, -1);
   std::vector<uint8_t> tk_cls(P, 0);
@@ -218,15 +321,83 @@ int BaGraph::finalize() {
     tk_cls[k] = (uint8_t)cls;
     hm_begin[S3(te_pph_[3 * e + 2]) + 1]++;
   }
-  for (int v = 0; v < C; ++v) hm_begin[v + 1] += hm_begin[v];
-  std::vector<int> hfill(hm_begin.begin(), hm_begin.end() - 1), hm_p1(Et);
-  std::vector<uint8_t> hm_cls(Et);
-  for (int k = 0; k < P; ++k) {   // landmark order keeps each motion vertex's edges landmark-sorted
-    if (tk_h[k] < 0) continue;
-    int q = hfill[tk_h[k]]++;
-    hm_p1[q] = k; hm_cls[q] = tk_cls[k];
+  std::vector<int> hm_p1;
+  std::vector<uint8_t> hm_cls;
+  std::vector<Chunk> ter_chunks;
+  if (!tiled) {
+    for (int v = 0; v < C; ++v) hm_begin[v + 1] += hm_begin[v];
+    std::vector<int> hfill(hm_begin.begin(), hm_begin.end() - 1);
+    hm_p1.resize(Et); hm_cls.resize(Et);
+    for (int k = 0; k < P; ++k) {   // landmark order keeps each motion vertex's edges landmark-sorted
+      if (tk_h[k] < 0) continue;
+      int q = hfill[tk_h[k]]++;
+      hm_p1[q] = k; hm_cls[q] = tk_cls[k];
+    }
+    make_chunks(hm_begin, ter_chunks);
   }
-  std::vector<Chunk> ter_chunks; make_chunks(hm_begin, ter_chunks);
+  lap("ternary / chunked streams");
+  // ---- tiles: tile-local landmark of every edge, vertex-sorted order of the tile's edges, segments of one vertex ----
+  std::vector<uint16_t> ob_perm, tr_perm;
+  std::vector<uint8_t> lm_lml;
+  std::vector<Seg> osegs, tsegs;
+  if (tiled) {
+    ob_perm.resize(Eo); tr_perm.resize(P); lm_lml.resize(Eo);
+    // tiles are independent: each worker handles a contiguous range of tiles into its own segment lists, which are then
+    // concatenated in tile order (segment indices of a tile are rebased by the lists that precede it)
+    const int ntl = (int)tiles.size();
+    const int NW = std::max(1, std::min(NT, ntl / 64 + 1));
+    std::vector<std::vector<Seg>> w_os(NW), w_ts(NW);
+    parallel_for(NW, [&](int wt, int wn) {
+      std::vector<int> keys(std::max(VDO_TILE_E, VDO_TILE_L)), idx(keys.size()), bucket;
+      std::vector<Seg>& los = w_os[wt]; std::vector<Seg>& lts = w_ts[wt];
+      // stable sort of idx[0..n) by keys[idx] (counting sort over the key range when it is small), then cut into segments
+      auto sort_and_cut = [&](int n, int base, std::vector<uint16_t>& perm, std::vector<Seg>& segs) {
+        if (n == 0) return;
+        int lo = keys[idx[0]], hi = lo;
+        for (int a = 1; a < n; ++a) { lo = std::min(lo, keys[idx[a]]); hi = std::max(hi, keys[idx[a]]); }
+        const int range = hi - lo + 1;
+        if (range <= 8 * n + 64) {
+          bucket.assign(range + 1, 0);
+          for (int a = 0; a < n; ++a) bucket[keys[idx[a]] - lo + 1]++;
+          for (int r = 0; r < range; ++r) bucket[r + 1] += bucket[r];
+          for (int a = 0; a < n; ++a) perm[base + bucket[keys[idx[a]] - lo]++] = (uint16_t)idx[a];
+        } else {
+          std::stable_sort(idx.begin(), idx.begin() + n, [&](int x, int y) { return keys[x] < keys[y]; });
+          for (int a = 0; a < n; ++a) perm[base + a] = (uint16_t)idx[a];
+        }
+        for (int a = 0; a < n;) {
+          const int v = keys[perm[base + a]];
+          int b = a;
+          while (b < n && b - a < VDO_SEG && keys[perm[base + b]] == v) ++b;
+          segs.push_back(Seg{v, base + a, b - a, 0});
+          a = b;
+        }
+      };
+      const int ta = (int)((int64_t)ntl * wt / wn), tb = (int)((int64_t)ntl * (wt + 1) / wn);
+      for (int ti = ta; ti < tb; ++ti) {
+        Tile& tl = tiles[ti];
+        for (int k = tl.k0; k < tl.k1; ++k) for (int e = lm_begin[k]; e < lm_begin[k + 1]; ++e) lm_lml[e] = (uint8_t)(k - tl.k0);
+        const int ne = tl.e1 - tl.e0;
+        for (int i = 0; i < ne; ++i) { keys[i] = lm_cam[tl.e0 + i]; idx[i] = i; }
+        tl.os0 = (int)los.size();
+        sort_and_cut(ne, tl.e0, ob_perm, los);
+        tl.os1 = (int)los.size();
+        int nt = 0;
+        for (int k = tl.k0; k < tl.k1; ++k) if (tk_h[k] >= 0) { keys[k - tl.k0] = tk_h[k]; idx[nt++] = k - tl.k0; }
+        tl.ts0 = (int)lts.size();
+        sort_and_cut(nt, tl.k0, tr_perm, lts);
+        tl.ts1 = (int)lts.size();
+      }
+    });
+    for (int wt = 0; wt < NW; ++wt) {
+      const int ta = (int)((int64_t)ntl * wt / NW), tb = (int)((int64_t)ntl * (wt + 1) / NW);
+      const int ob = (int)osegs.size(), tb0 = (int)tsegs.size();
+      for (int ti = ta; ti < tb; ++ti) { tiles[ti].os0 += ob; tiles[ti].os1 += ob; tiles[ti].ts0 += tb0; tiles[ti].ts1 += tb0; }
+      osegs.insert(osegs.end(), w_os[wt].begin(), w_os[wt].end());
+      tsegs.insert(tsegs.end(), w_ts[wt].begin(), w_ts[wt].end());
+    }
+  }
+  lap("tile segments");
   // ---- se3-se3 edges (priors first, j = -1) and H_pp adjacency ----
   const int Ese = Ep + Es;
   std::vector<int> se_i(Ese), se_j(Ese);
@@ -268,6 +439,7 @@ int BaGraph::finalize() {
   std::vector<double> pt_int(3 * (size_t)P);
   for (int k = 0; k < P; ++k) for (int i = 0; i < 3; ++i) pt_int[3 * (size_t)k + i] = h_pt_[3 * (size_t)old_of_new[k] + i];
 
+  lap("se3 edges, states");
   // ---- upload ----
   BaDev& d = d_;
   d.C = C; d.P = P; d.T = T; d.Tstat = Tstat; d.own = (rank == 0) ? 1 : 0;
@@ -279,8 +451,18 @@ int BaGraph::finalize() {
   d.tk_begin = upload(tk_begin);
   d.lm_obs_begin = upload(lm_begin); d.lm_cam = upload(lm_cam); d.lm_z = upload(lm_z); d.lm_cls = upload(lm_cls); d.lm_omega = dalloc<double>(Eo);
   d.tk_h = upload(tk_h); d.tk_cls = upload(tk_cls); d.tk_omega = dalloc<double>(P);
-  d.vm_pt = upload(vm_pt); d.vm_z = upload(vm_z); d.vm_cls = upload(vm_cls); d.vm_omega = dalloc<double>(Eo); d.obs_chunks = upload(obs_chunks);
-  d.hm_p1 = upload(hm_p1); d.hm_cls = upload(hm_cls); d.hm_omega = dalloc<double>(Et); d.ter_chunks = upload(ter_chunks);
+  d.tiled = tiled ? 1 : 0;
+  if (!tiled) {
+    d.vm_pt = upload(vm_pt); d.vm_z = upload(vm_z); d.vm_cls = upload(vm_cls); d.vm_omega = dalloc<double>(Eo); d.obs_chunks = upload(obs_chunks);
+    d.hm_p1 = upload(hm_p1); d.hm_cls = upload(hm_cls); d.hm_omega = dalloc<double>(Et); d.ter_chunks = upload(ter_chunks);
+  } else {
+    d.n_tiles = (int)tiles.size(); d.n_tiles_stat = n_tiles_stat; d.n_osegs = (int)osegs.size(); d.n_tsegs = (int)tsegs.size();
+    d.tiles = upload(tiles); d.osegs = upload(osegs); d.tsegs = upload(tsegs);
+    d.ob_perm = upload(ob_perm); d.tr_perm = upload(tr_perm); d.lm_lml = upload(lm_lml);
+    d.pt_Q = dalloc<double>(9 * (size_t)std::max(P - Tstat, 1));
+    d.accO = dalloc<double>(16 * (size_t)C); d.accT = dalloc<double>(16 * (size_t)C); d.acc6 = dalloc<double>(6 * (size_t)C);
+    d.vh = dalloc<double>(6 * (size_t)C);
+  }
   d.se_i = upload(se_i); d.se_j = upload(se_j); d.se_Z = upload(se_Z); d.se_w = upload(se_w); d.se_delta = upload(se_d); d.se_Hoff = dalloc<double>(36 * (size_t)Ese);
   d.nbr_begin = upload(nbr_begin); d.nbr_edge = upload(nbr_edge); d.nbr_other = upload(nbr_other); d.nbr_tr = upload(nbr_tr);
   d.Hpp = dalloc<double>(42 * (size_t)C); d.bp = d.Hpp + 36 * (size_t)C; d.hll = dalloc<double>(P); d.bl = dalloc<double>(3 * (size_t)P);
@@ -293,13 +475,14 @@ int BaGraph::finalize() {
   d.pcr_b = dalloc<double>(12 * (size_t)C);
   d.xp = dalloc<double>(6 * (size_t)C); d.r = dalloc<double>(6 * (size_t)C); d.z = dalloc<double>(6 * (size_t)C);
   d.p = dalloc<double>(6 * (size_t)C); d.Ap = dalloc<double>(6 * (size_t)C); d.rhs = dalloc<double>(6 * (size_t)C);
-  d.zl = dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P); d.vw = dalloc<double>(6 * (size_t)C);
+  d.zl = tiled ? nullptr : dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P); d.vw = dalloc<double>(6 * (size_t)C);
   oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
   d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
   d.scal = dalloc<double>(SC_N);
   d.n_part_pap = 148; d.n_part_rz = std::max(1, n_paths) * 8;
   d.part_pap = dalloc<double>(d.n_part_pap); d.part_rz = dalloc<double>(d.n_part_rz);
   be_->sync();
+  lap("alloc + upload");
   // host staging is no longer needed (keep the landmark map for read-back)
   std::vector<double>().swap(ob_z_); std::vector<double>().swap(ob_w_); std::vector<double>().swap(ob_d_); std::vector<int>().swap(ob_cp_);
   std::vector<int>().swap(te_pph_); std::vector<double>().swap(te_w_); std::vector<double>().swap(te_d_);

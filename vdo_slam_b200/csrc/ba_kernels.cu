@@ -469,6 +469,10 @@ __global__ void __launch_bounds__(128) k_apply_update(BaDev d, double lambda, in
   if (threadIdx.x == 0 && s != 0.0) atomicAdd(d.scal + SC_SCALE, s);
 }
 
+}  // namespace vdo
+#include "ba_tile_kernels.cuh"
+namespace vdo {
+
 // ---------------------------------------------------------------------------------------------------------------
 // NCCL is resolved at run time (dlopen) so that the library links without it and picks up the copy torch already loaded
 struct NcclApi {
@@ -539,12 +543,42 @@ struct CudaBackend : BaBackend {
     if ((grid) > 0) { kern<<<(grid), (block), 0, st>>>(__VA_ARGS__); ++n_launch; } \
   } while (0)
 
+  template <typename K> void launch_tiles(K kern, size_t smem, const BaDev& d, int tile0, int n) {
+    if (n > 0) { kern<<<n, VDO_TILE_L, smem, st>>>(d, tile0); ++n_launch; }
+  }
+  void tile_lin(BaDev& d, bool write, int part) {   // part: 0 static tiles, 1 chain tiles, -1 both
+    const int ns = d.n_tiles_stat, nc = d.n_tiles - d.n_tiles_stat;
+    if (part != 1) { if (write) launch_tiles(k_tile_lin<false, true>, tile_smem_bytes<LIN_ST>(), d, 0, ns); else launch_tiles(k_tile_lin<false, false>, tile_smem_bytes<LIN_ST>(), d, 0, ns); }
+    if (part != 0) { if (write) launch_tiles(k_tile_lin<true, true>, tile_smem_bytes<LIN_CH>(), d, ns, nc); else launch_tiles(k_tile_lin<true, false>, tile_smem_bytes<LIN_CH>(), d, ns, nc); }
+  }
+  void tile_schur(BaDev& d, int mode, int part, cudaStream_t chain_stream) {
+    const int ns = d.n_tiles_stat, nc = d.n_tiles - d.n_tiles_stat;
+    const size_t bs = tile_smem_bytes<SCH_ST>(), bc = tile_smem_bytes<SCH_CH>();
+    if (part != 1 && ns > 0) {
+      if (mode == 0) k_tile_schur<false, 0><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
+      else if (mode == 1) k_tile_schur<false, 1><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
+      else k_tile_schur<false, 2><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
+      ++n_launch;
+    }
+    if (part != 0 && nc > 0) {
+      if (mode == 0) k_tile_schur<true, 0><<<nc, VDO_TILE_L, bc, chain_stream>>>(d, ns);
+      else if (mode == 1) k_tile_schur<true, 1><<<nc, VDO_TILE_L, bc, chain_stream>>>(d, ns);
+      else k_tile_schur<true, 2><<<nc, VDO_TILE_L, bc, chain_stream>>>(d, ns);
+      ++n_launch;
+    }
+  }
   void lin_tracklets(BaDev& d, bool write) override {
+    if (d.tiled) { tile_lin(d, write, -1); return; }
     if (write) { LAUNCH(k_lin_static<true>, nblk(d.Tstat, 256), 256, d); LAUNCH(k_lin_tracklets<true>, nblk(d.T - d.Tstat, 128), 128, d); }
     else { LAUNCH(k_lin_static<false>, nblk(d.Tstat, 256), 256, d); LAUNCH(k_lin_tracklets<false>, nblk(d.T - d.Tstat, 128), 128, d); }
   }
-  void lin_vertex_obs(BaDev& d) override { auto k = k_vertex_sym<0, true>; LAUNCH(k, d.n_obs_chunks, 128, d); }
-  void lin_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<0, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
+  // tiled layout: the tile kernels of lin_tracklets(write) have already formed the vertex-side sums in the world frame;
+  // lin_vertex_obs turns them into H_pp / b_p, lin_vertex_ter has nothing left to do (same split for precond_* and schur_vertex_*)
+  void lin_vertex_obs(BaDev& d) override {
+    if (d.tiled) { LAUNCH(k_tile_finalize_lin, nblk(d.C, 128), 128, d); return; }
+    auto k = k_vertex_sym<0, true>; LAUNCH(k, d.n_obs_chunks, 128, d);
+  }
+  void lin_vertex_ter(BaDev& d) override { if (d.tiled) return; auto k = k_vertex_sym<0, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
   void lin_se3_edges(BaDev& d, bool write) override {
     if (write) LAUNCH(k_lin_se3_edges<true>, nblk(d.Ese, 64), 64, d); else LAUNCH(k_lin_se3_edges<false>, nblk(d.Ese, 64), 64, d);
   }
@@ -555,26 +589,43 @@ struct CudaBackend : BaBackend {
   }
   void factor_landmarks(BaDev& d, double lambda) override { LAUNCH(k_factor_landmarks, nblk(d.T, 128), 128, d, lambda); }
   void precond_begin(BaDev& d, double lambda) override { LAUNCH(k_precond_begin, nblk(d.C * 36, 128), 128, d, lambda); }
-  void precond_vertex_obs(BaDev& d) override { auto k = k_vertex_sym<1, true>; LAUNCH(k, d.n_obs_chunks, 128, d); }
-  void precond_vertex_ter(BaDev& d) override { auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
+  void precond_vertex_obs(BaDev& d) override {
+    if (d.tiled) {
+      launch_tiles(k_tile_precond<false>, tile_smem_bytes<PRE_ST>(), d, 0, d.n_tiles_stat);
+      launch_tiles(k_tile_precond<true>, tile_smem_bytes<PRE_CH>(), d, d.n_tiles_stat, d.n_tiles - d.n_tiles_stat);
+      LAUNCH(k_tile_finalize_precond, nblk(d.C, 128), 128, d);
+      return;
+    }
+    auto k = k_vertex_sym<1, true>; LAUNCH(k, d.n_obs_chunks, 128, d);
+  }
+  void precond_vertex_ter(BaDev& d) override { if (d.tiled) return; auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
   void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_paths * PCR_CL, 256, d, lambda); }
   void schur_landmarks(BaDev& d, int mode, const double* v) override {
+    if (d.tiled) { tile_schur(d, mode, -1, st); return; }
     const int g = nblk((d.T - d.Tstat) * 8, 128), gs = nblk(d.Tstat, 256);
     if (mode == 0) { LAUNCH(k_schur_static<0>, gs, 256, d, d.zl); LAUNCH(k_schur_chains8<0>, g, 128, d, v, d.zl); }
     else if (mode == 1) { LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); LAUNCH(k_schur_chains8<1>, g, 128, d, v, d.zl); }
     else { LAUNCH(k_schur_static<2>, gs, 256, d, d.xl); LAUNCH(k_schur_chains8<2>, g, 128, d, v, d.xl); }
   }
   void schur_landmarks_part(BaDev& d, int mode, const double* v, int part) override {
+    if (d.tiled) { tile_schur(d, 1, part, st); return; }
     const int g = nblk((d.T - d.Tstat) * 8, 128), gs = nblk(d.Tstat, 256);
     if (part == 0) LAUNCH(k_schur_static<1>, gs, 256, d, d.zl); else LAUNCH(k_schur_chains8<1>, g, 128, d, v, d.zl);
     (void)mode;
   }
   void lin_tracklets_part(BaDev& d, bool write, int part) override {
+    if (d.tiled) { tile_lin(d, true, part); return; }
     (void)write;
     if (part == 0) LAUNCH(k_lin_static<true>, nblk(d.Tstat, 256), 256, d); else LAUNCH(k_lin_tracklets<true>, nblk(d.T - d.Tstat, 128), 128, d);
   }
-  void schur_vertex_obs(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
-  void schur_vertex_ter(BaDev& d, double sign, double* out) override { LAUNCH(k_schur_vertex<false>, d.n_ter_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0); }
+  void schur_vertex_obs(BaDev& d, double sign, double* out) override {
+    if (d.tiled) { LAUNCH(k_tile_finalize_schur, nblk(d.C, 128), 128, d, sign, out, out == d.Ap ? 1 : 0); return; }
+    LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0);
+  }
+  void schur_vertex_ter(BaDev& d, double sign, double* out) override {
+    if (d.tiled) return;
+    LAUNCH(k_schur_vertex<false>, d.n_ter_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0);
+  }
   void set_scalars(BaDev& d, double lambda, double tol2) {
     if (lambda != cur_lambda || tol2 != cur_tol2 || d.scal != cur_scal) { LAUNCH(k_set_scalars, 1, 1, d, lambda, tol2); cur_lambda = lambda; cur_tol2 = tol2; cur_scal = d.scal; }
   }
@@ -608,6 +659,18 @@ struct CudaBackend : BaBackend {
       const int gch = nblk((d.T - d.Tstat) * 8, 128), gst = nblk(d.Tstat, 256);
       for (int b = 0; b < n; ++b) {
         LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, (const double*)d.p, d.Ap);
+        if (d.tiled) {
+          // fork: static tiles on st, chain tiles on st2 (independent landmark sets); both scatter into acc6 with atomics
+          CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
+          tile_schur(d, 1, -1, st2);
+          CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
+          LAUNCH(k_tile_finalize_schur, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1);
+          LAUNCH(k_pcg_dot, 148, 256, d);
+          LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
+          LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
+          LAUNCH(k_pcg_scalars, 1, 256, d);
+          continue;
+        }
         // fork: static landmarks on st, chains on st2 (independent landmark sets; the chain kernel is latency-bound)
         CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
         LAUNCH(k_schur_static<1>, gst, 256, d, d.zl);
@@ -652,6 +715,13 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { std::snprintf(err, errlen, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return nullptr; }
   if (prop.major != 10) { std::snprintf(err, errlen, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor); return nullptr; }
   if ((e = cudaSetDevice(device)) != cudaSuccess) { std::snprintf(err, errlen, "cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+  {
+    auto optin = [&](const void* f, size_t bytes) { if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); };
+    optin((const void*)k_tile_lin<false, true>, tile_smem_bytes<LIN_ST>()); optin((const void*)k_tile_lin<false, false>, tile_smem_bytes<LIN_ST>());
+    optin((const void*)k_tile_lin<true, true>, tile_smem_bytes<LIN_CH>()); optin((const void*)k_tile_lin<true, false>, tile_smem_bytes<LIN_CH>());
+    optin((const void*)k_tile_schur<false, 0>, tile_smem_bytes<SCH_ST>()); optin((const void*)k_tile_schur<false, 1>, tile_smem_bytes<SCH_ST>()); optin((const void*)k_tile_schur<false, 2>, tile_smem_bytes<SCH_ST>());
+    optin((const void*)k_tile_schur<true, 0>, tile_smem_bytes<SCH_CH>()); optin((const void*)k_tile_schur<true, 1>, tile_smem_bytes<SCH_CH>()); optin((const void*)k_tile_schur<true, 2>, tile_smem_bytes<SCH_CH>());
+  }
   CudaBackend* b = new CudaBackend;
   b->dev = device;
   if ((e = cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking)) != cudaSuccess) { std::snprintf(err, errlen, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete b; return nullptr; }

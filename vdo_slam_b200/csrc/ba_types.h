@@ -25,10 +25,24 @@
 #include <stddef.h>
 
 #define VDO_CHUNK 512
+// Tiled layout (default): the landmark side is cut into tiles of whole tracklets, at most VDO_TILE_L landmarks and
+// VDO_TILE_E EdgeSE3PointXYZ per tile.  One CTA owns one tile: landmark blocks are staged in shared memory, the
+// landmark-side sums are formed there, and the se3-vertex-side sums are formed by walking the tile's edges in
+// vertex-sorted order (ob_perm / tr_perm) in warp-sized segments of one vertex each -- one reduction + a handful of
+// atomics per segment.  Edges are therefore stored ONCE (landmark-major); the vertex-major copies of the chunked
+// layout do not exist in this mode.
+#define VDO_TILE_L 256
+#define VDO_TILE_E 1024
+#define VDO_SEG 32
 
 namespace vdo {
 
 struct Chunk { int v, begin, end, pad; };
+// tile: landmarks [k0,k1), EdgeSE3PointXYZ [e0,e1) (landmark-major), tracklets [t0,t1), vertex-sorted segments of the
+// pointxyz edges [os0,os1) and of the ternary edges [ts0,ts1)
+struct Tile { int k0, k1, e0, e1, t0, t1, os0, os1, ts0, ts1, pad0, pad1; };
+// segment: <= VDO_SEG consecutive entries of ob_perm (or tr_perm) starting at `begin`, all on se3 vertex v
+struct Seg { int v, begin, n, pad; };
 
 struct BaDev {
   int own = 1;     // 1 on the rank that accumulates the se3-se3 edges / se3 parts of scalar sums (rank 0), 0 elsewhere
@@ -56,6 +70,17 @@ struct BaDev {
   double *zl = 0, *xl = 0;                                    // 3P each
   double *vw = 0;   // 6C: per-vertex world-frame image [gamma, beta] of the vector the landmark pass multiplies (see body_vertex_transform)
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each
+  // ---- tiled layout ----
+  int tiled = 0, n_tiles_stat = 0, n_tiles = 0, n_osegs = 0, n_tsegs = 0;
+  Tile* tiles = 0; Seg* osegs = 0; Seg* tsegs = 0;
+  uint16_t* ob_perm = 0;   // Eobs: position in the tile's camera-sorted order -> tile-local edge index (e - e0)
+  uint16_t* tr_perm = 0;   // P: position (k0 + i) in the tile's motion-vertex-sorted order -> tile-local landmark index of p1
+  uint8_t* lm_lml = 0;     // Eobs: tile-local landmark index of each pointxyz edge
+  double* pt_Q = 0;        // 9 per chain landmark (index k - Tstat): Q_k = (R_{k-1} ... R_{kb})^T, rotates landmark k into the
+                           // frame in which its tracklet's H_ll is (scalar tridiagonal) (x) I3
+  double *accO = 0, *accT = 0;   // 16 per se3 vertex: world-frame sums of the pointxyz / ternary edges (see tile_acc16)
+  double* acc6 = 0;        // 6 per se3 vertex: world-frame Hpl*z sums of one Schur product
+  double* vh = 0;          // 6C: per-vertex world-frame image of v as seen by ternary edges (vw is the pointxyz one)
   double* scal = 0;  // device scalars, see SC_* below
   double *part_pap = 0, *part_rz = 0;   // per-CTA partial sums of p.Ap (<= 148) and r.z (n_paths * 8): summed in a FIXED order so that
                                         // every rank of a sharded solve computes bit-identical PCG scalars (and convergence flags)
