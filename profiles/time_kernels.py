@@ -16,6 +16,6 @@ G = capi.BatchGraph(ctx, g)
 r = G.optimize(max_iterations=a.iters, gain_threshold=0.0)
 out = {"workload": a.workload, "sizes": graph_sizes(g), "lm": {k: v for k, v in r.items() if k != "chi2"}, "ms": {}}
 for n in ["lin_tracklets", "chi2_tracklets", "lin_vertex_obs", "lin_vertex_ter", "lin_se3_edges", "linearize", "factor_landmarks", "precond",
-          "schur_landmarks", "schur_vertex_obs", "schur_vertex_ter", "hpp_mul", "pcg_dot", "pcg_step", "pcg_iterate8"]:
+          "schur_landmarks", "schur_static", "schur_chains", "lin_static", "lin_chains", "schur_vertex_obs", "schur_vertex_ter", "hpp_mul", "pcg_dot", "pcg_step", "pcg_iterate8"]:
     out["ms"][n] = G.time_kernel(n, a.reps)
 print(json.dumps(out))

@@ -39,13 +39,15 @@ struct EmulBackend : BaBackend {
 
 
   // ---- tiled layout: the phases of ba_tile_kernels.cuh as serial loops (segments summed lane by lane) ----
-  struct SmBuf {
-    std::vector<double> P, OM, EW, Z, IS, F, OMT, Y, QS, TC, E2; std::vector<int> HH; std::vector<uint8_t> LML;
+  struct SmBuf {   // stashes only; the views alias the global arrays (tile_views_global)
+    std::vector<double> OMs, EW, Z, Y, IS, TC, E2, OMTs;
     TileSm sm;
-    SmBuf() : P(3 * VDO_TILE_L), OM(VDO_TILE_E), EW(3 * VDO_TILE_E), Z(3 * VDO_TILE_L), IS(VDO_TILE_L), F(VDO_TILE_L), OMT(VDO_TILE_L), Y(3 * VDO_TILE_L),
-              QS(9 * VDO_TILE_L), TC(4 * VDO_TILE_L), E2(3 * VDO_TILE_L), HH(VDO_TILE_L), LML(VDO_TILE_E) {
-      sm.P = P.data(); sm.OM = OM.data(); sm.EW = EW.data(); sm.Z = Z.data(); sm.IS = IS.data(); sm.F = F.data(); sm.OMT = OMT.data(); sm.Y = Y.data();
-      sm.QS = QS.data(); sm.TC = TC.data(); sm.E2 = E2.data(); sm.HH = HH.data(); sm.LML = LML.data();
+    SmBuf() : OMs(VDO_TILE_E), EW(3 * VDO_TILE_E), Z(3 * VDO_TILE_L), Y(3 * VDO_TILE_L), IS(VDO_TILE_L), TC(4 * VDO_TILE_L), E2(3 * VDO_TILE_L), OMTs(VDO_TILE_L) {}
+    TileSm& bind(const BaDev& d, const Tile& tl, bool precond, bool lin) {
+      tile_views_global(d, tl, precond, sm);
+      sm.EW = EW.data(); sm.Z = Z.data(); sm.Y = Y.data(); sm.IS = IS.data(); sm.TC = TC.data(); sm.E2 = E2.data();
+      if (lin) { sm.OM = OMs.data(); sm.OMT = OMTs.data(); }
+      return sm;
     }
   } sb;
   template <int N, typename F> static void seg_loop(const BaDev& d, const Seg* segs, int s0, int s1, double* dst_base, int stride, int nused, F item) {
@@ -59,15 +61,14 @@ struct EmulBackend : BaBackend {
     }
   }
   void tile_lin(BaDev& d, bool write) {
-    TileSm& sm = sb.sm;
     double chi = 0;
     for (int ti = 0; ti < d.n_tiles; ++ti) {
       const Tile tl = d.tiles[ti];
       const bool chains = ti >= d.n_tiles_stat;
       const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
-      for (int j = 0; j < nl; ++j) tile_stage_p(d, tl, j, sm);
+      TileSm& sm = sb.bind(d, tl, false, true);
       if (!chains) {
-        for (int i = 0; i < ne; ++i) chi += write ? tile_lin_edge<true>(d, tl, i, d.lm_lml[tl.e0 + i], sm) : tile_lin_edge<false>(d, tl, i, d.lm_lml[tl.e0 + i], sm);
+        for (int i = 0; i < ne; ++i) chi += write ? tile_lin_edge<true>(d, tl, i, sm.LML[i], sm) : tile_lin_edge<false>(d, tl, i, sm.LML[i], sm);
         if (write) for (int j = 0; j < nl; ++j) {
           double dsum = 0, b[3] = {0, 0, 0};
           tile_lin_landmark_obs(d, tl, j, sm, dsum, b);
@@ -78,7 +79,7 @@ struct EmulBackend : BaBackend {
         std::vector<double> ds(nl, 0.0), bb(3 * (size_t)nl, 0.0);
         for (int j = 0; j < nl; ++j) {
           const int k = tl.k0 + j;
-          for (int i = d.lm_obs_begin[k] - tl.e0; i < d.lm_obs_begin[k + 1] - tl.e0; ++i) chi += write ? tile_lin_edge<true>(d, tl, i, j, sm) : tile_lin_edge<false>(d, tl, i, j, sm);
+          for (int i = sm.LB[j] - tl.e0; i < sm.LB[j + 1] - tl.e0; ++i) chi += write ? tile_lin_edge<true>(d, tl, i, j, sm) : tile_lin_edge<false>(d, tl, i, j, sm);
           if (write) tile_lin_landmark_obs(d, tl, j, sm, ds[j], &bb[3 * j]);
           chi += write ? tile_lin_ternary<true>(d, tl, j, sm, ds[j], &bb[3 * j]) : tile_lin_ternary<false>(d, tl, j, sm, ds[j], &bb[3 * j]);
         }
@@ -99,32 +100,25 @@ struct EmulBackend : BaBackend {
     d.scal[SC_CHI2] += chi;
   }
   void tile_precond(BaDev& d) {
-    TileSm& sm = sb.sm;
     for (int ti = 0; ti < d.n_tiles; ++ti) {
       const Tile tl = d.tiles[ti];
       const bool chains = ti >= d.n_tiles_stat;
-      for (int j = 0; j < tl.k1 - tl.k0; ++j) {
-        tile_stage_p(d, tl, j, sm);
-        sm.IS[j] = d.pt_g[tl.k0 + j];
-        if (chains) { sm.F[j] = d.tk_gamma[tl.k0 + j]; sm.OMT[j] = d.tk_omega[tl.k0 + j]; }
-      }
+      TileSm& sm = sb.bind(d, tl, true, false);
       seg_loop<16>(d, d.osegs, tl.os0, tl.os1, d.accO, 16, 10, [&](const Seg& sg, int l, const double* t, double* acc) { tile_pre_oseg_item(d, tl, sg, l, sm, t, acc); });
       if (chains) seg_loop<16>(d, d.tsegs, tl.ts0, tl.ts1, d.accT, 16, 10, [&](const Seg& sg, int l, const double* t, double* acc) { tile_pre_tseg_item(d, tl, sg, l, sm, t, acc); });
     }
     for (int v = 0; v < d.C; ++v) tile_finalize_precond(d, v);
   }
   template <int MODE> void tile_schur(BaDev& d) {
-    TileSm& sm = sb.sm;
     for (int ti = 0; ti < d.n_tiles; ++ti) {
       const Tile tl = d.tiles[ti];
       const bool chains = ti >= d.n_tiles_stat;
       const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
+      TileSm& sm = sb.bind(d, tl, false, false);
       if (!chains) {
-        for (int j = 0; j < nl; ++j) tile_stage_p(d, tl, j, sm);
-        for (int i = 0; i < ne; ++i) tile_schur_edge<MODE>(d, tl, i, d.lm_lml[tl.e0 + i], sm);
+        for (int i = 0; i < ne; ++i) tile_schur_edge<MODE>(d, tl, i, sm);
         for (int j = 0; j < nl; ++j) tile_schur_static_landmark<MODE>(d, tl, j, sm);
       } else {
-        for (int j = 0; j < nl; ++j) tile_schur_chain_stage(d, tl, j, sm);
         for (int j = 0; j < nl; ++j) tile_schur_chain_u<MODE>(d, tl, j, sm);
         for (int j = 0; j < nl; ++j) tile_schur_chain_y<MODE>(d, tl, j, sm);
         for (int jt = 0; jt < tl.t1 - tl.t0; ++jt) tile_schur_chain_walk(d, tl, jt, sm);

@@ -28,7 +28,7 @@ class BaGraph {
   const std::string& error() const { return err_; }
 
  private:
-  template <typename T> T* dalloc(size_t n) { bytes_ += n * sizeof(T); T* p = (T*)be_->alloc(n ? n * sizeof(T) : sizeof(T)); owned_.push_back(p); return p; }
+  template <typename T> T* dalloc(size_t n) { bytes_ += n * sizeof(T); T* p = (T*)be_->alloc(n * sizeof(T) + 16); owned_.push_back(p); return p; }   // +16: the tile kernels' bulk copies round ranges up to 16 B
   template <typename T> T* upload(const std::vector<T>& v) { T* p = dalloc<T>(v.size()); if (!v.empty()) be_->h2d(p, v.data(), v.size() * sizeof(T)); return p; }
   void linearize();                 // buildSystem
   double robust_chi2();             // computeActiveErrors + activeRobustChi2

@@ -374,12 +374,44 @@ __device__ __forceinline__ double pcr_solve_path(const BaDev& d, cg::cluster_gro
   const size_t N6 = 6 * (size_t)d.C, N36 = 36 * (size_t)d.C;
   const double* src = r;
   int cur = 0;
+  // The operator rows of level l + 1 do not depend on the vector, so they are fetched into registers BEFORE the cluster
+  // barrier that closes level l: after the barrier only the (L2-resident) vector entries b[v - s], b[v + s] are on the critical
+  // path.  KP items per thread are prefetched (paths up to KP * 2048 / 6 vertices); longer paths read the rest directly.
+  constexpr int KP = 3;
+  double pa[KP][6], pg[KP][6];
+  auto fetch = [&](int l) {
+    const int s = 1 << l;
+    const double* A = d.pcr_A + l * N36; const double* G = d.pcr_G + l * N36;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int w = tid + k * nth;
+      const int v = pb + w / 6, row = w % 6;
+      const bool ia = w < n_items && v - s >= pb, ig = w < n_items && v + s < pe;
+      const double* a = A + 36 * (size_t)v + 6 * row; const double* g = G + 36 * (size_t)v + 6 * row;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { pa[k][i] = ia ? a[i] : 0.0; pg[k][i] = ig ? g[i] : 0.0; }
+    }
+  };
+  if (nl > 0) fetch(0);
   for (int l = 0; l < nl; ++l) {
     double* dst = d.pcr_b + cur * N6;
-    for (int w = tid; w < n_items; w += nth) {
-      const int v = pb + w / 6, row = w % 6;
-      dst[6 * (size_t)v + row] = pcr_apply_row(v, row, pb, pe, 1 << l, d.pcr_A + l * N36, d.pcr_G + l * N36, src);
+    const int s = 1 << l;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int w = tid + k * nth;
+      if (w < n_items) {
+        const int v = pb + w / 6, row = w % 6;
+        double o = src[6 * (size_t)v + row];
+        if (v - s >= pb) { const double* x = src + 6 * (size_t)(v - s); o += pa[k][0] * x[0] + pa[k][1] * x[1] + pa[k][2] * x[2] + pa[k][3] * x[3] + pa[k][4] * x[4] + pa[k][5] * x[5]; }
+        if (v + s < pe) { const double* x = src + 6 * (size_t)(v + s); o += pg[k][0] * x[0] + pg[k][1] * x[1] + pg[k][2] * x[2] + pg[k][3] * x[3] + pg[k][4] * x[4] + pg[k][5] * x[5]; }
+        dst[6 * (size_t)v + row] = o;
+      }
     }
+    for (int w = tid + KP * nth; w < n_items; w += nth) {
+      const int v = pb + w / 6, row = w % 6;
+      dst[6 * (size_t)v + row] = pcr_apply_row(v, row, pb, pe, s, d.pcr_A + l * N36, d.pcr_G + l * N36, src);
+    }
+    if (l + 1 < nl) fetch(l + 1);
     cl.sync();
     src = dst; cur = 1 - cur;
   }
@@ -548,12 +580,12 @@ struct CudaBackend : BaBackend {
   }
   void tile_lin(BaDev& d, bool write, int part) {   // part: 0 static tiles, 1 chain tiles, -1 both
     const int ns = d.n_tiles_stat, nc = d.n_tiles - d.n_tiles_stat;
-    if (part != 1) { if (write) launch_tiles(k_tile_lin<false, true>, tile_smem_bytes<LIN_ST>(), d, 0, ns); else launch_tiles(k_tile_lin<false, false>, tile_smem_bytes<LIN_ST>(), d, 0, ns); }
-    if (part != 0) { if (write) launch_tiles(k_tile_lin<true, true>, tile_smem_bytes<LIN_CH>(), d, ns, nc); else launch_tiles(k_tile_lin<true, false>, tile_smem_bytes<LIN_CH>(), d, ns, nc); }
+    if (part != 1) { if (write) launch_tiles(k_tile_lin<false, true>, SMEM_LIN_ST, d, 0, ns); else launch_tiles(k_tile_lin<false, false>, SMEM_LIN_ST, d, 0, ns); }
+    if (part != 0) { if (write) launch_tiles(k_tile_lin<true, true>, SMEM_LIN_CH, d, ns, nc); else launch_tiles(k_tile_lin<true, false>, SMEM_LIN_CH, d, ns, nc); }
   }
   void tile_schur(BaDev& d, int mode, int part, cudaStream_t chain_stream) {
     const int ns = d.n_tiles_stat, nc = d.n_tiles - d.n_tiles_stat;
-    const size_t bs = tile_smem_bytes<SCH_ST>(), bc = tile_smem_bytes<SCH_CH>();
+    const size_t bs = SMEM_SCH_ST, bc = SMEM_SCH_CH;
     if (part != 1 && ns > 0) {
       if (mode == 0) k_tile_schur<false, 0><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
       else if (mode == 1) k_tile_schur<false, 1><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
@@ -591,8 +623,8 @@ struct CudaBackend : BaBackend {
   void precond_begin(BaDev& d, double lambda) override { LAUNCH(k_precond_begin, nblk(d.C * 36, 128), 128, d, lambda); }
   void precond_vertex_obs(BaDev& d) override {
     if (d.tiled) {
-      launch_tiles(k_tile_precond<false>, tile_smem_bytes<PRE_ST>(), d, 0, d.n_tiles_stat);
-      launch_tiles(k_tile_precond<true>, tile_smem_bytes<PRE_CH>(), d, d.n_tiles_stat, d.n_tiles - d.n_tiles_stat);
+      launch_tiles(k_tile_precond<false>, SMEM_PRE_ST, d, 0, d.n_tiles_stat);
+      launch_tiles(k_tile_precond<true>, SMEM_PRE_CH, d, d.n_tiles_stat, d.n_tiles - d.n_tiles_stat);
       LAUNCH(k_tile_finalize_precond, nblk(d.C, 128), 128, d);
       return;
     }
@@ -717,10 +749,11 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) { std::snprintf(err, errlen, "cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
   {
     auto optin = [&](const void* f, size_t bytes) { if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); };
-    optin((const void*)k_tile_lin<false, true>, tile_smem_bytes<LIN_ST>()); optin((const void*)k_tile_lin<false, false>, tile_smem_bytes<LIN_ST>());
-    optin((const void*)k_tile_lin<true, true>, tile_smem_bytes<LIN_CH>()); optin((const void*)k_tile_lin<true, false>, tile_smem_bytes<LIN_CH>());
-    optin((const void*)k_tile_schur<false, 0>, tile_smem_bytes<SCH_ST>()); optin((const void*)k_tile_schur<false, 1>, tile_smem_bytes<SCH_ST>()); optin((const void*)k_tile_schur<false, 2>, tile_smem_bytes<SCH_ST>());
-    optin((const void*)k_tile_schur<true, 0>, tile_smem_bytes<SCH_CH>()); optin((const void*)k_tile_schur<true, 1>, tile_smem_bytes<SCH_CH>()); optin((const void*)k_tile_schur<true, 2>, tile_smem_bytes<SCH_CH>());
+    optin((const void*)k_tile_lin<false, true>, SMEM_LIN_ST); optin((const void*)k_tile_lin<false, false>, SMEM_LIN_ST);
+    optin((const void*)k_tile_lin<true, true>, SMEM_LIN_CH); optin((const void*)k_tile_lin<true, false>, SMEM_LIN_CH);
+    optin((const void*)k_tile_schur<false, 0>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 1>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 2>, SMEM_SCH_ST);
+    optin((const void*)k_tile_precond<false>, SMEM_PRE_ST); optin((const void*)k_tile_precond<true>, SMEM_PRE_CH);
+    optin((const void*)k_tile_schur<true, 0>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 1>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 2>, SMEM_SCH_CH);
   }
   CudaBackend* b = new CudaBackend;
   b->dev = device;

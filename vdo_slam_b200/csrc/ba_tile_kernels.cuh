@@ -1,10 +1,15 @@
 // ba_tile_kernels.cuh -- sm_100a kernels of the tiled batch-LM layout (included by ba_kernels.cu; bodies in ba_tiles.cuh).
 //
-// One CTA (VDO_TILE_L = 256 threads) per tile.  Phases:
-//   k_tile_lin     stage landmark blocks in smem -> per edge: residual, Huber weight (written once to HBM), e_w stash ->
-//                  per landmark: H_ll / b_l -> per vertex-sorted segment: 16 world-frame sums, warp-transpose reduction, atomics
-//   k_tile_precond stage -> per segment: 10 sums of the diagonal blocks of Hpl Hll^-1 Hlp
-//   k_tile_schur   stage -> per edge / landmark: Hlp v -> tracklet solve in smem (chains: scalar tridiagonal in the Q-rotated
+// One CTA (VDO_TILE_L = 256 threads) per tile.  Every contiguous range of a global array the tile needs (landmark block,
+// pivots, edge weights / cameras / tile-local landmark ids, the vertex-sorted permutation, the segment descriptors, Q_k) is
+// brought into shared memory by ONE elected thread with 1-D bulk async copies (cp.async.bulk.shared::cluster.global, the
+// TMA engine) completing on an mbarrier, so that all of the tile's HBM traffic is in flight at once and the phases below
+// run out of shared memory; only the per-vertex gathers (poses / world-frame vectors, L2-resident) and the edge
+// measurements of the linearisation are ordinary loads.  Phases:
+//   k_tile_lin     per edge: residual, Huber weight (written once to HBM), e_w stash -> per landmark: H_ll / b_l ->
+//                  per vertex-sorted segment: 16 world-frame sums, warp-transpose reduction, atomics
+//   k_tile_precond per segment: 10 sums of the diagonal blocks of Hpl Hll^-1 Hlp
+//   k_tile_schur   per edge / landmark: Hlp v -> tracklet solve in smem (chains: scalar tridiagonal in the Q-rotated
 //                  frame) -> per segment: Hpl z, 6 sums.  z never leaves the SM for modes 0 / 1.
 // Bytes per launch (algorithmic, every array touched once): see bench.py kernel_bytes and DESIGN.md section 5.
 #pragma once
@@ -12,44 +17,55 @@
 
 namespace vdo {
 
-enum { SM_P = 1, SM_OM = 2, SM_EW = 4, SM_Z = 8, SM_IS = 16, SM_F = 32, SM_OMT = 64, SM_Y = 128, SM_QS = 256, SM_TC = 512, SM_E2 = 1024,
-       SM_HH = 2048, SM_LML = 4096 };
+constexpr int TILE_OSEG_CAP = 128;   // segment descriptors staged per tile; tiles with more read them from global memory
+constexpr int TILE_TSEG_CAP = 64;
 
-template <int FL>
-__host__ __device__ constexpr size_t tile_smem_bytes() {
-  size_t n = 0;
-  n += (FL & SM_P) ? 3 * VDO_TILE_L * 8 : 0;
-  n += (FL & SM_OM) ? VDO_TILE_E * 8 : 0;
-  n += (FL & SM_EW) ? 3 * VDO_TILE_E * 8 : 0;
-  n += (FL & SM_Z) ? 3 * VDO_TILE_L * 8 : 0;
-  n += (FL & SM_IS) ? VDO_TILE_L * 8 : 0;
-  n += (FL & SM_F) ? VDO_TILE_L * 8 : 0;
-  n += (FL & SM_OMT) ? VDO_TILE_L * 8 : 0;
-  n += (FL & SM_Y) ? 3 * VDO_TILE_L * 8 : 0;
-  n += (FL & SM_QS) ? 9 * VDO_TILE_L * 8 : 0;
-  n += (FL & SM_TC) ? 4 * VDO_TILE_L * 8 : 0;
-  n += (FL & SM_E2) ? 3 * VDO_TILE_L * 8 : 0;
-  n += (FL & SM_HH) ? VDO_TILE_L * 4 : 0;
-  n += (FL & SM_LML) ? VDO_TILE_E : 0;
-  return n;
+// ---- mbarrier + 1-D bulk copy (PTX ISA: mbarrier.*, cp.async.bulk) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-template <int FL>
-__device__ __forceinline__ void tile_carve(TileSm& sm, double* b) {
-  if (FL & SM_P) { sm.P = b; b += 3 * VDO_TILE_L; }
-  if (FL & SM_OM) { sm.OM = b; b += VDO_TILE_E; }
-  if (FL & SM_EW) { sm.EW = b; b += 3 * VDO_TILE_E; }
-  if (FL & SM_Z) { sm.Z = b; b += 3 * VDO_TILE_L; }
-  if (FL & SM_IS) { sm.IS = b; b += VDO_TILE_L; }
-  if (FL & SM_F) { sm.F = b; b += VDO_TILE_L; }
-  if (FL & SM_OMT) { sm.OMT = b; b += VDO_TILE_L; }
-  if (FL & SM_Y) { sm.Y = b; b += 3 * VDO_TILE_L; }
-  if (FL & SM_QS) { sm.QS = b; b += 9 * VDO_TILE_L; }
-  if (FL & SM_TC) { sm.TC = b; b += 4 * VDO_TILE_L; }
-  if (FL & SM_E2) { sm.E2 = b; b += 3 * VDO_TILE_L; }
-  int* ib = reinterpret_cast<int*>(b);
-  if (FL & SM_HH) { sm.HH = ib; ib += VDO_TILE_L; }
-  if (FL & SM_LML) { sm.LML = reinterpret_cast<uint8_t*>(ib); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n"   /* suspend-time hint: waiters sleep instead of spinning */
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Carves the CTA's dynamic shared memory.  view(): a staged copy of g[first, first + count) -- the copy starts at the
+// enclosing 16-byte boundary and is rounded up to 16 bytes (bulk copies need both; every device array is allocated with 16
+// spare bytes at its end), the returned pointer addresses element `first`.  Only the elected thread issues copies.
+struct TileStager {
+  char* cur; uint64_t* bar; bool issue; uint32_t tx = 0;
+  __device__ TileStager(void* base, uint64_t* b, bool is) : cur((char*)base), bar(b), issue(is) {}
+  template <typename T> __device__ __forceinline__ T* view(const T* g, size_t first, int count, int cap) {
+    const uintptr_t a = (uintptr_t)(g + first);
+    const uint32_t delta = (uint32_t)(a & 15), bytes = (delta + (uint32_t)count * (uint32_t)sizeof(T) + 15u) & ~15u;
+    char* dst = cur;
+    cur += view_bytes<T>(cap);
+    if (issue && count > 0) { bulk_g2s(dst, (const void*)(a - delta), bytes, bar); tx += bytes; }
+    return (T*)(dst + delta);
+  }
+  template <typename T> __device__ __forceinline__ T* stash(int cap) { T* p = (T*)cur; cur += (cap * sizeof(T) + 15) & ~(size_t)15; return p; }
+  template <typename T> __host__ __device__ static constexpr size_t view_bytes(int cap) { return ((cap * sizeof(T) + 15) & ~(size_t)15) + 16; }
+  __device__ __forceinline__ void commit() { if (issue) mbar_arrive_expect_tx(bar, tx); }
+};
+template <typename T> constexpr size_t vb(int cap) { return TileStager::view_bytes<T>(cap); }
+constexpr size_t sb(size_t n) { return (n + 15) & ~(size_t)15; }
 
 // Reduce N (power of two, <= 32) per-lane values over the warp with N/2 + N/4 + ... + 1 (+ log2(32/N)) shuffles instead of
 // 5 N: at each level a lane keeps one half of its values and hands the other half to its partner.  On return v[0] is the
@@ -81,23 +97,92 @@ __device__ __forceinline__ void seg_flush(double (&acc)[N], int lane, double* ds
   if ((lane & (32 / N - 1)) == 0 && idx < NUSED && tot != 0.0) atomicAdd(dst + idx, tot);
 }
 
+// segment views: descriptors staged when they fit, vertex translations prefetched into smem by the first threads
+struct SegViews { const Seg* seg; double* st; int n; bool staged; };
+__device__ __forceinline__ SegViews seg_views(TileStager& sg, const Seg* g, int s0, int s1, int cap) {
+  SegViews v;
+  v.n = s1 - s0; v.staged = v.n <= cap;
+  const Seg* staged = sg.view<Seg>(g, (size_t)s0, v.staged ? v.n : 0, cap);
+  v.seg = v.staged ? staged : g + s0;
+  v.st = sg.stash<double>(3 * cap);
+  return v;
+}
+__device__ __forceinline__ void seg_prefetch_t(const BaDev& d, const SegViews& v, int tid) {
+  if (v.staged)
+    for (int s = tid; s < v.n; s += VDO_TILE_L) {
+      const double* T = d.se3 + 12 * (size_t)v.seg[s].v;
+      v.st[3 * s] = T[9]; v.st[3 * s + 1] = T[10]; v.st[3 * s + 2] = T[11];
+    }
+}
+// runs item(sg, lane, t, acc) over the tile's segments, one warp per segment, and flushes the N sums to dst + stride * vertex
+template <int N, int NUSED, typename F>
+__device__ __forceinline__ void seg_loop(const BaDev& d, const SegViews& v, double* dst, int stride, int tid, F item) {
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int s = warp; s < v.n; s += VDO_TILE_L / 32) {
+    const Seg sg = v.seg[s];
+    double t[3];
+    if (v.staged) { t[0] = v.st[3 * s]; t[1] = v.st[3 * s + 1]; t[2] = v.st[3 * s + 2]; }
+    else { const double* T = d.se3 + 12 * (size_t)sg.v; t[0] = T[9]; t[1] = T[10]; t[2] = T[11]; }
+    double acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.0;
+    if (lane < sg.n) item(sg, lane, t, acc);
+    if (lane + 32 < sg.n) item(sg, lane + 32, t, acc);
+    seg_flush<N, NUSED>(acc, lane, dst + (size_t)stride * sg.v);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------------------------------
-constexpr int LIN_ST = SM_P | SM_OM | SM_EW | SM_LML;
-constexpr int LIN_CH = LIN_ST | SM_TC | SM_E2 | SM_OMT | SM_HH;
+// shared-memory budgets (must mirror the carve order inside the kernels)
+constexpr size_t SEGS_O = vb<Seg>(TILE_OSEG_CAP) + sb(3 * TILE_OSEG_CAP * 8), SEGS_T = vb<Seg>(TILE_TSEG_CAP) + sb(3 * TILE_TSEG_CAP * 8);
+constexpr size_t SMEM_LIN_ST = vb<double>(3 * VDO_TILE_L) + vb<int>(VDO_TILE_L + 1) + vb<int>(VDO_TILE_E) + vb<uint8_t>(VDO_TILE_E) + vb<uint16_t>(VDO_TILE_E) + SEGS_O +
+                               sb(VDO_TILE_E * 8) + sb(3 * VDO_TILE_E * 8);
+constexpr size_t SMEM_LIN_CH = SMEM_LIN_ST + vb<int>(VDO_TILE_L) + vb<uint8_t>(VDO_TILE_L) + vb<uint16_t>(VDO_TILE_L) + SEGS_T + sb(VDO_TILE_L * 8) + sb(4 * VDO_TILE_L * 8) +
+                               sb(3 * VDO_TILE_L * 8);
+constexpr size_t SMEM_PRE_ST = vb<double>(3 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<double>(VDO_TILE_E) + vb<uint8_t>(VDO_TILE_E) + vb<uint16_t>(VDO_TILE_E) + SEGS_O;
+constexpr size_t SMEM_PRE_CH = SMEM_PRE_ST + vb<double>(VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<uint16_t>(VDO_TILE_L) + SEGS_T;
+constexpr size_t SMEM_SCH_ST = vb<double>(3 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L + 1) + vb<double>(VDO_TILE_E) + vb<int>(VDO_TILE_E) + vb<uint8_t>(VDO_TILE_E) +
+                               vb<uint16_t>(VDO_TILE_E) + SEGS_O + sb(3 * VDO_TILE_E * 8) + sb(3 * VDO_TILE_L * 8);
+constexpr size_t SMEM_SCH_CH = vb<double>(3 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L + 1) + vb<double>(VDO_TILE_E) + vb<int>(VDO_TILE_E) + vb<uint8_t>(VDO_TILE_E) +
+                               vb<uint16_t>(VDO_TILE_E) + SEGS_O + vb<double>(9 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L) + vb<uint16_t>(VDO_TILE_L) + SEGS_T +
+                               sb(3 * VDO_TILE_L * 8) + sb(3 * VDO_TILE_L * 8) + sb(VDO_TILE_L * 8);
 
 template <bool CHAINS, bool WRITE>
 __global__ void __launch_bounds__(VDO_TILE_L) k_tile_lin(BaDev d, int tile0) {
-  extern __shared__ double tile_sh[];
+  extern __shared__ __align__(16) unsigned char tile_sh[];
   __shared__ double red[32];
-  TileSm sm;
-  tile_carve<CHAINS ? LIN_CH : LIN_ST>(sm, tile_sh);
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
   const Tile tl = d.tiles[tile0 + blockIdx.x];
-  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0, tid = threadIdx.x;
-  if (tid < nl) tile_stage_p(d, tl, tid, sm);
+  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
+  if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
+  TileStager sg(tile_sh, &bar, tid == 0);
+  TileSm sm;
+  sm.P = sg.view<double>(d.pt, 3 * (size_t)tl.k0, 3 * nl, 3 * VDO_TILE_L);
+  sm.LB = sg.view<int>(d.lm_obs_begin, (size_t)tl.k0, nl + 1, VDO_TILE_L + 1);
+  sm.CAM = sg.view<int>(d.lm_cam, (size_t)tl.e0, ne, VDO_TILE_E);
+  sm.LML = sg.view<uint8_t>(d.lm_lml, (size_t)tl.e0, (!CHAINS || WRITE) ? ne : 0, VDO_TILE_E);
+  sm.PERM = sg.view<uint16_t>(d.ob_perm, (size_t)tl.e0, WRITE ? ne : 0, VDO_TILE_E);
+  SegViews os = seg_views(sg, d.osegs, tl.os0, WRITE ? tl.os1 : tl.os0, TILE_OSEG_CAP);
+  sm.OM = sg.stash<double>(VDO_TILE_E);
+  sm.EW = sg.stash<double>(3 * VDO_TILE_E);
+  SegViews ts{nullptr, nullptr, 0, true};
+  if (CHAINS) {
+    sm.HH = sg.view<int>(d.tk_h, (size_t)tl.k0, nl, VDO_TILE_L);
+    sm.TCLS = sg.view<uint8_t>(d.tk_cls, (size_t)tl.k0, nl, VDO_TILE_L);
+    sm.TPERM = sg.view<uint16_t>(d.tr_perm, (size_t)tl.k0, WRITE ? nl : 0, VDO_TILE_L);
+    ts = seg_views(sg, d.tsegs, tl.ts0, WRITE ? tl.ts1 : tl.ts0, TILE_TSEG_CAP);
+    sm.OMT = sg.stash<double>(VDO_TILE_L);
+    sm.TC = sg.stash<double>(4 * VDO_TILE_L);
+    sm.E2 = sg.stash<double>(3 * VDO_TILE_L);
+  }
+  sg.commit();
+  mbar_wait(&bar, 0);
+  if (WRITE) { seg_prefetch_t(d, os, tid); if (CHAINS) seg_prefetch_t(d, ts, tid); }
   double chi = 0.0;
   if (!CHAINS) {
-    for (int i = tid; i < ne; i += VDO_TILE_L) chi += tile_lin_edge<WRITE>(d, tl, i, d.lm_lml[(size_t)tl.e0 + i], sm);
+    for (int i = tid; i < ne; i += VDO_TILE_L) chi += tile_lin_edge<WRITE>(d, tl, i, sm.LML[i], sm);
     if (WRITE) {
       __syncthreads();
       if (tid < nl) {
@@ -110,8 +195,7 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_lin(BaDev d, int tile0) {
   } else {
     double dsum = 0.0, b[3] = {0, 0, 0};
     if (tid < nl) {
-      const int k = tl.k0 + tid;
-      const int ib = d.lm_obs_begin[k] - tl.e0, ie = d.lm_obs_begin[k + 1] - tl.e0;
+      const int ib = sm.LB[tid] - tl.e0, ie = sm.LB[tid + 1] - tl.e0;
       for (int i = ib; i < ie; ++i) chi += tile_lin_edge<WRITE>(d, tl, i, tid, sm);
       if (WRITE) tile_lin_landmark_obs(d, tl, tid, sm, dsum, b);
       chi += tile_lin_ternary<WRITE>(d, tl, tid, sm, dsum, b);
@@ -127,93 +211,89 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_lin(BaDev d, int tile0) {
     }
   }
   if (WRITE) {
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int s = tl.os0 + warp; s < tl.os1; s += VDO_TILE_L / 32) {
-      const Seg sg = d.osegs[s];
-      const double* T = d.se3 + 12 * (size_t)sg.v;
-      const double t[3] = {T[9], T[10], T[11]};
-      double acc[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-      if (lane < sg.n) tile_lin_oseg_item(d, tl, sg, lane, sm, t, acc);
-      seg_flush<16, 16>(acc, lane, d.accO + 16 * (size_t)sg.v);
-    }
-    if (CHAINS) {
-      for (int s = tl.ts0 + warp; s < tl.ts1; s += VDO_TILE_L / 32) {
-        const Seg sg = d.tsegs[s];
-        const double* T = d.se3 + 12 * (size_t)sg.v;
-        const double t[3] = {T[9], T[10], T[11]};
-        double acc[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        if (lane < sg.n) tile_lin_tseg_item(d, tl, sg, lane, sm, t, acc);
-        seg_flush<16, 16>(acc, lane, d.accT + 16 * (size_t)sg.v);
-      }
-    }
+    seg_loop<16, 16>(d, os, d.accO, 16, tid, [&](const Seg& s, int l, const double* t, double* acc) { tile_lin_oseg_item(d, tl, s, l, sm, t, acc); });
+    if (CHAINS) seg_loop<16, 16>(d, ts, d.accT, 16, tid, [&](const Seg& s, int l, const double* t, double* acc) { tile_lin_tseg_item(d, tl, s, l, sm, t, acc); });
   }
   chi = block_sum(chi, red);
   if (tid == 0 && chi != 0.0) atomicAdd(d.scal + SC_CHI2, chi);
 }
 
-constexpr int PRE_ST = SM_P | SM_IS;
-constexpr int PRE_CH = SM_P | SM_IS | SM_F | SM_OMT;
 template <bool CHAINS>
 __global__ void __launch_bounds__(VDO_TILE_L) k_tile_precond(BaDev d, int tile0) {
-  extern __shared__ double tile_sh[];
-  TileSm sm;
-  tile_carve<CHAINS ? PRE_CH : PRE_ST>(sm, tile_sh);
+  extern __shared__ __align__(16) unsigned char tile_sh[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
   const Tile tl = d.tiles[tile0 + blockIdx.x];
-  const int nl = tl.k1 - tl.k0, tid = threadIdx.x;
-  if (tid < nl) {
-    tile_stage_p(d, tl, tid, sm);
-    sm.IS[tid] = d.pt_g[tl.k0 + tid];
-    if (CHAINS) { sm.F[tid] = d.tk_gamma[tl.k0 + tid]; sm.OMT[tid] = d.tk_omega[tl.k0 + tid]; }
-  }
+  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
+  if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int s = tl.os0 + warp; s < tl.os1; s += VDO_TILE_L / 32) {
-    const Seg sg = d.osegs[s];
-    const double* T = d.se3 + 12 * (size_t)sg.v;
-    const double t[3] = {T[9], T[10], T[11]};
-    double acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-    if (lane < sg.n) tile_pre_oseg_item(d, tl, sg, lane, sm, t, acc);
-    seg_flush<16, 10>(acc, lane, d.accO + 16 * (size_t)sg.v);
-  }
+  TileStager sg(tile_sh, &bar, tid == 0);
+  TileSm sm;
+  sm.P = sg.view<double>(d.pt, 3 * (size_t)tl.k0, 3 * nl, 3 * VDO_TILE_L);
+  sm.S = sg.view<double>(d.pt_g, (size_t)tl.k0, nl, VDO_TILE_L);
+  sm.OM = sg.view<double>(d.lm_omega, (size_t)tl.e0, ne, VDO_TILE_E);
+  sm.LML = sg.view<uint8_t>(d.lm_lml, (size_t)tl.e0, ne, VDO_TILE_E);
+  sm.PERM = sg.view<uint16_t>(d.ob_perm, (size_t)tl.e0, ne, VDO_TILE_E);
+  SegViews os = seg_views(sg, d.osegs, tl.os0, tl.os1, TILE_OSEG_CAP);
+  SegViews ts{nullptr, nullptr, 0, true};
   if (CHAINS) {
-    for (int s = tl.ts0 + warp; s < tl.ts1; s += VDO_TILE_L / 32) {
-      const Seg sg = d.tsegs[s];
-      const double* T = d.se3 + 12 * (size_t)sg.v;
-      const double t[3] = {T[9], T[10], T[11]};
-      double acc[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-      if (lane < sg.n) tile_pre_tseg_item(d, tl, sg, lane, sm, t, acc);
-      seg_flush<16, 10>(acc, lane, d.accT + 16 * (size_t)sg.v);
-    }
+    sm.GAM = sg.view<double>(d.tk_gamma, (size_t)tl.k0, nl, VDO_TILE_L);
+    sm.OMT = sg.view<double>(d.tk_omega, (size_t)tl.k0, nl, VDO_TILE_L);
+    sm.TPERM = sg.view<uint16_t>(d.tr_perm, (size_t)tl.k0, nl, VDO_TILE_L);
+    ts = seg_views(sg, d.tsegs, tl.ts0, tl.ts1, TILE_TSEG_CAP);
   }
+  sg.commit();
+  mbar_wait(&bar, 0);
+  seg_prefetch_t(d, os, tid);
+  if (CHAINS) seg_prefetch_t(d, ts, tid);
+  __syncthreads();
+  seg_loop<16, 10>(d, os, d.accO, 16, tid, [&](const Seg& s, int l, const double* t, double* acc) { tile_pre_oseg_item(d, tl, s, l, sm, t, acc); });
+  if (CHAINS) seg_loop<16, 10>(d, ts, d.accT, 16, tid, [&](const Seg& s, int l, const double* t, double* acc) { tile_pre_tseg_item(d, tl, s, l, sm, t, acc); });
 }
 
-constexpr int SCH_ST = SM_P | SM_OM | SM_EW | SM_Z | SM_LML;
-constexpr int SCH_CH = SM_P | SM_OM | SM_Z | SM_IS | SM_F | SM_OMT | SM_Y | SM_QS | SM_HH | SM_LML;
 template <bool CHAINS, int MODE>
 __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur(BaDev d, int tile0) {
-  extern __shared__ double tile_sh[];
+  extern __shared__ __align__(16) unsigned char tile_sh[];
+  __shared__ __align__(8) uint64_t bar;
   if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
-  TileSm sm;
-  tile_carve<CHAINS ? SCH_CH : SCH_ST>(sm, tile_sh);
+  const int tid = threadIdx.x;
   const Tile tl = d.tiles[tile0 + blockIdx.x];
-  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0, tid = threadIdx.x;
+  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
+  const bool scatter = MODE != 2;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  TileStager sg(tile_sh, &bar, tid == 0);
+  TileSm sm;
+  sm.P = sg.view<double>(d.pt, 3 * (size_t)tl.k0, 3 * nl, 3 * VDO_TILE_L);
+  sm.S = sg.view<double>(d.pt_s, (size_t)tl.k0, nl, VDO_TILE_L);
+  sm.LB = sg.view<int>(d.lm_obs_begin, (size_t)tl.k0, nl + 1, VDO_TILE_L + 1);
+  sm.OM = sg.view<double>(d.lm_omega, (size_t)tl.e0, ne, VDO_TILE_E);
+  sm.CAM = sg.view<int>(d.lm_cam, (size_t)tl.e0, MODE != 0 ? ne : 0, VDO_TILE_E);
+  sm.LML = sg.view<uint8_t>(d.lm_lml, (size_t)tl.e0, ne, VDO_TILE_E);
+  sm.PERM = sg.view<uint16_t>(d.ob_perm, (size_t)tl.e0, scatter ? ne : 0, VDO_TILE_E);
+  SegViews os = seg_views(sg, d.osegs, tl.os0, scatter ? tl.os1 : tl.os0, TILE_OSEG_CAP);
+  SegViews ts{nullptr, nullptr, 0, true};
   if (!CHAINS) {
-    if (tid < nl) tile_stage_p(d, tl, tid, sm);
-    __syncthreads();
-    for (int i = tid; i < ne; i += VDO_TILE_L) tile_schur_edge<MODE>(d, tl, i, d.lm_lml[(size_t)tl.e0 + i], sm);
+    sm.EW = sg.stash<double>(3 * VDO_TILE_E);
+    sm.Z = sg.stash<double>(3 * VDO_TILE_L);
+  } else {
+    sm.QS = sg.view<double>(d.pt_Q, 9 * (size_t)(tl.k0 - d.Tstat), 9 * nl, 9 * VDO_TILE_L);
+    sm.OMT = sg.view<double>(d.tk_omega, (size_t)tl.k0, nl, VDO_TILE_L);
+    sm.HH = sg.view<int>(d.tk_h, (size_t)tl.k0, nl, VDO_TILE_L);
+    sm.TPERM = sg.view<uint16_t>(d.tr_perm, (size_t)tl.k0, scatter ? nl : 0, VDO_TILE_L);
+    ts = seg_views(sg, d.tsegs, tl.ts0, scatter ? tl.ts1 : tl.ts0, TILE_TSEG_CAP);
+    sm.Z = sg.stash<double>(3 * VDO_TILE_L);
+    sm.Y = sg.stash<double>(3 * VDO_TILE_L);
+    sm.IS = sg.stash<double>(VDO_TILE_L);
+  }
+  sg.commit();
+  mbar_wait(&bar, 0);
+  if (scatter) { seg_prefetch_t(d, os, tid); if (CHAINS) seg_prefetch_t(d, ts, tid); }
+  if (!CHAINS) {
+    for (int i = tid; i < ne; i += VDO_TILE_L) tile_schur_edge<MODE>(d, tl, i, sm);
     __syncthreads();
     if (tid < nl) tile_schur_static_landmark<MODE>(d, tl, tid, sm);
   } else {
-    if (tid < nl) tile_schur_chain_stage(d, tl, tid, sm);
-    __syncthreads();
     if (tid < nl) tile_schur_chain_u<MODE>(d, tl, tid, sm);
     __syncthreads();
     if (tid < nl) tile_schur_chain_y<MODE>(d, tl, tid, sm);
@@ -222,31 +302,10 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur(BaDev d, int tile0) {
     __syncthreads();
     if (tid < nl) tile_schur_chain_z<MODE>(d, tl, tid, sm);
   }
-  if (MODE == 2) return;
+  if (!scatter) return;
   __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int s = tl.os0 + warp; s < tl.os1; s += VDO_TILE_L / 32) {
-    const Seg sg = d.osegs[s];
-    const double* T = d.se3 + 12 * (size_t)sg.v;
-    const double t[3] = {T[9], T[10], T[11]};
-    double acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-    if (lane < sg.n) tile_schur_oseg_item(d, tl, sg, lane, sm, t, acc);
-    seg_flush<8, 6>(acc, lane, d.acc6 + 6 * (size_t)sg.v);
-  }
-  if (CHAINS) {
-    for (int s = tl.ts0 + warp; s < tl.ts1; s += VDO_TILE_L / 32) {
-      const Seg sg = d.tsegs[s];
-      const double* T = d.se3 + 12 * (size_t)sg.v;
-      const double t[3] = {T[9], T[10], T[11]};
-      double acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-      if (lane < sg.n) tile_schur_tseg_item(d, tl, sg, lane, sm, t, acc);
-      seg_flush<8, 6>(acc, lane, d.acc6 + 6 * (size_t)sg.v);
-    }
-  }
+  seg_loop<8, 6>(d, os, d.acc6, 6, tid, [&](const Seg& s, int l, const double* t, double* acc) { tile_schur_oseg_item(d, tl, s, l, sm, t, acc); });
+  if (CHAINS) seg_loop<8, 6>(d, ts, d.acc6, 6, tid, [&](const Seg& s, int l, const double* t, double* acc) { tile_schur_tseg_item(d, tl, s, l, sm, t, acc); });
 }
 
 __global__ void __launch_bounds__(128) k_tile_finalize_lin(BaDev d) {

@@ -20,21 +20,44 @@
 
 namespace vdo {
 
+// Tile-local views.  "view" members alias a contiguous range of a global array, element 0 = the tile's first landmark /
+// edge / segment: in the CUDA kernels they point at shared-memory copies brought in by bulk async copies (TMA) at kernel
+// start, in the emulation straight at the global arrays.  "stash" members are per-tile scratch written by the phases.
 struct TileSm {
-  double* P = 0;     // 3*TL  landmark positions
-  double* OM = 0;    // TE    pointxyz omega per tile-local edge
-  double* EW = 0;    // 3*TE  lin: e_w per edge ; schur (static): per-edge term of Hlp v
-  double* Z = 0;     // 3*TL  schur: world-frame z per landmark (chains: g-hat first)
-  double* IS = 0;    // TL    1 / pivot
-  double* F = 0;     // TL    omega_k / pivot_k
-  double* OMT = 0;   // TL    ternary omega of edge (k, k+1)
-  double* Y = 0;     // 3*TL  chains: y-hat / z-hat
-  double* QS = 0;    // 9*TL  chains: Q_k
-  double* TC = 0;    // 4*TL  lin chains: (omega, omega e') handed to landmark k+1
-  double* E2 = 0;    // 3*TL  lin chains: e' of edge (k, k+1)
-  int* HH = 0;       // TL    motion vertex of edge (k, k+1) or -1
-  uint8_t* LML = 0;  // TE    tile-local landmark of each tile-local edge
+  // views
+  double* P = 0;       // pt            3 / landmark
+  double* S = 0;       // pt_s (Schur) or pt_g (preconditioner)   1 / landmark
+  double* GAM = 0;     // tk_gamma      1 / landmark (preconditioner, chains)
+  double* QS = 0;      // pt_Q          9 / landmark (chains)
+  int* HH = 0;         // tk_h          motion vertex of edge (k, k+1) or -1
+  uint8_t* TCLS = 0;   // tk_cls
+  int* LB = 0;         // lm_obs_begin  nl + 1 entries, global edge indices
+  int* CAM = 0;        // lm_cam        1 / edge
+  uint8_t* LML = 0;    // lm_lml        1 / edge
+  uint16_t* PERM = 0;  // ob_perm       1 / edge
+  uint16_t* TPERM = 0; // tr_perm       1 / landmark
+  const Seg* OSEG = 0; const Seg* TSEG = 0;   // the tile's segments
+  double* OST = 0; double* TST = 0;           // translation of each segment's vertex (3 / segment), or null
+  // views in the Schur / preconditioner kernels, stashes in the linearisation
+  double* OM = 0;      // lm_omega      1 / edge
+  double* OMT = 0;     // tk_omega      1 / landmark
+  // stashes
+  double* EW = 0;      // 3 / edge      lin: e_w ; schur (static): the edge's term of Hlp v
+  double* Z = 0;       // 3 / landmark  schur: world-frame z (chains: g-hat first)
+  double* Y = 0;       // 3 / landmark  chains: y-hat / z-hat
+  double* IS = 0;      // 1 / landmark  1 / pivot
+  double* TC = 0;      // 4 / landmark  lin chains: (omega, omega e') handed to landmark k+1
+  double* E2 = 0;      // 3 / landmark  lin chains: e' of edge (k, k+1)
 };
+// emulation / reference wiring of the views straight onto the global arrays
+inline void tile_views_global(const BaDev& d, const Tile& tl, bool precond, TileSm& sm) {
+  sm.P = d.pt + 3 * (size_t)tl.k0; sm.S = (precond ? d.pt_g : d.pt_s) + tl.k0; sm.GAM = d.tk_gamma + tl.k0;
+  sm.QS = d.pt_Q ? d.pt_Q + 9 * ((ptrdiff_t)tl.k0 - d.Tstat) : nullptr;
+  sm.HH = d.tk_h + tl.k0; sm.TCLS = d.tk_cls + tl.k0; sm.LB = d.lm_obs_begin + tl.k0;
+  sm.CAM = d.lm_cam + tl.e0; sm.LML = d.lm_lml + tl.e0; sm.PERM = d.ob_perm + tl.e0; sm.TPERM = d.tr_perm + tl.k0;
+  sm.OSEG = d.osegs + tl.os0; sm.TSEG = d.tsegs + tl.ts0; sm.OST = nullptr; sm.TST = nullptr;
+  sm.OM = d.lm_omega + tl.e0; sm.OMT = d.tk_omega + tl.k0;
+}
 
 VDO_HD void acc16_add(double* a, double om, const double* w, const double* e) {
   a[0] += om;
@@ -54,15 +77,11 @@ VDO_HD void acc10_add(double* a, double om, const double* w) {
 // ---------------------------------------------------------------------------------------------------------------
 // linearisation
 // ---------------------------------------------------------------------------------------------------------------
-VDO_HD void tile_stage_p(const BaDev& d, const Tile& tl, int j, TileSm& sm) {
-  const double* p = d.pt + 3 * (size_t)(tl.k0 + j);
-  sm.P[3 * j] = p[0]; sm.P[3 * j + 1] = p[1]; sm.P[3 * j + 2] = p[2];
-}
 // one EdgeSE3PointXYZ (tile-local index i): robust chi2; with WRITE the robustified weight (global + stash) and e_w
 template <bool WRITE>
 VDO_HD double tile_lin_edge(const BaDev& d, const Tile& tl, int i, int lml, TileSm& sm) {
   const size_t e = (size_t)tl.e0 + i;
-  const double* T = d.se3 + 12 * (size_t)d.lm_cam[e];
+  const double* T = d.se3 + 12 * (size_t)sm.CAM[i];
   const double* z = d.lm_z + 3 * e;
   const double w[3] = {sm.P[3 * lml] - T[9], sm.P[3 * lml + 1] - T[10], sm.P[3 * lml + 2] - T[11]};
   double Rz[3]; rot_apply(T, z, Rz);
@@ -73,14 +92,13 @@ VDO_HD double tile_lin_edge(const BaDev& d, const Tile& tl, int i, int lml, Tile
   if (WRITE) {
     const double om = wi * hw;
     d.lm_omega[e] = om;
-    sm.OM[i] = om; sm.EW[3 * i] = ew[0]; sm.EW[3 * i + 1] = ew[1]; sm.EW[3 * i + 2] = ew[2]; sm.LML[i] = (uint8_t)lml;
+    sm.OM[i] = om; sm.EW[3 * i] = ew[0]; sm.EW[3 * i + 1] = ew[1]; sm.EW[3 * i + 2] = ew[2];
   }
   return rho;
 }
 // landmark sums of the pointxyz edges of landmark j (tile-local): hll part and b_l part
 VDO_HD void tile_lin_landmark_obs(const BaDev& d, const Tile& tl, int j, const TileSm& sm, double& dsum, double* b) {
-  const int k = tl.k0 + j;
-  const int ib = d.lm_obs_begin[k] - tl.e0, ie = d.lm_obs_begin[k + 1] - tl.e0;
+  const int ib = sm.LB[j] - tl.e0, ie = sm.LB[j + 1] - tl.e0;
   for (int i = ib; i < ie; ++i) {
     const double om = sm.OM[i];
     dsum += om;
@@ -92,16 +110,16 @@ VDO_HD void tile_lin_landmark_obs(const BaDev& d, const Tile& tl, int j, const T
 template <bool WRITE>
 VDO_HD double tile_lin_ternary(const BaDev& d, const Tile& tl, int j, TileSm& sm, double& dsum, double* b) {
   const int k = tl.k0 + j;
-  const int h = d.tk_h[k];
+  const int h = sm.HH[j];
   if (h < 0) {
-    if (WRITE) { d.tk_omega[k] = 0.0; sm.TC[4 * j] = sm.TC[4 * j + 1] = sm.TC[4 * j + 2] = sm.TC[4 * j + 3] = 0.0; sm.OMT[j] = 0.0; sm.HH[j] = -1; }
+    if (WRITE) { d.tk_omega[k] = 0.0; sm.TC[4 * j] = sm.TC[4 * j + 1] = sm.TC[4 * j + 2] = sm.TC[4 * j + 3] = 0.0; sm.OMT[j] = 0.0; }
     return 0.0;
   }
   const double* H = d.se3 + 12 * (size_t)h;
   const double w[3] = {sm.P[3 * j + 3] - H[9], sm.P[3 * j + 4] - H[10], sm.P[3 * j + 5] - H[11]};
   double q[3]; rot_t_apply(H, w, q);
   const double err[3] = {sm.P[3 * j] - q[0], sm.P[3 * j + 1] - q[1], sm.P[3 * j + 2] - q[2]};
-  const int cls = d.tk_cls[k];
+  const int cls = sm.TCLS[j];
   const double wi = d.ter_cls_w[cls];
   double rho, hw; huber(wi * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]), d.ter_cls_d[cls], rho, hw);
   if (WRITE) {
@@ -112,7 +130,7 @@ VDO_HD double tile_lin_ternary(const BaDev& d, const Tile& tl, int j, TileSm& sm
     double Re[3]; rot_apply(H, err, Re);
     sm.TC[4 * j] = om; sm.TC[4 * j + 1] = om * Re[0]; sm.TC[4 * j + 2] = om * Re[1]; sm.TC[4 * j + 3] = om * Re[2];
     sm.E2[3 * j] = Re[0]; sm.E2[3 * j + 1] = Re[1]; sm.E2[3 * j + 2] = Re[2];
-    sm.OMT[j] = om; sm.HH[j] = h;
+    sm.OMT[j] = om;
   }
   return rho;
 }
@@ -139,30 +157,29 @@ VDO_HD void tile_chain_Q(const BaDev& d, const Tile& tl, int jt) {
 }
 // one lane of a pointxyz segment: world-frame sums for vertex sg.v   (linearisation: 16 sums)
 VDO_HD void tile_lin_oseg_item(const BaDev& d, const Tile& tl, const Seg& sg, int l, const TileSm& sm, const double* t, double* acc) {
-  const int i = d.ob_perm[sg.begin + l];
+  const int i = sm.PERM[sg.begin - tl.e0 + l];
   const int j = sm.LML[i];
   const double w[3] = {sm.P[3 * j] - t[0], sm.P[3 * j + 1] - t[1], sm.P[3 * j + 2] - t[2]};
   acc16_add(acc, sm.OM[i], w, sm.EW + 3 * i);
 }
 VDO_HD void tile_lin_tseg_item(const BaDev& d, const Tile& tl, const Seg& sg, int l, const TileSm& sm, const double* t, double* acc) {
-  const int j = d.tr_perm[sg.begin + l];
+  const int j = sm.TPERM[sg.begin - tl.k0 + l];
   const double w[3] = {sm.P[3 * j + 3] - t[0], sm.P[3 * j + 4] - t[1], sm.P[3 * j + 5] - t[2]};
   acc16_add(acc, sm.OMT[j], w, sm.E2 + 3 * j);
 }
 // preconditioner: diagonal blocks of Hpl Hll^-1 Hlp seen from the vertex (10 sums, weight omega^2 * (Hll^-1 scalar))
 VDO_HD void tile_pre_oseg_item(const BaDev& d, const Tile& tl, const Seg& sg, int l, const TileSm& sm, const double* t, double* acc) {
-  const int i = d.ob_perm[sg.begin + l];
-  const size_t e = (size_t)tl.e0 + i;
-  const int j = d.lm_lml[e];
-  const double om = d.lm_omega[e];
+  const int i = sm.PERM[sg.begin - tl.e0 + l];
+  const int j = sm.LML[i];
+  const double om = sm.OM[i];
   const double w[3] = {sm.P[3 * j] - t[0], sm.P[3 * j + 1] - t[1], sm.P[3 * j + 2] - t[2]};
-  acc10_add(acc, om * om * sm.IS[j], w);           // IS staged with pt_g
+  acc10_add(acc, om * om * sm.S[j], w);            // S views pt_g here
 }
 VDO_HD void tile_pre_tseg_item(const BaDev& d, const Tile& tl, const Seg& sg, int l, const TileSm& sm, const double* t, double* acc) {
-  const int j = d.tr_perm[sg.begin + l];
+  const int j = sm.TPERM[sg.begin - tl.k0 + l];
   const double om = sm.OMT[j];
   const double w[3] = {sm.P[3 * j + 3] - t[0], sm.P[3 * j + 4] - t[1], sm.P[3 * j + 5] - t[2]};
-  acc10_add(acc, om * om * sm.F[j], w);            // F staged with tk_gamma
+  acc10_add(acc, om * om * sm.GAM[j], w);
 }
 
 // per-vertex conversion of the world-frame sums into the vertex' local frame.
@@ -257,14 +274,13 @@ VDO_HD void tile_finalize_schur(const BaDev& d, int v, double sign, double* __re
 // Schur products.  mode 0: z = Hll^-1 bl ; mode 1: z = Hll^-1 (Hlp v) ; mode 2: xl = Hll^-1 (bl - Hlp v) (written to d.xl).
 // Modes 0 and 1 do not write z: the tile scatters Hpl z into acc6 straight from shared memory.
 // ---------------------------------------------------------------------------------------------------------------
-// static tiles, per edge: stash omega / landmark and (mode != 0) the edge's term of Hlp v
+// static tiles, per edge (mode != 0): the edge's term of Hlp v
 template <int MODE>
-VDO_HD void tile_schur_edge(const BaDev& d, const Tile& tl, int i, int lml, TileSm& sm) {
-  const size_t e = (size_t)tl.e0 + i;
-  const double om = d.lm_omega[e];
-  sm.OM[i] = om; sm.LML[i] = (uint8_t)lml;
+VDO_HD void tile_schur_edge(const BaDev& d, const Tile& tl, int i, TileSm& sm) {
   if (MODE != 0) {
-    const double* w = d.vw + 6 * (size_t)d.lm_cam[e];
+    const int lml = sm.LML[i];
+    const double om = sm.OM[i];
+    const double* w = d.vw + 6 * (size_t)sm.CAM[i];
     double pxb[3]; cross3(sm.P + 3 * lml, w + 3, pxb);
     sm.EW[3 * i] = om * (w[0] + 2 * pxb[0]); sm.EW[3 * i + 1] = om * (w[1] + 2 * pxb[1]); sm.EW[3 * i + 2] = om * (w[2] + 2 * pxb[2]);
   }
@@ -274,7 +290,7 @@ VDO_HD void tile_schur_static_landmark(const BaDev& d, const Tile& tl, int j, Ti
   const int k = tl.k0 + j;
   double u[3] = {0, 0, 0};
   if (MODE != 0) {
-    const int ib = d.lm_obs_begin[k] - tl.e0, ie = d.lm_obs_begin[k + 1] - tl.e0;
+    const int ib = sm.LB[j] - tl.e0, ie = sm.LB[j + 1] - tl.e0;
     for (int i = ib; i < ie; ++i) { u[0] += sm.EW[3 * i]; u[1] += sm.EW[3 * i + 1]; u[2] += sm.EW[3 * i + 2]; }
   }
   double y[3];
@@ -283,13 +299,13 @@ VDO_HD void tile_schur_static_landmark(const BaDev& d, const Tile& tl, int j, Ti
     const double* b = d.bl + 3 * (size_t)k;
     y[0] = b[0] - u[0]; y[1] = b[1] - u[1]; y[2] = b[2] - u[2];
   }
-  const double is = 1.0 / d.pt_s[k];
+  const double is = 1.0 / sm.S[j];
   if (MODE == 2) { double* o = d.xl + 3 * (size_t)k; o[0] = y[0] * is; o[1] = y[1] * is; o[2] = y[2] * is; }
   else { sm.Z[3 * j] = y[0] * is; sm.Z[3 * j + 1] = y[1] * is; sm.Z[3 * j + 2] = y[2] * is; }
 }
 // one lane of a pointxyz segment: acc6 += -omega [z ; 2 w x z]
 VDO_HD void tile_schur_oseg_item(const BaDev& d, const Tile& tl, const Seg& sg, int l, const TileSm& sm, const double* t, double* acc) {
-  const int i = d.ob_perm[sg.begin + l];
+  const int i = sm.PERM[sg.begin - tl.e0 + l];
   const int j = sm.LML[i];
   const double om = sm.OM[i];
   const double* z = sm.Z + 3 * j;
@@ -298,36 +314,22 @@ VDO_HD void tile_schur_oseg_item(const BaDev& d, const Tile& tl, const Seg& sg, 
   acc[0] -= om * z[0]; acc[1] -= om * z[1]; acc[2] -= om * z[2];
   acc[3] -= 2 * om * c[0]; acc[4] -= 2 * om * c[1]; acc[5] -= 2 * om * c[2];
 }
-// chains, phase 0 per landmark: stage position, Q, pivots, ternary omega / vertex
-VDO_HD void tile_schur_chain_stage(const BaDev& d, const Tile& tl, int j, TileSm& sm) {
-  const int k = tl.k0 + j;
-  tile_stage_p(d, tl, j, sm);
-  const double* Q = d.pt_Q + 9 * (size_t)(k - d.Tstat);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) sm.QS[9 * j + i] = Q[i];
-  const double is = 1.0 / d.pt_s[k], om = d.tk_omega[k];
-  sm.IS[j] = is; sm.F[j] = om * is; sm.OMT[j] = om; sm.HH[j] = d.tk_h[k];
-}
-// chains, phase 1 per landmark: u-hat without the outgoing ternary term; g-hat of the incoming edge into sm.Z
+// chains, phase 1 per landmark: 1 / pivot; u-hat without the outgoing ternary term; g-hat of the incoming edge into sm.Z
 template <int MODE>
 VDO_HD void tile_schur_chain_u(const BaDev& d, const Tile& tl, int j, TileSm& sm) {
-  const int k = tl.k0 + j;
   const double* p = sm.P + 3 * j;
   const double* Q = sm.QS + 9 * j;
-  double u[3] = {0, 0, 0};
-  const int ib = d.lm_obs_begin[k] - tl.e0, ie = d.lm_obs_begin[k + 1] - tl.e0;
-  for (int i = ib; i < ie; ++i) {
-    const size_t e = (size_t)tl.e0 + i;
-    const double om = d.lm_omega[e];
-    sm.OM[i] = om; sm.LML[i] = (uint8_t)j;
-    if (MODE != 0) {
-      const double* w = d.vw + 6 * (size_t)d.lm_cam[e];
+  sm.IS[j] = 1.0 / sm.S[j];
+  double uh[3] = {0, 0, 0}, gh[3] = {0, 0, 0};
+  if (MODE != 0) {
+    double u[3] = {0, 0, 0};
+    const int ib = sm.LB[j] - tl.e0, ie = sm.LB[j + 1] - tl.e0;
+    for (int i = ib; i < ie; ++i) {
+      const double om = sm.OM[i];
+      const double* w = d.vw + 6 * (size_t)sm.CAM[i];
       double pxb[3]; cross3(p, w + 3, pxb);
       u[0] += om * (w[0] + 2 * pxb[0]); u[1] += om * (w[1] + 2 * pxb[1]); u[2] += om * (w[2] + 2 * pxb[2]);
     }
-  }
-  double uh[3] = {0, 0, 0}, gh[3] = {0, 0, 0};
-  if (MODE != 0) {
     rot_apply(Q, u, uh);
     const int hp = j > 0 ? sm.HH[j - 1] : -1;
     if (hp >= 0) {
@@ -361,16 +363,30 @@ VDO_HD void tile_schur_chain_y(const BaDev& d, const Tile& tl, int j, TileSm& sm
 // chains, phase 3 per tracklet: scalar forward / backward substitution in the rotated frame (three right-hand sides)
 VDO_HD void tile_schur_chain_walk(const BaDev& d, const Tile& tl, int jt, TileSm& sm) {
   const int jb = d.tk_begin[tl.t0 + jt] - tl.k0, je = d.tk_begin[tl.t0 + jt + 1] - tl.k0;
+  // forward: y_j = y_j + f_{j-1} y_{j-1}, f = omega / pivot.  The operands of step j + 1 are fetched before step j's FMAs so
+  // that the recurrence costs one dependent FMA per step, not a shared-memory round trip.
   double y0 = sm.Y[3 * jb], y1 = sm.Y[3 * jb + 1], y2 = sm.Y[3 * jb + 2];
+  double f = sm.OMT[jb] * sm.IS[jb];
+  double n0 = 0, n1 = 0, n2 = 0;
+  if (jb + 1 < je) { n0 = sm.Y[3 * jb + 3]; n1 = sm.Y[3 * jb + 4]; n2 = sm.Y[3 * jb + 5]; }
   for (int j = jb + 1; j < je; ++j) {
-    const double f = sm.F[j - 1];
-    y0 = sm.Y[3 * j] + f * y0; y1 = sm.Y[3 * j + 1] + f * y1; y2 = sm.Y[3 * j + 2] + f * y2;
+    const double c0 = n0, c1 = n1, c2 = n2, cf = f;
+    f = sm.OMT[j] * sm.IS[j];
+    if (j + 1 < je) { n0 = sm.Y[3 * j + 3]; n1 = sm.Y[3 * j + 4]; n2 = sm.Y[3 * j + 5]; }
+    y0 = c0 + cf * y0; y1 = c1 + cf * y1; y2 = c2 + cf * y2;
     sm.Y[3 * j] = y0; sm.Y[3 * j + 1] = y1; sm.Y[3 * j + 2] = y2;
   }
+  // backward: z_j = y_j / s_j + (omega_j / s_j) z_{j+1}
   double z0 = 0, z1 = 0, z2 = 0;
+  double is = sm.IS[je - 1];
+  double a0 = y0 * is, a1 = y1 * is, a2 = y2 * is, c = 0.0;   // last landmark: no successor (omega = 0)
   for (int j = je - 1; j >= jb; --j) {
-    const double om = (j < je - 1) ? sm.OMT[j] : 0.0, is = sm.IS[j];
-    z0 = (sm.Y[3 * j] + om * z0) * is; z1 = (sm.Y[3 * j + 1] + om * z1) * is; z2 = (sm.Y[3 * j + 2] + om * z2) * is;
+    const double b0 = a0, b1 = a1, b2 = a2, bc = c;
+    if (j > jb) {
+      is = sm.IS[j - 1];
+      a0 = sm.Y[3 * j - 3] * is; a1 = sm.Y[3 * j - 2] * is; a2 = sm.Y[3 * j - 1] * is; c = sm.OMT[j - 1] * is;
+    }
+    z0 = b0 + bc * z0; z1 = b1 + bc * z1; z2 = b2 + bc * z2;
     sm.Y[3 * j] = z0; sm.Y[3 * j + 1] = z1; sm.Y[3 * j + 2] = z2;
   }
 }
@@ -383,7 +399,7 @@ VDO_HD void tile_schur_chain_z(const BaDev& d, const Tile& tl, int j, TileSm& sm
 }
 // one lane of a ternary segment: a' = R_H z_k - z_{k+1} = Q_{k+1}^T (zh_k - zh_{k+1});  acc6 += omega [a' ; w' x a']
 VDO_HD void tile_schur_tseg_item(const BaDev& d, const Tile& tl, const Seg& sg, int l, const TileSm& sm, const double* t, double* acc) {
-  const int j = d.tr_perm[sg.begin + l];
+  const int j = sm.TPERM[sg.begin - tl.k0 + l];
   const double dz[3] = {sm.Y[3 * j] - sm.Y[3 * j + 3], sm.Y[3 * j + 1] - sm.Y[3 * j + 4], sm.Y[3 * j + 2] - sm.Y[3 * j + 5]};
   double a[3]; rot_t_apply(sm.QS + 9 * (j + 1), dz, a);
   const double w[3] = {sm.P[3 * j + 3] - t[0], sm.P[3 * j + 4] - t[1], sm.P[3 * j + 5] - t[2]};

@@ -32,8 +32,8 @@
 // atomics per segment.  Edges are therefore stored ONCE (landmark-major); the vertex-major copies of the chunked
 // layout do not exist in this mode.
 #define VDO_TILE_L 256
-#define VDO_TILE_E 1024
-#define VDO_SEG 32
+#define VDO_TILE_E 768
+#define VDO_SEG 64
 
 namespace vdo {
 
@@ -41,7 +41,7 @@ struct Chunk { int v, begin, end, pad; };
 // tile: landmarks [k0,k1), EdgeSE3PointXYZ [e0,e1) (landmark-major), tracklets [t0,t1), vertex-sorted segments of the
 // pointxyz edges [os0,os1) and of the ternary edges [ts0,ts1)
 struct Tile { int k0, k1, e0, e1, t0, t1, os0, os1, ts0, ts1, pad0, pad1; };
-// segment: <= VDO_SEG consecutive entries of ob_perm (or tr_perm) starting at `begin`, all on se3 vertex v
+// segment: <= VDO_SEG consecutive entries of ob_perm (or tr_perm) starting at `begin`, all on se3 vertex v (one warp, two entries per lane)
 struct Seg { int v, begin, n, pad; };
 
 struct BaDev {
