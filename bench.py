@@ -76,30 +76,42 @@ def graph_h2d_bytes(g) -> int:
 
 
 def kernel_bytes(g) -> dict:
-    """Compulsory HBM bytes per launch of each hot kernel in THIS implementation's formulation (DESIGN.md section
-    "Kernels"): every input byte that must be read once + every output byte written once.  Gathers that re-read the
-    se3 state / per-vertex vectors (<= 1.3 MB, L2 resident) are not counted, landmark gathers (p, zl) are."""
+    """Compulsory HBM bytes per launch of each hot kernel of the TILED layout: every array a tile
+    stages or writes, counted once.  Per-vertex gathers (poses, world-frame vectors: <= 1.3 MB, L2 resident) and the segment
+    descriptors (16 B per <= 64 edges) are not counted."""
     P = len(g["pt"])
     dyn = np.zeros(P, bool)
     if len(g["ter_pph"]):
         dyn[g["ter_pph"][:, 0]] = True; dyn[g["ter_pph"][:, 1]] = True
     Pd = int(dyn.sum()); Ps = P - Pd
     Epd = int(dyn[g["obs_cp"][:, 1]].sum()); Eps = len(g["obs_cp"]) - Epd
-    Ep, Et = len(g["obs_cp"]), len(g["ter_pph"])
+    C = len(g["se3"])
     return {
-        "lin_static": 37 * Eps + 68 * Ps,          # edge: cam 4 + z 24 + cls 1 + omega' 8 ; landmark: p 24 + begin 4 + hll 8 + bl 24 + omega 8
-        "lin_chains": 37 * Epd + 73 * Pd,          # + motion index 4 + class 1 per landmark
-        "lin_vertex_obs": 61 * Ep,                 # pt 4 + z 24 + cls 1 + landmark gather 24 + omega' 8
-        "lin_vertex_ter": 61 * Et,                 # p1 4 + cls 1 + two landmark gathers 48 + omega' 8
-        "schur_static": 12 * Eps + 60 * Ps,        # edge: cam 4 + omega 8 ; landmark: p 24 + begin 4 + pivot 8 + out 24
-        "schur_chains": 12 * Epd + 72 * Pd,        # + motion index 4 + omega 8
-        "schur_vertex_obs": 60 * Ep,               # pt 4 + omega 8 + landmark 24 + zl 24
-        "schur_vertex_ter": 84 * Et,               # p1 4 + omega 8 + p2 24 + zl 48
+        # edge: cam 4 + z 24 + cls 1 + tile-local landmark 1 + permutation 2 + omega' (written) 8 ; landmark: p 24 + begin 4 + tk_omega 8 + hll 8 + bl 24
+        "lin_static": 40 * Eps + 68 * Ps,
+        # landmark additionally: motion index 4 + class 1 + permutation 2 + Q_k (written) 72
+        "lin_chains": 40 * Epd + 147 * Pd,
+        # per vertex: two 16-sum accumulators read + cleared, pose, H_pp block + b_p read-modify-write
+        "lin_finalize": (2 * 16 * 8 * 2 + 96 + 2 * 336) * C,
+        # edge: omega' 8 + cam 4 + tile-local landmark 1 + permutation 2 ; landmark: p 24 + pivot 8 + begin 4
+        "schur_static": 15 * Eps + 36 * Ps,
+        # landmark additionally: Q_k 72 + tk_omega 8 + motion index 4 + permutation 2
+        "schur_chains": 15 * Epd + 122 * Pd,
+        "schur_finalize": (6 * 8 * 2 + 96 + 2 * 48) * C,
     }
+
+
+def trace(msg):
+    """VDO_BENCH_TRACE=1: stage markers on stderr (with a faulthandler stack dump if a stage stalls), for diagnosing multi-rank runs."""
+    if os.environ.get("VDO_BENCH_TRACE"):
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} t={time.time() % 1000:.1f}] {msg}\n"); sys.stderr.flush()
 
 
 def run_ours(args, rank, world, local_rank):
     import torch
+    if os.environ.get("VDO_BENCH_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("VDO_BENCH_TRACE_AFTER", "90")), repeat=False, file=sys.stderr)
     from vdo_slam_b200 import capi
     from vdo_slam_b200.synth import make_batch_graph, graph_sizes, algorithmic_bytes_per_iter
 
@@ -108,16 +120,20 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    trace('generating graph')
     g = make_batch_graph(**WORKLOADS[args.workload])
     sz = graph_sizes(g)
+    trace('context')
     ctx = capi.Context(local_rank)
     if world > 1:
         ctx.init_comm(rank, world, dist)       # NCCL communicator of the library (id broadcast over torch.distributed)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     # ---- device-resident arm: graph already in HBM, each step = reset estimates (D2D) + full LM solve ----
+    trace('ingest resident graph')
     G = capi.BatchGraph(ctx, g)
     info = G.info()
+    trace('warmup')
 
     def step():
         G.reset()
@@ -125,6 +141,7 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(args.warmup):
         r = step()
+    trace('timed region')
     sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
@@ -152,6 +169,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end arm: host buffers -> C ABI (ingest, H2D, solve, D2H) every step ----
     h2d = graph_h2d_bytes(g) // world + (g["se3"].nbytes if world > 1 else 0)   # per rank: its shard of the edge/landmark arrays (+ the replicated se3 state)
     d2h = int(g["se3"].nbytes + g["pt"].nbytes)
+    trace('e2e arm')
     e2e_steps = max(1, min(args.steps, 3))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -169,6 +187,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_val = e_iters / e2e_s
 
     # ---- per-kernel CUDA-event timings (vdo_graph_time_kernel: back-to-back launches on the library's stream) ----
+    trace('kernel timings')
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -176,7 +195,7 @@ def run_ours(args, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    kb = kernel_bytes(g)
+    kb = {k: v // world for k, v in kernel_bytes(g).items()}      # sharded solves: each rank streams its 1/world of the tracklets
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
@@ -185,26 +204,41 @@ def run_ours(args, rank, world, local_rank):
     pcg_per_it = pcg / max(iters, 1)
     trials_per_it = 1.0
     kernels = {}
-    for name, per_lm_iter in [("lin_static", 1 + trials_per_it), ("lin_chains", 1 + trials_per_it), ("lin_vertex_obs", 1), ("lin_vertex_ter", 1),
-                              ("schur_static", pcg_per_it), ("schur_chains", pcg_per_it), ("schur_vertex_obs", pcg_per_it),
-                              ("schur_vertex_ter", pcg_per_it)]:
-        ms_k = G.time_kernel(name, 20)
+    # bench name -> (vdo_graph_time_kernel name, launches per LM iteration)
+    table = [("lin_static", "lin_static", 1), ("lin_chains", "lin_chains", 1), ("lin_finalize", "lin_vertex_obs", 1),
+             ("schur_static", "schur_static", pcg_per_it + 2 * trials_per_it), ("schur_chains", "schur_chains", pcg_per_it + 2 * trials_per_it),
+             ("schur_finalize", "schur_vertex_obs", pcg_per_it + trials_per_it)]
+    for name, tk_name, per_lm_iter in table:
+        trace('time ' + tk_name)
+        ms_k = G.time_kernel(tk_name, 20)
         gbs = kb[name] / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
         kernels[name] = {"ms": ms_k, "algorithmic_bytes": kb[name], "GBps": gbs, "frac": gbs / peak,
                          "launches_per_lm_iter": per_lm_iter, "ms_per_lm_iter": ms_k * per_lm_iter, "traffic": traffic.get(name)}
-    top = max(kernels, key=lambda k: kernels[k]["ms_per_lm_iter"])
+    for name, tk_name, per_lm_iter in [("precond_solve(pcg_step)", "pcg_step", pcg_per_it), ("precond_build", "precond", trials_per_it),
+                                       ("chi2_only", "chi2_tracklets", 1 + trials_per_it), ("hpp_mul", "hpp_mul", pcg_per_it), ("pcg_iterate8", "pcg_iterate8", pcg_per_it / 8.0)]:
+        ms_k = G.time_kernel(tk_name, 20)
+        kernels[name] = {"ms": ms_k, "launches_per_lm_iter": per_lm_iter, "ms_per_lm_iter": ms_k * per_lm_iter, "note": "latency-bound; no byte count claimed"}
+    hbm = [k for k in kernels if "algorithmic_bytes" in kernels[k]]
+    top = max(hbm, key=lambda k: kernels[k]["ms_per_lm_iter"])
     roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[top]["frac"], "traffic": kernels[top]["traffic"], "peak_source": peak_src + " (burst figure: kernel timed alone)",
                 "algorithmic_bytes_per_launch": kernels[top]["algorithmic_bytes"], "ms_per_launch": kernels[top]["ms"],
                 "how": "vdo_graph_time_kernel: 20 back-to-back launches between CUDA events on the library stream"}
-    lin_names = ["lin_static", "lin_chains", "lin_vertex_obs", "lin_vertex_ter"]
+    lin_names = ["lin_static", "lin_chains", "lin_finalize"]
     lin_ms = sum(kernels[k]["ms"] for k in lin_names); lin_bytes = sum(kernels[k]["algorithmic_bytes"] for k in lin_names)
     jac = {"kernels": lin_names, "ms": lin_ms, "algorithmic_bytes": lin_bytes, "GBps": lin_bytes / (lin_ms * 1e-3) / 1e9,
-           "frac": lin_bytes / (lin_ms * 1e-3) / 1e9 / peak, "survey_formula_bytes": algorithmic_bytes_per_iter(g),
-           "frac_with_survey_formula": algorithmic_bytes_per_iter(g) / (lin_ms * 1e-3) / 1e9 / peak}
+           "frac": lin_bytes / (lin_ms * 1e-3) / 1e9 / peak, "survey_formula_bytes": algorithmic_bytes_per_iter(g) // world,
+           "frac_with_survey_formula": algorithmic_bytes_per_iter(g) / world / (lin_ms * 1e-3) / 1e9 / peak,
+           "note": "frac: this implementation's compulsory bytes (edges stored once, vertex-side sums kept on chip); frac_with_survey_formula: SURVEY 8(d)'s explicit-block byte count (216 E_p + 412 E_t + 416 E_o + 96 P + 272 C) over the same time"}
     lin_ms_per_iter = ms_lin / max(iters, 1)
 
     # ---- config 2 (per-frame PoseOptimizationFlow2, 2 000 points): latency-bound single-kernel LM, reported beside the headline ----
+    trace('rank-0 extras')
+    # the per-frame numbers below are single-GPU paths: they run on a context WITHOUT the multi-rank communicator (a sharded
+    # context would make the tracker's windowed BA wait for ranks that are not taking part)
+    ctx_multi = ctx
+    if world > 1 and rank == 0:
+        ctx = capi.Context(local_rank)
     flow2 = None
     if rank == 0:
         try:
@@ -284,7 +318,8 @@ def run_ours(args, rank, world, local_rank):
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": f"{args.workload}: " + json.dumps(WORKLOADS[args.workload]), "sizes": sz,
                           "step": f"one full LM solve (<= {LM_MAX_ITERS} iterations, gain < {LM_GAIN}) from the same initial estimates",
-                          "l2": "edge streams (%.0f MB) exceed the 126 MB L2; no explicit flush" % (info["device_bytes"] / 1e6),
+                          "l2": "device-resident graph (%.0f MB) exceeds the 126 MB L2 and every kernel streams > L2-size of it; no explicit flush" % (info["device_bytes"] / 1e6),
+                          "layout": "tiled (one CTA per <=256-landmark / <=768-edge tile, TMA bulk staging)",
                           "multi_gpu": (f"tracklets sharded round-robin over {world} ranks, se3 state replicated, NCCL all-reduce of H_pp/b_p per linearisation, of S*p per PCG iteration, of chi2/scale per LM trial" if world > 1 else "single GPU")},
                "lm_iters_per_step": iters / args.steps, "pcg_iters_per_lm_iter": pcg / max(iters, 1),
                "ms_linearize_per_lm_iter": lin_ms_per_iter, "ms_solve_per_lm_iter": ms_solve / max(iters, 1),
@@ -292,6 +327,7 @@ def run_ours(args, rank, world, local_rank):
                "e2e": {"value": e2e_val, "unit": "LM iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "steps": e2e_steps, "note": "host numpy buffers -> vdo_graph_* C ABI (ingest + H2D + solve + D2H) each step"},
                "roofline": roofline, "jacobian_assembly": jac, "kernels": kernels, "per_frame_flow2": flow2, "per_frame_image_side": image_side, "per_frame_pipeline": pipeline, "cpu_baseline": cpu}
+    trace('done')
     if world > 1:
         dist.destroy_process_group()
     return out

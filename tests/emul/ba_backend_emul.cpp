@@ -25,6 +25,12 @@ struct EmulBackend : BaBackend {
   void allreduce_sum(double* b, size_t n) override { if (world > 1 && coll) coll(b, n, 0, coll_user); }
   void allreduce_max(double* b, size_t n) override { if (world > 1 && coll) coll(b, n, 1, coll_user); }
   std::chrono::steady_clock::time_point t0[4];
+  struct MallocArena : HostArena {
+    char* raw_alloc(size_t b) override { return (char*)std::malloc(b); }
+    void raw_free(char* p) override { std::free(p); }
+    ~MallocArena() override { destroy(); }
+  } arena;
+  HostArena& staging() override { return arena; }
   void* alloc(size_t b) override { return std::calloc(1, b ? b : 1); }
   void free_(void* p) override { std::free(p); }
   void h2d(void* d, const void* s, size_t b) override { std::memcpy(d, s, b); }

@@ -15,6 +15,23 @@
 namespace vdo {
 
 namespace {
+// Host-side worker threads of finalize() (graph ingestion is memory-latency-bound scatter work; the reference's own
+// graph construction is single-threaded, src/Optimizer.cc:1232-1930).  VDO_HOST_THREADS overrides the default.
+int host_threads() {
+  static int n = [] {
+    const char* e = std::getenv("VDO_HOST_THREADS");
+    int v = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    return std::max(1, std::min(v, 64));
+  }();
+  return n;
+}
+template <typename F> void parallel_for(int nthreads, F fn) {   // fn(thread index, thread count)
+  if (nthreads <= 1) { fn(0, 1); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back([=] { fn(t, nthreads); });
+  fn(0, nthreads);
+  for (auto& x : th) x.join();
+}
 struct Phase {
   BaBackend* be; float* acc; bool on;
   Phase(BaBackend* b, float* a, bool o) : be(b), acc(a), on(o) { if (on) be->timer_start(3); }
@@ -22,8 +39,24 @@ struct Phase {
 };
 }  // namespace
 
+void BaGraph::copy_bytes(void* dst, const void* src, size_t bytes) {
+  if (bytes < ((size_t)8 << 20)) { std::memcpy(dst, src, bytes); return; }
+  parallel_for(std::min(host_threads(), 8), [&](int t, int n) {
+    const size_t a = (bytes * t / n) & ~(size_t)63, b = t + 1 == n ? bytes : ((bytes * (t + 1) / n) & ~(size_t)63);
+    std::memcpy((char*)dst + a, (const char*)src + a, b - a);
+  });
+}
+void BaGraph::fill_bytes(void* dst, int byte, size_t bytes) {
+  if (bytes < ((size_t)8 << 20)) { std::memset(dst, byte, bytes); return; }
+  parallel_for(std::min(host_threads(), 8), [&](int t, int n) {
+    const size_t a = (bytes * t / n) & ~(size_t)63, b = t + 1 == n ? bytes : ((bytes * (t + 1) / n) & ~(size_t)63);
+    std::memset((char*)dst + a, byte, b - a);
+  });
+}
+
 BaGraph::~BaGraph() {
   if (finalized_) be_->release(d_);
+  drop_stage();
   for (void* p : owned_) be_->free_(p);
 }
 
@@ -31,8 +64,9 @@ int BaGraph::set_vertices(int n_se3, const double* se3, int n_pt, const double* 
   if (finalized_) return fail(VDO_ERR_STATE, "set_vertices after finalize");
   if (n_se3 < 0 || n_pt < 0 || (n_se3 && !se3) || (n_pt && !pt)) return fail(VDO_ERR_ARG, "set_vertices: bad arguments");
   n_se3_ = n_se3; n_pt_ = n_pt;
-  h_se3_.assign(se3, se3 + 12 * (size_t)n_se3);
-  h_pt_.assign(pt, pt + 3 * (size_t)n_pt);
+  h_se3_ = HostBuf<double>(); h_pt_ = HostBuf<double>();
+  append(h_se3_, se3, 12 * (size_t)n_se3);
+  append(h_pt_, pt, 3 * (size_t)n_pt);
   return VDO_OK;
 }
 int BaGraph::add_prior(int n, const int* v, const double* Z, const double* w) {
@@ -53,8 +87,8 @@ int BaGraph::add_obs(int n, const int* cp, const double* z, const double* w, con
   if (finalized_) return fail(VDO_ERR_STATE, "add after finalize");
   for (int i = 0; i < n; ++i)
     if (cp[2 * i] < 0 || cp[2 * i] >= n_se3_ || cp[2 * i + 1] < 0 || cp[2 * i + 1] >= n_pt_) return fail(VDO_ERR_ARG, "pointxyz edge: vertex out of range");
-  ob_cp_.insert(ob_cp_.end(), cp, cp + 2 * (size_t)n); ob_z_.insert(ob_z_.end(), z, z + 3 * (size_t)n);
-  ob_w_.insert(ob_w_.end(), w, w + n); ob_d_.insert(ob_d_.end(), delta, delta + n);
+  append(ob_cp_, cp, 2 * (size_t)n); append(ob_z_, z, 3 * (size_t)n);
+  append(ob_w_, w, (size_t)n); append(ob_d_, delta, (size_t)n);
   return VDO_OK;
 }
 int BaGraph::add_ter(int n, const int* pph, const double* w, const double* delta) {
@@ -62,7 +96,7 @@ int BaGraph::add_ter(int n, const int* pph, const double* w, const double* delta
   for (int i = 0; i < n; ++i)
     if (pph[3 * i] < 0 || pph[3 * i] >= n_pt_ || pph[3 * i + 1] < 0 || pph[3 * i + 1] >= n_pt_ || pph[3 * i + 2] < 0 || pph[3 * i + 2] >= n_se3_)
       return fail(VDO_ERR_ARG, "landmark-motion edge: vertex out of range");
-  te_pph_.insert(te_pph_.end(), pph, pph + 3 * (size_t)n); te_w_.insert(te_w_.end(), w, w + n); te_d_.insert(te_d_.end(), delta, delta + n);
+  append(te_pph_, pph, 3 * (size_t)n); append(te_w_, w, (size_t)n); append(te_d_, delta, (size_t)n);
   return VDO_OK;
 }
 
@@ -79,23 +113,6 @@ struct ClassTable {
     return id;
   }
 };
-// Host-side worker threads of finalize() (graph ingestion is memory-latency-bound scatter work; the reference's own
-// graph construction is single-threaded, src/Optimizer.cc:1232-1930).  VDO_HOST_THREADS overrides the default.
-int host_threads() {
-  static int n = [] {
-    const char* e = std::getenv("VDO_HOST_THREADS");
-    int v = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    return std::max(1, std::min(v, 64));
-  }();
-  return n;
-}
-template <typename F> void parallel_for(int nthreads, F fn) {   // fn(thread index, thread count)
-  if (nthreads <= 1) { fn(0, 1); return; }
-  std::vector<std::thread> th;
-  for (int t = 1; t < nthreads; ++t) th.emplace_back([=] { fn(t, nthreads); });
-  fn(0, nthreads);
-  for (auto& x : th) x.join();
-}
 void make_chunks(const std::vector<int>& begin, std::vector<Chunk>& out) {
   for (int v = 0; v + 1 < (int)begin.size(); ++v)
     for (int b = begin[v]; b < begin[v + 1]; b += VDO_CHUNK) out.push_back(Chunk{v, b, std::min(b + VDO_CHUNK, begin[v + 1]), 0});
@@ -156,7 +173,7 @@ int BaGraph::finalize() {
   lap("se3 paths");
   // ---- tracklets: chains of landmarks linked by ternary edges ----
   (void)0;
-  std::vector<int> next(P, -1), prev(P, -1), ter_of(P, -1);
+  HostBuf<int> next = stage_fill<int>(P, 0xFF), prev = stage_fill<int>(P, 0xFF), ter_of = stage_fill<int>(P, 0xFF);
   for (int e = 0; e < Et_all; ++e) {
     int p1 = te_pph_[3 * e], p2 = te_pph_[3 * e + 1];
     if (p1 == p2 || next[p1] != -1 || prev[p2] != -1)
@@ -164,7 +181,8 @@ int BaGraph::finalize() {
     next[p1] = p2; prev[p2] = p1; ter_of[p1] = e;
   }
   new_of_old_.assign(P, -1);
-  std::vector<int> old_of_new(P), tk_begin;
+  HostBuf<int> old_of_new = stage<int>(P);
+  std::vector<int> tk_begin;
   int cnt = 0;
   // Tracklet order.  Static landmarks (tracklets of one vertex) first, then the chains: the two groups run different
   // kernels.  Inside each group tracklets are ordered by the first se3 vertex that observes them (chains: by the motion
@@ -173,9 +191,13 @@ int BaGraph::finalize() {
   // Multi-GPU: tracklets are dealt round-robin to the ranks (each group separately, in this order); a rank keeps only its
   // own landmarks and their edges, the se3 state is replicated.
   const int rank = be_->rank, world = be_->world;
-  std::vector<int> first_cam(P, C);
-  for (int e = 0; e < Eo_all; ++e) { int& f = first_cam[ob_cp_[2 * e + 1]]; f = std::min(f, S3(ob_cp_[2 * e])); }
-  auto counting_sort = [&](std::vector<int>& ids, const std::vector<int>& key_of_id, int nkeys) {   // stable
+  HostBuf<int> first_cam = stage<int>(P);
+  for (int p = 0; p < P; ++p) first_cam[p] = C;
+  parallel_for(host_threads(), [&](int t, int n) {      // each worker owns a landmark range and scans the edge list
+    const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
+    for (int e = 0; e < Eo_all; ++e) { const int p = ob_cp_[2 * e + 1]; if (p >= lo && p < hi) { const int c = S3(ob_cp_[2 * e]); if (c < first_cam[p]) first_cam[p] = c; } }
+  });
+  auto counting_sort = [&](std::vector<int>& ids, const HostBuf<int>& key_of_id, int nkeys) {   // stable
     std::vector<int> cntk(nkeys + 1, 0), out(ids.size());
     for (int id : ids) cntk[key_of_id[id] + 1]++;
     for (int k = 0; k < nkeys; ++k) cntk[k + 1] += cntk[k];
@@ -190,7 +212,7 @@ int BaGraph::finalize() {
   }
   counting_sort(stat_ids, first_cam, C + 1);
   {
-    std::vector<int> first_h(P, 0);
+    HostBuf<int> first_h = stage_fill<int>(P, 0);
     for (int p : chain_heads) first_h[p] = S3(te_pph_[3 * ter_of[p] + 2]);
     counting_sort(chain_heads, first_cam, C + 1);
     counting_sort(chain_heads, first_h, C + 1);
@@ -211,7 +233,6 @@ int BaGraph::finalize() {
   if (n_seen != P) return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges contain a cycle");
   const int P_all = P;
   P = cnt;                      // from here on P = landmarks owned by this rank
-  old_of_new.resize(P);
   tk_begin.push_back(cnt);
   const int T = (int)tk_begin.size() - 1;
 
@@ -222,7 +243,7 @@ int BaGraph::finalize() {
   // into landmark order by worker threads that each own a contiguous landmark range and scan the edge list in order, so the
   // order of a landmark's edges is the caller's order whatever the thread count.
   const int NT = host_threads();
-  std::vector<uint8_t> ecls(Eo_all);
+  HostBuf<uint8_t> ecls = stage<uint8_t>(Eo_all);
   {
     double lw = 0, ld = 0; int lc = -1;
     for (int e = 0; e < Eo_all; ++e) {
@@ -234,13 +255,13 @@ int BaGraph::finalize() {
     }
   }
   lap("  edge classes");
-  std::vector<int> kof(Eo_all);
+  HostBuf<int> kof = stage<int>(Eo_all);
   parallel_for(NT, [&](int t, int n) {
     const int a = (int)((int64_t)Eo_all * t / n), b = (int)((int64_t)Eo_all * (t + 1) / n);
     for (int e = a; e < b; ++e) kof[e] = new_of_old_[ob_cp_[2 * e + 1]];
   });
   lap("  kof");
-  std::vector<int> lm_begin(P + 1, 0);
+  HostBuf<int> lm_begin = stage_fill<int>((size_t)P + 1, 0);
   parallel_for(NT, [&](int t, int n) {
     const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
     for (int e = 0; e < Eo_all; ++e) { const int k = kof[e]; if (k >= lo && k < hi) lm_begin[k + 1]++; }
@@ -248,9 +269,10 @@ int BaGraph::finalize() {
   lap("  count");
   for (int k = 0; k < P; ++k) lm_begin[k + 1] += lm_begin[k];
   const int Eo = lm_begin[P];
-  std::vector<int> fill(lm_begin.begin(), lm_begin.end() - 1), lm_cam(Eo);
-  std::vector<double> lm_z(3 * (size_t)Eo);
-  std::vector<uint8_t> lm_cls(Eo);
+  HostBuf<int> fill = stage<int>(P), lm_cam = stage<int>(Eo);
+  copy_bytes(fill.p, lm_begin.p, sizeof(int) * (size_t)P);
+  HostBuf<double> lm_z = stage<double>(3 * (size_t)Eo);
+  HostBuf<uint8_t> lm_cls = stage<uint8_t>(Eo);
   lap("  prefix + alloc");
   parallel_for(NT, [&](int t, int n) {
     const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
@@ -263,7 +285,6 @@ int BaGraph::finalize() {
       lm_cls[pos] = ecls[e];
     }
   });
-  std::vector<int>().swap(kof);
   lap("landmark-major stream");
   // ---- layout choice: tiles of whole tracklets (default) or, when a tracklet is too large for a tile (more than
   //      VDO_TILE_L landmarks or VDO_TILE_E pointxyz edges) or VDO_BA_LAYOUT=chunked is set, the chunked vertex-major layout ----
@@ -307,8 +328,8 @@ int BaGraph::finalize() {
   make_chunks(vm_begin, obs_chunks);
   }
   // ---- ternary edges: per landmark (as p1) and motion-vertex-major ----
-  std::vector<int> tk_h(P, -1);
-  std::vector<uint8_t> tk_cls(P, 0);
+  HostBuf<int> tk_h = stage_fill<int>(P, 0xFF);
+  HostBuf<uint8_t> tk_cls = stage_fill<uint8_t>(P, 0);
   std::vector<int> hm_begin(C + 1, 0);
   int Et = 0;
   for (int e = 0; e < Et_all; ++e) {
@@ -337,11 +358,11 @@ int BaGraph::finalize() {
   }
   lap("ternary / chunked streams");
   // ---- tiles: tile-local landmark of every edge, vertex-sorted order of the tile's edges, segments of one vertex ----
-  std::vector<uint16_t> ob_perm, tr_perm;
-  std::vector<uint8_t> lm_lml;
+  HostBuf<uint16_t> ob_perm, tr_perm;
+  HostBuf<uint8_t> lm_lml;
   std::vector<Seg> osegs, tsegs;
   if (tiled) {
-    ob_perm.resize(Eo); tr_perm.resize(P); lm_lml.resize(Eo);
+    ob_perm = stage<uint16_t>(Eo); tr_perm = stage_fill<uint16_t>(P, 0); lm_lml = stage<uint8_t>(Eo);
     // tiles are independent: each worker handles a contiguous range of tiles into its own segment lists, which are then
     // concatenated in tile order (segment indices of a tile are rebased by the lists that precede it)
     const int ntl = (int)tiles.size();
@@ -351,7 +372,7 @@ int BaGraph::finalize() {
       std::vector<int> keys(std::max(VDO_TILE_E, VDO_TILE_L)), idx(keys.size()), bucket;
       std::vector<Seg>& los = w_os[wt]; std::vector<Seg>& lts = w_ts[wt];
       // stable sort of idx[0..n) by keys[idx] (counting sort over the key range when it is small), then cut into segments
-      auto sort_and_cut = [&](int n, int base, std::vector<uint16_t>& perm, std::vector<Seg>& segs) {
+      auto sort_and_cut = [&](int n, int base, HostBuf<uint16_t>& perm, std::vector<Seg>& segs) {
         if (n == 0) return;
         int lo = keys[idx[0]], hi = lo;
         for (int a = 1; a < n; ++a) { lo = std::min(lo, keys[idx[a]]); hi = std::max(hi, keys[idx[a]]); }
@@ -433,11 +454,14 @@ int BaGraph::finalize() {
     else if (a == b + 1) { pcr_edge[a] = e; pcr_tr[a] = 0; }   // M(a, b) = H_ab
   }
   int pcr_levels = 0; while ((1 << pcr_levels) < max_len) ++pcr_levels;
-  std::vector<double> se3_int(12 * (size_t)C);
+  HostBuf<double> se3_int = stage<double>(12 * (size_t)C);
   for (int o = 0; o < C; ++o) std::memcpy(&se3_int[12 * (size_t)S3(o)], &h_se3_[12 * (size_t)o], 96);
   // ---- states in internal landmark order ----
-  std::vector<double> pt_int(3 * (size_t)P);
-  for (int k = 0; k < P; ++k) for (int i = 0; i < 3; ++i) pt_int[3 * (size_t)k + i] = h_pt_[3 * (size_t)old_of_new[k] + i];
+  HostBuf<double> pt_int = stage<double>(3 * (size_t)P);
+  parallel_for(NT, [&](int t, int n) {
+    const int a = (int)((int64_t)P * t / n), b = (int)((int64_t)P * (t + 1) / n);
+    for (int k = a; k < b; ++k) for (int i = 0; i < 3; ++i) pt_int[3 * (size_t)k + i] = h_pt_[3 * (size_t)old_of_new[k] + i];
+  });
 
   lap("se3 edges, states");
   // ---- upload ----
@@ -446,7 +470,8 @@ int BaGraph::finalize() {
   P_all_ = P_all; d.Eobs = Eo; d.Eter = Et; d.Ese = Ese;
   d.n_obs_chunks = (int)obs_chunks.size(); d.n_ter_chunks = (int)ter_chunks.size(); d.n_nbr = (int)nbr_edge.size();
   d.se3 = upload(se3_int); d.pt = upload(pt_int);
-  d.se3_init = upload(se3_int); d.pt_init = upload(pt_int);
+  d.se3_init = dalloc<double>(12 * (size_t)C); d.pt_init = dalloc<double>(3 * (size_t)P);
+  be_->d2d(d.se3_init, d.se3, 96 * (size_t)C); be_->d2d(d.pt_init, d.pt, 24 * (size_t)P);
   d.se3_bk = dalloc<double>(12 * (size_t)C); d.pt_bk = dalloc<double>(3 * (size_t)P);
   d.tk_begin = upload(tk_begin);
   d.lm_obs_begin = upload(lm_begin); d.lm_cam = upload(lm_cam); d.lm_z = upload(lm_z); d.lm_cls = upload(lm_cls); d.lm_omega = dalloc<double>(Eo);
@@ -484,10 +509,12 @@ int BaGraph::finalize() {
   be_->sync();
   lap("alloc + upload");
   // host staging is no longer needed (keep the landmark map for read-back)
-  std::vector<double>().swap(ob_z_); std::vector<double>().swap(ob_w_); std::vector<double>().swap(ob_d_); std::vector<int>().swap(ob_cp_);
-  std::vector<int>().swap(te_pph_); std::vector<double>().swap(te_w_); std::vector<double>().swap(te_d_);
+  ob_z_ = HostBuf<double>(); ob_w_ = HostBuf<double>(); ob_d_ = HostBuf<double>(); ob_cp_ = HostBuf<int>();
+  te_pph_ = HostBuf<int>(); te_w_ = HostBuf<double>(); te_d_ = HostBuf<double>();
   std::vector<double>().swap(se_Z_); std::vector<double>().swap(pr_Z_);
-  std::vector<double>().swap(h_se3_); std::vector<double>().swap(h_pt_);
+  h_se3_ = HostBuf<double>(); h_pt_ = HostBuf<double>();
+  n_prior_ = Ep;
+  drop_stage();                 // every upload above has completed (sync): the staging arena can be rewound
   finalized_ = true;
   return VDO_OK;
 }
@@ -500,13 +527,18 @@ int BaGraph::get_vertices(double* se3, double* pt) {
     for (int o = 0; o < d_.C; ++o) std::memcpy(se3 + 12 * (size_t)o, &tmp[12 * (size_t)new_se3_of_old_[o]], 96);
   }
   if (pt) {
-    std::vector<double> tmp(3 * (size_t)d_.P);
+    HostBuf<double> tmp = stage<double>(3 * (size_t)d_.P);
     be_->d2h(tmp.data(), d_.pt, 24 * (size_t)d_.P);
-    for (int o = 0; o < P_all_; ++o) {      // landmarks owned by other ranks are left untouched in the caller's buffer
-      int k = new_of_old_[o];
-      if (k < 0) continue;
-      pt[3 * (size_t)o] = tmp[3 * (size_t)k]; pt[3 * (size_t)o + 1] = tmp[3 * (size_t)k + 1]; pt[3 * (size_t)o + 2] = tmp[3 * (size_t)k + 2];
-    }
+    const int Pa = P_all_;
+    parallel_for(std::min(host_threads(), 8), [&](int t, int n) {     // landmarks owned by other ranks are left untouched in the caller's buffer
+      const int a = (int)((int64_t)Pa * t / n), b = (int)((int64_t)Pa * (t + 1) / n);
+      for (int o = a; o < b; ++o) {
+        const int k = new_of_old_[o];
+        if (k < 0) continue;
+        pt[3 * (size_t)o] = tmp[3 * (size_t)k]; pt[3 * (size_t)o + 1] = tmp[3 * (size_t)k + 1]; pt[3 * (size_t)o + 2] = tmp[3 * (size_t)k + 2];
+      }
+    });
+    drop_stage();
   }
   return VDO_OK;
 }
@@ -518,7 +550,7 @@ int BaGraph::reset_vertices() {
   return VDO_OK;
 }
 int BaGraph::info(int64_t out[8]) const {
-  out[0] = d_.C; out[1] = d_.P; out[2] = d_.Eobs; out[3] = d_.Eter; out[4] = d_.Ese; out[5] = (int64_t)pr_w_.size(); out[6] = d_.T; out[7] = (int64_t)bytes_;
+  out[0] = d_.C; out[1] = d_.P; out[2] = d_.Eobs; out[3] = d_.Eter; out[4] = d_.Ese; out[5] = n_prior_; out[6] = d_.T; out[7] = (int64_t)bytes_;
   return VDO_OK;
 }
 
@@ -721,6 +753,9 @@ int BaGraph::time_kernel(const char* name, int reps, float* ms_avg) {
     return true;
   };
   // a valid, never-converging PCG state: linearise + factor at the last lambda, rhs, init
+  if (d.tiled) {   // a previous timing of a tile kernel alone leaves its vertex-side sums behind: start clean
+    be_->zero(d.accO, 128 * (size_t)d.C); be_->zero(d.accT, 128 * (size_t)d.C); be_->zero(d.acc6, 48 * (size_t)d.C);
+  }
   linearize();
   be_->factor_landmarks(d, lam);
   be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); be_->allreduce_sum(d.Minv, 36 * (size_t)d.C); be_->precond_factor(d, lam);

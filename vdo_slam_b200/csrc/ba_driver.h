@@ -9,6 +9,19 @@
 
 namespace vdo {
 
+// array in the backend's staging arena: plain memory, NOT zero-initialised, valid until the graph releases the arena
+template <typename T> struct HostBuf {
+  T* p = nullptr; size_t n = 0;
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T* begin() { return p; }
+  T* end() { return p + n; }
+};
+
 class BaGraph {
  public:
   explicit BaGraph(BaBackend* be) : be_(be) {}
@@ -29,6 +42,20 @@ class BaGraph {
 
  private:
   template <typename T> T* dalloc(size_t n) { bytes_ += n * sizeof(T); T* p = (T*)be_->alloc(n * sizeof(T) + 16); owned_.push_back(p); return p; }   // +16: the tile kernels' bulk copies round ranges up to 16 B
+  template <typename T> HostBuf<T> stage(size_t n) { hold_stage(); HostBuf<T> b; b.n = n; b.p = (T*)be_->staging().take(n * sizeof(T) + 16); return b; }
+  template <typename T> HostBuf<T> stage_fill(size_t n, int byte) { HostBuf<T> b = stage<T>(n); fill_bytes(b.p, byte, n * sizeof(T)); return b; }
+  template <typename T> void append(HostBuf<T>& b, const T* src, size_t n) {
+    HostBuf<T> nb = stage<T>(b.n + n);
+    if (b.n) copy_bytes(nb.p, b.p, b.n * sizeof(T));
+    copy_bytes(nb.p + b.n, src, n * sizeof(T));
+    b = nb;
+  }
+  template <typename T> T* upload(const HostBuf<T>& v) { T* p = dalloc<T>(v.size()); if (!v.empty()) be_->h2d_async(p, v.data(), v.size() * sizeof(T)); return p; }
+  void hold_stage() { if (!holds_stage_) { be_->staging().acquire(); holds_stage_ = true; } }
+  void drop_stage() { if (holds_stage_) { be_->staging().release(); holds_stage_ = false; } }
+  static void copy_bytes(void* dst, const void* src, size_t bytes);   // threaded for large blocks
+  static void fill_bytes(void* dst, int byte, size_t bytes);
+  bool holds_stage_ = false;
   template <typename T> T* upload(const std::vector<T>& v) { T* p = dalloc<T>(v.size()); if (!v.empty()) be_->h2d(p, v.data(), v.size() * sizeof(T)); return p; }
   void linearize();                 // buildSystem
   double robust_chi2();             // computeActiveErrors + activeRobustChi2
@@ -47,11 +74,12 @@ class BaGraph {
   double last_lambda_ = 1.0;
   // host staging (until finalize)
   int n_se3_ = 0, n_pt_ = 0, P_all_ = 0;
-  std::vector<double> h_se3_, h_pt_;
+  HostBuf<double> h_se3_, h_pt_;
   std::vector<int> pr_v_; std::vector<double> pr_Z_, pr_w_;
   std::vector<int> se_ij_; std::vector<double> se_Z_, se_w_, se_d_;
-  std::vector<int> ob_cp_; std::vector<double> ob_z_, ob_w_, ob_d_;
-  std::vector<int> te_pph_; std::vector<double> te_w_, te_d_;
+  HostBuf<int> ob_cp_; HostBuf<double> ob_z_, ob_w_, ob_d_;
+  HostBuf<int> te_pph_; HostBuf<double> te_w_, te_d_;
+  int n_prior_ = 0;
   std::vector<int> new_of_old_;     // landmark renumbering
   std::vector<int> new_se3_of_old_; // se3 renumbering (path order)
 };

@@ -18,6 +18,7 @@
 #include <nccl.h>
 
 #include <map>
+#include <set>
 #include <utility>
 
 #include "ba_bodies.cuh"
@@ -551,14 +552,46 @@ struct CudaBackend : BaBackend {
   cudaEvent_t ev0[4], ev1[4];
   ~CudaBackend() override {
     for (int i = 0; i < 4; ++i) { cudaEventDestroy(ev0[i]); cudaEventDestroy(ev1[i]); }
+    for (auto& kv : pool) cudaFree(kv.second);
+    arena.destroy();
     if (comm) g_nccl.CommDestroy(comm);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
   }
-  void* alloc(size_t b) override { void* p = nullptr; CK(cudaMalloc(&p, b ? b : 8)); CK(cudaMemsetAsync(p, 0, b ? b : 8, st)); return p; }
-  void free_(void* p) override { cudaFree(p); }
+  // pinned staging arena (graph ingestion builds its upload streams in it) and a caching device allocator: graphs of the
+  // same shape are created again and again by the callers (one per window / per solve), so freed blocks are kept and
+  // handed back by exact size instead of going through cudaFree / cudaMalloc (both synchronise the device)
+  struct PinnedArena : HostArena {
+    char* raw_alloc(size_t b) override { void* p = nullptr; if (cudaHostAlloc(&p, b, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = std::malloc(b); pageable.insert(p); } return (char*)p; }
+    void raw_free(char* p) override { if (pageable.count(p)) { pageable.erase(p); std::free(p); } else cudaFreeHost(p); }
+    std::set<void*> pageable;
+  } arena;
+  HostArena& staging() override { return arena; }
+  std::multimap<size_t, void*> pool;      // free device blocks by size
+  std::map<void*, size_t> live;           // size of every block handed out
+  size_t pool_bytes = 0;
+  static constexpr size_t POOL_MAX = (size_t)24 << 30;
+  void* alloc(size_t b) override {
+    b = b ? b : 8;
+    void* p = nullptr;
+    auto it = pool.find(b);
+    if (it != pool.end()) { p = it->second; pool_bytes -= b; pool.erase(it); }
+    else CK(cudaMalloc(&p, b));
+    live[p] = b;
+    CK(cudaMemsetAsync(p, 0, b, st));
+    return p;
+  }
+  void free_(void* p) override {
+    auto it = live.find(p);
+    if (it == live.end()) { cudaFree(p); return; }
+    const size_t b = it->second;
+    live.erase(it);
+    if (pool_bytes + b <= POOL_MAX) { pool.emplace(b, p); pool_bytes += b; }   // all users are ordered on st: no synchronisation needed
+    else cudaFree(p);
+  }
+  void h2d_async(void* d, const void* s, size_t b) override { CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); }
   void h2d(void* d, const void* s, size_t b) override { CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
   void d2h(void* d, const void* s, size_t b) override { CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
   void d2d(void* d, const void* s, size_t b) override { CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); }

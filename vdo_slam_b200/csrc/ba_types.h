@@ -23,6 +23,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <vector>
 
 #define VDO_CHUNK 512
 // Tiled layout (default): the landmark side is cut into tiles of whole tracklets, at most VDO_TILE_L landmarks and
@@ -90,6 +91,39 @@ struct BaDev {
 enum { SC_CHI2 = 0, SC_SCALE = 1, SC_MAXDIAG = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9,
        SC_LAMBDA = 10, SC_TOL2 = 11, SC_N = 16 };
 
+// Grow-only host staging arena (pinned memory in the CUDA backend): graph ingestion builds every stream it uploads directly
+// in it, so host->device copies run at PCIe speed without a bounce buffer and repeated graphs pay no page faults.  Memory
+// is handed out until the last user releases the arena; then it is rewound (and coalesced into one block).
+struct HostArena {
+  struct Block { char* p; size_t cap, used; };
+  std::vector<Block> blocks;
+  int users = 0;
+  virtual ~HostArena() {}
+  virtual char* raw_alloc(size_t bytes) = 0;
+  virtual void raw_free(char* p) = 0;
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    for (Block& b : blocks) if (b.cap - b.used >= bytes) { void* r = b.p + b.used; b.used += bytes; return r; }
+    const size_t cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+    Block nb{raw_alloc(cap), cap, bytes};
+    blocks.push_back(nb);
+    return nb.p;
+  }
+  void acquire() { ++users; }
+  void release() {
+    if (--users > 0) return;
+    users = 0;
+    if (blocks.size() > 1) {
+      size_t total = 0;
+      for (Block& b : blocks) { total += b.cap; raw_free(b.p); }
+      blocks.clear();
+      blocks.push_back(Block{raw_alloc(total), total, 0});
+    }
+    for (Block& b : blocks) b.used = 0;
+  }
+  void destroy() { for (Block& b : blocks) raw_free(b.p); blocks.clear(); }
+};
+
 // The backend: memory + one function per kernel.  Implemented for CUDA in ba_kernels.cu (the product) and, for the
 // CPU-only host-logic tests, as serial loops over the same per-thread bodies in tests/emul/ba_backend_emul.cpp.
 struct BaBackend {
@@ -101,6 +135,8 @@ struct BaBackend {
   virtual void* alloc(size_t bytes) = 0;            // zero-initialised
   virtual void free_(void* p) = 0;
   virtual void h2d(void* dst, const void* src, size_t bytes) = 0;
+  virtual void h2d_async(void* dst, const void* src, size_t bytes) { h2d(dst, src, bytes); }   // src in staging memory; ordered on the stream
+  virtual HostArena& staging() = 0;
   virtual void d2h(void* dst, const void* src, size_t bytes) = 0;   // synchronises the stream first
   virtual void d2d(void* dst, const void* src, size_t bytes) = 0;
   virtual void zero(void* dst, size_t bytes) = 0;
