@@ -123,6 +123,32 @@ int vdo_graph_info(const vdo_graph *g, int64_t out[8]);
 int vdo_graph_debug_linearize(vdo_graph *g, double *Hpp_diag, double *bp, double *Hll_diag, double *bl, double *chi2);
 
 /* ------------------------------------------------------------------------------------------------
+ * .g2o files: the on-disk format of the graphs the reference dumps around every batch optimisation
+ * (optimizer.save(...), src/Optimizer.cc:806,808,1934,1936 -> g2o/core/optimizable_graph.cpp:589-622, element syntax in
+ * g2o/types/{vertex_se3,vertex_pointxyz,edge_se3,edge_se3_prior,edge_se3_pointxyz,types_dyn_slam3d,parameter_se3_offset}.cpp,
+ * tags in g2o/types/types_slam3d.cpp:37-57).  Host-only.  Edge arrays use compact vertex indices (position of the vertex in
+ * the file), the *_id arrays keep the file ids; information matrices are returned as written (upper triangle: 21 / 6
+ * values).  Robust kernels are not part of the format, so vdo_graph_from_g2o takes the Huber deltas as arguments. */
+typedef struct vdo_g2o vdo_g2o;
+int vdo_g2o_read(const char *path, vdo_g2o **out);   /* on a parse error *out still carries the message (vdo_g2o_error) */
+void vdo_g2o_free(vdo_g2o *g);
+const char *vdo_g2o_error(const vdo_g2o *g);
+/* out: n_se3, n_pt, n_prior, n_se3_edges, n_pointxyz_edges, n_motion_edges, n_fixed, n_offset_params */
+int vdo_g2o_counts(const vdo_g2o *g, int64_t out[8]);
+/* int arrays: se3_id pt_id fixed_id prior_v se3e_ij obs_cp ter_pph ; double arrays: se3 pt prior_Z prior_info se3e_Z
+ * se3e_info obs_z obs_info ter_meas ter_info offset */
+int vdo_g2o_get_i32(const vdo_g2o *g, const char *name, int *dst, int64_t cap);
+int vdo_g2o_get_f64(const vdo_g2o *g, const char *name, double *dst, int64_t cap);
+/* parsed file -> finalised graph; VDO_ERR_UNSUPPORTED unless every information matrix is w*I, motion measurements are
+ * zero and the sensor offset is the identity, i.e. the family src/Optimizer.cc constructs */
+int vdo_graph_from_g2o(vdo_ctx *ctx, const vdo_g2o *file, double delta_se3, double delta_pointxyz, double delta_motion, vdo_graph **out);
+/* arrays in the layout of vdo_graph_add_* -> file; ids NULL: se3 vertex i -> i, point j -> n_se3 + j; precision <= 0: 17 digits */
+int vdo_g2o_write(const char *path, int n_se3, const double *se3, const int *se3_id, int n_pt, const double *pt, const int *pt_id, int n_fixed,
+                  const int *fixed_id, int n_prior, const int *prior_v, const double *prior_Z, const double *prior_w, int n_se3e, const int *se3e_ij,
+                  const double *se3e_Z, const double *se3e_w, int n_obs, const int *obs_cp, const double *obs_z, const double *obs_w, int n_ter,
+                  const int *ter_pph, const double *ter_w, int precision);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-frame joint optical-flow / SE(3) refinement.  Replaces Optimizer::PoseOptimizationFlow2 (object motion,
  * src/Optimizer.cc:2755-2972: prior information 0.5*I2, optimize(200)) and Optimizer::PoseOptimizationFlow2Cam (camera
  * pose, src/Optimizer.cc:2333-2542: prior 0.3*I2, optimize(100)), i.e. the g2o graph of one VertexSE3Expmap + n

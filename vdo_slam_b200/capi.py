@@ -129,8 +129,84 @@ class Context:
             pass
 
 
+def g2o_read(ctx: "Context", path: str) -> dict:
+    """Parse a .g2o file (the reference's optimizer.save() dumps) into the dict layout of synth.make_batch_graph plus the file
+    ids (se3_id / pt_id / fixed_id) and the information matrices as written (prior_info / se3e_info: n x 21, obs_info /
+    ter_info: n x 6, upper triangles)."""
+    L = ctx.L
+    h = C.c_void_p()
+    rc = L.vdo_g2o_read(path.encode(), C.byref(h))
+    if rc != 0:
+        L.vdo_g2o_error.restype = C.c_char_p
+        msg = L.vdo_g2o_error(h).decode() if h else "cannot open"
+        if h:
+            L.vdo_g2o_free(h)
+        raise VdoError(f"vdo_g2o_read({path}) failed ({rc}): {msg}")
+    try:
+        cnt = (C.c_int64 * 8)()
+        ctx.check(L.vdo_g2o_counts(h, cnt), "vdo_g2o_counts")
+        n_se3, n_pt, n_pr, n_se, n_ob, n_te, n_fix, n_off = list(cnt)
+
+        def geti(name, shape):
+            a = np.zeros(shape, np.int32)
+            ctx.check(L.vdo_g2o_get_i32(h, name.encode(), _ip(a), C.c_int64(a.size)), name)
+            return a
+
+        def getf(name, shape):
+            a = np.zeros(shape, np.float64)
+            ctx.check(L.vdo_g2o_get_f64(h, name.encode(), _dp(a), C.c_int64(a.size)), name)
+            return a
+        g = {"se3": getf("se3", (n_se3, 12)), "pt": getf("pt", (n_pt, 3)), "se3_id": geti("se3_id", (n_se3,)), "pt_id": geti("pt_id", (n_pt,)),
+             "fixed_id": geti("fixed_id", (n_fix,)), "prior_v": geti("prior_v", (n_pr,)), "prior_Z": getf("prior_Z", (n_pr, 12)),
+             "prior_info": getf("prior_info", (n_pr, 21)), "se3e_ij": geti("se3e_ij", (n_se, 2)), "se3e_Z": getf("se3e_Z", (n_se, 12)),
+             "se3e_info": getf("se3e_info", (n_se, 21)), "obs_cp": geti("obs_cp", (n_ob, 2)), "obs_z": getf("obs_z", (n_ob, 3)),
+             "obs_info": getf("obs_info", (n_ob, 6)), "ter_pph": geti("ter_pph", (n_te, 3)), "ter_meas": getf("ter_meas", (n_te, 3)),
+             "ter_info": getf("ter_info", (n_te, 6)), "offset": getf("offset", (n_off, 13))}
+        g["prior_w"] = g["prior_info"][:, 0].copy(); g["se3e_w"] = g["se3e_info"][:, 0].copy()
+        g["obs_w"] = g["obs_info"][:, 0].copy(); g["ter_w"] = g["ter_info"][:, 0].copy()
+        return g
+    finally:
+        L.vdo_g2o_free(h)
+
+
+def g2o_write(ctx: "Context", path: str, g: dict, precision: int = 0):
+    """Write a graph in the make_batch_graph layout as a .g2o file (ids from g['se3_id'] / g['pt_id'] when present)."""
+    se3, pt = _f64(g["se3"]), _f64(g["pt"])
+    sid = _i32(g["se3_id"]) if "se3_id" in g else None
+    pid = _i32(g["pt_id"]) if "pt_id" in g else None
+    fix = _i32(g.get("fixed_id", np.zeros(0, np.int32)))
+    pv, pZ, pw = _i32(g["prior_v"]), _f64(g["prior_Z"]), _f64(g["prior_w"])
+    ij, sZ, sw = _i32(g["se3e_ij"]), _f64(g["se3e_Z"]), _f64(g["se3e_w"])
+    cp, oz, ow = _i32(g["obs_cp"]), _f64(g["obs_z"]), _f64(g["obs_w"])
+    pph, tw = _i32(g["ter_pph"]), _f64(g["ter_w"])
+    ctx.check(ctx.L.vdo_g2o_write(path.encode(), len(se3), _dp(se3), _ip(sid) if sid is not None else None, len(pt), _dp(pt),
+                                  _ip(pid) if pid is not None else None, len(fix), _ip(fix), len(pv), _ip(pv), _dp(pZ), _dp(pw), len(sw), _ip(ij), _dp(sZ), _dp(sw),
+                                  len(ow), _ip(cp), _dp(oz), _dp(ow), len(tw), _ip(pph), _dp(tw), int(precision)), "vdo_g2o_write")
+
+
 class BatchGraph:
     """vdo_graph: the factor graph of Optimizer::FullBatchOptimization / PartialBatchOptimization."""
+
+    @classmethod
+    def from_g2o(cls, ctx: "Context", path: str, delta_se3: float, delta_pointxyz: float, delta_motion: float):
+        """Load a .g2o file straight into a finalised graph (vdo_g2o_read + vdo_graph_from_g2o)."""
+        L = ctx.L
+        f = C.c_void_p()
+        rc = L.vdo_g2o_read(path.encode(), C.byref(f))
+        if rc != 0:
+            if f:
+                L.vdo_g2o_free(f)
+            raise VdoError(f"vdo_g2o_read({path}) failed ({rc})")
+        try:
+            cnt = (C.c_int64 * 8)()
+            ctx.check(L.vdo_g2o_counts(f, cnt), "vdo_g2o_counts")
+            self = cls.__new__(cls)
+            self.ctx, self.h = ctx, C.c_void_p()
+            self.n_se3, self.n_pt = int(cnt[0]), int(cnt[1])
+            ctx.check(L.vdo_graph_from_g2o(ctx.h, f, C.c_double(delta_se3), C.c_double(delta_pointxyz), C.c_double(delta_motion), C.byref(self.h)), "vdo_graph_from_g2o")
+            return self
+        finally:
+            L.vdo_g2o_free(f)
 
     def __init__(self, ctx: Context, g: dict):
         """g: dict in the layout of vdo_slam_b200.synth.make_batch_graph."""
