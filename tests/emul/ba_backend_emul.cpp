@@ -84,7 +84,6 @@ struct EmulBackend : BaBackend {
       } else {
         std::vector<double> ds(nl, 0.0), bb(3 * (size_t)nl, 0.0);
         for (int j = 0; j < nl; ++j) {
-          const int k = tl.k0 + j;
           for (int i = sm.LB[j] - tl.e0; i < sm.LB[j + 1] - tl.e0; ++i) chi += write ? tile_lin_edge<true>(d, tl, i, j, sm) : tile_lin_edge<false>(d, tl, i, j, sm);
           if (write) tile_lin_landmark_obs(d, tl, j, sm, ds[j], &bb[3 * j]);
           chi += write ? tile_lin_ternary<true>(d, tl, j, sm, ds[j], &bb[3 * j]) : tile_lin_ternary<false>(d, tl, j, sm, ds[j], &bb[3 * j]);

@@ -1,13 +1,16 @@
 // ba_kernels.cu -- sm_100a kernels of the batch factor-graph path and the CUDA implementation of BaBackend.
 //
 // All arithmetic is fp64 (g2o runs in double).  The path is HBM/L2-bound stream-gather-reduce work over
-// edge streams, so the kernels are organised around coalesced edge streams and shuffle reductions, not tensor cores:
-//   * landmark side  : one thread per tracklet walks its landmark-major edge stream (k_lin_tracklets, k_schur_landmarks)
-//   * se3-vertex side: one CTA per <=512-edge chunk of a vertex's edge stream, per-thread accumulation of the 21+6
-//                      (or 6) entries, warp-shuffle tree + one smem hop, then <=36 atomics per chunk
-//   * reduced system : matrix-free S*v (above two passes) inside a PCG whose preconditioner is block-tridiagonal along
-//                      the se3-se3 edge chains, solved by parallel cyclic reduction (one CTA per chain)
-// Kernel bodies live in ba_bodies.cuh (shared with the serial emulation under tests/emul).
+// edge streams, so the kernels are organised around coalesced / bulk-copied edge streams and shuffle reductions, not tensor
+// cores.  Two layouts of the landmark / edge side share this backend (chosen per graph by BaGraph::finalize, d.tiled):
+//   * tiled (default, ba_tile_kernels.cuh): one CTA per tile of whole tracklets, TMA-staged landmark blocks, landmark-side
+//     sums in shared memory, se3-vertex-side sums in the world frame over vertex-sorted warp segments; edges stored once
+//   * chunked (this file; graphs whose tracklets do not fit a tile): one thread per tracklet on the landmark-major stream
+//     (k_lin_tracklets, k_schur_*), one CTA per <=512-edge chunk of a vertex's own copy of the edge stream (k_vertex_sym,
+//     k_schur_vertex: 21+6 or 6 per-thread accumulators, warp-shuffle tree + one smem hop, <=42 atomics per chunk)
+// Common to both: the reduced system is applied matrix-free inside a PCG whose preconditioner is block-tridiagonal along the
+// se3-se3 edge chains and solved by parallel cyclic reduction (one thread-block cluster per chain); 8 PCG iterations are one
+// CUDA-graph launch.  Kernel bodies live in ba_bodies.cuh / ba_tiles.cuh (shared with the serial emulation under tests/emul).
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 

@@ -10,9 +10,9 @@
 //   landmark-major EdgeSE3PointXYZ stream (sorted by landmark): lm_obs_begin[P+1], lm_cam[E], lm_z[E*3], lm_cls[E] (u8),
 //                        lm_omega[E] (robustified weight, rewritten by every linearisation)
 //   per landmark k:      tk_h[k]  = motion vertex of the ternary edge (k, k+1), or -1;  tk_cls[k]; tk_omega[k]
-//   vertex-major EdgeSE3PointXYZ stream (sorted by se3 vertex): vm_pt[E], vm_z[E*3], vm_cls[E], vm_omega[E],
+//   (chunked layout only) vertex-major EdgeSE3PointXYZ stream (sorted by se3 vertex): vm_pt[E], vm_z[E*3], vm_cls[E], vm_omega[E],
 //                        cut into chunks {vertex, begin, end} of at most VDO_CHUNK edges
-//   vertex-major ternary stream (sorted by motion vertex): hm_p1[Et] (landmark index of p1; p2 = p1 + 1), hm_cls, hm_omega,
+//   (chunked layout only) vertex-major ternary stream (sorted by motion vertex): hm_p1[Et] (landmark index of p1; p2 = p1 + 1), hm_cls, hm_omega,
 //                        chunks likewise
 //   se3-se3 edges (prior: j = -1): se_i, se_j, se_Z[*12], se_w, se_delta, se_Hoff[*36] (J_i^T W J_j, written by linearise)
 //   adjacency for H_pp * v: nbr_begin[C+1], nbr_edge[], nbr_other[], nbr_tr[] (1: use block transposed)
