@@ -18,6 +18,7 @@
 #ifndef VDO_B200_H
 #define VDO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -147,6 +148,17 @@ int vdo_g2o_write(const char *path, int n_se3, const double *se3, const int *se3
                   const int *fixed_id, int n_prior, const int *prior_v, const double *prior_Z, const double *prior_w, int n_se3e, const int *se3e_ij,
                   const double *se3e_Z, const double *se3e_w, int n_obs, const int *obs_cp, const double *obs_z, const double *obs_w, int n_ter,
                   const int *ter_pph, const double *ter_w, int precision);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-frame input files of the reference's driver (example/vdo_slam.cc:98-141): PNG image / 16-bit disparity
+ * (cv::imread UNCHANGED, :105-110), Middlebury .flo (cv::optflow::readOpticalFlow, :117), text label mask (LoadMask,
+ * :253-450).  Host-only decoders; colour pixels in OpenCV order (BGR / BGRA), 16-bit samples host-endian. */
+int vdo_io_png_info(const char *path, int *w, int *h, int *channels, int *bit_depth);
+int vdo_io_read_png(const char *path, void *dst, size_t dst_bytes);            /* h x w x channels, uint8 or uint16 */
+int vdo_io_read_png_gray_f32(const char *path, float *dst, int w, int h);      /* == imD.convertTo(imD_f, CV_32F) */
+int vdo_io_flo_info(const char *path, int *w, int *h);
+int vdo_io_read_flo(const char *path, float *dst, size_t dst_floats);          /* h x w x 2 (u, v) = CV_32FC2 */
+int vdo_io_read_mask_txt(const char *path, int32_t *dst, int w, int h);        /* CV_32SC1, zeros where the file has zeros */
 
 /* ------------------------------------------------------------------------------------------------
  * Per-frame joint optical-flow / SE(3) refinement.  Replaces Optimizer::PoseOptimizationFlow2 (object motion,

@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     bad = [r for r in res if r[1] != 0]
     rc = 1 if bad else 0
     if not bad:
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + [r[0] for r in res]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + [r[0] for r in res] + ["-lz"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log += " ".join(cmd) + "\n" + r.stdout + r.stderr
         rc = r.returncode

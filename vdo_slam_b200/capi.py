@@ -620,3 +620,33 @@ class Tracker:
             self.close()
         except Exception:
             pass
+
+
+# ---- per-frame input files of the reference's driver (vdo_io_*, host-only) ----
+def io_read_png(ctx: "Context", path: str) -> np.ndarray:
+    """cv::imread(path, UNCHANGED): uint8 / uint16, HxW or HxWxC in BGR[A] order."""
+    w, h, ch, bd = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    ctx.check(ctx.L.vdo_io_png_info(path.encode(), C.byref(w), C.byref(h), C.byref(ch), C.byref(bd)), f"vdo_io_png_info({path})")
+    a = np.zeros((h.value, w.value, ch.value), np.uint8 if bd.value == 8 else np.uint16)
+    ctx.check(ctx.L.vdo_io_read_png(path.encode(), a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes)), f"vdo_io_read_png({path})")
+    return a[:, :, 0] if ch.value == 1 else a
+
+
+def io_read_png_gray_f32(ctx: "Context", path: str, w: int, h: int) -> np.ndarray:
+    a = np.zeros((h, w), np.float32)
+    ctx.check(ctx.L.vdo_io_read_png_gray_f32(path.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(w), C.c_int(h)), f"vdo_io_read_png_gray_f32({path})")
+    return a
+
+
+def io_read_flo(ctx: "Context", path: str) -> np.ndarray:
+    w, h = C.c_int(), C.c_int()
+    ctx.check(ctx.L.vdo_io_flo_info(path.encode(), C.byref(w), C.byref(h)), f"vdo_io_flo_info({path})")
+    a = np.zeros((h.value, w.value, 2), np.float32)
+    ctx.check(ctx.L.vdo_io_read_flo(path.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(a.size)), f"vdo_io_read_flo({path})")
+    return a
+
+
+def io_read_mask_txt(ctx: "Context", path: str, w: int, h: int) -> np.ndarray:
+    a = np.zeros((h, w), np.int32)
+    ctx.check(ctx.L.vdo_io_read_mask_txt(path.encode(), _ip(a), C.c_int(w), C.c_int(h)), f"vdo_io_read_mask_txt({path})")
+    return a
