@@ -161,6 +161,21 @@ int vdo_io_read_flo(const char *path, float *dst, size_t dst_floats);          /
 int vdo_io_read_mask_txt(const char *path, int32_t *dst, int w, int h);        /* CV_32SC1, zeros where the file has zeros */
 
 /* ------------------------------------------------------------------------------------------------
+ * Result files and error metrics (the step after the path): System::SaveResults (src/System.cc:66-244) and
+ * Tracking::GetMetricError (src/Tracking.cc:3243-3386), in the reference's float arithmetic and text format
+ * (fixed, 9 decimals).  Per-frame entry lists are flattened: n_per_frame[i] entries for frame i (entry 0 = the camera,
+ * skipped by both functions like the reference's `for j = 1`), labels / matrices of all frames back to back.  Host-only. */
+int vdo_results_write_poses(const char *path, int start_frame, int n, const float *T16);   /* initial_/refined_stereo_new.txt, cam_pose_gt_stereo.txt */
+/* obj_mot_stereo[_rf]_new.txt: body-frame motion toInvMatrix(pose_pre) * H * pose_pre ; pose_pre16 == NULL: as stored (obj_mot_gt.txt) */
+int vdo_results_write_object_motions(const char *path, int start_frame, int n_frames, const int *n_per_frame, const int *labels, const float *H16,
+                                     const float *pose_pre16);
+int vdo_results_write_object_centres(const char *path, int start_frame, int n_frames, const int *n_per_frame, const int *labels, const float *centre3);
+/* out4 = {camera t, camera R [deg], objects t, objects R [deg]} (means); each_obj_* have max_id - 1 entries (may be NULL) */
+int vdo_metric_error(int n_cam, const float *cam16, const float *cam_gt16, int n_frames, const int *n_per_frame, const int *labels,
+                     const unsigned char *obj_stat, const float *H16, const float *pose_pre16, const float *H_gt16, int max_id, float out4[4],
+                     float *each_obj_t, float *each_obj_r, int *each_obj_count);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-frame joint optical-flow / SE(3) refinement.  Replaces Optimizer::PoseOptimizationFlow2 (object motion,
  * src/Optimizer.cc:2755-2972: prior information 0.5*I2, optimize(200)) and Optimizer::PoseOptimizationFlow2Cam (camera
  * pose, src/Optimizer.cc:2333-2542: prior 0.3*I2, optimize(100)), i.e. the g2o graph of one VertexSE3Expmap + n

@@ -650,3 +650,51 @@ def io_read_mask_txt(ctx: "Context", path: str, w: int, h: int) -> np.ndarray:
     a = np.zeros((h, w), np.int32)
     ctx.check(ctx.L.vdo_io_read_mask_txt(path.encode(), _ip(a), C.c_int(w), C.c_int(h)), f"vdo_io_read_mask_txt({path})")
     return a
+
+
+# ---- result files / metrics (vdo_results_*, vdo_metric_error; host-only) ----
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _flatten_frames(per_frame):
+    """list (frames) of lists (entries) of arrays -> (counts i32, stacked f32 array)"""
+    cnt = np.array([len(f) for f in per_frame], np.int32)
+    flat = [np.asarray(m, np.float32) for f in per_frame for m in f]
+    return cnt, (np.stack(flat) if flat else np.zeros((0, 4, 4), np.float32))
+
+
+def results_write_poses(ctx: "Context", path: str, poses, start_frame: int = 0):
+    P = np.ascontiguousarray(np.asarray(poses, np.float32).reshape(-1, 16))
+    ctx.check(ctx.L.vdo_results_write_poses(path.encode(), C.c_int(start_frame), C.c_int(len(P)), _fp(P)), "vdo_results_write_poses")
+
+
+def results_write_object_motions(ctx: "Context", path: str, motions, labels, pose_pre=None, start_frame: int = 0):
+    cnt, H = _flatten_frames(motions)
+    H = np.ascontiguousarray(H.reshape(-1, 16))
+    lab = np.ascontiguousarray(np.concatenate([np.asarray(l, np.int32) for l in labels]) if len(labels) else np.zeros(0, np.int32))
+    L = None
+    if pose_pre is not None:
+        L = np.ascontiguousarray(_flatten_frames(pose_pre)[1].reshape(-1, 16))
+    ctx.check(ctx.L.vdo_results_write_object_motions(path.encode(), C.c_int(start_frame), C.c_int(len(cnt)), _ip(cnt), _ip(lab), _fp(H),
+                                                     _fp(L) if L is not None else None), "vdo_results_write_object_motions")
+
+
+def results_write_object_centres(ctx: "Context", path: str, centres, labels, start_frame: int = 0):
+    cnt = np.array([len(f) for f in centres], np.int32)
+    Cn = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float32).reshape(-1, 3) for f in centres]) if len(centres) else np.zeros((0, 3), np.float32))
+    lab = np.ascontiguousarray(np.concatenate([np.asarray(l, np.int32) for l in labels]) if len(labels) else np.zeros(0, np.int32))
+    ctx.check(ctx.L.vdo_results_write_object_centres(path.encode(), C.c_int(start_frame), C.c_int(len(cnt)), _ip(cnt), _ip(lab), _fp(Cn)), "vdo_results_write_object_centres")
+
+
+def metric_error(ctx: "Context", cam, cam_gt, motions, pose_pre, motions_gt, labels, obj_stat, max_id: int) -> dict:
+    Cm = np.ascontiguousarray(np.asarray(cam, np.float32).reshape(-1, 16)); Cg = np.ascontiguousarray(np.asarray(cam_gt, np.float32).reshape(-1, 16))
+    cnt, H = _flatten_frames(motions)
+    H = np.ascontiguousarray(H.reshape(-1, 16)); L = np.ascontiguousarray(_flatten_frames(pose_pre)[1].reshape(-1, 16)); G = np.ascontiguousarray(_flatten_frames(motions_gt)[1].reshape(-1, 16))
+    lab = np.ascontiguousarray(np.concatenate([np.asarray(l, np.int32) for l in labels]))
+    st = np.ascontiguousarray(np.concatenate([np.asarray(s, np.uint8) for s in obj_stat]))
+    out = np.zeros(4, np.float32); n = max(max_id - 1, 0)
+    et, er, ec = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+    ctx.check(ctx.L.vdo_metric_error(C.c_int(len(Cm)), _fp(Cm), _fp(Cg), C.c_int(len(cnt)), _ip(cnt), _ip(lab), st.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(H), _fp(L), _fp(G),
+                                     C.c_int(max_id), _fp(out), _fp(et), _fp(er), _ip(ec)), "vdo_metric_error")
+    return {"cam_t": float(out[0]), "cam_r": float(out[1]), "obj_t": float(out[2]), "obj_r": float(out[3]), "each_t": et, "each_r": er, "each_count": ec}
