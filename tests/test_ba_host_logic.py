@@ -151,3 +151,22 @@ def test_tracklet_too_large_for_a_tile_falls_back_to_the_chunked_layout(ectx):
     ro = po.ba_optimize(g, max_iters=2, gain_threshold=0)              # (the oracle's sparse Cholesky is the slow side here)
     assert r["iterations"] == ro["iters"]
     assert np.abs(G.vertices()[0] - ro["se3"]).max() < 1e-6 and np.abs(G.vertices()[1] - ro["pt"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("seed,frames,objs,ns,nd", [(21, 6, 1, 40, 10), (22, 45, 4, 900, 600), (23, 12, 0, 700, 0), (24, 25, 3, 5, 300), (25, 3, 1, 2000, 30)])
+def test_tiled_layout_first_linearisation_and_schur_products_match_chunked(ectx, monkeypatch, seed, frames, objs, ns, nd):
+    """Shape sweep (few / many tracklets per tile, static-only, dynamic-heavy, more edges than one tile holds): the first
+    linearisation (H_pp, b_p, H_ll, b_l, chi2) and three LM iterations agree between the two layouts."""
+    g = make_batch_graph(n_frames=frames, n_objects=objs, n_static=ns, n_dynamic=nd, seed=seed)
+    out = {}
+    for lay in ("tiled", "chunked"):
+        monkeypatch.setenv("VDO_BA_LAYOUT", lay)
+        G = capi.BatchGraph(ectx, g)
+        lin = [np.asarray(x) for x in G.debug_linearize()]
+        r = G.optimize(max_iterations=3, gain_threshold=0)
+        out[lay] = (lin, r, G.vertices())
+    for x, y in zip(out["tiled"][0], out["chunked"][0]):
+        assert np.abs(x - y).max() <= 1e-9 * max(1.0, np.abs(y).max())
+    assert out["tiled"][1]["iterations"] == out["chunked"][1]["iterations"]
+    np.testing.assert_allclose(out["tiled"][2][0], out["chunked"][2][0], atol=1e-9)
+    np.testing.assert_allclose(out["tiled"][2][1], out["chunked"][2][1], atol=1e-9)
