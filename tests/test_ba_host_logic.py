@@ -170,3 +170,20 @@ def test_tiled_layout_first_linearisation_and_schur_products_match_chunked(ectx,
     assert out["tiled"][1]["iterations"] == out["chunked"][1]["iterations"]
     np.testing.assert_allclose(out["tiled"][2][0], out["chunked"][2][0], atol=1e-9)
     np.testing.assert_allclose(out["tiled"][2][1], out["chunked"][2][1], atol=1e-9)
+
+
+def test_ingest_is_independent_of_the_host_thread_count(ectx, monkeypatch):
+    """Graph ingestion is threaded (stable bucket partition of the edge list, per-tile sorts); the device layout -- and with it
+    every sum order -- must not depend on the number of workers."""
+    g = make_batch_graph(n_frames=25, n_objects=2, n_static=1200, n_dynamic=300, seed=9)
+    res = []
+    for nthreads in ("1", "5", "16"):
+        monkeypatch.setenv("VDO_HOST_THREADS", nthreads)
+        G = capi.BatchGraph(ectx, g)
+        lin = [np.asarray(x) for x in G.debug_linearize()]
+        G.optimize(max_iterations=3, gain_threshold=0)
+        res.append((lin, G.vertices()))
+    for lin, v in res[1:]:
+        for x, y in zip(lin, res[0][0]):
+            assert np.array_equal(x, y)
+        assert np.array_equal(v[0], res[0][1][0]) and np.array_equal(v[1], res[0][1][1])

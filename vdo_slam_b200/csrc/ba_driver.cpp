@@ -18,12 +18,9 @@ namespace {
 // Host-side worker threads of finalize() (graph ingestion is memory-latency-bound scatter work; the reference's own
 // graph construction is single-threaded, src/Optimizer.cc:1232-1930).  VDO_HOST_THREADS overrides the default.
 int host_threads() {
-  static int n = [] {
-    const char* e = std::getenv("VDO_HOST_THREADS");
-    int v = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    return std::max(1, std::min(v, 64));
-  }();
-  return n;
+  const char* e = std::getenv("VDO_HOST_THREADS");
+  const int v = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  return std::max(1, std::min(v, 64));
 }
 template <typename F> void parallel_for(int nthreads, F fn) {   // fn(thread index, thread count)
   if (nthreads <= 1) { fn(0, 1); return; }
@@ -180,6 +177,7 @@ int BaGraph::finalize() {
       return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges must form simple chains (one predecessor / successor per landmark)");
     next[p1] = p2; prev[p2] = p1; ter_of[p1] = e;
   }
+  lap("  chain links");
   new_of_old_.assign(P, -1);
   HostBuf<int> old_of_new = stage<int>(P);
   std::vector<int> tk_begin;
@@ -191,12 +189,39 @@ int BaGraph::finalize() {
   // Multi-GPU: tracklets are dealt round-robin to the ranks (each group separately, in this order); a rank keeps only its
   // own landmarks and their edges, the se3 state is replicated.
   const int rank = be_->rank, world = be_->world;
-  HostBuf<int> first_cam = stage<int>(P);
-  for (int p = 0; p < P; ++p) first_cam[p] = C;
-  parallel_for(host_threads(), [&](int t, int n) {      // each worker owns a landmark range and scans the edge list
-    const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
-    for (int e = 0; e < Eo_all; ++e) { const int p = ob_cp_[2 * e + 1]; if (p >= lo && p < hi) { const int c = S3(ob_cp_[2 * e]); if (c < first_cam[p]) first_cam[p] = c; } }
+  // Edge partition: the pointxyz edges are split, in the caller's order, into NB buckets of consecutive (old) landmark ids --
+  // a stable parallel counting sort by bucket (chunk t of the edge list counts, then writes its edge indices behind the
+  // chunks before it).  Everything per-landmark below (first camera, edge count, the scatter into landmark order) is then
+  // done by the worker that owns the bucket, reading only its own edges: O(E) work in total and the same result for any
+  // thread count.
+  const int NT = host_threads(), NB = NT, P0 = std::max(P, 1);
+  auto bucket_of = [NB, P0](int p) { return (int)((int64_t)p * NB / P0); };
+  std::vector<int64_t> tb((size_t)NT * NB + 1, 0);
+  parallel_for(NT, [&](int t, int n) {
+    const int a = (int)((int64_t)Eo_all * t / n), b = (int)((int64_t)Eo_all * (t + 1) / n);
+    int64_t* c = &tb[(size_t)t * NB];
+    for (int e = a; e < b; ++e) c[bucket_of(ob_cp_[2 * e + 1])]++;
   });
+  std::vector<int64_t> off((size_t)NB * NT + 1, 0);      // off[b * NT + t]: first slot of chunk t inside bucket b
+  { int64_t run = 0; for (int b = 0; b < NB; ++b) for (int t = 0; t < NT; ++t) { off[(size_t)b * NT + t] = run; run += tb[(size_t)t * NB + b]; } off[(size_t)NB * NT] = run; }
+  HostBuf<int> eidx = stage<int>(Eo_all);
+  parallel_for(NT, [&](int t, int n) {
+    const int a = (int)((int64_t)Eo_all * t / n), b = (int)((int64_t)Eo_all * (t + 1) / n);
+    std::vector<int64_t> cur(NB);
+    for (int k = 0; k < NB; ++k) cur[k] = off[(size_t)k * NT + t];
+    for (int e = a; e < b; ++e) eidx[cur[bucket_of(ob_cp_[2 * e + 1])]++] = e;
+  });
+  HostBuf<int> first_cam = stage<int>(P), cnt_old = stage_fill<int>(P, 0);
+  parallel_for(NB, [&](int b, int) {
+    const int lo = (int)(((int64_t)b * P + NB - 1) / NB), hi = (int)(((int64_t)(b + 1) * P + NB - 1) / NB);   // landmarks p with bucket_of(p) == b
+    for (int p = lo; p < hi && p < P; ++p) first_cam[p] = C;
+    for (int64_t q = off[(size_t)b * NT]; q < off[(size_t)(b + 1) * NT]; ++q) {
+      const int e = eidx[q], p = ob_cp_[2 * e + 1], c = S3(ob_cp_[2 * e]);
+      if (c < first_cam[p]) first_cam[p] = c;
+      cnt_old[p]++;
+    }
+  });
+  lap("  first_cam scan");
   auto counting_sort = [&](std::vector<int>& ids, const HostBuf<int>& key_of_id, int nkeys) {   // stable
     std::vector<int> cntk(nkeys + 1, 0), out(ids.size());
     for (int id : ids) cntk[key_of_id[id] + 1]++;
@@ -205,11 +230,11 @@ int BaGraph::finalize() {
     ids.swap(out);
   };
   std::vector<int> stat_ids, chain_heads;
-  int n_seen = 0;
   for (int p = 0; p < P; ++p) {
-    if (prev[p] == -1 && next[p] == -1) { stat_ids.push_back(p); ++n_seen; }
-    else if (prev[p] == -1) { chain_heads.push_back(p); for (int q = p; q != -1; q = next[q]) ++n_seen; }
+    if (prev[p] != -1) continue;
+    if (next[p] == -1) stat_ids.push_back(p); else chain_heads.push_back(p);
   }
+  lap("  collect heads");
   counting_sort(stat_ids, first_cam, C + 1);
   {
     HostBuf<int> first_h = stage_fill<int>(P, 0);
@@ -217,23 +242,38 @@ int BaGraph::finalize() {
     counting_sort(chain_heads, first_cam, C + 1);
     counting_sort(chain_heads, first_h, C + 1);
   }
-  int t_idx = 0;
-  for (int p : stat_ids) {
-    if ((t_idx++ % world) != rank) continue;
-    tk_begin.push_back(cnt);
-    new_of_old_[p] = cnt; old_of_new[cnt++] = p;
-  }
-  const int Tstat = cnt;
-  t_idx = 0;
-  for (int p : chain_heads) {
-    if ((t_idx++ % world) != rank) continue;
-    tk_begin.push_back(cnt);
-    for (int q = p; q != -1; q = next[q]) { new_of_old_[q] = cnt; old_of_new[cnt++] = q; }
-  }
+  lap("  counting sorts");
+  // chain lengths (parallel walks); every landmark must be a static point or lie on a chain that starts at a head
+  const int n_heads = (int)chain_heads.size();
+  std::vector<int> chain_len(n_heads);
+  std::vector<int64_t> seen_part(NT, 0);
+  parallel_for(NT, [&](int t, int n) {
+    const int a = (int)((int64_t)n_heads * t / n), b = (int)((int64_t)n_heads * (t + 1) / n);
+    int64_t sum = 0;
+    for (int i = a; i < b; ++i) { int len = 0; for (int q = chain_heads[i]; q != -1; q = next[q]) ++len; chain_len[i] = len; sum += len; }
+    seen_part[t] = sum;
+  });
+  int64_t n_seen = (int64_t)stat_ids.size();
+  for (int64_t v : seen_part) n_seen += v;
   if (n_seen != P) return fail(VDO_ERR_UNSUPPORTED, "landmark-motion edges contain a cycle");
+  // deal the tracklets to the ranks (round-robin in sorted order) and number the kept landmarks
+  std::vector<int> stat_keep, head_keep, head_len;
+  if (world == 1) { stat_keep.swap(stat_ids); head_keep.swap(chain_heads); head_len.swap(chain_len); }
+  else {
+    for (size_t i = rank; i < stat_ids.size(); i += world) stat_keep.push_back(stat_ids[i]);
+    for (size_t i = rank; i < chain_heads.size(); i += world) { head_keep.push_back(chain_heads[i]); head_len.push_back(chain_len[i]); }
+  }
+  const int Tstat = (int)stat_keep.size(), Tch = (int)head_keep.size();
+  tk_begin.resize((size_t)Tstat + Tch + 1);
+  { int run = Tstat; for (int i = 0; i < Tch; ++i) { tk_begin[Tstat + i] = run; run += head_len[i]; } tk_begin[Tstat + Tch] = run; cnt = run; }
+  parallel_for(NT, [&](int t, int n) {
+    const int a = (int)((int64_t)Tstat * t / n), b = (int)((int64_t)Tstat * (t + 1) / n);
+    for (int i = a; i < b; ++i) { tk_begin[i] = i; new_of_old_[stat_keep[i]] = i; old_of_new[i] = stat_keep[i]; }
+    const int c = (int)((int64_t)Tch * t / n), d2 = (int)((int64_t)Tch * (t + 1) / n);
+    for (int i = c; i < d2; ++i) { int k = tk_begin[Tstat + i]; for (int q = head_keep[i]; q != -1; q = next[q]) { new_of_old_[q] = k; old_of_new[k++] = q; } }
+  });
   const int P_all = P;
   P = cnt;                      // from here on P = landmarks owned by this rank
-  tk_begin.push_back(cnt);
   const int T = (int)tk_begin.size() - 1;
 
   lap("tracklet order");
@@ -242,44 +282,55 @@ int BaGraph::finalize() {
   // Edge classes first (sequential; consecutive edges almost always share their (information, delta) pair), then the scatter
   // into landmark order by worker threads that each own a contiguous landmark range and scan the edge list in order, so the
   // order of a landmark's edges is the caller's order whatever the thread count.
-  const int NT = host_threads();
   HostBuf<uint8_t> ecls = stage<uint8_t>(Eo_all);
   {
-    double lw = 0, ld = 0; int lc = -1;
-    for (int e = 0; e < Eo_all; ++e) {
-      if (lc < 0 || ob_w_[e] != lw || ob_d_[e] != ld) {
-        lc = oc.get(ob_w_[e], ob_d_[e]); lw = ob_w_[e]; ld = ob_d_[e];
-        if (lc > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on pointxyz edges");
+    // fast path: every edge carries the first edge's (information, delta) pair (checked in parallel)
+    std::vector<char> uniform(NT, 1);
+    if (Eo_all > 0) {
+      const double w0 = ob_w_[0], d0 = ob_d_[0];
+      parallel_for(NT, [&](int t, int n) {
+        const int a = (int)((int64_t)Eo_all * t / n), b = (int)((int64_t)Eo_all * (t + 1) / n);
+        char u = 1;
+        for (int e = a; e < b; ++e) if (ob_w_[e] != w0 || ob_d_[e] != d0) { u = 0; break; }
+        uniform[t] = u;
+      });
+    }
+    bool all_uniform = Eo_all > 0;
+    for (char u : uniform) all_uniform = all_uniform && u;
+    if (all_uniform) { const int c0 = oc.get(ob_w_[0], ob_d_[0]); fill_bytes(ecls.p, c0, (size_t)Eo_all); }
+    else {
+      double lw = 0, ld = 0; int lc = -1;
+      for (int e = 0; e < Eo_all; ++e) {
+        if (lc < 0 || ob_w_[e] != lw || ob_d_[e] != ld) {
+          lc = oc.get(ob_w_[e], ob_d_[e]); lw = ob_w_[e]; ld = ob_d_[e];
+          if (lc > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on pointxyz edges");
+        }
+        ecls[e] = (uint8_t)lc;
       }
-      ecls[e] = (uint8_t)lc;
     }
   }
   lap("  edge classes");
-  HostBuf<int> kof = stage<int>(Eo_all);
+  // edges per landmark in the new order (gathered from the per-old-landmark counts), prefix sum, then the scatter: the worker
+  // that owns a bucket walks its edges in the caller's order and appends each to its landmark's slot range
+  HostBuf<int> lm_begin = stage<int>((size_t)P + 1);
+  lm_begin[0] = 0;
   parallel_for(NT, [&](int t, int n) {
-    const int a = (int)((int64_t)Eo_all * t / n), b = (int)((int64_t)Eo_all * (t + 1) / n);
-    for (int e = a; e < b; ++e) kof[e] = new_of_old_[ob_cp_[2 * e + 1]];
-  });
-  lap("  kof");
-  HostBuf<int> lm_begin = stage_fill<int>((size_t)P + 1, 0);
-  parallel_for(NT, [&](int t, int n) {
-    const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
-    for (int e = 0; e < Eo_all; ++e) { const int k = kof[e]; if (k >= lo && k < hi) lm_begin[k + 1]++; }
+    const int a = (int)((int64_t)P * t / n), b = (int)((int64_t)P * (t + 1) / n);
+    for (int k = a; k < b; ++k) lm_begin[k + 1] = cnt_old[old_of_new[k]];
   });
   lap("  count");
   for (int k = 0; k < P; ++k) lm_begin[k + 1] += lm_begin[k];
   const int Eo = lm_begin[P];
-  HostBuf<int> fill = stage<int>(P), lm_cam = stage<int>(Eo);
-  copy_bytes(fill.p, lm_begin.p, sizeof(int) * (size_t)P);
+  HostBuf<int> lm_cam = stage<int>(Eo);
   HostBuf<double> lm_z = stage<double>(3 * (size_t)Eo);
   HostBuf<uint8_t> lm_cls = stage<uint8_t>(Eo);
+  fill_bytes(cnt_old.p, 0, sizeof(int) * (size_t)P_all);        // reused: edges of the (old) landmark written so far
   lap("  prefix + alloc");
-  parallel_for(NT, [&](int t, int n) {
-    const int lo = (int)((int64_t)P * t / n), hi = (int)((int64_t)P * (t + 1) / n);
-    for (int e = 0; e < Eo_all; ++e) {
-      const int k = kof[e];
-      if (k < lo || k >= hi) continue;
-      const int pos = fill[k]++;
+  parallel_for(NB, [&](int b, int) {
+    for (int64_t q = off[(size_t)b * NT]; q < off[(size_t)(b + 1) * NT]; ++q) {
+      const int e = eidx[q], p = ob_cp_[2 * e + 1], k = new_of_old_[p];
+      if (k < 0) continue;                                       // landmark owned by another rank
+      const int pos = lm_begin[k] + cnt_old[p]++;
       lm_cam[pos] = new_se3_of_old_[ob_cp_[2 * e]];
       lm_z[3 * (size_t)pos] = ob_z_[3 * (size_t)e]; lm_z[3 * (size_t)pos + 1] = ob_z_[3 * (size_t)e + 1]; lm_z[3 * (size_t)pos + 2] = ob_z_[3 * (size_t)e + 2];
       lm_cls[pos] = ecls[e];
@@ -332,15 +383,30 @@ int BaGraph::finalize() {
   HostBuf<uint8_t> tk_cls = stage_fill<uint8_t>(P, 0);
   std::vector<int> hm_begin(C + 1, 0);
   int Et = 0;
-  for (int e = 0; e < Et_all; ++e) {
-    int k = new_of_old_[te_pph_[3 * e]];
-    if (k < 0) continue;
-    ++Et;
-    tk_h[k] = S3(te_pph_[3 * e + 2]);
-    int cls = tc.get(te_w_[e], te_d_[e]);
-    if (cls > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on landmark-motion edges");
-    tk_cls[k] = (uint8_t)cls;
-    hm_begin[S3(te_pph_[3 * e + 2]) + 1]++;
+  {
+    HostBuf<uint8_t> tcls = stage<uint8_t>(Et_all);
+    double lw = 0, ld = 0; int lc = -1;
+    for (int e = 0; e < Et_all; ++e) {                       // classes: sequential with a last-value cache (one map look-up per change)
+      if (lc < 0 || te_w_[e] != lw || te_d_[e] != ld) {
+        lc = tc.get(te_w_[e], te_d_[e]); lw = te_w_[e]; ld = te_d_[e];
+        if (lc > 255) return fail(VDO_ERR_UNSUPPORTED, "more than 256 distinct (information, Huber delta) pairs on landmark-motion edges");
+      }
+      tcls[e] = (uint8_t)lc;
+    }
+    std::vector<int> et_part(NT, 0);
+    parallel_for(NT, [&](int t, int n) {                     // every landmark is p1 of at most one edge: the writes are disjoint
+      const int a = (int)((int64_t)Et_all * t / n), b = (int)((int64_t)Et_all * (t + 1) / n);
+      int cnt_t = 0;
+      for (int e = a; e < b; ++e) {
+        const int k = new_of_old_[te_pph_[3 * e]];
+        if (k < 0) continue;
+        ++cnt_t;
+        tk_h[k] = S3(te_pph_[3 * e + 2]); tk_cls[k] = tcls[e];
+      }
+      et_part[t] = cnt_t;
+    });
+    for (int c : et_part) Et += c;
+    if (!tiled) for (int k = 0; k < P; ++k) if (tk_h[k] >= 0) hm_begin[tk_h[k] + 1]++;
   }
   std::vector<int> hm_p1;
   std::vector<uint8_t> hm_cls;
