@@ -201,7 +201,7 @@ int vdo_g2o_get_f64(const vdo_g2o* g, const char* name, double* dst, int64_t cap
 // Builds a vdo_graph from a parsed file.  The batch solver covers exactly the family the reference constructs: scalar
 // information w * I on every edge, zero landmark-motion measurement, identity sensor offset -- anything else is
 // VDO_ERR_UNSUPPORTED (never approximated).  delta_*: Huber deltas of the three robustified edge families (<= 0: none), as
-// src/Optimizer.cc sets them on the edges it creates (:1352-1353, :1430-1435, :1740-1741).
+// src/Optimizer.cc sets them on the edges it creates (deltaHuberCamMot / deltaHuber3D / deltaHuberObjMot = 1e-4, :1352; :213).
 int vdo_graph_from_g2o(vdo_ctx* ctx, const vdo_g2o* f, double delta_se3, double delta_pointxyz, double delta_motion, vdo_graph** out) {
   if (!ctx || !f || !out) return VDO_ERR_ARG;
   *out = nullptr;
