@@ -198,7 +198,7 @@ def run_ours(args, rank, world, local_rank):
     kb = {k: v // world for k, v in kernel_bytes(g).items()}      # sharded solves: each rank streams its 1/world of the tracklets
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}) if world == 1 else {}   # measured on 1 GPU (whole graph)
     except Exception:
         pass
     pcg_per_it = pcg / max(iters, 1)
