@@ -169,7 +169,6 @@ int BaGraph::finalize() {
   auto S3 = [&](int old_id) { return new_se3_of_old_[old_id]; };
   lap("se3 paths");
   // ---- tracklets: chains of landmarks linked by ternary edges ----
-  (void)0;
   HostBuf<int> next = stage_fill<int>(P, 0xFF), prev = stage_fill<int>(P, 0xFF), ter_of = stage_fill<int>(P, 0xFF);
   for (int e = 0; e < Et_all; ++e) {
     int p1 = te_pph_[3 * e], p2 = te_pph_[3 * e + 1];
