@@ -50,6 +50,9 @@ typedef struct {
   long oplus_calls;
 } ba_t;
 
+#include <time.h>
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 static inline int blk_dim(const ba_t *g, int blk) { return blk < g->n_pt ? 3 : 6; }
 static inline int blk_col(const ba_t *g, int blk) { return blk < g->n_pt ? 3 * blk : 3 * g->n_pt + 6 * (blk - g->n_pt); }
 
@@ -367,25 +370,34 @@ static void ba_free(ba_t *g) {
  * stats[4]=seconds total.
  * Returns the number of iterations performed (like optimize()), or -1 on structural failure.
  */
-#include <time.h>
-static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+#include "ba_block.h"
 
-int vdo_oracle_ba_optimize(int n_se3, double *se3, int n_pt, double *pt,
+static int ba_optimize_impl(int n_se3, double *se3, int n_pt, double *pt,
                            int n_prior, const int *prior_v, const double *prior_Z, const double *prior_w,
                            int n_se3e, const int *se3e_ij, const double *se3e_Z, const double *se3e_w, const double *se3e_delta,
                            int n_obs, const int *obs_cp, const double *obs_z, const double *obs_w, const double *obs_delta,
                            int n_ter, const int *ter_pph, const double *ter_w, const double *ter_delta,
-                           int max_iters, double gain_threshold, int verbose, double *chi2_hist, double *stats) {
+                           int max_iters, double gain_threshold, int verbose, double *chi2_hist, double *stats,
+                           int solver, const int *se3_pos, int nthreads, double *lam_hist, double time_budget_s, double *t_hist) {
   ba_t G; memset(&G, 0, sizeof G);
   ba_t *g = &G;
+  blk_t BK; blk_t *B = &BK;
   g->n_se3 = n_se3; g->se3 = se3; g->n_pt = n_pt; g->pt = pt;
   g->n_prior = n_prior; g->prior_v = prior_v; g->prior_Z = prior_Z; g->prior_w = prior_w;
   g->n_se3e = n_se3e; g->se3e_ij = se3e_ij; g->se3e_Z = se3e_Z; g->se3e_w = se3e_w; g->se3e_delta = se3e_delta;
   g->n_obs = n_obs; g->obs_cp = obs_cp; g->obs_z = obs_z; g->obs_w = obs_w; g->obs_delta = obs_delta;
   g->n_ter = n_ter; g->ter_pph = ter_pph; g->ter_w = ter_w; g->ter_delta = ter_delta;
-  double t_start = now_s(), t_lin = 0;
-  build_structure(g);
-  chol_symbolic(g);
+  double t_start = now_s(), t_lin = 0, t_setup = 0;
+  if (solver == 0) {
+    build_structure(g);
+    chol_symbolic(g);
+  } else {                                  /* blocked solver (ba_block.h): same system, same solution */
+    g->n = 3 * n_pt + 6 * n_se3;
+    g->b = (double *)calloc((size_t)g->n + 1, sizeof(double));
+    g->x = (double *)calloc((size_t)g->n + 1, sizeof(double));
+    blk_structure(g, B, se3_pos, nthreads);
+  }
+  t_setup = now_s() - t_start;
   const int P = n_pt, C = n_se3, n = g->n;
   double *bk_se3 = (double *)malloc(sizeof(double) * 12 * (size_t)(C > 0 ? C : 1));
   double *bk_pt = (double *)malloc(sizeof(double) * 3 * (size_t)(P > 0 ? P : 1));
@@ -397,17 +409,17 @@ int vdo_oracle_ba_optimize(int n_se3, double *se3, int n_pt, double *pt,
   for (int it = 0; it < max_iters && !stop_flag && ok; ++it) {
     /* ---- OptimizationAlgorithmLevenberg::solve ---- */
     double current = robust_chi2(g), temp = current, ini = current;
-    build_system(g);
-    if (it == 0) {                                  /* computeLambdaInit: tau * max |H_jj| */
-      double md = 0;
-      for (int j = 0; j < n; ++j) { double d = fabs(g->Ax[g->Ap[j + 1] - 1]); if (d > md) md = d; }
-      lambda = 1e-5 * md; ni = 2; nbad = 0;
-    }
+    double md = 0;
+    if (solver == 0) {
+      build_system(g);
+      if (it == 0) for (int j = 0; j < n; ++j) { double d = fabs(g->Ax[g->Ap[j + 1] - 1]); if (d > md) md = d; }
+    } else md = blk_build_system(g, B);
+    if (it == 0) { lambda = 1e-5 * md; ni = 2; nbad = 0; }   /* computeLambdaInit: tau * max |H_jj| */
     double rho = 0; int qmax = 0, result_ok = 1;
     do {
       memcpy(bk_se3, g->se3, sizeof(double) * 12 * C); memcpy(bk_pt, g->pt, sizeof(double) * 3 * P);   /* push */
       double t0 = now_s();
-      int ok2 = chol_solve(g, lambda);
+      int ok2 = solver == 0 ? chol_solve(g, lambda) : blk_solve(g, B, lambda);
       t_lin += now_s() - t0;
       if (!ok2) memcpy(g->x, g->b, sizeof(double) * n);  /* linear_solver_csparse.h:124-126: x was pre-loaded with b and the failed factorisation leaves it there */
       apply_update(g);
@@ -440,8 +452,11 @@ int vdo_oracle_ba_optimize(int n_se3, double *se3, int n_pt, double *pt,
     if (chi2_check < chi_now && it > 0) ok = 0;
     chi2_check = chi_now;
     if (chi2_hist) chi2_hist[it + 1] = chi_now;
-    if (verbose) fprintf(stderr, "[oracle] iteration= %d\t chi2= %.9g\t lambda= %.6g\t levenbergIter= %d\n", it, chi_now, lambda, qmax);
+    if (lam_hist) lam_hist[it] = lambda;
+    if (t_hist) t_hist[it] = now_s() - t_start;
+    if (verbose) fprintf(stderr, "[oracle] iteration= %d\t chi2= %.9g\t lambda= %.6g\t levenbergIter= %d\t t= %.1fs\n", it, chi_now, lambda, qmax, now_s() - t_start);
     ++iters_done;
+    if (time_budget_s > 0 && now_s() - t_start > time_budget_s) break;    /* bench only: bounded sample of the solve */
     if (gain_threshold > 0) {                        /* postIteration: SparseOptimizerTerminateAction */
       if (it == 0) last_chi_action = chi_now;
       else {
@@ -451,10 +466,40 @@ int vdo_oracle_ba_optimize(int n_se3, double *se3, int n_pt, double *pt,
       }
     }
   }
-  if (stats) { stats[0] = lambda; stats[1] = (double)trials; stats[2] = (double)g->lnz; stats[3] = t_lin; stats[4] = now_s() - t_start; }
+  if (stats) {
+    stats[0] = lambda; stats[1] = (double)trials; stats[2] = (double)g->lnz; stats[3] = t_lin; stats[4] = now_s() - t_start; stats[5] = t_setup;
+    if (solver != 0) { stats[2] = (double)B->toff[B->T] * BLK_NB * BLK_NB; stats[6] = B->t_schur; stats[7] = B->t_chol; }
+  }
   free(bk_se3); free(bk_pt);
-  ba_free(g);
+  if (solver == 0) ba_free(g); else { free(g->b); free(g->x); blk_free(B); }
   return iters_done;
+}
+
+int vdo_oracle_ba_optimize(int n_se3, double *se3, int n_pt, double *pt,
+                           int n_prior, const int *prior_v, const double *prior_Z, const double *prior_w,
+                           int n_se3e, const int *se3e_ij, const double *se3e_Z, const double *se3e_w, const double *se3e_delta,
+                           int n_obs, const int *obs_cp, const double *obs_z, const double *obs_w, const double *obs_delta,
+                           int n_ter, const int *ter_pph, const double *ter_w, const double *ter_delta,
+                           int max_iters, double gain_threshold, int verbose, double *chi2_hist, double *stats) {
+  return ba_optimize_impl(n_se3, se3, n_pt, pt, n_prior, prior_v, prior_Z, prior_w, n_se3e, se3e_ij, se3e_Z, se3e_w, se3e_delta,
+                          n_obs, obs_cp, obs_z, obs_w, obs_delta, n_ter, ter_pph, ter_w, ter_delta,
+                          max_iters, gain_threshold, verbose, chi2_hist, stats, 0, NULL, 1, NULL, 0.0, NULL);
+}
+
+/* Same LM, blocked linear solver (ba_block.h).  se3_pos[v] = position of se3 vertex v in the elimination order (NULL: identity);
+ * nthreads <= 0: all;  lam_hist[i] = lambda after iteration i;  time_budget_s > 0 stops after the iteration that crosses it
+ * (bench.py's bounded CPU sample); t_hist[i] = seconds since the call started when iteration i ended; stats[5..7] = setup / Schur /
+ * band-Cholesky seconds. */
+int vdo_oracle_ba_optimize_blocked(int n_se3, double *se3, int n_pt, double *pt,
+                           int n_prior, const int *prior_v, const double *prior_Z, const double *prior_w,
+                           int n_se3e, const int *se3e_ij, const double *se3e_Z, const double *se3e_w, const double *se3e_delta,
+                           int n_obs, const int *obs_cp, const double *obs_z, const double *obs_w, const double *obs_delta,
+                           int n_ter, const int *ter_pph, const double *ter_w, const double *ter_delta,
+                           int max_iters, double gain_threshold, int verbose, double *chi2_hist, double *stats,
+                           const int *se3_pos, int nthreads, double *lam_hist, double time_budget_s, double *t_hist) {
+  return ba_optimize_impl(n_se3, se3, n_pt, pt, n_prior, prior_v, prior_Z, prior_w, n_se3e, se3e_ij, se3e_Z, se3e_w, se3e_delta,
+                          n_obs, obs_cp, obs_z, obs_w, obs_delta, n_ter, ter_pph, ter_w, ter_delta,
+                          max_iters, gain_threshold, verbose, chi2_hist, stats, 1, se3_pos, nthreads, lam_hist, time_budget_s, t_hist);
 }
 
 /* ---- small debugging / test entry points ---- */

@@ -54,6 +54,55 @@ def ba_optimize(g, max_iters=300, gain_threshold=1e-4, verbose=False):
                 stats=dict(lam=stats[0], trials=int(stats[1]), lnz=int(stats[2]), t_linear=stats[3], t_total=stats[4]))
 
 
+def se3_frame_order(g):
+    """Elimination positions of the se3 vertices for the blocked solver: by frame (camera k, then the motion vertices k -> k+1),
+    which makes the reduced matrix banded.  The frame of a motion vertex is the camera that observes p1 of one of its ternary
+    edges; a motion vertex without ternary edges inherits the frame of its smoothness neighbour (or goes last)."""
+    C = len(g["se3"])
+    n_cam = int(g.get("n_cam", 0)) or int(g["obs_cp"][:, 0].max()) + 1
+    key = np.full(C, np.inf)
+    key[:n_cam] = np.arange(n_cam)
+    if len(g["ter_pph"]):
+        cam_of_pt = np.full(len(g["pt"]), -1, np.int64)
+        cam_of_pt[g["obs_cp"][:, 1]] = g["obs_cp"][:, 0]
+        key[g["ter_pph"][:, 2]] = cam_of_pt[g["ter_pph"][:, 0]] + 0.5
+    for _ in range(4):
+        bad = ~np.isfinite(key)
+        if not bad.any():
+            break
+        for i, j in g["se3e_ij"]:
+            if bad[i] and not bad[j]:
+                key[i] = key[j] - 1
+            elif bad[j] and not bad[i]:
+                key[j] = key[i] + 1
+    order = np.argsort(key, kind="stable")
+    pos = np.empty(C, np.int32)
+    pos[order] = np.arange(C, dtype=np.int32)
+    return pos
+
+
+def ba_optimize_blocked(g, max_iters=300, gain_threshold=1e-4, verbose=False, se3_pos="frame", nthreads=0, time_budget_s=0.0):
+    """Same LM as ba_optimize with the blocked direct solver of oracle/ba_block.h (points eliminated per tracklet, tiled band
+    Cholesky of the reduced matrix, OpenMP).  se3_pos: "frame" (se3_frame_order), None (identity) or an int array."""
+    L = lib()
+    se3 = g["se3"].copy()
+    pt = g["pt"].copy()
+    hist = np.zeros(max_iters + 1)
+    lam = np.zeros(max_iters + 1)
+    t_hist = np.zeros(max_iters + 1)
+    stats = np.zeros(8)
+    if isinstance(se3_pos, str):
+        se3_pos = se3_frame_order(g)
+    pos_arg = _p(np.ascontiguousarray(se3_pos, np.int32), C.c_int) if se3_pos is not None else None
+    L.vdo_oracle_ba_optimize_blocked.restype = C.c_int
+    n = L.vdo_oracle_ba_optimize_blocked(*_graph_args(g, se3, pt), C.c_int(max_iters), C.c_double(gain_threshold), C.c_int(int(verbose)),
+                                         _p(hist, C.c_double), _p(stats, C.c_double), pos_arg, C.c_int(int(nthreads)),
+                                         _p(lam, C.c_double), C.c_double(float(time_budget_s)), _p(t_hist, C.c_double))
+    return dict(se3=se3, pt=pt, iters=n, chi2=hist[: n + 1].copy(), lam=lam[:n].copy(), t_iter=t_hist[:n].copy(),
+                stats=dict(lam=stats[0], trials=int(stats[1]), band_doubles=int(stats[2]), t_linear=stats[3], t_total=stats[4],
+                           t_setup=stats[5], t_schur=stats[6], t_chol=stats[7]))
+
+
 def ba_dense_system(g):
     L = lib()
     se3 = g["se3"].copy()

@@ -4,7 +4,9 @@ The reference cannot be built or imported in this image (no Eigen3 / OpenCV C++ 
 no fixtures of its own, and its demo data is an external download -- so the vectors below are the ORACLE's outputs, frozen:
 they pin the oracle against drift (tests/test_golden.py, CPU) and give the GPU parity tests a committed target that does not
 depend on rebuilding the oracle on the GPU box.  Re-run only when the oracle is deliberately changed:
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py              # the small cases (seconds)
+    python tests/golden/make_golden.py --config4    # BASELINE config 4, full LM solve (blocked oracle solver, ~10 s on 8 cores)
+    python tests/golden/make_golden.py --config5    # BASELINE config 5, full LM solve (~5 min on 8 cores, 4 GB)
 """
 import os
 import sys
@@ -19,7 +21,34 @@ from vdo_slam_b200.synth import make_batch_graph, make_flow_problem  # noqa: E40
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+CONFIG4 = dict(n_frames=200, n_objects=5, n_static=40000, n_dynamic=10000, seed=4)
+CONFIG5 = dict(n_frames=1000, n_objects=50, n_static=800000, n_dynamic=200000, seed=5, obj_span=(100, 400))
+
+
+def graph_fingerprint(g):
+    """A few sums over the generated graph: the GPU test regenerates the graph from the seed and checks it is the same one."""
+    return np.array([g["se3"].sum(), g["pt"].sum(), g["obs_z"].sum(), g["se3e_Z"].sum(), float(g["obs_cp"].astype(np.int64).sum()),
+                     float(g["ter_pph"].astype(np.int64).sum())])
+
+
+def big(name, cfg, pt_stride):
+    """Full LM solve of a BASELINE config by the oracle (blocked direct solver, oracle/ba_block.h: the same Cholesky solve of the
+    full system as oracle/ba_lm.c's scalar one, which tests/test_oracle_ba.py checks on small graphs).  Keeps: iteration count,
+    chi2 / lambda history, every se3 vertex, every pt_stride-th point."""
+    g = make_batch_graph(**cfg)
+    r = po.ba_optimize_blocked(g, max_iters=300, gain_threshold=1e-4, verbose=True)
+    idx = np.arange(0, len(g["pt"]), pt_stride)
+    np.savez_compressed(os.path.join(HERE, name), iters=r["iters"], chi2=r["chi2"], lam=r["lam"], se3=r["se3"], pt_idx=idx,
+                        pt=r["pt"][idx], fingerprint=graph_fingerprint(g), trials=r["stats"]["trials"],
+                        cfg=np.array(repr(cfg)), oracle_seconds=r["stats"]["t_total"])
+    print(name, "iters", r["iters"], "chi2", r["chi2"][0], "->", r["chi2"][-1], "seconds", r["stats"]["t_total"])
+
+
 def main():
+    if "--config4" in sys.argv:
+        return big("ba_config4.npz", CONFIG4, 7)
+    if "--config5" in sys.argv:
+        return big("ba_config5.npz", CONFIG5, 59)
     # batch LM (Optimizer::FullBatchOptimization constants): 10 frames, 1 object, 120 static + 40 dynamic tracks
     g = make_batch_graph(n_frames=10, n_objects=1, n_static=120, n_dynamic=40, seed=42)
     r = po.ba_optimize(g, max_iters=12, gain_threshold=1e-4)

@@ -99,3 +99,32 @@ def test_generator_shapes():
     if s["E_t"]:
         assert (g["ter_pph"][:, 1] == g["ter_pph"][:, 0] + 1).all()
         assert g["ter_pph"][:, 2].min() >= 10 and g["ter_pph"][:, 2].max() < s["C"]
+
+
+# ---- the blocked direct solver (oracle/ba_block.h) is the same Cholesky solve as the scalar one (oracle/ba_lm.c) ----
+@pytest.mark.parametrize("cfg", [dict(n_frames=30, n_objects=2, n_static=1500, n_dynamic=300, seed=1),
+                                 dict(n_frames=16, n_objects=3, n_static=300, n_dynamic=500, seed=5),
+                                 dict(n_frames=20, n_objects=0, n_static=800, n_dynamic=0, seed=2)])
+def test_blocked_solver_equals_the_scalar_sparse_cholesky(cfg):
+    g = make_batch_graph(**cfg)
+    a = po.ba_optimize(g)
+    for pos, nt in (("frame", 1), ("frame", 3), (None, 2)):
+        b = po.ba_optimize_blocked(g, se3_pos=pos, nthreads=nt)
+        assert a["iters"] == b["iters"]
+        np.testing.assert_allclose(a["chi2"], b["chi2"], rtol=1e-8)
+        assert np.abs(a["se3"] - b["se3"]).max() < 1e-7 and np.abs(a["pt"] - b["pt"]).max() < 1e-7
+
+
+def test_blocked_solver_is_deterministic_across_thread_counts():
+    g = make_batch_graph(n_frames=25, n_objects=2, n_static=900, n_dynamic=250, seed=11)
+    a = po.ba_optimize_blocked(g, nthreads=1)
+    b = po.ba_optimize_blocked(g, nthreads=5)
+    assert a["iters"] == b["iters"] and np.array_equal(a["se3"], b["se3"]) and np.array_equal(a["pt"], b["pt"])
+
+
+def test_first_lm_step_of_both_solvers_agrees_tightly():
+    # one LM iteration = one linear solve: the two factorisations must agree to solver precision
+    g = make_batch_graph(n_frames=40, n_objects=2, n_static=2500, n_dynamic=600, seed=3)
+    a = po.ba_optimize(g, max_iters=1, gain_threshold=0.0)
+    b = po.ba_optimize_blocked(g, max_iters=1, gain_threshold=0.0)
+    assert np.abs(a["se3"] - b["se3"]).max() < 1e-11 and np.abs(a["pt"] - b["pt"]).max() < 1e-10

@@ -344,7 +344,7 @@ int BaGraph::finalize() {
   {
     const char* env = std::getenv("VDO_BA_LAYOUT");
     if (env && std::string(env) == "chunked") tiled = false;
-    Tile cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    Tile cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto close = [&](int t) { if (cur.t1 > cur.t0) tiles.push_back(cur); cur.t0 = cur.t1 = t; cur.k0 = cur.k1 = tk_begin[t]; cur.e0 = cur.e1 = lm_begin[tk_begin[t]]; };
     for (int t = 0; t < T && tiled; ++t) {
       if (t == Tstat) { close(t); n_tiles_stat = (int)tiles.size(); }
@@ -424,20 +424,21 @@ int BaGraph::finalize() {
   lap("ternary / chunked streams");
   // ---- tiles: tile-local landmark of every edge, vertex-sorted order of the tile's edges, segments of one vertex ----
   HostBuf<uint16_t> ob_perm, tr_perm;
-  HostBuf<uint8_t> lm_lml;
-  std::vector<Seg> osegs, tsegs;
+  HostBuf<uint8_t> lm_lml, ob_slml;
+  std::vector<Seg> osegs, tsegs, osegs2, tsegs2;
   if (tiled) {
-    ob_perm = stage<uint16_t>(Eo); tr_perm = stage_fill<uint16_t>(P, 0); lm_lml = stage<uint8_t>(Eo);
+    ob_perm = stage<uint16_t>(Eo); tr_perm = stage_fill<uint16_t>(P, 0); lm_lml = stage<uint8_t>(Eo); ob_slml = stage<uint8_t>(Eo);
     // tiles are independent: each worker handles a contiguous range of tiles into its own segment lists, which are then
     // concatenated in tile order (segment indices of a tile are rebased by the lists that precede it)
     const int ntl = (int)tiles.size();
     const int NW = std::max(1, std::min(NT, ntl / 64 + 1));
-    std::vector<std::vector<Seg>> w_os(NW), w_ts(NW);
+    std::vector<std::vector<Seg>> w_os(NW), w_ts(NW), w_os2(NW), w_ts2(NW);
     parallel_for(NW, [&](int wt, int wn) {
       std::vector<int> keys(std::max(VDO_TILE_E, VDO_TILE_L)), idx(keys.size()), bucket;
       std::vector<Seg>& los = w_os[wt]; std::vector<Seg>& lts = w_ts[wt];
+      std::vector<Seg>& los2 = w_os2[wt]; std::vector<Seg>& lts2 = w_ts2[wt];
       // stable sort of idx[0..n) by keys[idx] (counting sort over the key range when it is small), then cut into segments
-      auto sort_and_cut = [&](int n, int base, HostBuf<uint16_t>& perm, std::vector<Seg>& segs) {
+      auto sort_and_cut = [&](int n, int base, HostBuf<uint16_t>& perm, std::vector<Seg>& segs, std::vector<Seg>& segs2) {
         if (n == 0) return;
         int lo = keys[idx[0]], hi = lo;
         for (int a = 1; a < n; ++a) { lo = std::min(lo, keys[idx[a]]); hi = std::max(hi, keys[idx[a]]); }
@@ -458,6 +459,13 @@ int BaGraph::finalize() {
           segs.push_back(Seg{v, base + a, b - a, 0});
           a = b;
         }
+        for (int a = 0; a < n;) {                 // the same runs cut at VDO_SEG2 entries (Schur kernels: one thread per (run, component))
+          const int v = keys[perm[base + a]];
+          int b = a;
+          while (b < n && b - a < VDO_SEG2 && keys[perm[base + b]] == v) ++b;
+          segs2.push_back(Seg{v, base + a, b - a, 0});
+          a = b;
+        }
       };
       const int ta = (int)((int64_t)ntl * wt / wn), tb = (int)((int64_t)ntl * (wt + 1) / wn);
       for (int ti = ta; ti < tb; ++ti) {
@@ -465,22 +473,28 @@ int BaGraph::finalize() {
         for (int k = tl.k0; k < tl.k1; ++k) for (int e = lm_begin[k]; e < lm_begin[k + 1]; ++e) lm_lml[e] = (uint8_t)(k - tl.k0);
         const int ne = tl.e1 - tl.e0;
         for (int i = 0; i < ne; ++i) { keys[i] = lm_cam[tl.e0 + i]; idx[i] = i; }
-        tl.os0 = (int)los.size();
-        sort_and_cut(ne, tl.e0, ob_perm, los);
-        tl.os1 = (int)los.size();
+        tl.os0 = (int)los.size(); tl.qo0 = (int)los2.size();
+        sort_and_cut(ne, tl.e0, ob_perm, los, los2);
+        tl.os1 = (int)los.size(); tl.qo1 = (int)los2.size();
+        for (int q = 0; q < ne; ++q) ob_slml[tl.e0 + q] = lm_lml[tl.e0 + ob_perm[tl.e0 + q]];     // tile-local landmark in sorted order
         int nt = 0;
         for (int k = tl.k0; k < tl.k1; ++k) if (tk_h[k] >= 0) { keys[k - tl.k0] = tk_h[k]; idx[nt++] = k - tl.k0; }
-        tl.ts0 = (int)lts.size();
-        sort_and_cut(nt, tl.k0, tr_perm, lts);
-        tl.ts1 = (int)lts.size();
+        tl.ts0 = (int)lts.size(); tl.qt0 = (int)lts2.size();
+        sort_and_cut(nt, tl.k0, tr_perm, lts, lts2);
+        tl.ts1 = (int)lts.size(); tl.qt1 = (int)lts2.size();
       }
     });
     for (int wt = 0; wt < NW; ++wt) {
       const int ta = (int)((int64_t)ntl * wt / NW), tb = (int)((int64_t)ntl * (wt + 1) / NW);
-      const int ob = (int)osegs.size(), tb0 = (int)tsegs.size();
-      for (int ti = ta; ti < tb; ++ti) { tiles[ti].os0 += ob; tiles[ti].os1 += ob; tiles[ti].ts0 += tb0; tiles[ti].ts1 += tb0; }
+      const int ob = (int)osegs.size(), tb0 = (int)tsegs.size(), ob2 = (int)osegs2.size(), tb2 = (int)tsegs2.size();
+      for (int ti = ta; ti < tb; ++ti) {
+        tiles[ti].os0 += ob; tiles[ti].os1 += ob; tiles[ti].ts0 += tb0; tiles[ti].ts1 += tb0;
+        tiles[ti].qo0 += ob2; tiles[ti].qo1 += ob2; tiles[ti].qt0 += tb2; tiles[ti].qt1 += tb2;
+      }
       osegs.insert(osegs.end(), w_os[wt].begin(), w_os[wt].end());
       tsegs.insert(tsegs.end(), w_ts[wt].begin(), w_ts[wt].end());
+      osegs2.insert(osegs2.end(), w_os2[wt].begin(), w_os2[wt].end());
+      tsegs2.insert(tsegs2.end(), w_ts2[wt].begin(), w_ts2[wt].end());
     }
   }
   lap("tile segments");
@@ -547,10 +561,15 @@ int BaGraph::finalize() {
     d.hm_p1 = upload(hm_p1); d.hm_cls = upload(hm_cls); d.hm_omega = dalloc<double>(Et); d.ter_chunks = upload(ter_chunks);
   } else {
     d.n_tiles = (int)tiles.size(); d.n_tiles_stat = n_tiles_stat; d.n_osegs = (int)osegs.size(); d.n_tsegs = (int)tsegs.size();
-    d.tiles = upload(tiles); d.osegs = upload(osegs); d.tsegs = upload(tsegs);
-    d.ob_perm = upload(ob_perm); d.tr_perm = upload(tr_perm); d.lm_lml = upload(lm_lml);
+    d.capE_st = d.capE_ch = 16;
+    for (int ti = 0; ti < d.n_tiles; ++ti) {
+      int& cap = ti < n_tiles_stat ? d.capE_st : d.capE_ch;
+      cap = std::max(cap, (tiles[ti].e1 - tiles[ti].e0 + 15) & ~15);
+    }
+    d.tiles = upload(tiles); d.osegs = upload(osegs); d.tsegs = upload(tsegs); d.osegs2 = upload(osegs2); d.tsegs2 = upload(tsegs2);
+    d.ob_perm = upload(ob_perm); d.tr_perm = upload(tr_perm); d.lm_lml = upload(lm_lml); d.ob_slml = upload(ob_slml);
     d.pt_Q = dalloc<double>(9 * (size_t)std::max(P - Tstat, 1));
-    d.accO = dalloc<double>(16 * (size_t)C); d.accT = dalloc<double>(16 * (size_t)C); d.acc6 = dalloc<double>(6 * (size_t)C);
+    d.accO = dalloc<double>(16 * (size_t)C); d.accT = dalloc<double>(16 * (size_t)C); d.acc6 = dalloc<double>(12 * (size_t)C);
     d.vh = dalloc<double>(6 * (size_t)C);
   }
   d.se_i = upload(se_i); d.se_j = upload(se_j); d.se_Z = upload(se_Z); d.se_w = upload(se_w); d.se_delta = upload(se_d); d.se_Hoff = dalloc<double>(36 * (size_t)Ese);
@@ -569,7 +588,8 @@ int BaGraph::finalize() {
   oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
   d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
   d.scal = dalloc<double>(SC_N);
-  d.n_part_pap = 148; d.n_part_rz = std::max(1, n_paths) * 8;
+  d.n_part_pap = tiled ? std::max(1, (C + 127) / 128) : 148;    // tiled: one partial of p.Ap per CTA of the finalize kernel (128 vertices each)
+  d.n_part_rz = std::max(1, n_paths) * 8;
   d.part_pap = dalloc<double>(d.n_part_pap); d.part_rz = dalloc<double>(d.n_part_rz);
   be_->sync();
   lap("alloc + upload");

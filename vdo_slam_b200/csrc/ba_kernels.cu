@@ -619,18 +619,19 @@ struct CudaBackend : BaBackend {
     if (part != 1) { if (write) launch_tiles(k_tile_lin<false, true>, SMEM_LIN_ST, d, 0, ns); else launch_tiles(k_tile_lin<false, false>, SMEM_LIN_ST, d, 0, ns); }
     if (part != 0) { if (write) launch_tiles(k_tile_lin<true, true>, SMEM_LIN_CH, d, ns, nc); else launch_tiles(k_tile_lin<true, false>, SMEM_LIN_CH, d, ns, nc); }
   }
+  // modes 0 / 1 (rhs, S*p): k_tile_schur2 (one thread per (run, component) on the vertex side); mode 2 (back-substitution): k_tile_schur
   void tile_schur(BaDev& d, int mode, int part, cudaStream_t chain_stream) {
     const int ns = d.n_tiles_stat, nc = d.n_tiles - d.n_tiles_stat;
     const size_t bs = SMEM_SCH_ST, bc = SMEM_SCH_CH;
     if (part != 1 && ns > 0) {
-      if (mode == 0) k_tile_schur<false, 0><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
-      else if (mode == 1) k_tile_schur<false, 1><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
+      if (mode == 0) k_tile_schur2<false, 0><<<ns, VDO_TILE_L, smem_sch2(false, d.capE_st), st>>>(d, 0, d.capE_st);
+      else if (mode == 1) k_tile_schur2<false, 1><<<ns, VDO_TILE_L, smem_sch2(false, d.capE_st), st>>>(d, 0, d.capE_st);
       else k_tile_schur<false, 2><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
       ++n_launch;
     }
     if (part != 0 && nc > 0) {
-      if (mode == 0) k_tile_schur<true, 0><<<nc, VDO_TILE_L, bc, chain_stream>>>(d, ns);
-      else if (mode == 1) k_tile_schur<true, 1><<<nc, VDO_TILE_L, bc, chain_stream>>>(d, ns);
+      if (mode == 0) k_tile_schur2<true, 0><<<nc, VDO_TILE_L, smem_sch2(true, d.capE_ch), chain_stream>>>(d, ns, d.capE_ch);
+      else if (mode == 1) k_tile_schur2<true, 1><<<nc, VDO_TILE_L, smem_sch2(true, d.capE_ch), chain_stream>>>(d, ns, d.capE_ch);
       else k_tile_schur<true, 2><<<nc, VDO_TILE_L, bc, chain_stream>>>(d, ns);
       ++n_launch;
     }
@@ -687,7 +688,7 @@ struct CudaBackend : BaBackend {
     if (part == 0) LAUNCH(k_lin_static<true>, nblk(d.Tstat, 256), 256, d); else LAUNCH(k_lin_tracklets<true>, nblk(d.T - d.Tstat, 128), 128, d);
   }
   void schur_vertex_obs(BaDev& d, double sign, double* out) override {
-    if (d.tiled) { LAUNCH(k_tile_finalize_schur, nblk(d.C, 128), 128, d, sign, out, out == d.Ap ? 1 : 0); return; }
+    if (d.tiled) { LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, sign, out, out == d.Ap ? 1 : 0, 0); return; }
     LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0);
   }
   void schur_vertex_ter(BaDev& d, double sign, double* out) override {
@@ -705,7 +706,7 @@ struct CudaBackend : BaBackend {
     LAUNCH(k_pcg_init, d.n_paths * PCR_CL, 256, d);
     LAUNCH(k_pcg_init_fin, 1, 256, d);
   }
-  void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, 148, 256, d); }   // always 148 CTAs: part_pap has exactly 148 slots
+  void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, d.n_part_pap, 256, d); }   // one CTA per slot of part_pap
   void pcg_step(BaDev& d, double tol2) override {
     set_scalars(d, cur_lambda, tol2);
     LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
@@ -732,8 +733,7 @@ struct CudaBackend : BaBackend {
           CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
           tile_schur(d, 1, -1, st2);
           CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
-          LAUNCH(k_tile_finalize_schur, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1);
-          LAUNCH(k_pcg_dot, 148, 256, d);
+          LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1, 1);      // Ap -= B^T sums, and the partials of p.Ap
           LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
           LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
           LAUNCH(k_pcg_scalars, 1, 256, d);
@@ -749,7 +749,7 @@ struct CudaBackend : BaBackend {
         schur_vertex_obs(d, -1.0, d.Ap);
         if (d.n_ter_chunks > 0) { k_schur_vertex<false><<<d.n_ter_chunks, 128, 0, st2>>>(d, -1.0, d.Ap, 1); ++n_launch; }
         CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
-        LAUNCH(k_pcg_dot, 148, 256, d);
+        LAUNCH(k_pcg_dot, d.n_part_pap, 256, d);
         LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
         LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
         LAUNCH(k_pcg_scalars, 1, 256, d);
@@ -789,6 +789,8 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
     optin((const void*)k_tile_lin<true, true>, SMEM_LIN_CH); optin((const void*)k_tile_lin<true, false>, SMEM_LIN_CH);
     optin((const void*)k_tile_schur<false, 0>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 1>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 2>, SMEM_SCH_ST);
     optin((const void*)k_tile_precond<false>, SMEM_PRE_ST); optin((const void*)k_tile_precond<true>, SMEM_PRE_CH);
+    optin((const void*)k_tile_schur2<false, 0>, smem_sch2(false, VDO_TILE_E)); optin((const void*)k_tile_schur2<false, 1>, smem_sch2(false, VDO_TILE_E));
+    optin((const void*)k_tile_schur2<true, 0>, smem_sch2(true, VDO_TILE_E)); optin((const void*)k_tile_schur2<true, 1>, smem_sch2(true, VDO_TILE_E));
     optin((const void*)k_tile_schur<true, 0>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 1>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 2>, SMEM_SCH_CH);
   }
   CudaBackend* b = new CudaBackend;

@@ -308,6 +308,211 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur(BaDev d, int tile0) {
   if (CHAINS) seg_loop<8, 6>(d, ts, d.acc6, 6, tid, [&](const Seg& s, int l, const double* t, double* acc) { tile_schur_tseg_item(d, tl, s, l, sm, t, acc); });
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------------
+// Schur products, modes 0 / 1 (rhs and S*p of the PCG), second generation.
+//
+// What changed against k_tile_schur (kept for mode 2, the back-substitution, which has no vertex side):
+//  * per-edge work is 6 FMAs in both directions.  Forward: u_j = sum_e om_e (gamma_c + 2 p_j x beta_c) =
+//    (sum om gamma) + 2 p_j x (sum om beta): one 6-vector FMA per edge, one cross product per LANDMARK.  Backward: the edge's
+//    force / torque on its vertex, -om [z_j ; 2 (p_j - t_c) x z_j], is summed as om [z_j ; p_j x z_j] (again a per-landmark
+//    6-vector, kept in shared memory) -- i.e. the torque is taken about the WORLD origin and moved to the vertex origin by the
+//    per-vertex finalize kernel (torque_v = torque_0 - t_v x force).
+//  * the vertex side is ONE THREAD PER (RUN, COMPONENT): the tile's edges in vertex-sorted order are cut into runs of one
+//    vertex and at most VDO_SEG2 = 16 entries (osegs2 / tsegs2); a thread adds its component over its run from shared memory
+//    and issues one fp64 atomic.  No shuffles, no selects, no idle lanes on short runs (chain tiles average 8 entries per
+//    vertex: the warp-per-segment scheme of k_tile_schur ran them at 12 % lane utilisation).
+//  * only warp 0 polls the mbarrier; the other warps sleep in the CTA barrier.
+// acc6 layout (12 / vertex): [F_o, M_o, F_t, M_t]  pointxyz force / world-origin torque, ternary force / torque.
+//  * the per-edge arrays are staged with the launch's own capacity (capE = the largest edge count of the tiles of this launch,
+//    known at ingest) instead of VDO_TILE_E: chain tiles (one pointxyz edge per landmark) fit 4 CTAs per SM.
+constexpr int TILE_OSEG2_CAP_ST = 192, TILE_OSEG2_CAP_CH = 96, TILE_TSEG2_CAP = 96;
+struct Seg2Views { const Seg* seg; int n; };
+__device__ __forceinline__ Seg2Views seg2_views(TileStager& sg, const Seg* g, int s0, int s1, int cap) {
+  Seg2Views v;
+  v.n = s1 - s0;
+  const bool staged = v.n <= cap;
+  const Seg* st = sg.view<Seg>(g, (size_t)s0, staged ? v.n : 0, cap);
+  v.seg = staged ? st : g + s0;
+  return v;
+}
+inline size_t smem_sch2(bool chains, int capE) {      // must mirror the carve order inside k_tile_schur2
+  size_t b = vb<double>(3 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L + 1) + vb<double>(capE) + vb<int>(capE) + vb<uint16_t>(capE) + vb<uint8_t>(capE) +
+             vb<Seg>(chains ? TILE_OSEG2_CAP_CH : TILE_OSEG2_CAP_ST) + sb(6 * VDO_TILE_L * 8);
+  if (chains) b += vb<double>(9 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L) + vb<uint16_t>(VDO_TILE_L) + vb<Seg>(TILE_TSEG2_CAP) + sb(3 * VDO_TILE_L * 8);
+  return b;
+}
+
+template <bool CHAINS, int MODE>
+__global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur2(BaDev d, int tile0, int capE) {
+  extern __shared__ __align__(16) unsigned char tile_sh[];
+  __shared__ __align__(8) uint64_t bar;
+  if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
+  const int tid = threadIdx.x;
+  const Tile tl = d.tiles[tile0 + blockIdx.x];
+  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  TileStager sg(tile_sh, &bar, tid == 0);
+  double* sP = sg.view<double>(d.pt, 3 * (size_t)tl.k0, 3 * nl, 3 * VDO_TILE_L);
+  double* sS = sg.view<double>(d.pt_s, (size_t)tl.k0, nl, VDO_TILE_L);
+  int* sLB = sg.view<int>(d.lm_obs_begin, (size_t)tl.k0, nl + 1, VDO_TILE_L + 1);
+  double* sOM = sg.view<double>(d.lm_omega, (size_t)tl.e0, ne, capE);
+  int* sCAM = sg.view<int>(d.lm_cam, (size_t)tl.e0, MODE != 0 ? ne : 0, capE);
+  uint16_t* sPERM = sg.view<uint16_t>(d.ob_perm, (size_t)tl.e0, ne, capE);
+  uint8_t* sSLML = sg.view<uint8_t>(d.ob_slml, (size_t)tl.e0, ne, capE);
+  const Seg2Views os = seg2_views(sg, d.osegs2, tl.qo0, tl.qo1, CHAINS ? TILE_OSEG2_CAP_CH : TILE_OSEG2_CAP_ST);
+  double* sZM = sg.stash<double>(6 * VDO_TILE_L);           // per landmark: [z ; p x z]   (chains: its first half holds g^ until the walk)
+  double *sQ = nullptr, *sOMT = nullptr, *sZ = sZM, *sY = nullptr;
+  int* sHH = nullptr; uint16_t* sTPERM = nullptr;
+  Seg2Views ts{nullptr, 0};
+  if (CHAINS) {
+    sQ = sg.view<double>(d.pt_Q, 9 * (size_t)(tl.k0 - d.Tstat), 9 * nl, 9 * VDO_TILE_L);
+    sOMT = sg.view<double>(d.tk_omega, (size_t)tl.k0, nl, VDO_TILE_L);
+    sHH = sg.view<int>(d.tk_h, (size_t)tl.k0, nl, VDO_TILE_L);
+    sTPERM = sg.view<uint16_t>(d.tr_perm, (size_t)tl.k0, nl, VDO_TILE_L);
+    ts = seg2_views(sg, d.tsegs2, tl.qt0, tl.qt1, TILE_TSEG2_CAP);
+    sY = sg.stash<double>(3 * VDO_TILE_L);
+  }
+  sg.commit();
+  if (tid < 32) mbar_wait(&bar, 0);
+  __syncthreads();
+  // ---- landmark phase ----
+  double p[3] = {0, 0, 0}, u[3] = {0, 0, 0};
+  if (tid < nl) {
+    p[0] = sP[3 * tid]; p[1] = sP[3 * tid + 1]; p[2] = sP[3 * tid + 2];
+    if (MODE == 1) {
+      double a[6] = {0, 0, 0, 0, 0, 0};
+      const int ib = sLB[tid] - tl.e0, ie = sLB[tid + 1] - tl.e0;
+      for (int i = ib; i < ie; ++i) {
+        const double om = sOM[i];
+        const double* w = d.vw + 6 * (size_t)sCAM[i];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) a[c] += om * w[c];
+      }
+      double pxb[3]; cross3(p, a + 3, pxb);
+      u[0] = a[0] + 2 * pxb[0]; u[1] = a[1] + 2 * pxb[1]; u[2] = a[2] + 2 * pxb[2];
+    } else {
+      const double* b = d.bl + 3 * ((size_t)tl.k0 + tid);
+      u[0] = b[0]; u[1] = b[1]; u[2] = b[2];
+    }
+  }
+  if (!CHAINS) {
+    if (tid < nl) {
+      const double is = 1.0 / sS[tid];
+      const double z[3] = {u[0] * is, u[1] * is, u[2] * is};
+      double m[3]; cross3(p, z, m);
+      double* o = sZM + 6 * tid;
+      o[0] = z[0]; o[1] = z[1]; o[2] = z[2]; o[3] = m[0]; o[4] = m[1]; o[5] = m[2];
+    }
+  } else {
+    // chains: H_ll of a tracklet is (scalar tridiagonal) (x) I3 in the frame x^_k = Q_k x_k (see ba_tiles.cuh)
+    double uh[3] = {0, 0, 0};
+    if (tid < nl) {
+      const double* Q = sQ + 9 * tid;
+      double gh[3] = {0, 0, 0};
+      if (MODE == 1) {
+        rot_apply(Q, u, uh);
+        const int hp = tid > 0 ? sHH[tid - 1] : -1;
+        if (hp >= 0) {                                   // incoming ternary edge (k-1, k)
+          const double* w = d.vh + 6 * (size_t)hp;
+          double pxb[3]; cross3(p, w + 3, pxb);
+          const double g[3] = {w[0] - pxb[0], w[1] - pxb[1], w[2] - pxb[2]};
+          rot_apply(Q, g, gh);
+          const double om = sOMT[tid - 1];
+          uh[0] -= om * gh[0]; uh[1] -= om * gh[1]; uh[2] -= om * gh[2];
+        }
+        sZ[3 * tid] = gh[0]; sZ[3 * tid + 1] = gh[1]; sZ[3 * tid + 2] = gh[2];
+      } else rot_apply(Q, u, uh);                        // mode 0: b^ = Q b_l
+    }
+    if (MODE == 1) {
+      __syncthreads();
+      if (tid < nl && sHH[tid] >= 0) {                   // outgoing ternary edge (k, k+1)
+        const double om = sOMT[tid];
+        uh[0] += om * sZ[3 * tid + 3]; uh[1] += om * sZ[3 * tid + 4]; uh[2] += om * sZ[3 * tid + 5];
+      }
+    }
+    if (tid < nl) { sY[3 * tid] = uh[0]; sY[3 * tid + 1] = uh[1]; sY[3 * tid + 2] = uh[2]; sS[tid] = 1.0 / sS[tid]; }
+    __syncthreads();
+    if (tid < tl.t1 - tl.t0) {
+      TileSm sm; sm.Y = sY; sm.OMT = sOMT; sm.IS = sS;
+      tile_schur_chain_walk(d, tl, tid, sm);
+    }
+    __syncthreads();
+    double zm[6] = {0, 0, 0, 0, 0, 0}, am[6] = {0, 0, 0, 0, 0, 0};
+    if (tid < nl) {
+      rot_t_apply(sQ + 9 * tid, sY + 3 * tid, zm);
+      cross3(p, zm, zm + 3);
+      if (sHH[tid] >= 0) {                                 // ternary edge (k, k+1): a' = Q_{k+1}^T (z^_k - z^_{k+1}); om [a' ; p_{k+1} x a']
+        const double dz[3] = {sY[3 * tid] - sY[3 * tid + 3], sY[3 * tid + 1] - sY[3 * tid + 4], sY[3 * tid + 2] - sY[3 * tid + 5]};
+        double a[3]; rot_t_apply(sQ + 9 * (tid + 1), dz, a);
+        double c[3]; cross3(sP + 3 * tid + 3, a, c);
+        const double om = sOMT[tid];
+        am[0] = om * a[0]; am[1] = om * a[1]; am[2] = om * a[2]; am[3] = om * c[0]; am[4] = om * c[1]; am[5] = om * c[2];
+      }
+    }
+    __syncthreads();                                       // every thread has read Q / z^: their space is reused
+    if (tid < nl) {
+      double* o = sZM + 6 * tid; double* o2 = sQ + 6 * tid;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { o[c] = zm[c]; o2[c] = am[c]; }
+    }
+  }
+  __syncthreads();
+  // ---- vertex phase: one thread per (run, component) ----
+  for (int item = tid; item < 6 * os.n; item += VDO_TILE_L) {
+    const int s = item / 6, c = item - 6 * s;
+    const Seg sgm = os.seg[s];
+    const int q0 = sgm.begin - tl.e0;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int q = q0; q < q0 + sgm.n; ++q) acc += sOM[sPERM[q]] * sZM[6 * (int)sSLML[q] + c];
+    if (acc != 0.0) atomicAdd(d.acc6 + 12 * (size_t)sgm.v + c, c < 3 ? -acc : -2.0 * acc);
+  }
+  if (CHAINS) {
+    for (int item = tid; item < 6 * ts.n; item += VDO_TILE_L) {
+      const int s = item / 6, c = item - 6 * s;
+      const Seg sgm = ts.seg[s];
+      const int q0 = sgm.begin - tl.k0;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int q = q0; q < q0 + sgm.n; ++q) acc += sQ[6 * (int)sTPERM[q] + c];
+      if (acc != 0.0) atomicAdd(d.acc6 + 12 * (size_t)sgm.v + 6 + c, acc);
+    }
+  }
+}
+
+// per vertex: out_v += sign * B^T [F ; M - t x (2 F_o + F_t)] (torque moved to the vertex origin); clears the sums.
+// With dot != 0 also the CTA's share of p . out (fixed order) into part_pap[blockIdx.x]: the PCG's p.Ap without another launch.
+__global__ void __launch_bounds__(128) k_tile_finalize_schur2(BaDev d, double sign, double* __restrict__ out, int check_done, int dot) {
+  __shared__ double red[32];
+  if (check_done && d.scal[SC_DONE] != 0.0) return;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (v < d.C) {
+    const double* T = d.se3 + 12 * (size_t)v;
+    double* a = d.acc6 + 12 * (size_t)v;
+    const double F[3] = {a[0] + a[6], a[1] + a[7], a[2] + a[8]};
+    const double G[3] = {2 * a[0] + a[6], 2 * a[1] + a[7], 2 * a[2] + a[8]};
+    double txg[3]; cross3(T + 9, G, txg);
+    const double M[3] = {a[3] + a[9] - txg[0], a[4] + a[10] - txg[1], a[5] + a[11] - txg[2]};
+    double o0[3], o1[3];
+    rot_t_apply(T, F, o0); rot_t_apply(T, M, o1);
+    double* o = out + 6 * (size_t)v;
+    o[0] += sign * o0[0]; o[1] += sign * o0[1]; o[2] += sign * o0[2]; o[3] += sign * o1[0]; o[4] += sign * o1[1]; o[5] += sign * o1[2];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = 0.0;
+    if (dot) {
+      const double* pv = d.p + 6 * (size_t)v;
+      s = pv[0] * o[0] + pv[1] * o[1] + pv[2] * o[2] + pv[3] * o[3] + pv[4] * o[4] + pv[5] * o[5];
+    }
+  }
+  if (dot) {
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) d.part_pap[blockIdx.x] = s;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_tile_finalize_lin(BaDev d) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < d.C) tile_finalize_lin(d, v);

@@ -35,13 +35,15 @@
 #define VDO_TILE_L 256
 #define VDO_TILE_E 768
 #define VDO_SEG 64
+#define VDO_SEG2 16   // Schur kernels: runs of one vertex cut at 16 entries, one thread per (run, component)
 
 namespace vdo {
 
 struct Chunk { int v, begin, end, pad; };
 // tile: landmarks [k0,k1), EdgeSE3PointXYZ [e0,e1) (landmark-major), tracklets [t0,t1), vertex-sorted segments of the
 // pointxyz edges [os0,os1) and of the ternary edges [ts0,ts1)
-struct Tile { int k0, k1, e0, e1, t0, t1, os0, os1, ts0, ts1, pad0, pad1; };
+// [qo0,qo1) / [qt0,qt1): the same vertex-sorted runs cut at VDO_SEG2 entries (osegs2 / tsegs2)
+struct Tile { int k0, k1, e0, e1, t0, t1, os0, os1, ts0, ts1, qo0, qo1, qt0, qt1, pad0, pad1; };
 // segment: <= VDO_SEG consecutive entries of ob_perm (or tr_perm) starting at `begin`, all on se3 vertex v (one warp, two entries per lane)
 struct Seg { int v, begin, n, pad; };
 
@@ -73,14 +75,18 @@ struct BaDev {
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each
   // ---- tiled layout ----
   int tiled = 0, n_tiles_stat = 0, n_tiles = 0, n_osegs = 0, n_tsegs = 0;
-  Tile* tiles = 0; Seg* osegs = 0; Seg* tsegs = 0;
+  int capE_st = 16, capE_ch = 16;   // largest pointxyz-edge count of a static / chain tile, rounded up to 16 (shared-memory capacity of the launches)
+  Tile* tiles = 0; Seg* osegs = 0; Seg* tsegs = 0; Seg* osegs2 = 0; Seg* tsegs2 = 0;
+  uint8_t* ob_slml = 0;    // Eobs: tile-local landmark of the edge at each position of the camera-sorted order (= lm_lml[e0 + ob_perm[q]])
   uint16_t* ob_perm = 0;   // Eobs: position in the tile's camera-sorted order -> tile-local edge index (e - e0)
   uint16_t* tr_perm = 0;   // P: position (k0 + i) in the tile's motion-vertex-sorted order -> tile-local landmark index of p1
   uint8_t* lm_lml = 0;     // Eobs: tile-local landmark index of each pointxyz edge
   double* pt_Q = 0;        // 9 per chain landmark (index k - Tstat): Q_k = (R_{k-1} ... R_{kb})^T, rotates landmark k into the
                            // frame in which its tracklet's H_ll is (scalar tridiagonal) (x) I3
   double *accO = 0, *accT = 0;   // 16 per se3 vertex: world-frame sums of the pointxyz / ternary edges (see tile_acc16)
-  double* acc6 = 0;        // 6 per se3 vertex: world-frame Hpl*z sums of one Schur product
+  double* acc6 = 0;        // 12 per se3 vertex: world-frame Hpl*z sums of one Schur product.  CUDA backend: [F_o, M_o, F_t, M_t] = force and
+                           // torque ABOUT THE WORLD ORIGIN of the pointxyz / ternary edges (k_tile_schur2; the finalize kernel moves the
+                           // torque to the vertex origin).  Emulation: the first 6 hold [force, torque about the vertex origin].
   double* vh = 0;          // 6C: per-vertex world-frame image of v as seen by ternary edges (vw is the pointxyz one)
   double* scal = 0;  // device scalars, see SC_* below
   double *part_pap = 0, *part_rz = 0;   // per-CTA partial sums of p.Ap (<= 148) and r.z (n_paths * 8): summed in a FIXED order so that
