@@ -219,6 +219,7 @@ void vdo_frame_destroy(vdo_frame *f);
 int vdo_frame_upload(vdo_frame *f, const unsigned char *gray, const float *depth, const float *flow, const int *mask);
 /* Tracking::GrabImageRGBD depth pre-processing (src/Tracking.cc:180-204): d < 0 -> 0, else bf / (d / factor), in place on the
  * resident depth; depth_out (may be NULL) receives the result so the caller's cv::Mat can be mutated like the reference does */
+/* bf <= 0: clamp negatives to 0 only (the reference's VirtualKITTI branch) */
 int vdo_frame_depth_prep(vdo_frame *f, float bf, float factor, float *depth_out);
 /* ORBextractor::operator() (include/ORBextractor.h:47-49, src/ORBextractor.cc:1035-1110) on the resident gray image:
  * pyramid (cv::resize INTER_LINEAR chain), FAST-9/16 per 30-px cell with threshold fallback, octree distribution, IC_Angle.
@@ -331,7 +332,10 @@ typedef struct vdo_tracker_params {
   int window_size, overlap_size;     /* WINDOW_SIZE, OVERLAP_SIZE */
   int local_batch;                   /* bLocalBatch: run PartialBatchOptimization inside vdo_tracker_track on the reference's schedule
                                         ((f_id - OVERLAP + 1) % (WINDOW - OVERLAP) == 0 && f_id >= WINDOW - 1, src/Tracking.cc:1150-1160) */
-  int reserved[3];
+  int dataset;                       /* ChooseData / mTestData (src/Tracking.cc:150-160): 1 OMD, 2 KITTI, 3 VirtualKITTI; 0 = KITTI when is_kitti else OMD.
+                                        OMD and KITTI convert the raw disparity to depth (bf / (d / factor)); VirtualKITTI only clamps negatives
+                                        to 0 (src/Tracking.cc:180-204) */
+  int reserved[2];
 } vdo_tracker_params;
 void vdo_tracker_params_default(vdo_tracker_params *p);
 int vdo_tracker_create(vdo_ctx *ctx, const vdo_tracker_params *params, vdo_tracker **out);
@@ -341,13 +345,15 @@ const char *vdo_tracker_last_error(const vdo_tracker *t);
  * overwritten with metric depth like the reference does to the caller's cv::Mat (src/Tracking.cc:180-204); flow: h x w x 2 f32;
  * mask: h x w i32 -- when writeback != 0 it receives the propagated labels (UpdateMask, :3062).  gt_sem_ids: semantic ids that have a
  * ground-truth object pose in this frame (vObjPose_gt[i][1]); the reference only estimates motion for objects present in the
- * ground truth of both frames (:767-810).  Tcw_out: 4x4 row-major f32 = the returned mCurrentFrame.mTcw. */
-int vdo_tracker_track(vdo_tracker *t, const unsigned char *gray, float *depth, const float *flow, int *mask, int n_gt,
+ * ground truth of both frames (:767-810).  Tcw_out: 4x4 row-major f32 = the returned mCurrentFrame.mTcw.
+ * width / height: size of the four buffers; VDO_ERR_ARG unless they equal the tracker's (the buffers are read -- and with writeback
+ * written -- as width x height arrays). */
+int vdo_tracker_track(vdo_tracker *t, int width, int height, const unsigned char *gray, float *depth, const float *flow, int *mask, int n_gt,
                       const int *gt_sem_ids, int writeback, float *Tcw_out);
 /* Named read-back of the frame state after the last call ('f' arrays are f32, the others i32; out may be NULL to query the size):
  * Tcw mVelocity mvKeys mvStatKeysTmp mvStatDepthTmp mvCorres mvFlowNext mvStat3DPointTmp nStaInlierID mvObjKeys mvObjDepth
  * mvObjCorres mvObjFlowNext mvObj3DPoint vSemObjLabel vObjLabel nDynInlierID vFlow_3d nModLabel nSemPosition bObjStat vObjMod
- * TemperalMatch_subset max_id f_id; stage_ms (9 x f32, accumulated host wall-clock per stage since creation: upload+depth, mask,
+ * vObjCentre3D TemperalMatch_subset max_id f_id; stage_ms (9 x f32, accumulated host wall-clock per stage since creation: upload+depth, mask,
  * frame build (ORB + static filter + object samples), look-ups, initial camera model, camera LM, objects, renewal, windowed BA);
  * local_ba (2 x i32: windowed optimisations run, their LM iterations) */
 int vdo_tracker_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
@@ -360,8 +366,10 @@ int vdo_tracker_batch_optimize(vdo_tracker *t, int mode, const vdo_lm_options *o
 /* test hook: the arrays the builder passes to vdo_graph_* for a mode.  f64 names: se3 pt prior_Z prior_w se3e_Z se3e_w se3e_delta
  * obs_z obs_w obs_delta ter_w ter_delta; i32 names: prior_v se3e_ij obs_cp ter_pph.  out may be NULL to query the element count. */
 int vdo_tracker_graph_export(vdo_tracker *t, int mode, const char *name, void *out, int cap_elems, int *n_elems);
-/* map read-back: vmCameraPose (n_frames x 16 f32), vmRigidMotion (every frame's motions concatenated, 16 f32 each, entry 0 = camera
- * motion), vnRMLabel (i32, same order), n_frames (i32) */
+/* map read-back (include/Map.h:34-84): vmCameraPose / vmCameraPose_RF (n_frames x 16 f32: the windowed BA refines the first, the full
+ * batch the second, src/Optimizer.cc:1058-1101 / :2094-2133), vmRigidMotion / vmRigidMotion_RF (every frame's motions concatenated, 16 f32
+ * each, entry 0 = camera motion), vmRigidCentre (3 f32 each, same order), vnRMLabel (i32, same order), n_per_frame (entries per frame,
+ * i32), n_frames (i32) */
 int vdo_tracker_map_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
 
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back

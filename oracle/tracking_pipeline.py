@@ -12,8 +12,9 @@ f32 = np.float32
 
 
 def mul4(A, B):
-    """cv::Mat float product: double accumulation, one rounding."""
-    return (np.asarray(A, f32).astype(np.float64) @ np.asarray(B, f32).astype(np.float64)).astype(f32)
+    """cv::Mat A * B of two 4x4 CV_32F: OpenCV's own gemm (its small-matrix branch: float accumulation, left to right)."""
+    import cv2
+    return cv2.gemm(np.ascontiguousarray(A, f32), np.ascontiguousarray(B, f32), 1.0, None, 0.0)
 
 
 def inv4(T):
@@ -21,7 +22,8 @@ def inv4(T):
     T = np.asarray(T, f32)
     I = np.eye(4, dtype=f32)
     I[:3, :3] = T[:3, :3].T
-    I[:3, 3] = (-(T[:3, :3].T.astype(np.float64) @ T[:3, 3].astype(np.float64))).astype(f32)
+    import cv2
+    I[:3, 3:4] = cv2.gemm(np.ascontiguousarray(T[:3, :3]), np.ascontiguousarray(T[:3, 3:4]), -1.0, None, 0.0, flags=cv2.GEMM_1_T)   # -R.t()*t: generic branch
     return I
 
 

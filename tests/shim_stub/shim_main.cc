@@ -29,8 +29,11 @@ int main(int argc, char** argv) {
     std::vector<int> ids(ngt);
     if (ngt) slurp(b + ".gt", ids.data(), (size_t)ngt * 4);
     std::vector<std::vector<float> > gt;
-    for (int id : ids) gt.push_back(std::vector<float>{(float)t, (float)id, 0, 0, 0, 0, 0, 0, 0, 0});
+    // ground-truth rows in the layout of example/vdo_slam.cc (frame, id, box 4, t 3, yaw): a made-up pose per object and frame so that
+    // the shim's ground-truth bookkeeping has something to chain
+    for (int id : ids) gt.push_back(std::vector<float>{(float)t, (float)id, 0, 0, 0, 0, 1.0f * id, 0.5f, 10.0f + 0.8f * t, 0.01f * t});
     cv::Mat Tcw_gt = cv::Mat::eye(4, 4, CV_32F);
+    Tcw_gt.at<float>(2, 3) = 0.8f * t;                       // camera-to-world ground truth as the driver passes it
     cv::Mat Tcw = SLAM.TrackRGBD(im, depth, flow, mask, Tcw_gt, gt, (double)t, imTraj, n);
     std::printf("POSE %d", t);
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) std::printf(" %.9g", Tcw.at<float>(i, j));
@@ -38,6 +41,6 @@ int main(int argc, char** argv) {
     std::ofstream(b + ".depth_out", std::ios::binary).write((const char*)depth.data, (std::streamsize)((size_t)w * h * 4));
     std::ofstream(b + ".mask_out", std::ios::binary).write((const char*)mask.data, (std::streamsize)((size_t)w * h * 4));
   }
-  SLAM.SaveResults(dir + "/results.txt");
+  SLAM.SaveResults(dir + "/out_");
   return 0;
 }

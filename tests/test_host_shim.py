@@ -86,4 +86,28 @@ def test_shim_matches_oracle_pipeline(tmp_path):
         assert np.abs(poses[t] - ref[t]).max() <= 1e-4
         assert np.array_equal(np.fromfile(str(tmp_path / f"f{t}.depth_out"), np.float32).reshape(h, w), ref_depth[t])
         assert np.array_equal(np.fromfile(str(tmp_path / f"f{t}.mask_out"), np.int32).reshape(h, w), ref_mask[t])
-    assert os.path.getsize(tmp_path / "results.txt") > 0
+    # SaveResults: the reference's seven files (src/System.cc:74-77, 128, 148, 166), poses as `frame r00 .. r23 0 0 0 1` with 9 decimals
+    names = ["obj_mot_stereo_new.txt", "obj_mot_stereo_rf_new.txt", "obj_mot_gt.txt", "obj_centre.txt", "initial_stereo_new.txt", "refined_stereo_new.txt",
+             "cam_pose_gt_stereo.txt"]
+    for nm in names:
+        assert os.path.exists(tmp_path / ("out_" + nm)), nm
+    ini = [l.split() for l in open(tmp_path / "out_initial_stereo_new.txt")]
+    assert len(ini) == n and all(len(r) == 17 and r[-4:] == ["0.000000000", "0.000000000", "0.000000000", "1.000000000"] for r in ini)
+    Twc = np.array(ini[1][1:13], np.float64).reshape(3, 4)
+    Tcw1 = ref[1].astype(np.float64)
+    assert np.abs(Twc[:, :3] - Tcw1[:3, :3].T).max() < 1e-4                                   # vmCameraPose = toInvMatrix(Tcw)
+    gt = [l.split() for l in open(tmp_path / "out_cam_pose_gt_stereo.txt")]
+    assert len(gt) == n and abs(float(gt[2][12]) - 1.6) < 1e-6                                 # Twc_gt of frame 2 relative to frame 0: z = 0.8 * 2
+    mot = [l.split() for l in open(tmp_path / "out_obj_mot_stereo_new.txt")]
+    mot_gt = [l.split() for l in open(tmp_path / "out_obj_mot_gt.txt")]
+    assert len(mot) == len(mot_gt) and all(len(r) == 18 for r in mot)
+
+
+def test_shim_rejects_mismatched_image_sizes(tmp_path):
+    # a depth / flow / mask of another size than the image must be refused before anything is copied (heap over-read otherwise)
+    _build()
+    src = open(os.path.join(SHIM, "shim_main.cc")).read()
+    assert "TrackRGBD" in src
+    sys_cc = open(os.path.join(ROOT, "vdo_slam_b200", "host", "System.cc")).read()
+    for needle in ("depthmap.cols != cols", "flowmap.cols != cols", "masksem.cols != cols", "frame size changed"):
+        assert needle in sys_cc

@@ -537,7 +537,7 @@ class TrackerParams(C.Structure):
                 ("depth_factor", C.c_float), ("th_depth_bg", C.c_float), ("th_depth_obj", C.c_float), ("max_track_bg", C.c_int), ("max_track_obj", C.c_int),
                 ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float), ("n_features", C.c_int), ("scale_factor", C.c_float), ("n_levels", C.c_int),
                 ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int), ("is_kitti", C.c_int), ("quirk", C.c_int), ("window_size", C.c_int),
-                ("overlap_size", C.c_int), ("local_batch", C.c_int), ("reserved", C.c_int * 3)]
+                ("overlap_size", C.c_int), ("local_batch", C.c_int), ("dataset", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class Tracker:
@@ -560,8 +560,10 @@ class Tracker:
         g = np.ascontiguousarray(gray, np.uint8); f = np.ascontiguousarray(flow, np.float32)
         ids = _i32(gt_ids)
         T = np.zeros((4, 4), np.float32)
-        rc = self.ctx.L.vdo_tracker_track(self.h_, g.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(depth), _fp(f), _ip(mask), C.c_int(len(ids)), _ip(ids),
-                                          C.c_int(int(writeback)), _fp(T))
+        h, w = g.shape
+        assert depth.shape == (h, w) and mask.shape == (h, w) and f.shape == (h, w, 2)
+        rc = self.ctx.L.vdo_tracker_track(self.h_, C.c_int(w), C.c_int(h), g.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(depth), _fp(f), _ip(mask), C.c_int(len(ids)),
+                                          _ip(ids), C.c_int(int(writeback)), _fp(T))
         if rc != 0:
             raise VdoError(f"vdo_tracker_track failed ({rc}): {self.ctx.L.vdo_tracker_last_error(self.h_).decode()}")
         return T

@@ -234,6 +234,14 @@ int BaGraph::finalize() {
     if (next[p] == -1) stat_ids.push_back(p); else chain_heads.push_back(p);
   }
   lap("  collect heads");
+  {   // static landmarks: by first observing camera, inside one camera by DESCENDING edge count -- the lanes of a warp that loops over
+      // its landmarks' edges then run the same trip counts (geometric track lengths: a warp of mixed landmarks idles ~55 % of its lanes)
+    int mx = 0;
+    for (int p : stat_ids) mx = std::max(mx, cnt_old[p]);
+    HostBuf<int> neg = stage<int>(P);
+    for (int p : stat_ids) neg[p] = mx - cnt_old[p];
+    counting_sort(stat_ids, neg, mx + 1);
+  }
   counting_sort(stat_ids, first_cam, C + 1);
   {
     HostBuf<int> first_h = stage_fill<int>(P, 0);
@@ -345,13 +353,24 @@ int BaGraph::finalize() {
     const char* env = std::getenv("VDO_BA_LAYOUT");
     if (env && std::string(env) == "chunked") tiled = false;
     Tile cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    auto close = [&](int t) { if (cur.t1 > cur.t0) tiles.push_back(cur); cur.t0 = cur.t1 = t; cur.k0 = cur.k1 = tk_begin[t]; cur.e0 = cur.e1 = lm_begin[tk_begin[t]]; };
+    // a tile also meets at most 255 distinct cameras (edges address them by an 8-bit slot): cam_tile[c] = serial of the tile that saw camera c last
+    std::vector<int> cam_tile(C, -1), fresh;
+    int tile_serial = 0, ncam_cur = 0;
+    auto close = [&](int t) {
+      if (cur.t1 > cur.t0) tiles.push_back(cur);
+      cur.t0 = cur.t1 = t; cur.k0 = cur.k1 = tk_begin[t]; cur.e0 = cur.e1 = lm_begin[tk_begin[t]];
+      ++tile_serial; ncam_cur = 0;
+    };
     for (int t = 0; t < T && tiled; ++t) {
       if (t == Tstat) { close(t); n_tiles_stat = (int)tiles.size(); }
-      const int nl = tk_begin[t + 1] - tk_begin[t], ne = lm_begin[tk_begin[t + 1]] - lm_begin[tk_begin[t]];
+      const int nl = tk_begin[t + 1] - tk_begin[t], ea = lm_begin[tk_begin[t]], eb = lm_begin[tk_begin[t + 1]], ne = eb - ea;
       if (nl > VDO_TILE_L || ne > VDO_TILE_E) { tiled = false; break; }
-      if ((cur.k1 - cur.k0) + nl > VDO_TILE_L || (cur.e1 - cur.e0) + ne > VDO_TILE_E) close(t);
-      cur.t1 = t + 1; cur.k1 = tk_begin[t + 1]; cur.e1 = lm_begin[tk_begin[t + 1]];
+      auto count_fresh = [&]() { fresh.clear(); for (int e = ea; e < eb; ++e) if (cam_tile[lm_cam[e]] != tile_serial) { cam_tile[lm_cam[e]] = tile_serial; fresh.push_back(lm_cam[e]); } };
+      count_fresh();
+      if ((cur.k1 - cur.k0) + nl > VDO_TILE_L || (cur.e1 - cur.e0) + ne > VDO_TILE_E || ncam_cur + (int)fresh.size() > 255) { close(t); count_fresh(); }
+      if ((int)fresh.size() > 255) { tiled = false; break; }                 // one tracklet seen by more than 255 cameras
+      ncam_cur += (int)fresh.size();
+      cur.t1 = t + 1; cur.k1 = tk_begin[t + 1]; cur.e1 = eb;
     }
     if (tiled) { if (cur.t1 > cur.t0) tiles.push_back(cur); if (Tstat == T) n_tiles_stat = (int)tiles.size(); }
     else tiles.clear();
@@ -424,19 +443,25 @@ int BaGraph::finalize() {
   lap("ternary / chunked streams");
   // ---- tiles: tile-local landmark of every edge, vertex-sorted order of the tile's edges, segments of one vertex ----
   HostBuf<uint16_t> ob_perm, tr_perm;
-  HostBuf<uint8_t> lm_lml, ob_slml;
+  HostBuf<uint8_t> lm_lml, lm_cslot, tk_hslot;
+  HostBuf<uint32_t> ob_ps;
+  std::vector<int> tile_verts;
   std::vector<Seg> osegs, tsegs, osegs2, tsegs2;
   if (tiled) {
-    ob_perm = stage<uint16_t>(Eo); tr_perm = stage_fill<uint16_t>(P, 0); lm_lml = stage<uint8_t>(Eo); ob_slml = stage<uint8_t>(Eo);
+    ob_perm = stage<uint16_t>(Eo); tr_perm = stage_fill<uint16_t>(P, 0); lm_lml = stage<uint8_t>(Eo); ob_ps = stage<uint32_t>(Eo);
+    lm_cslot = stage<uint8_t>(Eo); tk_hslot = stage_fill<uint8_t>(P, 0xFF);
     // tiles are independent: each worker handles a contiguous range of tiles into its own segment lists, which are then
     // concatenated in tile order (segment indices of a tile are rebased by the lists that precede it)
     const int ntl = (int)tiles.size();
     const int NW = std::max(1, std::min(NT, ntl / 64 + 1));
     std::vector<std::vector<Seg>> w_os(NW), w_ts(NW), w_os2(NW), w_ts2(NW);
+    std::vector<std::vector<int>> w_tv(NW);
+    std::vector<char> w_bad(NW, 0);
     parallel_for(NW, [&](int wt, int wn) {
       std::vector<int> keys(std::max(VDO_TILE_E, VDO_TILE_L)), idx(keys.size()), bucket;
       std::vector<Seg>& los = w_os[wt]; std::vector<Seg>& lts = w_ts[wt];
       std::vector<Seg>& los2 = w_os2[wt]; std::vector<Seg>& lts2 = w_ts2[wt];
+      std::vector<int>& ltv = w_tv[wt];
       // stable sort of idx[0..n) by keys[idx] (counting sort over the key range when it is small), then cut into segments
       auto sort_and_cut = [&](int n, int base, HostBuf<uint16_t>& perm, std::vector<Seg>& segs, std::vector<Seg>& segs2) {
         if (n == 0) return;
@@ -476,12 +501,28 @@ int BaGraph::finalize() {
         tl.os0 = (int)los.size(); tl.qo0 = (int)los2.size();
         sort_and_cut(ne, tl.e0, ob_perm, los, los2);
         tl.os1 = (int)los.size(); tl.qo1 = (int)los2.size();
-        for (int q = 0; q < ne; ++q) ob_slml[tl.e0 + q] = lm_lml[tl.e0 + ob_perm[tl.e0 + q]];     // tile-local landmark in sorted order
+        // sorted order: permutation and tile-local landmark in one word; the tile's camera list = the vertices of its sorted runs
+        tl.vs0 = (int)ltv.size();
+        int ncam = 0, nmot = 0;
+        for (int q = 0; q < ne; ++q) {
+          const int i = ob_perm[tl.e0 + q];
+          ob_ps[tl.e0 + q] = (uint32_t)i | ((uint32_t)lm_lml[tl.e0 + i] << 16);
+          const int cam = lm_cam[tl.e0 + i];
+          if (q == 0 || cam != lm_cam[tl.e0 + ob_perm[tl.e0 + q - 1]]) { ltv.push_back(cam); ++ncam; }
+          lm_cslot[tl.e0 + i] = (uint8_t)(ncam - 1);
+        }
         int nt = 0;
         for (int k = tl.k0; k < tl.k1; ++k) if (tk_h[k] >= 0) { keys[k - tl.k0] = tk_h[k]; idx[nt++] = k - tl.k0; }
         tl.ts0 = (int)lts.size(); tl.qt0 = (int)lts2.size();
         sort_and_cut(nt, tl.k0, tr_perm, lts, lts2);
         tl.ts1 = (int)lts.size(); tl.qt1 = (int)lts2.size();
+        for (int q = 0; q < nt; ++q) {
+          const int j = tr_perm[tl.k0 + q], h = tk_h[tl.k0 + j];
+          if (q == 0 || h != tk_h[tl.k0 + tr_perm[tl.k0 + q - 1]]) { ltv.push_back(h); ++nmot; }
+          tk_hslot[tl.k0 + j] = (uint8_t)(nmot - 1);
+        }
+        if (ncam > 255 || nmot > 255) w_bad[wt] = 1;
+        tl.nv = ncam | (nmot << 16);
       }
     });
     for (int wt = 0; wt < NW; ++wt) {
@@ -495,6 +536,10 @@ int BaGraph::finalize() {
       tsegs.insert(tsegs.end(), w_ts[wt].begin(), w_ts[wt].end());
       osegs2.insert(osegs2.end(), w_os2[wt].begin(), w_os2[wt].end());
       tsegs2.insert(tsegs2.end(), w_ts2[wt].begin(), w_ts2[wt].end());
+      const int vb0 = (int)tile_verts.size();
+      for (int ti = ta; ti < tb; ++ti) tiles[ti].vs0 += vb0;
+      tile_verts.insert(tile_verts.end(), w_tv[wt].begin(), w_tv[wt].end());
+      if (w_bad[wt]) return fail(VDO_ERR_UNSUPPORTED, "a tile meets more than 255 motion vertices");
     }
   }
   lap("tile segments");
@@ -561,13 +606,18 @@ int BaGraph::finalize() {
     d.hm_p1 = upload(hm_p1); d.hm_cls = upload(hm_cls); d.hm_omega = dalloc<double>(Et); d.ter_chunks = upload(ter_chunks);
   } else {
     d.n_tiles = (int)tiles.size(); d.n_tiles_stat = n_tiles_stat; d.n_osegs = (int)osegs.size(); d.n_tsegs = (int)tsegs.size();
-    d.capE_st = d.capE_ch = 16;
+    d.capE_st = d.capE_ch = 16; d.capV_st = d.capV_ch = d.capH_ch = 1;
     for (int ti = 0; ti < d.n_tiles; ++ti) {
-      int& cap = ti < n_tiles_stat ? d.capE_st : d.capE_ch;
+      const bool st = ti < n_tiles_stat;
+      int& cap = st ? d.capE_st : d.capE_ch;
       cap = std::max(cap, (tiles[ti].e1 - tiles[ti].e0 + 15) & ~15);
+      int& cv = st ? d.capV_st : d.capV_ch;
+      cv = std::max(cv, tiles[ti].nv & 0xFFFF);
+      if (!st) d.capH_ch = std::max(d.capH_ch, tiles[ti].nv >> 16);
     }
     d.tiles = upload(tiles); d.osegs = upload(osegs); d.tsegs = upload(tsegs); d.osegs2 = upload(osegs2); d.tsegs2 = upload(tsegs2);
-    d.ob_perm = upload(ob_perm); d.tr_perm = upload(tr_perm); d.lm_lml = upload(lm_lml); d.ob_slml = upload(ob_slml);
+    d.ob_perm = upload(ob_perm); d.tr_perm = upload(tr_perm); d.lm_lml = upload(lm_lml); d.ob_ps = upload(ob_ps);
+    d.tile_verts = upload(tile_verts); d.lm_cslot = upload(lm_cslot); d.tk_hslot = upload(tk_hslot);
     d.pt_Q = dalloc<double>(9 * (size_t)std::max(P - Tstat, 1));
     d.accO = dalloc<double>(16 * (size_t)C); d.accT = dalloc<double>(16 * (size_t)C); d.acc6 = dalloc<double>(12 * (size_t)C);
     d.vh = dalloc<double>(6 * (size_t)C);

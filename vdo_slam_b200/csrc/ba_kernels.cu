@@ -624,14 +624,16 @@ struct CudaBackend : BaBackend {
     const int ns = d.n_tiles_stat, nc = d.n_tiles - d.n_tiles_stat;
     const size_t bs = SMEM_SCH_ST, bc = SMEM_SCH_CH;
     if (part != 1 && ns > 0) {
-      if (mode == 0) k_tile_schur2<false, 0><<<ns, VDO_TILE_L, smem_sch2(false, d.capE_st), st>>>(d, 0, d.capE_st);
-      else if (mode == 1) k_tile_schur2<false, 1><<<ns, VDO_TILE_L, smem_sch2(false, d.capE_st), st>>>(d, 0, d.capE_st);
+      const size_t sm2 = smem_sch2(false, d.capE_st, d.capV_st, 1);
+      if (mode == 0) k_tile_schur2<false, 0><<<ns, VDO_TILE_L, sm2, st>>>(d, 0, d.capE_st, d.capV_st, 1);
+      else if (mode == 1) k_tile_schur2<false, 1><<<ns, VDO_TILE_L, sm2, st>>>(d, 0, d.capE_st, d.capV_st, 1);
       else k_tile_schur<false, 2><<<ns, VDO_TILE_L, bs, st>>>(d, 0);
       ++n_launch;
     }
     if (part != 0 && nc > 0) {
-      if (mode == 0) k_tile_schur2<true, 0><<<nc, VDO_TILE_L, smem_sch2(true, d.capE_ch), chain_stream>>>(d, ns, d.capE_ch);
-      else if (mode == 1) k_tile_schur2<true, 1><<<nc, VDO_TILE_L, smem_sch2(true, d.capE_ch), chain_stream>>>(d, ns, d.capE_ch);
+      const size_t sm2 = smem_sch2(true, d.capE_ch, d.capV_ch, d.capH_ch);
+      if (mode == 0) k_tile_schur2<true, 0><<<nc, VDO_TILE_L, sm2, chain_stream>>>(d, ns, d.capE_ch, d.capV_ch, d.capH_ch);
+      else if (mode == 1) k_tile_schur2<true, 1><<<nc, VDO_TILE_L, sm2, chain_stream>>>(d, ns, d.capE_ch, d.capV_ch, d.capH_ch);
       else k_tile_schur<true, 2><<<nc, VDO_TILE_L, bc, chain_stream>>>(d, ns);
       ++n_launch;
     }
@@ -789,8 +791,8 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
     optin((const void*)k_tile_lin<true, true>, SMEM_LIN_CH); optin((const void*)k_tile_lin<true, false>, SMEM_LIN_CH);
     optin((const void*)k_tile_schur<false, 0>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 1>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 2>, SMEM_SCH_ST);
     optin((const void*)k_tile_precond<false>, SMEM_PRE_ST); optin((const void*)k_tile_precond<true>, SMEM_PRE_CH);
-    optin((const void*)k_tile_schur2<false, 0>, smem_sch2(false, VDO_TILE_E)); optin((const void*)k_tile_schur2<false, 1>, smem_sch2(false, VDO_TILE_E));
-    optin((const void*)k_tile_schur2<true, 0>, smem_sch2(true, VDO_TILE_E)); optin((const void*)k_tile_schur2<true, 1>, smem_sch2(true, VDO_TILE_E));
+    optin((const void*)k_tile_schur2<false, 0>, smem_sch2(false, VDO_TILE_E, 255, 1)); optin((const void*)k_tile_schur2<false, 1>, smem_sch2(false, VDO_TILE_E, 255, 1));
+    optin((const void*)k_tile_schur2<true, 0>, smem_sch2(true, VDO_TILE_E, 255, 255)); optin((const void*)k_tile_schur2<true, 1>, smem_sch2(true, VDO_TILE_E, 255, 255));
     optin((const void*)k_tile_schur<true, 0>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 1>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 2>, SMEM_SCH_CH);
   }
   CudaBackend* b = new CudaBackend;

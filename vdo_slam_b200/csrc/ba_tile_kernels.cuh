@@ -318,65 +318,99 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur(BaDev d, int tile0) {
 //    force / torque on its vertex, -om [z_j ; 2 (p_j - t_c) x z_j], is summed as om [z_j ; p_j x z_j] (again a per-landmark
 //    6-vector, kept in shared memory) -- i.e. the torque is taken about the WORLD origin and moved to the vertex origin by the
 //    per-vertex finalize kernel (torque_v = torque_0 - t_v x force).
+//  * the per-vertex vectors vw / vh of the (few dozen) se3 vertices a tile meets are gathered into shared memory while the
+//    bulk copies are in flight; edges address them by an 8-bit slot (lm_cslot / tk_hslot, 1 B instead of a 4 B vertex index),
+//    so the landmark loop has no global gather on its critical path.
 //  * the vertex side is ONE THREAD PER (RUN, COMPONENT): the tile's edges in vertex-sorted order are cut into runs of one
 //    vertex and at most VDO_SEG2 = 16 entries (osegs2 / tsegs2); a thread adds its component over its run from shared memory
 //    and issues one fp64 atomic.  No shuffles, no selects, no idle lanes on short runs (chain tiles average 8 entries per
 //    vertex: the warp-per-segment scheme of k_tile_schur ran them at 12 % lane utilisation).
+//  * chains: the two scalar recurrences of the tracklet solve (forward y_j = c_j + f_{j-1} y_{j-1}, backward
+//    z_j = y_j / s_j + g_j z_{j+1}; the coefficients vanish at tracklet boundaries, so no segment bookkeeping) are CTA-wide
+//    scans: Kogge-Stone over the 32 lanes of a warp with shuffles, then a carry across the 8 warps through shared memory --
+//    instead of one thread per tracklet walking it (<= 53 of 256 threads busy, the rest waiting at the barrier).
 //  * only warp 0 polls the mbarrier; the other warps sleep in the CTA barrier.
+//  * per-edge / per-vertex arrays are staged with the launch's own capacities (largest tile of the launch, known at ingest):
+//    chain tiles (one pointxyz edge per landmark) fit 4 CTAs per SM.
 // acc6 layout (12 / vertex): [F_o, M_o, F_t, M_t]  pointxyz force / world-origin torque, ternary force / torque.
-//  * the per-edge arrays are staged with the launch's own capacity (capE = the largest edge count of the tiles of this launch,
-//    known at ingest) instead of VDO_TILE_E: chain tiles (one pointxyz edge per landmark) fit 4 CTAs per SM.
 constexpr int TILE_OSEG2_CAP_ST = 192, TILE_OSEG2_CAP_CH = 96, TILE_TSEG2_CAP = 96;
-struct Seg2Views { const Seg* seg; int n; };
-__device__ __forceinline__ Seg2Views seg2_views(TileStager& sg, const Seg* g, int s0, int s1, int cap) {
-  Seg2Views v;
-  v.n = s1 - s0;
-  const bool staged = v.n <= cap;
-  const Seg* st = sg.view<Seg>(g, (size_t)s0, staged ? v.n : 0, cap);
-  v.seg = staged ? st : g + s0;
-  return v;
-}
-inline size_t smem_sch2(bool chains, int capE) {      // must mirror the carve order inside k_tile_schur2
-  size_t b = vb<double>(3 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L + 1) + vb<double>(capE) + vb<int>(capE) + vb<uint16_t>(capE) + vb<uint8_t>(capE) +
+inline size_t smem_sch2(bool chains, int capE, int capV, int capH) {      // must mirror the carve order inside k_tile_schur2
+  size_t b = sb(6 * (size_t)capV * 8) + (chains ? sb(6 * (size_t)capH * 8) : 0) +
+             vb<double>(3 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L + 1) + vb<double>(capE) + vb<uint8_t>(capE) + vb<uint32_t>(capE) +
              vb<Seg>(chains ? TILE_OSEG2_CAP_CH : TILE_OSEG2_CAP_ST) + sb(6 * VDO_TILE_L * 8);
-  if (chains) b += vb<double>(9 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<int>(VDO_TILE_L) + vb<uint16_t>(VDO_TILE_L) + vb<Seg>(TILE_TSEG2_CAP) + sb(3 * VDO_TILE_L * 8);
+  if (chains) b += vb<double>(9 * VDO_TILE_L) + vb<double>(VDO_TILE_L) + vb<uint8_t>(VDO_TILE_L) + vb<uint16_t>(VDO_TILE_L) + vb<Seg>(TILE_TSEG2_CAP) + sb(64 * 8);
   return b;
 }
 
 template <bool CHAINS, int MODE>
-__global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur2(BaDev d, int tile0, int capE) {
+__global__ void __launch_bounds__(VDO_TILE_L, CHAINS ? 4 : 5) k_tile_schur2(BaDev d, int tile0, int capE, int capV, int capH) {
   extern __shared__ __align__(16) unsigned char tile_sh[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tab[16];                              // shared-memory offsets of the staged views (computed by warp 0 only)
   if (MODE == 1 && d.scal[SC_DONE] != 0.0) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Tile tl = d.tiles[tile0 + blockIdx.x];
-  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
-  if (tid == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  TileStager sg(tile_sh, &bar, tid == 0);
-  double* sP = sg.view<double>(d.pt, 3 * (size_t)tl.k0, 3 * nl, 3 * VDO_TILE_L);
-  double* sS = sg.view<double>(d.pt_s, (size_t)tl.k0, nl, VDO_TILE_L);
-  int* sLB = sg.view<int>(d.lm_obs_begin, (size_t)tl.k0, nl + 1, VDO_TILE_L + 1);
-  double* sOM = sg.view<double>(d.lm_omega, (size_t)tl.e0, ne, capE);
-  int* sCAM = sg.view<int>(d.lm_cam, (size_t)tl.e0, MODE != 0 ? ne : 0, capE);
-  uint16_t* sPERM = sg.view<uint16_t>(d.ob_perm, (size_t)tl.e0, ne, capE);
-  uint8_t* sSLML = sg.view<uint8_t>(d.ob_slml, (size_t)tl.e0, ne, capE);
-  const Seg2Views os = seg2_views(sg, d.osegs2, tl.qo0, tl.qo1, CHAINS ? TILE_OSEG2_CAP_CH : TILE_OSEG2_CAP_ST);
-  double* sZM = sg.stash<double>(6 * VDO_TILE_L);           // per landmark: [z ; p x z]   (chains: its first half holds g^ until the walk)
-  double *sQ = nullptr, *sOMT = nullptr, *sZ = sZM, *sY = nullptr;
-  int* sHH = nullptr; uint16_t* sTPERM = nullptr;
-  Seg2Views ts{nullptr, 0};
-  if (CHAINS) {
-    sQ = sg.view<double>(d.pt_Q, 9 * (size_t)(tl.k0 - d.Tstat), 9 * nl, 9 * VDO_TILE_L);
-    sOMT = sg.view<double>(d.tk_omega, (size_t)tl.k0, nl, VDO_TILE_L);
-    sHH = sg.view<int>(d.tk_h, (size_t)tl.k0, nl, VDO_TILE_L);
-    sTPERM = sg.view<uint16_t>(d.tr_perm, (size_t)tl.k0, nl, VDO_TILE_L);
-    ts = seg2_views(sg, d.tsegs2, tl.qt0, tl.qt1, TILE_TSEG2_CAP);
-    sY = sg.stash<double>(3 * VDO_TILE_L);
+  const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0, ncam = tl.nv & 0xFFFF, nmot = tl.nv >> 16;
+  double* sVW = (double*)tile_sh;                           // vw of the tile's cameras, vh of its motion vertices: fixed places, filled by warps 1..7
+  double* sVH = sVW + 6 * capV;
+  unsigned char* carve0 = tile_sh + sb(6 * (size_t)capV * 8) + (CHAINS ? sb(6 * (size_t)capH * 8) : 0);
+  if (warp == 0) {
+    // staging: warp 0 alone carves the views, issues the bulk copies (lane 0) and waits for them; the other warps meanwhile gather
+    // the per-vertex vectors and then sleep in the CTA barrier
+    if (lane == 0) mbar_init(&bar, 1);
+    __syncwarp();
+    TileStager sg(carve0, &bar, lane == 0);
+    auto off = [&](const void* ptr) { return (uint32_t)((const unsigned char*)ptr - tile_sh); };
+    uint32_t o[16];
+    o[0] = off(sg.view<double>(d.pt, 3 * (size_t)tl.k0, 3 * nl, 3 * VDO_TILE_L));
+    o[1] = off(sg.view<double>(d.pt_s, (size_t)tl.k0, nl, VDO_TILE_L));
+    o[2] = off(sg.view<int>(d.lm_obs_begin, (size_t)tl.k0, nl + 1, VDO_TILE_L + 1));
+    o[3] = off(sg.view<double>(d.lm_omega, (size_t)tl.e0, ne, capE));
+    o[4] = off(sg.view<uint8_t>(d.lm_cslot, (size_t)tl.e0, MODE != 0 ? ne : 0, capE));
+    o[5] = off(sg.view<uint32_t>(d.ob_ps, (size_t)tl.e0, ne, capE));
+    {
+      const int cap = CHAINS ? TILE_OSEG2_CAP_CH : TILE_OSEG2_CAP_ST, n = tl.qo1 - tl.qo0;
+      o[6] = off(sg.view<Seg>(d.osegs2, (size_t)tl.qo0, n <= cap ? n : 0, cap));
+    }
+    o[7] = off(sg.stash<double>(6 * VDO_TILE_L));
+    if (CHAINS) {
+      o[8] = off(sg.view<double>(d.pt_Q, 9 * (size_t)(tl.k0 - d.Tstat), 9 * nl, 9 * VDO_TILE_L));
+      o[9] = off(sg.view<double>(d.tk_omega, (size_t)tl.k0, nl, VDO_TILE_L));
+      o[10] = off(sg.view<uint8_t>(d.tk_hslot, (size_t)tl.k0, nl, VDO_TILE_L));
+      o[11] = off(sg.view<uint16_t>(d.tr_perm, (size_t)tl.k0, nl, VDO_TILE_L));
+      const int n = tl.qt1 - tl.qt0;
+      o[12] = off(sg.view<Seg>(d.tsegs2, (size_t)tl.qt0, n <= TILE_TSEG2_CAP ? n : 0, TILE_TSEG2_CAP));
+      o[13] = off(sg.stash<double>(64));
+    }
+    sg.commit();
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < (CHAINS ? 14 : 8); ++i) tab[i] = o[i];
+    }
+    mbar_wait(&bar, 0);
+  } else if (MODE == 1) {
+    for (int i = tid - 32; i < 6 * ncam; i += VDO_TILE_L - 32) { const int s = i / 6; sVW[i] = d.vw[6 * (size_t)d.tile_verts[tl.vs0 + s] + (i - 6 * s)]; }
+    if (CHAINS) for (int i = tid - 32; i < 6 * nmot; i += VDO_TILE_L - 32) { const int s = i / 6; sVH[i] = d.vh[6 * (size_t)d.tile_verts[tl.vs0 + ncam + s] + (i - 6 * s)]; }
   }
-  sg.commit();
-  if (tid < 32) mbar_wait(&bar, 0);
   __syncthreads();
+  double* sP = (double*)(tile_sh + tab[0]);
+  double* sS = (double*)(tile_sh + tab[1]);
+  const int* sLB = (const int*)(tile_sh + tab[2]);
+  const double* sOM = (const double*)(tile_sh + tab[3]);
+  const uint8_t* sCS = (const uint8_t*)(tile_sh + tab[4]);
+  const uint32_t* sPS = (const uint32_t*)(tile_sh + tab[5]);
+  const int n_os = tl.qo1 - tl.qo0;
+  const Seg* oseg = n_os <= (CHAINS ? TILE_OSEG2_CAP_CH : TILE_OSEG2_CAP_ST) ? (const Seg*)(tile_sh + tab[6]) : d.osegs2 + tl.qo0;
+  double* sZM = (double*)(tile_sh + tab[7]);                // per landmark [z ; p x z] at the end; chains: first half g^, second half z^ until then
+  double *sQ = nullptr, *sAM = nullptr, *sOMT = nullptr, *sZ = sZM, *sY = sZM + 3 * VDO_TILE_L, *sWS = nullptr;
+  const uint8_t* sHS = nullptr; const uint16_t* sTPERM = nullptr; const Seg* tseg = nullptr;
+  const int n_ts = tl.qt1 - tl.qt0;
+  if (CHAINS) {
+    sQ = (double*)(tile_sh + tab[8]); sAM = (double*)(((uintptr_t)sQ + 15) & ~(uintptr_t)15);   // Q_k's space holds the ternary sums at the end (16-byte aligned)
+    sOMT = (double*)(tile_sh + tab[9]); sHS = (const uint8_t*)(tile_sh + tab[10]); sTPERM = (const uint16_t*)(tile_sh + tab[11]);
+    tseg = n_ts <= TILE_TSEG2_CAP ? (const Seg*)(tile_sh + tab[12]) : d.tsegs2 + tl.qt0;
+    sWS = (double*)(tile_sh + tab[13]);
+  }
   // ---- landmark phase ----
   double p[3] = {0, 0, 0}, u[3] = {0, 0, 0};
   if (tid < nl) {
@@ -386,9 +420,9 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur2(BaDev d, int tile0, 
       const int ib = sLB[tid] - tl.e0, ie = sLB[tid + 1] - tl.e0;
       for (int i = ib; i < ie; ++i) {
         const double om = sOM[i];
-        const double* w = d.vw + 6 * (size_t)sCAM[i];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) a[c] += om * w[c];
+        const double2* w = reinterpret_cast<const double2*>(sVW + 6 * (int)sCS[i]);
+        const double2 w0 = w[0], w1 = w[1], w2 = w[2];
+        a[0] += om * w0.x; a[1] += om * w0.y; a[2] += om * w1.x; a[3] += om * w1.y; a[4] += om * w2.x; a[5] += om * w2.y;
       }
       double pxb[3]; cross3(p, a + 3, pxb);
       u[0] = a[0] + 2 * pxb[0]; u[1] = a[1] + 2 * pxb[1]; u[2] = a[2] + 2 * pxb[2];
@@ -402,20 +436,23 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur2(BaDev d, int tile0, 
       const double is = 1.0 / sS[tid];
       const double z[3] = {u[0] * is, u[1] * is, u[2] * is};
       double m[3]; cross3(p, z, m);
-      double* o = sZM + 6 * tid;
-      o[0] = z[0]; o[1] = z[1]; o[2] = z[2]; o[3] = m[0]; o[4] = m[1]; o[5] = m[2];
+      double2* o = reinterpret_cast<double2*>(sZM + 6 * tid);
+      o[0] = make_double2(z[0], z[1]); o[1] = make_double2(z[2], m[0]); o[2] = make_double2(m[1], m[2]);
     }
   } else {
     // chains: H_ll of a tracklet is (scalar tridiagonal) (x) I3 in the frame x^_k = Q_k x_k (see ba_tiles.cuh)
-    double uh[3] = {0, 0, 0};
-    if (tid < nl) {
+    const bool live = tid < nl;
+    const bool has_out = live && sHS[tid] != 255;
+    double uh[3] = {0, 0, 0}, is = 0.0, omt = 0.0;
+    if (live) {
       const double* Q = sQ + 9 * tid;
-      double gh[3] = {0, 0, 0};
+      is = 1.0 / sS[tid]; omt = sOMT[tid];
+      rot_apply(Q, u, uh);                               // mode 0: b^ = Q b_l
       if (MODE == 1) {
-        rot_apply(Q, u, uh);
-        const int hp = tid > 0 ? sHH[tid - 1] : -1;
-        if (hp >= 0) {                                   // incoming ternary edge (k-1, k)
-          const double* w = d.vh + 6 * (size_t)hp;
+        double gh[3] = {0, 0, 0};
+        const int hp = tid > 0 ? (int)sHS[tid - 1] : 255;
+        if (hp != 255) {                                 // incoming ternary edge (k-1, k)
+          const double* w = sVH + 6 * hp;
           double pxb[3]; cross3(p, w + 3, pxb);
           const double g[3] = {w[0] - pxb[0], w[1] - pxb[1], w[2] - pxb[2]};
           rot_apply(Q, g, gh);
@@ -423,61 +460,95 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur2(BaDev d, int tile0, 
           uh[0] -= om * gh[0]; uh[1] -= om * gh[1]; uh[2] -= om * gh[2];
         }
         sZ[3 * tid] = gh[0]; sZ[3 * tid + 1] = gh[1]; sZ[3 * tid + 2] = gh[2];
-      } else rot_apply(Q, u, uh);                        // mode 0: b^ = Q b_l
-    }
-    if (MODE == 1) {
-      __syncthreads();
-      if (tid < nl && sHH[tid] >= 0) {                   // outgoing ternary edge (k, k+1)
-        const double om = sOMT[tid];
-        uh[0] += om * sZ[3 * tid + 3]; uh[1] += om * sZ[3 * tid + 4]; uh[2] += om * sZ[3 * tid + 5];
       }
+      sS[tid] = omt * is;                                // f_j = om_j / s_j, read by landmark j + 1
     }
-    if (tid < nl) { sY[3 * tid] = uh[0]; sY[3 * tid + 1] = uh[1]; sY[3 * tid + 2] = uh[2]; sS[tid] = 1.0 / sS[tid]; }
     __syncthreads();
-    if (tid < tl.t1 - tl.t0) {
-      TileSm sm; sm.Y = sY; sm.OMT = sOMT; sm.IS = sS;
-      tile_schur_chain_walk(d, tl, tid, sm);
+    if (MODE == 1 && has_out) {                          // outgoing ternary edge (k, k+1)
+      uh[0] += omt * sZ[3 * tid + 3]; uh[1] += omt * sZ[3 * tid + 4]; uh[2] += omt * sZ[3 * tid + 5];
     }
+    // forward: y_j = u^_j + f_{j-1} y_{j-1}   (f = 0 across tracklet boundaries)
+    double a = (live && tid > 0) ? sS[tid - 1] : 0.0;
+    double b0 = uh[0], b1 = uh[1], b2 = uh[2];
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const double ap = __shfl_up_sync(0xffffffffu, a, dd), p0 = __shfl_up_sync(0xffffffffu, b0, dd), p1 = __shfl_up_sync(0xffffffffu, b1, dd), p2 = __shfl_up_sync(0xffffffffu, b2, dd);
+      if (lane >= dd) { b0 += a * p0; b1 += a * p1; b2 += a * p2; a *= ap; }
+    }
+    if (lane == 31) { sWS[4 * warp] = a; sWS[4 * warp + 1] = b0; sWS[4 * warp + 2] = b1; sWS[4 * warp + 3] = b2; }
+    __syncthreads();
+    {
+      double c0 = 0, c1 = 0, c2 = 0;
+      for (int w2 = 0; w2 < warp; ++w2) { const double a2 = sWS[4 * w2]; c0 = sWS[4 * w2 + 1] + a2 * c0; c1 = sWS[4 * w2 + 2] + a2 * c1; c2 = sWS[4 * w2 + 3] + a2 * c2; }
+      b0 += a * c0; b1 += a * c1; b2 += a * c2;          // y_j
+    }
+    // backward: z_j = y_j / s_j + (om_j / s_j) z_{j+1}
+    double g = live ? omt * is : 0.0;
+    double e0 = b0 * is, e1 = b1 * is, e2 = b2 * is;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const double gp = __shfl_down_sync(0xffffffffu, g, dd), p0 = __shfl_down_sync(0xffffffffu, e0, dd), p1 = __shfl_down_sync(0xffffffffu, e1, dd), p2 = __shfl_down_sync(0xffffffffu, e2, dd);
+      if (lane + dd < 32) { e0 += g * p0; e1 += g * p1; e2 += g * p2; g *= gp; }
+    }
+    if (lane == 0) { sWS[32 + 4 * warp] = g; sWS[32 + 4 * warp + 1] = e0; sWS[32 + 4 * warp + 2] = e1; sWS[32 + 4 * warp + 3] = e2; }
+    __syncthreads();
+    {
+      double c0 = 0, c1 = 0, c2 = 0;
+      for (int w2 = VDO_TILE_L / 32 - 1; w2 > warp; --w2) { const double g2 = sWS[32 + 4 * w2]; c0 = sWS[32 + 4 * w2 + 1] + g2 * c0; c1 = sWS[32 + 4 * w2 + 2] + g2 * c1; c2 = sWS[32 + 4 * w2 + 3] + g2 * c2; }
+      e0 += g * c0; e1 += g * c1; e2 += g * c2;          // z^_j
+    }
+    if (live) { sY[3 * tid] = e0; sY[3 * tid + 1] = e1; sY[3 * tid + 2] = e2; }
     __syncthreads();
     double zm[6] = {0, 0, 0, 0, 0, 0}, am[6] = {0, 0, 0, 0, 0, 0};
-    if (tid < nl) {
-      rot_t_apply(sQ + 9 * tid, sY + 3 * tid, zm);
+    if (live) {
+      const double zh[3] = {e0, e1, e2};
+      rot_t_apply(sQ + 9 * tid, zh, zm);
       cross3(p, zm, zm + 3);
-      if (sHH[tid] >= 0) {                                 // ternary edge (k, k+1): a' = Q_{k+1}^T (z^_k - z^_{k+1}); om [a' ; p_{k+1} x a']
-        const double dz[3] = {sY[3 * tid] - sY[3 * tid + 3], sY[3 * tid + 1] - sY[3 * tid + 4], sY[3 * tid + 2] - sY[3 * tid + 5]};
-        double a[3]; rot_t_apply(sQ + 9 * (tid + 1), dz, a);
-        double c[3]; cross3(sP + 3 * tid + 3, a, c);
-        const double om = sOMT[tid];
-        am[0] = om * a[0]; am[1] = om * a[1]; am[2] = om * a[2]; am[3] = om * c[0]; am[4] = om * c[1]; am[5] = om * c[2];
+      if (has_out) {                                       // ternary edge (k, k+1): a' = Q_{k+1}^T (z^_k - z^_{k+1}); om [a' ; p_{k+1} x a']
+        const double dz[3] = {e0 - sY[3 * tid + 3], e1 - sY[3 * tid + 4], e2 - sY[3 * tid + 5]};
+        double av[3]; rot_t_apply(sQ + 9 * (tid + 1), dz, av);
+        double cv[3]; cross3(sP + 3 * tid + 3, av, cv);
+        am[0] = omt * av[0]; am[1] = omt * av[1]; am[2] = omt * av[2]; am[3] = omt * cv[0]; am[4] = omt * cv[1]; am[5] = omt * cv[2];
       }
     }
     __syncthreads();                                       // every thread has read Q / z^: their space is reused
-    if (tid < nl) {
-      double* o = sZM + 6 * tid; double* o2 = sQ + 6 * tid;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) { o[c] = zm[c]; o2[c] = am[c]; }
+    if (live) {
+      double2* o = reinterpret_cast<double2*>(sZM + 6 * tid); double2* o2 = reinterpret_cast<double2*>(sAM + 6 * tid);
+      o[0] = make_double2(zm[0], zm[1]); o[1] = make_double2(zm[2], zm[3]); o[2] = make_double2(zm[4], zm[5]);
+      o2[0] = make_double2(am[0], am[1]); o2[1] = make_double2(am[2], am[3]); o2[2] = make_double2(am[4], am[5]);
     }
   }
   __syncthreads();
-  // ---- vertex phase: one thread per (run, component) ----
-  for (int item = tid; item < 6 * os.n; item += VDO_TILE_L) {
-    const int s = item / 6, c = item - 6 * s;
-    const Seg sgm = os.seg[s];
+  // ---- vertex phase: one thread per (run, component pair) ----
+  for (int item = tid; item < 3 * n_os; item += VDO_TILE_L) {
+    const int s = item / 3, c2 = item - 3 * s;
+    const Seg sgm = oseg[s];
     const int q0 = sgm.begin - tl.e0;
-    double acc = 0.0;
+    double ax = 0.0, ay = 0.0;
 #pragma unroll 4
-    for (int q = q0; q < q0 + sgm.n; ++q) acc += sOM[sPERM[q]] * sZM[6 * (int)sSLML[q] + c];
-    if (acc != 0.0) atomicAdd(d.acc6 + 12 * (size_t)sgm.v + c, c < 3 ? -acc : -2.0 * acc);
+    for (int q = q0; q < q0 + sgm.n; ++q) {
+      const uint32_t ps = sPS[q];
+      const double om = sOM[ps & 0xFFFFu];
+      const double2 zz = *reinterpret_cast<const double2*>(sZM + 6 * (int)(ps >> 16) + 2 * c2);
+      ax += om * zz.x; ay += om * zz.y;
+    }
+    // components (2 c2, 2 c2 + 1) of [F_o ; M_o] = -[sum om z ; 2 sum om p x z]
+    double* dst = d.acc6 + 12 * (size_t)sgm.v + 2 * c2;
+    const double fx = c2 == 0 ? -1.0 : (c2 == 1 ? -1.0 : -2.0), fy = c2 == 0 ? -1.0 : -2.0;
+    if (ax != 0.0) atomicAdd(dst, fx * ax);
+    if (ay != 0.0) atomicAdd(dst + 1, fy * ay);
   }
   if (CHAINS) {
-    for (int item = tid; item < 6 * ts.n; item += VDO_TILE_L) {
-      const int s = item / 6, c = item - 6 * s;
-      const Seg sgm = ts.seg[s];
+    for (int item = tid; item < 3 * n_ts; item += VDO_TILE_L) {
+      const int s = item / 3, c2 = item - 3 * s;
+      const Seg sgm = tseg[s];
       const int q0 = sgm.begin - tl.k0;
-      double acc = 0.0;
+      double ax = 0.0, ay = 0.0;
 #pragma unroll 4
-      for (int q = q0; q < q0 + sgm.n; ++q) acc += sQ[6 * (int)sTPERM[q] + c];
-      if (acc != 0.0) atomicAdd(d.acc6 + 12 * (size_t)sgm.v + 6 + c, acc);
+      for (int q = q0; q < q0 + sgm.n; ++q) { const double2 zz = *reinterpret_cast<const double2*>(sAM + 6 * (int)sTPERM[q] + 2 * c2); ax += zz.x; ay += zz.y; }
+      double* dst = d.acc6 + 12 * (size_t)sgm.v + 6 + 2 * c2;
+      if (ax != 0.0) atomicAdd(dst, ax);
+      if (ay != 0.0) atomicAdd(dst + 1, ay);
     }
   }
 }

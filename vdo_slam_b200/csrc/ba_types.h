@@ -43,7 +43,9 @@ struct Chunk { int v, begin, end, pad; };
 // tile: landmarks [k0,k1), EdgeSE3PointXYZ [e0,e1) (landmark-major), tracklets [t0,t1), vertex-sorted segments of the
 // pointxyz edges [os0,os1) and of the ternary edges [ts0,ts1)
 // [qo0,qo1) / [qt0,qt1): the same vertex-sorted runs cut at VDO_SEG2 entries (osegs2 / tsegs2)
-struct Tile { int k0, k1, e0, e1, t0, t1, os0, os1, ts0, ts1, qo0, qo1, qt0, qt1, pad0, pad1; };
+// [vs0, vs0 + ncam + nmot): the tile's own list of se3 vertices in tile_verts -- the cameras its pointxyz edges meet first, then the
+// motion vertices of its ternary edges; edges carry the 8-bit position in that list (lm_cslot / tk_hslot)
+struct Tile { int k0, k1, e0, e1, t0, t1, os0, os1, ts0, ts1, qo0, qo1, qt0, qt1, vs0, nv; };   // nv = ncam | nmot << 16
 // segment: <= VDO_SEG consecutive entries of ob_perm (or tr_perm) starting at `begin`, all on se3 vertex v (one warp, two entries per lane)
 struct Seg { int v, begin, n, pad; };
 
@@ -77,7 +79,11 @@ struct BaDev {
   int tiled = 0, n_tiles_stat = 0, n_tiles = 0, n_osegs = 0, n_tsegs = 0;
   int capE_st = 16, capE_ch = 16;   // largest pointxyz-edge count of a static / chain tile, rounded up to 16 (shared-memory capacity of the launches)
   Tile* tiles = 0; Seg* osegs = 0; Seg* tsegs = 0; Seg* osegs2 = 0; Seg* tsegs2 = 0;
-  uint8_t* ob_slml = 0;    // Eobs: tile-local landmark of the edge at each position of the camera-sorted order (= lm_lml[e0 + ob_perm[q]])
+  uint32_t* ob_ps = 0;     // Eobs: per position q of the camera-sorted order: ob_perm[q] | lm_lml[e0 + ob_perm[q]] << 16 (one load instead of two)
+  int* tile_verts = 0;     // per tile [vs0, vs0 + ncam + nmot): se3 vertices the tile meets (cameras, then motion vertices)
+  uint8_t* lm_cslot = 0;   // Eobs: position of the edge's camera in its tile's vertex list
+  uint8_t* tk_hslot = 0;   // P: position (counted from the tile's first motion vertex) of the motion vertex of ternary edge (k, k+1); 255 = no edge
+  int capV_st = 1, capV_ch = 1, capH_ch = 1;   // largest camera / motion-vertex list of a static / chain tile
   uint16_t* ob_perm = 0;   // Eobs: position in the tile's camera-sorted order -> tile-local edge index (e - e0)
   uint16_t* tr_perm = 0;   // P: position (k0 + i) in the tile's motion-vertex-sorted order -> tile-local landmark index of p1
   uint8_t* lm_lml = 0;     // Eobs: tile-local landmark index of each pointxyz edge

@@ -37,7 +37,7 @@ __global__ void k_depth_prep(float* __restrict__ d, int n, float bf, float facto
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = d[i];
-  d[i] = (v < 0.f) ? 0.f : __fdiv_rn(bf, __fdiv_rn(v, factor));   // mbf/(d/mDepthMapFactor), IEEE divisions (d == 0 -> +inf)
+  d[i] = (v < 0.f) ? 0.f : (bf > 0.f ? __fdiv_rn(bf, __fdiv_rn(v, factor)) : v);   // mbf/(d/mDepthMapFactor), IEEE divisions (d == 0 -> +inf); bf <= 0: clamp only
 }
 
 // ------------------------------------------------------------------------------------------------ pyramid

@@ -19,14 +19,19 @@
 namespace {
 using M4 = std::array<float, 16>;
 M4 eye4() { M4 m{}; m[0] = m[5] = m[10] = m[15] = 1.f; return m; }
-// cv::Mat float product: every entry accumulated in double, rounded once
+// cv::Mat A * B of two 4x4 CV_32F (e.g. `mCurrentFrame.mTcw * Converter::toInvMatrix(mLastFrame.mTcw)`, src/Tracking.cc:700-706):
+// OpenCV's gemm takes its small-matrix branch (no flags, inner dimension <= 4) and evaluates a0*b0 + a1*b1 + a2*b2 + a3*b3 in
+// FLOAT, left to right.  Pinned bit for bit against cv2.gemm (tests/test_results_io.py for the same formula in results_io.cpp;
+// the oracle pipeline calls cv2.gemm itself, so the tracker parity tests pin this one).
 M4 mul4(const M4& A, const M4& B) {
   M4 C{};
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) {
-      double s = 0;
-      for (int k = 0; k < 4; ++k) s += (double)A[4 * i + k] * (double)B[4 * k + j];
-      C[4 * i + j] = (float)s;
+      float s = A[4 * i] * B[j];
+      s = s + A[4 * i + 1] * B[4 + j];
+      s = s + A[4 * i + 2] * B[8 + j];
+      s = s + A[4 * i + 3] * B[12 + j];
+      C[4 * i + j] = s;
     }
   return C;
 }
@@ -55,11 +60,12 @@ struct FrameState {
   std::vector<int> nModLabel, nSemPosition, semPosiGt;                  // nModLabel, nSemPosition, nSemPosi_gt
   std::vector<unsigned char> bObjStat;
   std::vector<M4> vObjMod;
+  std::vector<float> vObjCentre3D;                                      // 3 per object (src/Tracking.cc:856-866)
   std::vector<std::vector<int>> vnObjID, vnObjInlierID;
   void clear_dynamic() {
     keys.clear(); statKeysTmp.clear(); corres.clear(); flowNext.clear(); statDepthTmp.clear(); stat3DTmp.clear(); statKeys.clear(); statDepth.clear();
     staInlierID.clear(); objKeys.clear(); objCorres.clear(); objFlowNext.clear(); objDepth.clear(); obj3D.clear(); semObjLabel.clear(); objLabel.clear();
-    dynInlierID.clear(); flow3d.clear(); nModLabel.clear(); nSemPosition.clear(); semPosiGt.clear(); bObjStat.clear(); vObjMod.clear(); vnObjID.clear();
+    dynInlierID.clear(); flow3d.clear(); nModLabel.clear(); nSemPosition.clear(); semPosiGt.clear(); bObjStat.clear(); vObjMod.clear(); vObjCentre3D.clear(); vnObjID.clear();
     vnObjInlierID.clear();
   }
 };
@@ -67,8 +73,9 @@ struct FrameState {
 struct MapSlice {        // what Tracking::Track pushes per frame (src/Tracking.cc:1016-1070)
   std::vector<std::vector<float>> featSta, depSta, p3dSta, featDyn, depDyn, p3dDyn;
   std::vector<std::vector<int>> assoSta, assoDyn, featLabel, rmLabel, smLabel;
-  std::vector<M4> cameraPose;
-  std::vector<std::vector<M4>> rigidMotion;
+  std::vector<M4> cameraPose, cameraPose_RF;              // vmCameraPose (updated by the windowed BA) / vmCameraPose_RF (by the full batch)
+  std::vector<std::vector<M4>> rigidMotion, rigidMotion_RF;
+  std::vector<std::vector<float>> rigidCentre;            // vmRigidCentre: 3 floats per entry (entry 0 = camera = 0)
 };
 }  // namespace
 
@@ -240,6 +247,7 @@ int track_frame(vdo_tracker* t, FrameState& C, FrameState& L) {
   }
   C.nModLabel.assign(ml.begin(), ml.begin() + nobj); C.nSemPosition.assign(sp.begin(), sp.begin() + nobj);
   C.bObjStat.assign(nobj, 1); C.vObjMod.assign(nobj, eye4()); C.vnObjID.assign(nobj, {}); C.vnObjInlierID.assign(nobj, {});
+  C.vObjCentre3D.assign(3 * (size_t)nobj, 0.f);
   std::vector<std::vector<int>> objIdNew(nobj);
   for (int i = 0; i < nobj; ++i) objIdNew[i].assign(oi.begin() + ob[i], oi.begin() + ob[i + 1]);
   // per object: ground-truth presence gate (:767-810), initial model (:1717-1849), joint flow / motion LM (src/Optimizer.cc:2755-2972).
@@ -263,11 +271,15 @@ int track_frame(vdo_tracker* t, FrameState& C, FrameState& L) {
     std::vector<int> nsub(np), sub(tot + 1);
     for (int j = 0; j < np; ++j) {
       const int i = live[j]; int q = offs[j];
+      float cs[3] = {0.f, 0.f, 0.f};
       for (int id : objIdNew[i]) {
         img2[2 * q] = C.objKeys[2 * id]; img2[2 * q + 1] = C.objKeys[2 * id + 1];
         unproject_world(L.objKeys[2 * id], L.objKeys[2 * id + 1], L.objDepth[id], p, L.Tcw, &obj3[3 * q]);
+        for (int r = 0; r < 3; ++r) cs[r] = cs[r] + obj3[3 * q + r];                       // ObjCentre3D_pre + x3D_p, float
         ++q;
       }
+      const float inv_n = (float)(1.0 / (double)objIdNew[i].size());                     // cv::Mat / size(): convertTo with alpha = 1/n, float
+      for (int r = 0; r < 3; ++r) C.vObjCentre3D[3 * (size_t)i + r] = cs[r] * inv_n;
       int pre = -1;
       for (size_t k = 0; k < L.nModLabel.size(); ++k) if (L.nModLabel[k] == C.nModLabel[i]) { pre = (int)k; break; }
       if (pre != -1) { has[j] = 1; const M4 mm = mul4(C.Tcw, L.vObjMod[pre]); std::memcpy(&Tmm[16 * j], mm.data(), 64); }
@@ -342,14 +354,17 @@ void push_map(vdo_tracker* t, const FrameState& C, bool first) {          // Tra
   m.featSta.push_back(C.statKeysTmp); m.depSta.push_back(C.statDepthTmp); m.p3dSta.push_back(C.stat3DTmp);
   m.featDyn.push_back(C.objKeys); m.depDyn.push_back(C.objDepth); m.p3dDyn.push_back(C.obj3D);
   m.cameraPose.push_back(first ? eye4() : inv4(C.Tcw));
+  m.cameraPose_RF.push_back(m.cameraPose.back());
   if (first) return;
   m.assoSta.push_back(C.staInlierID); m.assoDyn.push_back(C.dynInlierID); m.featLabel.push_back(C.objLabel);
   std::vector<M4> mot{inv4(t->velocity)}; std::vector<int> rl{0}, sl{0};
+  std::vector<float> cen{0.f, 0.f, 0.f};
   for (size_t i = 0; i < C.vObjMod.size(); ++i) {
     if (!C.bObjStat[i]) continue;
     mot.push_back(C.vObjMod[i]); rl.push_back(C.nModLabel[i]); sl.push_back(C.nSemPosition[i]);
+    for (int r = 0; r < 3; ++r) cen.push_back(C.vObjCentre3D[3 * i + r]);
   }
-  m.rigidMotion.push_back(mot); m.rmLabel.push_back(rl); m.smLabel.push_back(sl);
+  m.rigidMotion.push_back(mot); m.rigidMotion_RF.push_back(mot); m.rmLabel.push_back(rl); m.smLabel.push_back(sl); m.rigidCentre.push_back(cen);
 }
 
 // depth / mask at the truncated pixel of propagated keys (src/Tracking.cc:262-312)
@@ -387,10 +402,15 @@ extern "C" void vdo_tracker_destroy(vdo_tracker* t) {
 extern "C" const char* vdo_tracker_last_error(const vdo_tracker* t) { return t ? t->err.c_str() : "null tracker"; }
 
 // System::TrackRGBD / Tracking::GrabImageRGBD (include/System.h:49-51, src/Tracking.cc:164-648)
-extern "C" int vdo_tracker_track(vdo_tracker* t, const unsigned char* gray, float* depth, const float* flow, int* mask, int n_gt, const int* gt_sem_ids,
-                                 int writeback, float* Tcw_out) {
+extern "C" int vdo_tracker_track(vdo_tracker* t, int width, int height, const unsigned char* gray, float* depth, const float* flow, int* mask, int n_gt,
+                                 const int* gt_sem_ids, int writeback, float* Tcw_out) {
   if (!t || !gray || !depth || !flow || !mask || n_gt < 0) return VDO_ERR_ARG;
   const vdo_tracker_params& p = t->p;
+  if (width != p.width || height != p.height) {
+    t->err = "vdo_tracker_track: buffers are " + std::to_string(width) + "x" + std::to_string(height) + " but the tracker was created for " + std::to_string(p.width) + "x" +
+             std::to_string(p.height);
+    return VDO_ERR_ARG;
+  }
   if (!t->first) t->cur = 1 - t->cur;
   FrameState& C = t->fr[t->cur]; FrameState& L = t->fr[1 - t->cur];
   vdo_frame* img = C.img;
@@ -399,7 +419,8 @@ extern "C" int vdo_tracker_track(vdo_tracker* t, const unsigned char* gray, floa
   {
     StageTimer stage_timer_0(&t->stage_ms[0]);
     TK(vdo_frame_upload(C.img, gray, depth, flow, mask));
-    TK(vdo_frame_depth_prep(C.img, p.bf, p.depth_factor, writeback ? depth : nullptr));      // :180-204, in place on the caller's Mat
+    const int dataset = p.dataset ? p.dataset : (p.is_kitti ? 2 : 1);
+    TK(vdo_frame_depth_prep(C.img, dataset == 3 ? 0.f : p.bf, p.depth_factor, writeback ? depth : nullptr));      // :180-204, in place on the caller's Mat
   }
   if (!t->first) {                                                                            // UpdateMask (:2997-3110)
     const int n = (int)L.semObjLabel.size();
@@ -497,6 +518,7 @@ extern "C" int vdo_tracker_get(const vdo_tracker* t, const char* name, void* out
   if (s == "nSemPosition") return put_i(C.nSemPosition.data(), C.nSemPosition.size());
   if (s == "TemperalMatch_subset") return put_i(t->temperalMatchSubset.data(), t->temperalMatchSubset.size());
   if (s == "bObjStat") { std::vector<int> v(C.bObjStat.begin(), C.bObjStat.end()); return put_i(v.data(), v.size()); }
+  if (s == "vObjCentre3D") return put_f(C.vObjCentre3D.data(), C.vObjCentre3D.size());
   if (s == "vObjMod") { std::vector<float> v; for (auto& m : C.vObjMod) v.insert(v.end(), m.begin(), m.end()); return put_f(v.data(), v.size()); }
   if (s == "max_id") return put_i(&t->max_id, 1);
   if (s == "f_id") return put_i(&t->f_id, 1);
@@ -696,14 +718,18 @@ extern "C" int vdo_tracker_batch_optimize(vdo_tracker* t, int mode, const vdo_lm
   if (rc != VDO_OK) { t->err = std::string("batch optimisation failed: ") + vdo_last_error(t->ctx); return rc; }
   MapSlice& m = t->map;
   const int N = (int)m.featSta.size();
-  for (int i = 0; i < N; ++i) {                                                    // :2094-2172 / :983-1050
-    if (G.cam_vid[i] != -1) m.cameraPose[i] = from_iso(&se3[12 * (size_t)G.cam_vid[i]]);
+  // PartialBatchOptimization writes vmCameraPose / vmRigidMotion (src/Optimizer.cc:1058-1101); FullBatchOptimization writes
+  // vmCameraPose_RF[i + 1] / vmRigidMotion_RF and leaves the initial estimates alone (:2094-2133); both update the points
+  std::vector<M4>& camOut = mode == 1 ? m.cameraPose_RF : m.cameraPose;
+  std::vector<std::vector<M4>>& motOut = mode == 1 ? m.rigidMotion_RF : m.rigidMotion;
+  for (int i = 0; i < N; ++i) {
+    if (G.cam_vid[i] != -1 && (mode == 0 || i > 0)) camOut[i] = from_iso(&se3[12 * (size_t)G.cam_vid[i]]);
     for (size_t j = 0; j < G.makS[i].size(); ++j) if (G.makS[i][j] != -1) for (int k = 0; k < 3; ++k) m.p3dSta[i][3 * j + k] = (float)pt[3 * (size_t)G.makS[i][j] + k];
     for (size_t j = 0; j < G.makD[i].size(); ++j) if (G.makD[i][j] != -1) for (int k = 0; k < 3; ++k) m.p3dDyn[i][3 * j + k] = (float)pt[3 * (size_t)G.makD[i][j] + k];
   }
   for (int i = 0; i + 1 < N; ++i) {
     if (mode == 0) { if (G.cam_vid[i] != -1 && G.cam_vid[i + 1] != -1) m.rigidMotion[i][0] = mul4(inv4(m.cameraPose[i]), m.cameraPose[i + 1]); }   // :1001
-    for (size_t j = 1; j < G.mot_vid[i].size(); ++j) if (G.mot_vid[i][j] != -1) m.rigidMotion[i][j] = from_iso(&se3[12 * (size_t)G.mot_vid[i][j]]);
+    for (size_t j = 1; j < G.mot_vid[i].size(); ++j) if (G.mot_vid[i][j] != -1) motOut[i][j] = from_iso(&se3[12 * (size_t)G.mot_vid[i][j]]);
   }
   return VDO_OK;
 }
@@ -729,13 +755,18 @@ extern "C" int vdo_tracker_graph_export(vdo_tracker* t, int mode, const char* na
   return VDO_OK;
 }
 
-// map read-back: "vmCameraPose" (N x 16 f32), "vmRigidMotion" (all frames concatenated, 16 f32 each), "vnRMLabel" (i32, same order), "n_frames"
+// map read-back: "vmCameraPose" / "vmCameraPose_RF" (N x 16 f32), "vmRigidMotion" / "vmRigidMotion_RF" (all frames concatenated, 16 f32 each),
+// "vmRigidCentre" (3 f32 each, same order), "vnRMLabel" (i32, same order), "n_per_frame" (entries per frame, i32), "n_frames"
 extern "C" int vdo_tracker_map_get(const vdo_tracker* t, const char* name, void* out, int cap_elems, int* n_elems) {
   if (!t || !name || !n_elems) return VDO_ERR_ARG;
   const std::string s(name);
   std::vector<float> f; std::vector<int> iv; bool is_f = true;
   if (s == "vmCameraPose") for (auto& T : t->map.cameraPose) f.insert(f.end(), T.begin(), T.end());
+  else if (s == "vmCameraPose_RF") for (auto& T : t->map.cameraPose_RF) f.insert(f.end(), T.begin(), T.end());
   else if (s == "vmRigidMotion") { for (auto& fr : t->map.rigidMotion) for (auto& T : fr) f.insert(f.end(), T.begin(), T.end()); }
+  else if (s == "vmRigidMotion_RF") { for (auto& fr : t->map.rigidMotion_RF) for (auto& T : fr) f.insert(f.end(), T.begin(), T.end()); }
+  else if (s == "vmRigidCentre") { for (auto& fr : t->map.rigidCentre) f.insert(f.end(), fr.begin(), fr.end()); }
+  else if (s == "n_per_frame") { is_f = false; for (auto& fr : t->map.rmLabel) iv.push_back((int)fr.size()); }
   else if (s == "vnRMLabel") { is_f = false; for (auto& fr : t->map.rmLabel) iv.insert(iv.end(), fr.begin(), fr.end()); }
   else if (s == "n_frames") { is_f = false; iv.push_back((int)t->map.featSta.size()); }
   else return VDO_ERR_ARG;

@@ -17,6 +17,7 @@
 
 struct vdo_ctx;
 struct vdo_tracker;
+struct vdo_tracker_params;
 
 namespace VDO_SLAM {
 using namespace std;
@@ -35,16 +36,28 @@ class System {
   cv::Mat TrackRGBD(const cv::Mat &im, cv::Mat &depthmap, const cv::Mat &flowmap, const cv::Mat &masksem, const cv::Mat &mTcw_gt,
                     const vector<vector<float> > &vObjPose_gt, const double &timestamp, cv::Mat &imTraj, const int &nImage);
 
-  // camera trajectory and per-frame object motions as text (the reference's SaveResults writes its evaluation files; N4 in SURVEY.md 8f)
+  // `filename` is a path PREFIX (the reference passes a directory ending in '/'): writes obj_mot_stereo_new.txt, obj_mot_stereo_rf_new.txt,
+  // obj_mot_gt.txt, obj_centre.txt, initial_stereo_new.txt, refined_stereo_new.txt, cam_pose_gt_stereo.txt in the reference's text format
+  // (src/System.cc:66-193; the writers are vdo_results_* of the C ABI) and prints the mean stage timings (:196-237).  Failures are reported on cerr.
   void SaveResults(const string &filename);
 
+  struct Mat16 { float v[16]; };     // a 4x4 CV_32F matrix of the ground-truth bookkeeping
+
  private:
+  void UpdateGroundTruthMap(const cv::Mat &mTcw_gt, const vector<vector<float> > &vObjPose_gt);
+
   eSensor mSensor;
   vdo_ctx *mpCtx;
-  vdo_tracker *mpTracker;
+  vdo_tracker *mpTracker;            // created from the first frame's size (the reference never reads Camera.width / Camera.height)
+  vdo_tracker_params *mpParams;
   bool mbRGB, mbKitti;
+  int mnDataset;                     // ChooseData: 1 OMD, 2 KITTI, 3 VirtualKITTI
   vector<unsigned char> mGray;
-  vector<vector<float> > mTrajectory;
+  // ground-truth side of the Map (vmCameraPose_GT, vmObjPosePre, vmRigidMotion_GT; src/Tracking.cc:1101-1131), aligned with the tracker's map
+  Mat16 mOriginInv, mLastTcwGT;
+  vector<int> mLastSemGT;
+  vector<Mat16> mLastPoseGT, mvCamPoseGT;
+  vector<vector<Mat16> > mvObjPosePre, mvRigidMotionGT;
 };
 
 }  // namespace VDO_SLAM
