@@ -50,7 +50,7 @@ class OracleTracker:
         self.velocity = None
         self.last = None
         self.cur = None
-        self.map = dict(cameraPose=[], assoSta=[], assoDyn=[], featLabel=[], featSta=[], depSta=[], p3dSta=[], featDyn=[], depDyn=[], p3dDyn=[],
+        self.map = dict(cameraPose_RF=[], rigidMotion_RF=[], cameraPose=[], assoSta=[], assoDyn=[], featLabel=[], featSta=[], depSta=[], p3dSta=[], featDyn=[], depDyn=[], p3dDyn=[],
                         rigidMotion=[], rmLabel=[])
 
     # ---- Frame::Frame (src/Frame.cc:61-260) ----
@@ -110,7 +110,7 @@ class OracleTracker:
             C.Tcw = np.eye(4, dtype=f32)
             C.stat3DTmp = np.array([to.get3d_world(k, d, self.K4, np.eye(4, dtype=f32)) for k, d in zip(C.statKeysTmp, C.statDepthTmp)], f32).reshape(-1, 3)
             C.obj3D = np.array([to.get3d_world(k, d, self.K4, np.eye(4, dtype=f32)) for k, d in zip(C.objKeys, C.objDepth)], f32).reshape(-1, 3)
-            self.map["cameraPose"].append(np.eye(4, dtype=f32))
+            self.map["cameraPose"].append(np.eye(4, dtype=f32)); self.map["cameraPose_RF"].append(np.eye(4, dtype=f32))
             self.first = False
         else:
             self._track(C, L, depth, flow, mask)
@@ -193,13 +193,15 @@ class OracleTracker:
         C.statKeysTmp, C.corres, C.flowNext, C.staInlierID, C.statDepthTmp, C.stat3DTmp = S["keys"], S["corres"], S["flow"], S["inlier_id"], S["depth"], S["p3d"]
         C.objKeys, C.objDepth, C.objCorres, C.objFlowNext = O["keys"], O["depth"], O["corres"], O["flow"]
         C.semObjLabel, C.dynInlierID, C.objLabel, C.obj3D = O["sem"], O["inlier_id"], O["label"], O["p3d"]
-        self.map["cameraPose"].append(Twc); self.map["assoSta"].append(C.staInlierID.copy()); self.map["assoDyn"].append(C.dynInlierID.copy())
+        self.map["cameraPose"].append(Twc); self.map["cameraPose_RF"].append(Twc.copy()); self.map["assoSta"].append(C.staInlierID.copy()); self.map["assoDyn"].append(C.dynInlierID.copy())
         self.map["featLabel"].append(C.objLabel.copy())
         self.map["rigidMotion"].append([inv4(self.velocity)] + [C.vObjMod[i] for i in range(nobj) if C.bObjStat[i]])
+        self.map["rigidMotion_RF"].append([T.copy() for T in self.map["rigidMotion"][-1]])
         self.map["rmLabel"].append([0] + [C.nModLabel[i] for i in range(nobj) if C.bObjStat[i]])
 
     def batch_optimize(self, mode):
-        """PartialBatchOptimization / FullBatchOptimization on the map, with the write-back of src/Optimizer.cc:983-1050 / :2094-2172."""
+        """PartialBatchOptimization / FullBatchOptimization on the map, with the write-back of src/Optimizer.cc:1058-1101 (partial: into
+        vmCameraPose / vmRigidMotion) / :2094-2172 (full: into vmCameraPose_RF[i + 1] / vmRigidMotion_RF, the estimates themselves stay)."""
         from . import map_graph as mg
         g, meta = mg.build_graph(self.map, self.K4, mode, self.window)
         r = po.ba_optimize(g, max_iters=meta["max_iters"], gain_threshold=meta["gain"])
@@ -209,9 +211,11 @@ class OracleTracker:
             out = np.eye(4, dtype=f32)
             out[:3, :3] = mg.to_iso_matrix(T)[:9].reshape(3, 3).astype(f32); out[:3, 3] = T[9:].astype(f32)
             return out
+        cam_out = m["cameraPose"] if mode == "partial" else m["cameraPose_RF"]
+        mot_out = m["rigidMotion"] if mode == "partial" else m["rigidMotion_RF"]
         for i, v in enumerate(meta["cam_vid"]):
-            if v != -1:
-                m["cameraPose"][i] = from_iso(r["se3"][v])
+            if v != -1 and (mode == "partial" or i > 0):
+                cam_out[i] = from_iso(r["se3"][v])
         for i in range(len(m["p3dSta"])):
             for j, pidx in enumerate(meta["makS"][i]):
                 if pidx != -1:
@@ -224,6 +228,6 @@ class OracleTracker:
                 m["rigidMotion"][i][0] = mul4(inv4(m["cameraPose"][i]), m["cameraPose"][i + 1])
             for j in range(1, len(meta["mot_vid"][i])):
                 if meta["mot_vid"][i][j] != -1:
-                    m["rigidMotion"][i][j] = from_iso(r["se3"][meta["mot_vid"][i][j]])
+                    mot_out[i][j] = from_iso(r["se3"][meta["mot_vid"][i][j]])
         self.local_ba.append(r["iters"])
         return r

@@ -17,21 +17,28 @@ d = np.load(os.path.join(ROOT, "tests", "golden", name))
 ctx = capi.Context(0)
 G = capi.BatchGraph(ctx, g)
 out = {}
-for tol in [float(x) for x in os.environ.get("TOLS", "1e-8,1e-6,1e-5,1e-4").split(",")]:
+# variants "tol" or "tol:loose:switch" (forcing schedule: loose tolerance while the previous LM iteration gained more than `switch`)
+for var in os.environ.get("TOLS", "1e-8,1e-6,1e-5,1e-4").split(","):
+    parts = [float(x) for x in var.split(":")]
+    tol = parts[0]
+    kw = dict(pcg_rel_tol=tol)
+    if len(parts) == 3:
+        kw.update(pcg_loose_tol=parts[1], pcg_switch_gain=parts[2])
     G.reset()
-    G.optimize(pcg_rel_tol=tol)
+    G.optimize(**kw)
     G.reset()
     t0 = time.perf_counter()
-    r = G.optimize(pcg_rel_tol=tol)
+    r = G.optimize(**kw)
     dt = time.perf_counter() - t0
+    tol = var
     se3, pt = G.vertices()
     dd = iso_mul(iso_inv(se3), d["se3"])
     n = min(len(r["chi2"]), len(d["chi2"]))
-    out[f"tol{tol:g}"] = dict(iters=r["iterations"], golden_iters=int(d["iters"]), pcg=r["pcg_iterations"], ms=dt * 1e3, ms_total=r["ms_total"],
+    out[f"tol{tol}"] = dict(iters=r["iterations"], golden_iters=int(d["iters"]), pcg=r["pcg_iterations"], ms=dt * 1e3, ms_total=r["ms_total"],
                              max_pose=float(max(np.abs(iso_t(dd)).max(), np.abs(iso_R(dd) - np.eye(3)).max())),
                              max_point=float(np.abs(pt[d["pt_idx"]] - d["pt"]).max()), max_rel_chi2=float(np.abs(r["chi2"][:n] / d["chi2"][:n] - 1).max()),
                              lm_it_per_s=r["iterations"] / dt)
-    print(f"tol {tol:g}:", json.dumps(out[f"tol{tol:g}"]), flush=True)
+    print(f"tol {tol}:", json.dumps(out[f"tol{tol}"]), flush=True)
 G.reset(); G.optimize()
 kt = {}
 for k in ["schur_static", "schur_chains", "schur_vertex_obs", "hpp_mul", "pcg_step", "pcg_iterate8", "lin_static", "lin_chains", "lin_vertex_obs", "precond", "chi2_tracklets", "factor_landmarks"]:

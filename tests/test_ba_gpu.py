@@ -1,6 +1,7 @@
 """GPU parity tests of the batch factor-graph path (through the C ABI of libvdo_b200.so) against the CPU oracle.
-Tolerances: north_star asks pose / motion / point agreement <= 1e-4; the fp64 path is held to much tighter bounds
-here so that regressions show up early."""
+Tolerances: north_star asks pose / motion / point agreement <= 1e-4.  The only approximation on the GPU path is the PCG solve of the
+reduced system (default relative tolerance 1e-6, the oracle factorises directly): the default is held to 1e-5 here, and a 1e-10 solve
+to 1e-7, so that regressions show up early."""
 import numpy as np
 import pytest
 
@@ -46,11 +47,18 @@ def test_full_batch_lm_matches_oracle(ctx, seed, frames, objs, ns, nd):
     ro = po.ba_optimize(g, max_iters=300, gain_threshold=1e-4)
     assert r["iterations"] == ro["iters"]
     n = r["iterations"] + 1
-    np.testing.assert_allclose(r["chi2"][:n], ro["chi2"][:n], rtol=1e-7)
+    np.testing.assert_allclose(r["chi2"][:n], ro["chi2"][:n], rtol=1e-6)
     se3, pt = G.vertices()
     et, er = _pose_err(se3, ro["se3"])
-    assert et <= 1e-6 and er <= 1e-6           # north_star tolerance: 1e-4
-    assert np.abs(pt - ro["pt"]).max() <= 1e-6
+    assert et <= 1e-5 and er <= 1e-5           # north_star tolerance: 1e-4
+    assert np.abs(pt - ro["pt"]).max() <= 1e-5
+    G.reset()
+    r = G.optimize(max_iterations=300, gain_threshold=1e-4, pcg_rel_tol=1e-10)      # tight linear solves: the LM runs coincide
+    assert r["iterations"] == ro["iters"]
+    np.testing.assert_allclose(r["chi2"][:n], ro["chi2"][:n], rtol=1e-8)
+    se3, pt = G.vertices()
+    et, er = _pose_err(se3, ro["se3"])
+    assert et <= 1e-7 and er <= 1e-7 and np.abs(pt - ro["pt"]).max() <= 1e-7
 
 
 def test_partial_batch_constants_static_only(ctx):
@@ -61,7 +69,7 @@ def test_partial_batch_constants_static_only(ctx):
     ro = po.ba_optimize(g, max_iters=100, gain_threshold=1e-3)
     assert r["iterations"] == ro["iters"]
     se3, pt = G.vertices()
-    assert max(_pose_err(se3, ro["se3"])) <= 1e-6 and np.abs(pt - ro["pt"]).max() <= 1e-6
+    assert max(_pose_err(se3, ro["se3"])) <= 1e-5 and np.abs(pt - ro["pt"]).max() <= 1e-5
 
 
 def test_reset_and_repeat_is_reproducible_to_rounding(ctx):
@@ -85,7 +93,7 @@ def test_large_graph_properties(ctx):
     chi = r["chi2"]
     assert (np.diff(chi) <= 0).all() and chi[-1] < chi[0]
     ro = po.ba_optimize(g, max_iters=3, gain_threshold=0.0)
-    np.testing.assert_allclose(chi[:4], ro["chi2"][:4], rtol=1e-8)
+    np.testing.assert_allclose(chi[:4], ro["chi2"][:4], rtol=1e-6)
     se3, pt = G.vertices()
     assert np.isfinite(se3).all() and np.isfinite(pt).all()
 
@@ -115,4 +123,4 @@ def test_two_gpu_sharded_solve_matches_oracle(tmp_path):
     g = make_batch_graph(n_frames=30, n_objects=2, n_static=1500, n_dynamic=300, seed=1)
     ro = po.ba_optimize(g)
     assert int(d["iters"]) == ro["iters"]
-    assert np.abs(d["se3"] - ro["se3"]).max() < 1e-6 and np.abs(d["pt"] - ro["pt"]).max() < 1e-6
+    assert np.abs(d["se3"] - ro["se3"]).max() < 1e-5 and np.abs(d["pt"] - ro["pt"]).max() < 1e-5

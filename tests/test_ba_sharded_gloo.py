@@ -29,4 +29,4 @@ def test_two_rank_sharded_solve_matches_single_rank_oracle(tmp_path):
     ro = po.ba_optimize(g)
     assert int(d["iters"]) == ro["iters"]
     assert 0 < int(d["n_pt_local"]) < int(d["n_pt"])          # rank 0 really held only a shard
-    assert np.abs(d["se3"] - ro["se3"]).max() < 1e-6 and np.abs(d["pt"] - ro["pt"]).max() < 1e-6
+    assert np.abs(d["se3"] - ro["se3"]).max() < 1e-5 and np.abs(d["pt"] - ro["pt"]).max() < 1e-5

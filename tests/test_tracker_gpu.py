@@ -101,13 +101,14 @@ def test_map_graph_builder_and_batch_optimisation():
         g_in = tr.graph_export(mode)                                   # the builder's arrays at the map's current state
         meta = metas[name]
         r_ref = po.ba_optimize(g_in, max_iters=100 if mode == 0 else 300, gain_threshold=1e-3 if mode == 0 else 1e-4)
-        before = tr.map_get("vmCameraPose").reshape(-1, 4, 4).copy()
+        which = "vmCameraPose" if mode == 0 else "vmCameraPose_RF"       # src/Optimizer.cc:1058-1101 vs :2094-2133
+        before = tr.map_get(which).reshape(-1, 4, 4).copy()
         r = tr.batch_optimize(mode)
         assert r["iterations"] == r_ref["iters"], (name, r["iterations"], r_ref["iters"])
         assert r["sizes"]["n_se3"] == len(g_in["se3"]) and r["sizes"]["n_obs"] == len(g_in["obs_w"])
-        poses = tr.map_get("vmCameraPose").reshape(-1, 4, 4)
+        poses = tr.map_get(which).reshape(-1, 4, 4)
         for i, v in enumerate(meta["cam_vid"]):
-            if v == -1:
+            if v == -1 or (mode == 1 and i == 0):                    # the full batch leaves vmCameraPose_RF[0] alone
                 assert np.array_equal(poses[i], before[i]), (name, i)
                 continue
             iso = r_ref["se3"][v]
@@ -134,12 +135,16 @@ def test_windowed_and_full_batch_inside_the_pipeline():
     assert runs == len(orc.local_ba) == 2 and iters == sum(orc.local_ba)
     P = tr.map_get("vmCameraPose").reshape(-1, 4, 4)
     assert np.abs(P - np.array(orc.map["cameraPose"])).max() <= 1e-4
+    ini = tr.map_get("vmCameraPose").copy()
     r_ref = orc.batch_optimize("full")
     r = tr.batch_optimize(1)
     assert r["iterations"] == r_ref["iters"]
-    P = tr.map_get("vmCameraPose").reshape(-1, 4, 4)
-    assert np.abs(P - np.array(orc.map["cameraPose"])).max() <= 1e-4
-    M = tr.map_get("vmRigidMotion").reshape(-1, 4, 4)
-    M_ref = np.array([T for fr in orc.map["rigidMotion"] for T in fr])
+    assert np.array_equal(tr.map_get("vmCameraPose"), ini)            # the full batch refines the _RF copies only (src/Optimizer.cc:2094-2133)
+    P = tr.map_get("vmCameraPose_RF").reshape(-1, 4, 4)
+    assert np.abs(P - np.array(orc.map["cameraPose_RF"])).max() <= 1e-4 and np.abs(P - ini.reshape(-1, 4, 4)).max() > 0
+    M = tr.map_get("vmRigidMotion_RF").reshape(-1, 4, 4)
+    M_ref = np.array([T for fr in orc.map["rigidMotion_RF"] for T in fr])
     assert M.shape == M_ref.shape and np.abs(M - M_ref).max() <= 1e-4
+    M0 = tr.map_get("vmRigidMotion").reshape(-1, 4, 4)
+    assert np.abs(M0 - np.array([T for fr in orc.map["rigidMotion"] for T in fr])).max() <= 1e-4
     assert tr.map_get("vnRMLabel").tolist() == [int(l) for fr in orc.map["rmLabel"] for l in fr]

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libvdo_b200.so")
 class LMOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int), ("gain_threshold", C.c_double), ("max_trials", C.c_int),
                 ("pcg_rel_tol", C.c_double), ("pcg_max_iterations", C.c_int), ("verbose", C.c_int),
-                ("force_all_iterations", C.c_int)]
+                ("force_all_iterations", C.c_int), ("pcg_loose_tol", C.c_double), ("pcg_switch_gain", C.c_double)]
 
 
 class LMStats(C.Structure):
@@ -47,6 +47,12 @@ def load(path: str | None = None) -> C.CDLL:
     L = C.CDLL(path)
     L.vdo_last_error.restype = C.c_char_p
     L.vdo_ctx_stream.restype = C.c_uint64
+    # the structs below are mirrored by hand: refuse a library whose layout differs (it would write past the ctypes buffers)
+    for name, cls in (("vdo_lm_options", LMOptions), ("vdo_lm_stats", LMStats), ("vdo_tracker_params", globals().get("TrackerParams"))):
+        if cls is not None and hasattr(L, "vdo_abi_struct_size"):
+            n = L.vdo_abi_struct_size(name.encode())
+            if n != C.sizeof(cls):
+                raise VdoError(f"{path}: sizeof({name}) is {n} in the library but {C.sizeof(cls)} in capi.py -- rebuild the library or update the binding")
     _libs[path] = L
     return L
 
@@ -230,12 +236,18 @@ class BatchGraph:
             ctx.check(L.vdo_graph_add_edges_landmark_motion(self.h, len(w), _ip(pph), _dp(w), _dp(dl)), "add_edges_landmark_motion")
         ctx.check(L.vdo_graph_finalize(self.h), "vdo_graph_finalize")
 
-    def optimize(self, max_iterations=300, gain_threshold=1e-4, pcg_rel_tol=1e-8, pcg_max_iterations=2000,
-                 verbose=False, force_all_iterations=False):
+    def optimize(self, max_iterations=300, gain_threshold=1e-4, pcg_rel_tol=None, pcg_max_iterations=2000,
+                 verbose=False, force_all_iterations=False, pcg_loose_tol=None, pcg_switch_gain=None):
         o = LMOptions()
         self.ctx.L.vdo_lm_options_default(C.byref(o))
         o.max_iterations, o.gain_threshold = int(max_iterations), float(gain_threshold)
-        o.pcg_rel_tol, o.pcg_max_iterations = float(pcg_rel_tol), int(pcg_max_iterations)
+        o.pcg_max_iterations = int(pcg_max_iterations)
+        if pcg_rel_tol is not None:
+            o.pcg_rel_tol = float(pcg_rel_tol)
+        if pcg_loose_tol is not None:
+            o.pcg_loose_tol = float(pcg_loose_tol)
+        if pcg_switch_gain is not None:
+            o.pcg_switch_gain = float(pcg_switch_gain)
         o.verbose, o.force_all_iterations = int(verbose), int(force_all_iterations)
         st = LMStats()
         hist = np.zeros(max_iterations + 1)
@@ -608,7 +620,7 @@ class Tracker:
     def map_get(self, name: str):
         n = C.c_int(0)
         self.ctx.check(self.ctx.L.vdo_tracker_map_get(self.h_, name.encode(), None, C.c_int(0), C.byref(n)), "vdo_tracker_map_get")
-        out = np.zeros(max(n.value, 1), np.int32 if name in ("vnRMLabel", "n_frames") else np.float32)
+        out = np.zeros(max(n.value, 1), np.int32 if name in ("vnRMLabel", "n_frames", "n_per_frame") else np.float32)
         self.ctx.check(self.ctx.L.vdo_tracker_map_get(self.h_, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_int(len(out)), C.byref(n)), "vdo_tracker_map_get")
         return out[:n.value]
 

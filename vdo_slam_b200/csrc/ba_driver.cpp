@@ -634,6 +634,7 @@ int BaGraph::finalize() {
   d.pcr_b = dalloc<double>(12 * (size_t)C);
   d.xp = dalloc<double>(6 * (size_t)C); d.r = dalloc<double>(6 * (size_t)C); d.z = dalloc<double>(6 * (size_t)C);
   d.p = dalloc<double>(6 * (size_t)C); d.Ap = dalloc<double>(6 * (size_t)C); d.rhs = dalloc<double>(6 * (size_t)C);
+  d.p2 = dalloc<double>(6 * (size_t)C); d.ticket = dalloc<unsigned int>(4);
   d.zl = tiled ? nullptr : dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P); d.vw = dalloc<double>(6 * (size_t)C);
   oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
   d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
@@ -733,7 +734,8 @@ bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   be_->allreduce_sum(d.rhs, 6 * (size_t)d.C);
   be_->pcg_init(d);
   }
-  const double tol2 = opt.pcg_rel_tol * opt.pcg_rel_tol;
+  const double tol_now = cur_pcg_tol_ > 0 ? cur_pcg_tol_ : opt.pcg_rel_tol;
+  const double tol2 = tol_now * tol_now;
   const int batch = 8;
   double sc[SC_N];
   int it = 0;
@@ -760,7 +762,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
   if (!finalized_) return fail(VDO_ERR_STATE, "optimize before finalize");
   vdo_lm_options opt = o_in;
   if (opt.max_trials <= 0) opt.max_trials = 10;
-  if (opt.pcg_rel_tol <= 0) opt.pcg_rel_tol = 1e-8;
+  if (opt.pcg_rel_tol <= 0) opt.pcg_rel_tol = 1e-6;
   if (opt.pcg_max_iterations <= 0) opt.pcg_max_iterations = 2000;
   BaDev& d = d_;
   const int launches0 = be_->launches();
@@ -774,7 +776,14 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
   double chi_cur = robust_chi2();
   const double chi_init = chi_cur;
   if (hist) hist[0] = chi_cur;
+  // Forcing schedule of the inexact solves: while the previous LM iteration still gained more than pcg_switch_gain (relative chi2
+  // decrease), the reduced system is solved to pcg_loose_tol only; near convergence to pcg_rel_tol.  Disabled unless both are set.
+  double loose_tol = opt.pcg_loose_tol, switch_gain = opt.pcg_switch_gain;
+  if (const char* e = std::getenv("VDO_PCG_LOOSE")) loose_tol = std::atof(e);
+  if (const char* e = std::getenv("VDO_PCG_SWITCH")) switch_gain = std::atof(e);
+  double gain_prev = 1.0;
   for (int it = 0; it < opt.max_iterations && ((!stop_flag && ok) || opt.force_all_iterations); ++it) {
+    cur_pcg_tol_ = (loose_tol > opt.pcg_rel_tol && switch_gain > 0 && gain_prev > switch_gain) ? loose_tol : opt.pcg_rel_tol;
     const double ini = chi_cur;
     double current = chi_cur, temp = chi_cur;
     be_->timer_start(1);
@@ -831,6 +840,7 @@ int BaGraph::optimize(const vdo_lm_options& o_in, vdo_lm_stats* stats, double* h
     }
     ok = result_ok;
     const double chi_now = current;     // errors at the (restored) estimate == last accepted chi2
+    gain_prev = chi_now > 0 ? (ini - chi_now) / chi_now : 0.0;
     if (chi2_check < chi_now && it > 0) ok = false;
     chi2_check = chi_now;
     chi_cur = chi_now;

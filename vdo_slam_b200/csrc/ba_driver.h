@@ -72,6 +72,7 @@ class BaGraph {
   bool prof_on_ = false;
   float prof_ms_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double last_lambda_ = 1.0;
+  double cur_pcg_tol_ = 0.0;        // tolerance of the current LM iteration's solves (forcing schedule), 0 = opt.pcg_rel_tol
   // host staging (until finalize)
   int n_se3_ = 0, n_pt_ = 0, P_all_ = 0;
   HostBuf<double> h_se3_, h_pt_;

@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(256) k_pcg_init_fin(BaDev d) {
   __shared__ double red[33];
   const double rz = det_sum(d.part_rz, d.n_paths * PCR_CL, red);
   if (threadIdx.x != 0) return;
-  d.scal[SC_RZ] = rz; d.scal[SC_RZ0] = rz; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] = 0.0;
+  d.scal[SC_RZ] = rz; d.scal[SC_RZ0] = rz; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] = 0.0; d.scal[SC_BETA] = 0.0;
   d.scal[SC_DONE] = (rz > 0.0) ? 0.0 : 1.0;
 }
 __global__ void __launch_bounds__(256) k_pcg_dot(BaDev d) {
@@ -460,9 +460,12 @@ __global__ void __launch_bounds__(256) k_pcg_dot(BaDev d) {
   s = block_sum(s, red);
   if (threadIdx.x == 0) d.part_pap[blockIdx.x] = s;
 }
-// x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new += r.z
-__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step_a(BaDev d) {
+// x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new += r.z.  FUSED: p is passed explicitly (double-buffered) and the last CTA to
+// finish does the work of k_pcg_step_b's beta and of k_pcg_scalars.
+template <bool FUSED>
+__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step_a(BaDev d, const double* __restrict__ p) {
   __shared__ double red[33];
+  __shared__ int is_last;
   if (d.scal[SC_DONE] != 0.0) return;
   cg::cluster_group cl = cg::this_cluster();
   const double pap = det_sum(d.part_pap, d.n_part_pap, red), rz = d.scal[SC_RZ];
@@ -470,12 +473,72 @@ __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step
   const int path = blockIdx.x / PCR_CL;
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
   const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
-  for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.xp[q] += alpha * d.p[q]; d.r[q] -= alpha * d.Ap[q]; }
+  for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.xp[q] += alpha * p[q]; d.r[q] -= alpha * d.Ap[q]; }
   if (pe - pb > 1) cl.sync();
   double rzn = pcr_solve_path(d, cl, pb, pe, d.r, d.z);
   rzn = block_sum(rzn, red);
   if (threadIdx.x == 0) d.part_rz[blockIdx.x] = rzn;
+  if (!FUSED) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(d.ticket, 1u);
+    is_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double rz_new = det_sum(d.part_rz, d.n_paths * PCR_CL, red);
+  if (threadIdx.x != 0) return;
+  *d.ticket = 0u;
+  if (!(pap > 0.0) || !isfinite(pap) || !isfinite(rz_new)) { d.scal[SC_DONE] = 2.0; return; }
+  d.scal[SC_BETA] = rz_new / rz; d.scal[SC_RZ] = rz_new; d.scal[SC_ITERS] += 1.0;
+  if (rz_new <= d.scal[SC_TOL2] * d.scal[SC_RZ0]) d.scal[SC_DONE] = 1.0;
 }
+// ---- fused PCG iteration (single GPU): 4 dependent launches per iteration instead of 8 ----
+//   k_pcg_p_hpp            p_{k+1} = z + beta p_k (out of place, recomputed for the path neighbours), Ap = (Hpp + lambda I) p, vw / vh
+//   k_tile_schur2 x 2      Hpl Hll^-1 Hlp p (static and chain tiles, forked)
+//   k_tile_finalize_schur2 Ap -= B^T sums, partials of p.Ap
+//   k_pcg_step_a<true>     alpha, x, r, z = M^-1 r (PCR), partials of r.z; the LAST CTA to finish sums them (fixed order) and sets beta, rz,
+//                          the iteration count and the convergence flag
+__global__ void __launch_bounds__(128) k_pcg_p_hpp(BaDev d, const double* __restrict__ p_in, double* __restrict__ p_out, double* __restrict__ out) {
+  if (d.scal[SC_DONE] != 0.0) return;
+  const double lambda = d.scal[SC_LAMBDA], beta = d.scal[SC_BETA];
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= d.C) return;
+  double xv[6], o[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) { xv[r] = d.z[6 * (size_t)v + r] + beta * p_in[6 * (size_t)v + r]; p_out[6 * (size_t)v + r] = xv[r]; }
+  const double* H = d.Hpp + 36 * (size_t)v;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double s = lambda * xv[r];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s += H[6 * r + c] * xv[c];
+    o[r] = s;
+  }
+  for (int n = d.nbr_begin[v]; n < d.nbr_begin[v + 1]; ++n) {
+    const double* B = d.se_Hoff + 36 * (size_t)d.nbr_edge[n];
+    const size_t u = 6 * (size_t)d.nbr_other[n];
+    double xo[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) xo[c] = d.z[u + c] + beta * p_in[u + c];
+    if (d.nbr_tr[n]) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) o[r] += B[6 * c + r] * xo[c];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) o[r] += B[6 * r + c] * xo[c];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) out[6 * (size_t)v + r] = d.own ? o[r] : 0.0;
+  body_vertex_transform(d, v, p_out, d.vw);
+}
+
 __global__ void __launch_bounds__(256) k_pcg_step_b(BaDev d) {
   __shared__ double red[33];
   if (d.scal[SC_DONE] != 0.0) return;
@@ -690,7 +753,7 @@ struct CudaBackend : BaBackend {
     if (part == 0) LAUNCH(k_lin_static<true>, nblk(d.Tstat, 256), 256, d); else LAUNCH(k_lin_tracklets<true>, nblk(d.T - d.Tstat, 128), 128, d);
   }
   void schur_vertex_obs(BaDev& d, double sign, double* out) override {
-    if (d.tiled) { LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, sign, out, out == d.Ap ? 1 : 0, 0); return; }
+    if (d.tiled) { LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, sign, out, out == d.Ap ? 1 : 0, (const double*)nullptr); return; }
     LAUNCH(k_schur_vertex<true>, d.n_obs_chunks, 128, d, sign, out, out == d.Ap ? 1 : 0);
   }
   void schur_vertex_ter(BaDev& d, double sign, double* out) override {
@@ -711,7 +774,7 @@ struct CudaBackend : BaBackend {
   void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, d.n_part_pap, 256, d); }   // one CTA per slot of part_pap
   void pcg_step(BaDev& d, double tol2) override {
     set_scalars(d, cur_lambda, tol2);
-    LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
+    LAUNCH(k_pcg_step_a<false>, d.n_paths * PCR_CL, 256, d, (const double*)d.p);
     LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
     LAUNCH(k_pcg_scalars, 1, 256, d);
   }
@@ -729,18 +792,19 @@ struct CudaBackend : BaBackend {
       CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       const int gch = nblk((d.T - d.Tstat) * 8, 128), gst = nblk(d.Tstat, 256);
       for (int b = 0; b < n; ++b) {
-        LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, (const double*)d.p, d.Ap);
         if (d.tiled) {
+          // fused iteration (n is even: the search direction ends in d.p again)
+          const double* p_in = (b & 1) ? d.p2 : d.p; double* p_out = (b & 1) ? d.p : d.p2;
+          LAUNCH(k_pcg_p_hpp, nblk(d.C, 128), 128, d, p_in, p_out, d.Ap);
           // fork: static tiles on st, chain tiles on st2 (independent landmark sets); both scatter into acc6 with atomics
           CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
           tile_schur(d, 1, -1, st2);
           CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
-          LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1, 1);      // Ap -= B^T sums, and the partials of p.Ap
-          LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
-          LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
-          LAUNCH(k_pcg_scalars, 1, 256, d);
+          LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1, p_out);  // Ap -= B^T sums, and the partials of p.Ap
+          LAUNCH(k_pcg_step_a<true>, d.n_paths * PCR_CL, 256, d, (const double*)p_out);
           continue;
         }
+        LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, (const double*)d.p, d.Ap);
         // fork: static landmarks on st, chains on st2 (independent landmark sets; the chain kernel is latency-bound)
         CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
         LAUNCH(k_schur_static<1>, gst, 256, d, d.zl);
@@ -752,7 +816,7 @@ struct CudaBackend : BaBackend {
         if (d.n_ter_chunks > 0) { k_schur_vertex<false><<<d.n_ter_chunks, 128, 0, st2>>>(d, -1.0, d.Ap, 1); ++n_launch; }
         CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
         LAUNCH(k_pcg_dot, d.n_part_pap, 256, d);
-        LAUNCH(k_pcg_step_a, d.n_paths * PCR_CL, 256, d);
+        LAUNCH(k_pcg_step_a<false>, d.n_paths * PCR_CL, 256, d, (const double*)d.p);
         LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
         LAUNCH(k_pcg_scalars, 1, 256, d);
       }

@@ -554,8 +554,8 @@ __global__ void __launch_bounds__(VDO_TILE_L, CHAINS ? 4 : 5) k_tile_schur2(BaDe
 }
 
 // per vertex: out_v += sign * B^T [F ; M - t x (2 F_o + F_t)] (torque moved to the vertex origin); clears the sums.
-// With dot != 0 also the CTA's share of p . out (fixed order) into part_pap[blockIdx.x]: the PCG's p.Ap without another launch.
-__global__ void __launch_bounds__(128) k_tile_finalize_schur2(BaDev d, double sign, double* __restrict__ out, int check_done, int dot) {
+// With pdot != NULL also the CTA's share of pdot . out (fixed order) into part_pap[blockIdx.x]: the PCG's p.Ap without another launch.
+__global__ void __launch_bounds__(128) k_tile_finalize_schur2(BaDev d, double sign, double* __restrict__ out, int check_done, const double* __restrict__ pdot) {
   __shared__ double red[32];
   if (check_done && d.scal[SC_DONE] != 0.0) return;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -573,12 +573,12 @@ __global__ void __launch_bounds__(128) k_tile_finalize_schur2(BaDev d, double si
     o[0] += sign * o0[0]; o[1] += sign * o0[1]; o[2] += sign * o0[2]; o[3] += sign * o1[0]; o[4] += sign * o1[1]; o[5] += sign * o1[2];
 #pragma unroll
     for (int i = 0; i < 12; ++i) a[i] = 0.0;
-    if (dot) {
-      const double* pv = d.p + 6 * (size_t)v;
+    if (pdot) {
+      const double* pv = pdot + 6 * (size_t)v;
       s = pv[0] * o[0] + pv[1] * o[1] + pv[2] * o[2] + pv[3] * o[3] + pv[4] * o[4] + pv[5] * o[5];
     }
   }
-  if (dot) {
+  if (pdot) {
     s = block_sum(s, red);
     if (threadIdx.x == 0) d.part_pap[blockIdx.x] = s;
   }

@@ -35,7 +35,7 @@
 #define VDO_TILE_L 256
 #define VDO_TILE_E 768
 #define VDO_SEG 64
-#define VDO_SEG2 16   // Schur kernels: runs of one vertex cut at 16 entries, one thread per (run, component)
+#define VDO_SEG2 15   // Schur kernels: runs of one vertex cut at 15 entries (odd: threads walking consecutive full runs hit distinct shared-memory banks), one thread per (run, component pair)
 
 namespace vdo {
 
@@ -72,6 +72,8 @@ struct BaDev {
   double *pcr_A = 0, *pcr_G = 0;  // pcr_levels * C * 36 : elimination operators per level
   double *pcr_b = 0;              // 2 * C * 6 scratch of the solve   // per landmark: diagonal scalar of Hll^-1; per ternary edge: g_k + g_k+1 - 2 g_k,k+1
   double *xp = 0, *r = 0, *z = 0, *p = 0, *Ap = 0, *rhs = 0; // 6C each
+  double* p2 = 0;           // 6C: second buffer of the search direction (the fused PCG kernels write p_{k+1} = z + beta p_k out of place)
+  unsigned int* ticket = 0; // "last CTA done" counter of the fused PCG step
   double *zl = 0, *xl = 0;                                    // 3P each
   double *vw = 0;   // 6C: per-vertex world-frame image [gamma, beta] of the vector the landmark pass multiplies (see body_vertex_transform)
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each
@@ -101,7 +103,7 @@ struct BaDev {
 };
 
 enum { SC_CHI2 = 0, SC_SCALE = 1, SC_MAXDIAG = 2, SC_PAP = 3, SC_RZ = 4, SC_RZ_NEW = 5, SC_RZ0 = 6, SC_DONE = 7, SC_ITERS = 8, SC_BAD = 9,
-       SC_LAMBDA = 10, SC_TOL2 = 11, SC_N = 16 };
+       SC_LAMBDA = 10, SC_TOL2 = 11, SC_BETA = 12, SC_N = 16 };
 
 // Grow-only host staging arena (pinned memory in the CUDA backend): graph ingestion builds every stream it uploads directly
 // in it, so host->device copies run at PCIe speed without a bounce buffer and repeated graphs pay no page faults.  Memory

@@ -70,11 +70,20 @@ int vdo_graph_add_edges_se3_pointxyz(vdo_graph* g, int n, const int* cp, const d
 int vdo_graph_add_edges_landmark_motion(vdo_graph* g, int n, const int* pph, const double* w, const double* delta) { VDO_FWD(add_ter(n, pph, w, delta)) }
 int vdo_graph_finalize(vdo_graph* g) { VDO_FWD(finalize()) }
 
+int vdo_abi_struct_size(const char* name) {
+  if (!name) return -1;
+  const std::string s(name);
+  if (s == "vdo_lm_options") return (int)sizeof(vdo_lm_options);
+  if (s == "vdo_lm_stats") return (int)sizeof(vdo_lm_stats);
+  if (s == "vdo_tracker_params") return (int)sizeof(vdo_tracker_params);
+  return -1;
+}
+
 void vdo_lm_options_default(vdo_lm_options* o) {
   if (!o) return;
   std::memset(o, 0, sizeof *o);
   o->max_iterations = 300; o->gain_threshold = 1e-4; o->max_trials = 10;
-  o->pcg_rel_tol = 1e-8; o->pcg_max_iterations = 2000; o->verbose = 0; o->force_all_iterations = 0;
+  o->pcg_rel_tol = 1e-6; o->pcg_max_iterations = 2000; o->verbose = 0; o->force_all_iterations = 0; o->pcg_loose_tol = 0.0; o->pcg_switch_gain = 0.0;
 }
 int vdo_graph_optimize(vdo_graph* g, const vdo_lm_options* opt, vdo_lm_stats* stats, double* chi2_history) {
   vdo_lm_options o;
