@@ -94,10 +94,11 @@ def kernel_bytes(g) -> dict:
         # per vertex: two 16-sum accumulators read + cleared, pose, H_pp block + b_p read-modify-write
         "lin_finalize": (2 * 16 * 8 * 2 + 96 + 2 * 336) * C,
         # edge: omega' 8 + cam 4 + tile-local landmark 1 + permutation 2 ; landmark: p 24 + pivot 8 + begin 4
-        "schur_static": 15 * Eps + 36 * Ps,
-        # landmark additionally: Q_k 72 + tk_omega 8 + motion index 4 + permutation 2
-        "schur_chains": 15 * Epd + 122 * Pd,
-        "schur_finalize": (6 * 8 * 2 + 96 + 2 * 48) * C,
+        # (k_tile_schur2) edge: omega' 8 + camera slot 1 + permutation | tile-local landmark 4 ; landmark: p 24 + pivot 8 + begin 4
+        "schur_static": 13 * Eps + 36 * Ps,
+        # landmark additionally: Q_k 72 + tk_omega 8 + motion slot 1 + permutation 2
+        "schur_chains": 13 * Epd + 119 * Pd,
+        "schur_finalize": (12 * 8 * 2 + 96 + 2 * 48) * C,
     }
 
 
@@ -241,8 +242,9 @@ def run_ours(args, rank, world, local_rank):
     ctx_multi = ctx
     if world > 1 and rank == 0:
         ctx = capi.Context(local_rank)
+    lean = bool(os.environ.get("VDO_BENCH_LEAN"))      # development runs: skip the per-frame extras and the CPU baseline
     flow2 = None
-    if rank == 0:
+    if rank == 0 and not lean:
         try:
             from vdo_slam_b200.synth import make_flow_problem
             from oracle import pyoracle as po
@@ -268,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- image side of one KITTI-shaped frame (upload + depth prep + ORB + static filter + object sampling), host buffers ----
     image_side = None
-    if rank == 0:
+    if rank == 0 and not lean:
         try:
             import cv2
             from vdo_slam_b200.synth import make_frame
@@ -306,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- config 3: whole per-frame path (System::TrackRGBD) on a synthetic KITTI-shape sequence, host buffers in, pose out ----
     pipeline = None
-    if rank == 0:
+    if rank == 0 and not lean:
         try:
             pipeline = frames_per_second(ctx, n_frames=int(os.environ.get("VDO_BENCH_FRAMES", "40")))
         except Exception as e:  # pragma: no cover
@@ -314,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
 
     out = None
     if rank == 0:
-        cpu = cpu_baseline(args, g)
+        cpu = cpu_baseline(args, g) if not lean else None
         out = {"metric": "LM iterations/sec (batch factor-graph solve)", "value": value, "unit": "LM iters/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

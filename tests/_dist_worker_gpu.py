@@ -22,8 +22,13 @@ def run(rank, world, port, out_path):
         G = capi.BatchGraph(ctx, g)
         r = G.optimize()
         se3, pt = G.vertices_gathered(dist)
+        # BASELINE config 4 (the golden full solve of tests/golden/ba_config4.npz), sharded over the ranks
+        g4 = make_batch_graph(n_frames=200, n_objects=5, n_static=40000, n_dynamic=10000, seed=4)
+        G4 = capi.BatchGraph(ctx, g4)
+        r4 = G4.optimize()
+        se3_4, pt_4 = G4.vertices_gathered(dist)
         if rank == 0:
-            np.savez(out_path, se3=se3, pt=pt, iters=r["iterations"], chi2=r["chi2"])
+            np.savez(out_path, se3=se3, pt=pt, iters=r["iterations"], chi2=r["chi2"], c4_se3=se3_4, c4_pt=pt_4, c4_iters=r4["iterations"], c4_chi2=r4["chi2"])
     finally:
         dist.destroy_process_group()
 

@@ -124,3 +124,8 @@ def test_two_gpu_sharded_solve_matches_oracle(tmp_path):
     ro = po.ba_optimize(g)
     assert int(d["iters"]) == ro["iters"]
     assert np.abs(d["se3"] - ro["se3"]).max() < 1e-5 and np.abs(d["pt"] - ro["pt"]).max() < 1e-5
+    # BASELINE config 4 sharded over 2 ranks against the oracle's frozen full solve
+    gold = np.load(os.path.join(root, "tests", "golden", "ba_config4.npz"))
+    assert int(d["c4_iters"]) == int(gold["iters"])
+    np.testing.assert_allclose(d["c4_chi2"][: int(gold["iters"]) + 1], gold["chi2"], rtol=1e-6)
+    assert max(_pose_err(d["c4_se3"], gold["se3"])) <= 1e-5 and np.abs(d["c4_pt"][gold["pt_idx"]] - gold["pt"]).max() <= 1e-5

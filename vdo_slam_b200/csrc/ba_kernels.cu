@@ -539,6 +539,93 @@ __global__ void __launch_bounds__(128) k_pcg_p_hpp(BaDev d, const double* __rest
   body_vertex_transform(d, v, p_out, d.vw);
 }
 
+// ---- sharded PCG iteration: all-reduce of the 6C-vector S*p through peer memory (NVLink), inside the captured graph ----
+// Every rank holds, for each sender r, a slot of 6C doubles (double-buffered by the parity of an epoch counter).
+//   k_xchg_scatter  per vertex: this rank's partial (Hpp p on rank 0) - B^T (tile sums), stored straight into slot[rank] of EVERY
+//                   rank (remote stores); the last CTA to finish fences (system scope), bumps the epoch and stores it into
+//                   flag[rank] of every rank
+//   k_xchg_reduce   waits until all world flags carry the epoch, then sums the world slots IN RANK ORDER -- every rank adds the
+//                   same numbers in the same order, so Ap (and with it every PCG scalar and the convergence flag) is bit-identical
+//                   on all ranks -- and forms the CTA's share of p.Ap
+// Nothing here is enqueued by the host per iteration: the kernels are ordinary graph nodes.
+__global__ void __launch_bounds__(128) k_xchg_scatter(BaDev d, double sign, const double* __restrict__ own_part) {
+  __shared__ int is_last;
+  if (d.scal[SC_DONE] != 0.0) return;
+  const unsigned long long epoch = *d.xg_epoch + 1ull;            // the epoch this vector belongs to (bumped below by the last CTA)
+  const size_t n6 = 6 * (size_t)d.C;
+  const size_t slot = ((epoch & 1ull) * (size_t)d.xg_world + (size_t)d.xg_rank) * n6;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < d.C) {
+    const double* T = d.se3 + 12 * (size_t)v;
+    double* a = d.acc6 + 12 * (size_t)v;
+    const double F[3] = {a[0] + a[6], a[1] + a[7], a[2] + a[8]};
+    const double G[3] = {2 * a[0] + a[6], 2 * a[1] + a[7], 2 * a[2] + a[8]};
+    double txg[3]; cross3(T + 9, G, txg);
+    const double M[3] = {a[3] + a[9] - txg[0], a[4] + a[10] - txg[1], a[5] + a[11] - txg[2]};
+    double o0[3], o1[3];
+    rot_t_apply(T, F, o0); rot_t_apply(T, M, o1);
+    const double* op = own_part + 6 * (size_t)v;
+    const double o[6] = {op[0] + sign * o0[0], op[1] + sign * o0[1], op[2] + sign * o0[2], op[3] + sign * o1[0], op[4] + sign * o1[1], op[5] + sign * o1[2]};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = 0.0;
+    for (int r = 0; r < d.xg_world; ++r) {
+      double* dst = d.xg_slots[r] + slot + 6 * (size_t)v;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) dst[i] = o[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(d.ticket + 1, 1u);
+    is_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence_system();
+  d.ticket[1] = 0u;
+  *d.xg_epoch = epoch;
+  for (int r = 0; r < d.xg_world; ++r) {
+    volatile unsigned long long* f = d.xg_flags[r] + d.xg_rank;
+    *f = epoch;
+  }
+}
+__global__ void __launch_bounds__(128) k_xchg_reduce(BaDev d, double* __restrict__ out, const double* __restrict__ pdot) {
+  __shared__ double red[32];
+  __shared__ int failed;
+  if (d.scal[SC_DONE] != 0.0) return;
+  const unsigned long long epoch = *d.xg_epoch;
+  if (threadIdx.x == 0) {
+    failed = 0;
+    volatile unsigned long long* f = d.xg_flags[d.xg_rank];
+    const long long t0 = clock64();
+    for (int r = 0; r < d.xg_world; ++r)
+      while (f[r] < epoch) {
+        if (clock64() - t0 > 4000000000ll) { failed = 1; break; }       // ~2 s: a peer died; do not hang the GPU
+      }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (failed) { if (threadIdx.x == 0 && blockIdx.x == 0) d.scal[SC_DONE] = 3.0; return; }
+  const size_t n6 = 6 * (size_t)d.C;
+  const double* base = d.xg_slots[d.xg_rank] + (epoch & 1ull) * (size_t)d.xg_world * n6;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (v < d.C) {
+    double o[6] = {0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < d.xg_world; ++r) {
+      const volatile double* src = base + (size_t)r * n6 + 6 * (size_t)v;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) o[i] += src[i];
+    }
+    const double* pv = pdot + 6 * (size_t)v;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { out[6 * (size_t)v + i] = o[i]; s += pv[i] * o[i]; }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) d.part_pap[blockIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) k_pcg_step_b(BaDev d) {
   __shared__ double red[33];
   if (d.scal[SC_DONE] != 0.0) return;
@@ -580,6 +667,7 @@ struct NcclApi {
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   bool load() {
     if (h) return true;
@@ -590,6 +678,7 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
     GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
     return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
   }
@@ -612,6 +701,79 @@ struct CudaBackend : BaBackend {
     ++n_coll;
   }
   int n_coll = 0;
+  // ---- peer-memory exchange of the sharded PCG iteration: one buffer per rank (flags + 2 x world slots of 6C doubles), mapped into every
+  //      other rank through CUDA IPC (handles all-gathered over NCCL once per buffer size) ----
+  struct Xchg {
+    char* local = nullptr; size_t bytes = 0; int C = 0; bool ok = false, tried = false;
+    std::vector<char*> peer;                 // peer[r]: this process' mapping of rank r's buffer (peer[rank] == local)
+    double** d_slots = nullptr; unsigned long long** d_flags = nullptr; unsigned long long* d_epoch = nullptr;
+  } xg;
+  static constexpr size_t XG_HDR = 4096;     // flags (world x u64) + epoch live in the first page of the buffer
+  void xchg_release() {
+    drop_graphs();                           // captured PCG graphs carry the buffer's addresses
+    for (size_t r = 0; r < xg.peer.size(); ++r) if ((int)r != rank && xg.peer[r]) cudaIpcCloseMemHandle(xg.peer[r]);
+    xg.peer.clear();
+    if (xg.local) cudaFree(xg.local);
+    if (xg.d_slots) cudaFree(xg.d_slots);
+    if (xg.d_flags) cudaFree(xg.d_flags);
+    xg = Xchg();
+  }
+  // collective: every rank calls it with the same C.  Returns false (and the caller falls back to NCCL all-reduces) when peer mapping is unavailable.
+  bool xchg_setup(int C) {
+    if (xg.ok && xg.C >= C) return true;
+    if (xg.tried && !xg.ok) return false;
+    if (std::getenv("VDO_NO_PEER_EXCHANGE")) { xg.tried = true; return false; }
+    CK(cudaStreamSynchronize(st));
+    xchg_release();
+    xg.tried = true; xg.C = C;
+    xg.bytes = XG_HDR + sizeof(double) * 2 * (size_t)world * 6 * (size_t)C;
+    bool good = g_nccl.AllGather != nullptr;
+    if (good && cudaMalloc(&xg.local, xg.bytes) != cudaSuccess) { cudaGetLastError(); xg.local = nullptr; good = false; }
+    if (good) CK(cudaMemsetAsync(xg.local, 0, xg.bytes, st));
+    cudaIpcMemHandle_t mine; std::memset(&mine, 0, sizeof mine);
+    if (good && cudaIpcGetMemHandle(&mine, xg.local) != cudaSuccess) { cudaGetLastError(); good = false; }
+    // all-gather {ok flag, handle} -- also the agreement on whether every rank got this far
+    struct Rec { int ok; int pad; cudaIpcMemHandle_t h; };
+    Rec rec; rec.ok = good ? 1 : 0; rec.pad = 0; rec.h = mine;
+    char* d_all = nullptr; CK(cudaMalloc(&d_all, sizeof(Rec) * (size_t)world));
+    CK(cudaMemcpyAsync(d_all + sizeof(Rec) * (size_t)rank, &rec, sizeof(Rec), cudaMemcpyHostToDevice, st));
+    if (g_nccl.AllGather) {
+      ncclResult_t r = g_nccl.AllGather(d_all + sizeof(Rec) * (size_t)rank, d_all, sizeof(Rec), ncclChar, comm, st);
+      if (r != ncclSuccess) good = false;
+    }
+    std::vector<Rec> all(world);
+    CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * (size_t)world, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_all);
+    for (int r = 0; r < world; ++r) if (!all[r].ok) good = false;
+    if (good) {
+      xg.peer.assign(world, nullptr);
+      for (int r = 0; r < world && good; ++r) {
+        if (r == rank) { xg.peer[r] = xg.local; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; }
+        xg.peer[r] = (char*)ptr;
+      }
+    }
+    // agree on the outcome (a rank that failed to map a peer must take every rank down to the NCCL path)
+    double flag = good ? 0.0 : 1.0, *d_flag = nullptr;
+    CK(cudaMalloc(&d_flag, sizeof(double)));
+    CK(cudaMemcpyAsync(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+    allreduce_sum(d_flag, 1);
+    CK(cudaMemcpyAsync(&flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_flag);
+    if (flag != 0.0) { xchg_release(); xg.tried = true; std::fprintf(stderr, "[vdo_b200] rank %d: peer-memory exchange unavailable, using NCCL all-reduces per PCG iteration\n", rank); return false; }
+    std::vector<double*> hs(world); std::vector<unsigned long long*> hf(world);
+    for (int r = 0; r < world; ++r) { hf[r] = (unsigned long long*)xg.peer[r]; hs[r] = (double*)(xg.peer[r] + XG_HDR); }
+    CK(cudaMalloc(&xg.d_slots, sizeof(double*) * (size_t)world)); CK(cudaMalloc(&xg.d_flags, sizeof(unsigned long long*) * (size_t)world));
+    CK(cudaMemcpyAsync(xg.d_slots, hs.data(), sizeof(double*) * (size_t)world, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(xg.d_flags, hf.data(), sizeof(unsigned long long*) * (size_t)world, cudaMemcpyHostToDevice, st));
+    xg.d_epoch = (unsigned long long*)(xg.local + 8 * 256);       // behind the flags (world <= 256)
+    CK(cudaStreamSynchronize(st));
+    xg.ok = true;
+    return true;
+  }
   cudaStream_t st = nullptr, st2 = nullptr;   // st2: second branch inside the captured PCG graph
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_launch = 0;
@@ -620,6 +782,7 @@ struct CudaBackend : BaBackend {
     for (int i = 0; i < 4; ++i) { cudaEventDestroy(ev0[i]); cudaEventDestroy(ev1[i]); }
     for (auto& kv : pool) cudaFree(kv.second);
     arena.destroy();
+    xchg_release();
     if (comm) g_nccl.CommDestroy(comm);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -782,7 +945,14 @@ struct CudaBackend : BaBackend {
   // through device scalars so the captured kernel arguments never change)
   std::map<std::pair<const void*, int>, cudaGraphExec_t> graphs;
   void pcg_iterate(BaDev& d, double lambda, double tol2, int n) override {
-    if (world > 1) { BaBackend::pcg_iterate(d, lambda, tol2, n); return; }   // sharded: plain launches + NCCL between them
+    // sharded: the same captured graph with the all-reduce of S*p done by two kernels over peer memory (k_xchg_scatter / k_xchg_reduce);
+    // without peer mapping (or with the chunked layout) plain launches + one NCCL all-reduce per iteration
+    bool peer = false;
+    if (world > 1) {
+      peer = d.tiled && xchg_setup(d.C);
+      if (!peer) { BaBackend::pcg_iterate(d, lambda, tol2, n); return; }
+      d.xg_rank = rank; d.xg_world = world; d.xg_slots = xg.d_slots; d.xg_flags = xg.d_flags; d.xg_epoch = xg.d_epoch;
+    }
     set_scalars(d, lambda, tol2);
     auto key = std::make_pair((const void*)d.scal, n);
     auto it = graphs.find(key);
@@ -800,7 +970,11 @@ struct CudaBackend : BaBackend {
           CK(cudaEventRecord(ev_fork, st)); CK(cudaStreamWaitEvent(st2, ev_fork, 0));
           tile_schur(d, 1, -1, st2);
           CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
-          LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1, p_out);  // Ap -= B^T sums, and the partials of p.Ap
+          if (peer) {
+            LAUNCH(k_xchg_scatter, nblk(d.C, 128), 128, d, -1.0, (const double*)d.Ap);      // partial S*p into slot[rank] of every rank
+            LAUNCH(k_xchg_reduce, nblk(d.C, 128), 128, d, d.Ap, (const double*)p_out);      // sum of the slots in rank order, partials of p.Ap
+          } else
+            LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1, p_out);  // Ap -= B^T sums, and the partials of p.Ap
           LAUNCH(k_pcg_step_a<true>, d.n_paths * PCR_CL, 256, d, (const double*)p_out);
           continue;
         }
@@ -831,6 +1005,10 @@ struct CudaBackend : BaBackend {
     n_launch += per_batch[key];
   }
   std::map<std::pair<const void*, int>, int> per_batch;
+  void drop_graphs() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear(); per_batch.clear();
+  }
   void release(BaDev& d) override {
     for (auto it = graphs.begin(); it != graphs.end();) {
       if (it->first.first == (const void*)d.scal) { cudaGraphExecDestroy(it->second); per_batch.erase(it->first); it = graphs.erase(it); } else ++it;

@@ -73,7 +73,12 @@ struct BaDev {
   double *pcr_b = 0;              // 2 * C * 6 scratch of the solve   // per landmark: diagonal scalar of Hll^-1; per ternary edge: g_k + g_k+1 - 2 g_k,k+1
   double *xp = 0, *r = 0, *z = 0, *p = 0, *Ap = 0, *rhs = 0; // 6C each
   double* p2 = 0;           // 6C: second buffer of the search direction (the fused PCG kernels write p_{k+1} = z + beta p_k out of place)
-  unsigned int* ticket = 0; // "last CTA done" counter of the fused PCG step
+  unsigned int* ticket = 0; // "last CTA done" counters of the fused PCG step ([0]) and of the peer exchange ([1])
+  // ---- multi-GPU exchange of the sharded PCG iteration (CUDA backend, peer memory over NVLink; see k_xchg_scatter / k_xchg_reduce) ----
+  int xg_rank = 0, xg_world = 1;
+  double** xg_slots = 0;             // device array [world]: base of every rank's slot buffer (2 parities x world senders x 6C doubles)
+  unsigned long long** xg_flags = 0; // device array [world]: every rank's flag array (world entries: epoch of the last vector received from each sender)
+  unsigned long long* xg_epoch = 0;  // local epoch counter
   double *zl = 0, *xl = 0;                                    // 3P each
   double *vw = 0;   // 6C: per-vertex world-frame image [gamma, beta] of the vector the landmark pass multiplies (see body_vertex_transform)
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each

@@ -11,8 +11,11 @@
 //   Schur + dense LDLT   g2o/core/block_solver.hpp:352-486 ; g2o/solvers/linear_solver_dense.h:65-113
 //   quirk mode           SURVEY.md section 7.2 H1 (2-D flow vertices inside BlockSolver_6_3's 3x3 landmark blocks)
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -424,6 +427,323 @@ __global__ void __launch_bounds__(FL_THREADS) k_flow2_lm(FlowDev d) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------------------
+// Cluster version: one thread-block CLUSTER (FC_CL CTAs) per problem.  The per-point state (18 doubles: world point, flow and its
+// backup, error, the camera-frame point of the linearisation -- the 2x6 Jacobian is recomputed from it --, weight, H, b, delta)
+// lives in the CTAs' SHARED memory, structure-of-arrays, each CTA owning a contiguous 1/FC_CL of the points; a pass over the
+// points is then one point per thread out of shared memory instead of a strided walk over a global scratch array.  Sums over all
+// points are formed per CTA (shuffles + one smem hop), published in the CTA's shared memory and, after ONE cluster barrier, read by
+// every CTA through distributed shared memory and added in CTA order -- every CTA obtains bit-identical totals, so the scalar part
+// of the iteration (6x6 Cholesky, exp-map update, lambda logic) is simply executed by thread 0 of every CTA on its own copy of the
+// state: no broadcast, no second barrier.  Same arithmetic per point as k_flow2_lm; only the order of the sums differs.
+constexpr int FC_CL = 8, FC_THREADS = 256, FC_WARPS = FC_THREADS / 32, FC_FIELDS = 18;
+enum { C_XW = 0, C_F = 3, C_FBK = 5, C_ERR = 7, C_XL = 9, C_W = 12, C_H = 13, C_BL = 14, C_DL = 16 };
+
+struct ClusterRed {
+  double wred[FC_WARPS * FL_NV];        // per-warp partials
+  double part[2][FL_NV + 1];            // this CTA's partial sums (+ max), double-buffered across reductions
+  double tot[FL_NV + 1];                // cluster totals
+};
+// NV sums (+ one max, HAS_MAX) over all threads of the cluster; afterwards R.tot[0..NV) (and R.tot[NV]) hold the totals in every CTA
+template <int NV, bool HAS_MAX>
+__device__ __forceinline__ void cluster_reduce(double* acc, double mx, ClusterRed& R, int& phase) {
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cl = cgx::this_cluster();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double v = warp_sum(acc[i]);
+    if (lane == 0) R.wred[w * FL_NV + i] = v;
+  }
+  if (HAS_MAX) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if (lane == 0) R.wred[w * FL_NV + NV] = mx;
+  }
+  __syncthreads();
+  double* mine = R.part[phase & 1];
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int k = 0; k < FC_WARPS; ++k) s += R.wred[k * FL_NV + threadIdx.x];
+    mine[threadIdx.x] = s;
+  } else if (HAS_MAX && threadIdx.x == NV) {
+    double m = 0;
+    for (int k = 0; k < FC_WARPS; ++k) m = fmax(m, R.wred[k * FL_NV + NV]);
+    mine[NV] = m;
+  }
+  cl.sync();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int r = 0; r < FC_CL; ++r) s += cl.map_shared_rank(mine, r)[threadIdx.x];
+    R.tot[threadIdx.x] = s;
+  } else if (HAS_MAX && threadIdx.x == NV) {
+    double m = 0;
+    for (int r = 0; r < FC_CL; ++r) m = fmax(m, cl.map_shared_rank(mine, r)[NV]);
+    R.tot[NV] = m;
+  }
+  ++phase;
+  __syncthreads();
+}
+
+__global__ void __cluster_dims__(FC_CL, 1, 1) __launch_bounds__(FC_THREADS) k_flow2_lm_cl(FlowDev d, int npc) {
+  namespace cgx = cooperative_groups;
+  extern __shared__ __align__(16) double pt_sm[];        // FC_FIELDS x npc, field-major
+  __shared__ ClusterRed R;
+  __shared__ FlowShared S;
+  cgx::cluster_group cl = cgx::this_cluster();
+  const int prob = blockIdx.x / FC_CL, crank = (int)cl.block_rank(), tid = threadIdx.x;
+  const FlowProb P = d.prob[prob];
+  const int n = P.n;
+  const float* pts = d.pts + 2 * (size_t)P.offset;
+  const float* dep = d.depth + P.offset;
+  const float* flo = d.flow + 2 * (size_t)P.offset;
+  const double fx = P.K[0], fy = P.K[1], cx = P.K[2], cy = P.K[3];
+  const double w_rep = 0.1, w_prior = P.mode ? 0.5 : 0.3;
+  const double delta = (double)(float)sqrt((double)0.04f);
+  const double dsqr = (double)(float)(delta * delta);
+  const int max_iters = P.mode ? 200 : 100;
+  // this CTA's points: [i0, i1)
+  const int per = (n + FC_CL - 1) / FC_CL, i0 = min(n, crank * per), i1 = min(n, i0 + per), nloc = i1 - i0;
+  int phase = 0;
+#define PT(f, j) pt_sm[(size_t)(f) * npc + (j)]
+  if (n < 3) {   // reference: returns identity / 0 without optimising (Optimizer.cc:2449-2450, 2872-2873)
+    if (crank == 0) {
+      if (tid < 16) d.T_out[16 * prob + tid] = (tid % 5 == 0) ? 1.f : 0.f;
+      if (tid == 0) { d.stats[8 * prob] = -1; d.stats[8 * prob + 4] = 0; }
+      for (int i = tid; i < n; i += FC_THREADS) { d.inlier[P.offset + i] = 0; d.flow_out[2 * (size_t)(P.offset + i)] = flo[2 * i]; d.flow_out[2 * (size_t)(P.offset + i) + 1] = flo[2 * i + 1]; }
+    }
+    return;
+  }
+  if (tid == 0) {
+    const float* M = P.T_init;
+    double R0[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+    rot_to_quat(R0, S.q);
+    S.t[0] = M[3]; S.t[1] = M[7]; S.t[2] = M[11];
+    quat_normalize_pos(S.q);
+    quat_to_rot(S.q, S.R);
+    S.lambda = -1; S.ni = 2; S.nbad = 0; S.ok = 1; S.iters = 0; S.trials = 0; S.chi2_check = 0; S.last_trial_chi = 0;
+    for (int i = 0; i < 6; ++i) S.xp[i] = 0;
+  }
+  {
+    double Rwl[9], twl[3];
+    for (int r = 0; r < 3; ++r) {
+      double s = 0;
+      for (int c = 0; c < 3; ++c) { Rwl[3 * r + c] = P.Tcw_last[4 * c + r]; s += (double)P.Tcw_last[4 * c + r] * (double)P.Tcw_last[4 * c + 3]; }
+      twl[r] = (double)(float)(-s);
+    }
+    for (int j = tid; j < nloc; j += FC_THREADS) {
+      const int i = i0 + j;
+      const double ox = pts[2 * i], oy = pts[2 * i + 1], z = dep[i];
+      const double X[3] = {(ox - cx) * z / fx, (oy - cy) * z / fy, z};
+      for (int r = 0; r < 3; ++r) PT(C_XW + r, j) = Rwl[3 * r] * X[0] + Rwl[3 * r + 1] * X[1] + Rwl[3 * r + 2] * X[2] + twl[r];
+      PT(C_F, j) = flo[2 * i]; PT(C_F + 1, j) = flo[2 * i + 1];
+      PT(C_DL, j) = 0; PT(C_DL + 1, j) = 0;
+    }
+  }
+  __syncthreads();
+
+  // robust chi2 at the current (T, f); writes err[]; also carries the trial's scale sum.  Totals: R.tot[0] = chi2, R.tot[1] = scale
+  auto chi_pass = [&](double extra) {
+    double acc[2] = {0.0, extra};
+    for (int j = tid; j < nloc; j += FC_THREADS) {
+      const int i = i0 + j;
+      const double xw = PT(C_XW, j), yw = PT(C_XW + 1, j), zw = PT(C_XW + 2, j);
+      const double x = S.R[0] * xw + S.R[1] * yw + S.R[2] * zw + S.t[0];
+      const double y = S.R[3] * xw + S.R[4] * yw + S.R[5] * zw + S.t[1];
+      const double z = S.R[6] * xw + S.R[7] * yw + S.R[8] * zw + S.t[2];
+      const double f0 = PT(C_F, j), f1 = PT(C_F + 1, j);
+      const double ex = (double)pts[2 * i] + f0 - (x / z * fx + cx);
+      const double ey = (double)pts[2 * i + 1] + f1 - (y / z * fy + cy);
+      PT(C_ERR, j) = ex; PT(C_ERR + 1, j) = ey;
+      double rho, hw;
+      huber_f(w_rep * (ex * ex + ey * ey), delta, dsqr, rho, hw);
+      const double px = f0 - (double)flo[2 * i], py = f1 - (double)flo[2 * i + 1];
+      acc[0] += rho + w_prior * (px * px + py * py);
+    }
+    cluster_reduce<2, false>(acc, 0.0, R, phase);
+  };
+  auto jac = [&](int j, double* J) {      // 2x6 Jacobian of the linearisation point (types_six_dof_expmap.cpp:813-845)
+    const double x = PT(C_XL, j), y = PT(C_XL + 1, j), z = PT(C_XL + 2, j), z2 = z * z;
+    J[0] = x * y / z2 * fx; J[1] = -(1 + (x * x / z2)) * fx; J[2] = y / z * fx; J[3] = -1. / z * fx; J[4] = 0; J[5] = x / z2 * fx;
+    J[6] = (1 + y * y / z2) * fy; J[7] = -x * y / z2 * fy; J[8] = -x / z * fy; J[9] = 0; J[10] = -1. / z * fy; J[11] = y / z2 * fy;
+  };
+
+  chi_pass(0.0);
+  if (tid == 0) S.current = R.tot[0];
+  __syncthreads();
+
+  for (int it = 0; it < max_iters; ++it) {
+    if (!S.ok) break;
+    const double ini = S.current;
+    // ---- buildSystem ----
+    {
+      double acc[27];
+#pragma unroll
+      for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+      double maxh = 0.0;
+      for (int j = tid; j < nloc; j += FC_THREADS) {
+        const int i = i0 + j;
+        const double xw = PT(C_XW, j), yw = PT(C_XW + 1, j), zw = PT(C_XW + 2, j);
+        PT(C_XL, j) = S.R[0] * xw + S.R[1] * yw + S.R[2] * zw + S.t[0];
+        PT(C_XL + 1, j) = S.R[3] * xw + S.R[4] * yw + S.R[5] * zw + S.t[1];
+        PT(C_XL + 2, j) = S.R[6] * xw + S.R[7] * yw + S.R[8] * zw + S.t[2];
+        double J[12]; jac(j, J);
+        const double ex = PT(C_ERR, j), ey = PT(C_ERR + 1, j);
+        double rho, hw;
+        huber_f(w_rep * (ex * ex + ey * ey), delta, dsqr, rho, hw);
+        const double w = w_rep * hw, h = w + w_prior;
+        PT(C_W, j) = w; PT(C_H, j) = h;
+        PT(C_BL, j) = -(w * ex + w_prior * (PT(C_F, j) - (double)flo[2 * i]));
+        PT(C_BL + 1, j) = -(w * ey + w_prior * (PT(C_F + 1, j) - (double)flo[2 * i + 1]));
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          acc[21 + r] -= w * (J[r] * ex + J[6 + r] * ey);
+#pragma unroll
+          for (int c = r; c < 6; ++c) acc[q++] += w * (J[r] * J[c] + J[6 + r] * J[6 + c]);
+        }
+        maxh = fmax(maxh, h);
+      }
+      cluster_reduce<27, true>(acc, maxh, R, phase);
+      if (tid == 0) {
+        int q = 0;
+        for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { S.Hpp[6 * a + b] = R.tot[q]; S.Hpp[6 * b + a] = R.tot[q]; ++q; }
+        for (int a = 0; a < 6; ++a) S.bp[a] = R.tot[21 + a];
+        if (it == 0) {
+          double md = R.tot[27];
+          for (int a = 0; a < 6; ++a) md = fmax(md, fabs(S.Hpp[7 * a]));
+          S.lambda = 1e-5 * md; S.ni = 2; S.nbad = 0;
+        }
+        S.qmax = 0; S.stop_trials = 0;
+      }
+      __syncthreads();
+    }
+    // ---- lambda trials ----
+    while (true) {
+      const double lambda = S.lambda;
+      double acc[42];
+#pragma unroll
+      for (int i = 0; i < 42; ++i) acc[i] = 0.0;
+      for (int j = tid; j < nloc; j += FC_THREADS) {
+        PT(C_FBK, j) = PT(C_F, j); PT(C_FBK + 1, j) = PT(C_F + 1, j);
+        const double w = PT(C_W, j), h = PT(C_H, j), pp = h + lambda;
+        double J[12]; jac(j, J);
+        double B0[6], B1[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { B0[r] = w * J[r]; B1[r] = w * J[6 + r]; }
+        const double bl0 = PT(C_BL, j), bl1 = PT(C_BL + 1, j);
+        if (!d.quirk) {
+          const double ip = 1.0 / pp;
+          const double d0 = bl0 * ip, d1 = bl1 * ip;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            acc[36 + r] += B0[r] * d0 + B1[r] * d1;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[6 * r + c] += (B0[r] * B0[c] + B1[r] * B1[c]) * ip;
+          }
+        } else {
+          const double a = 1.0 / pp, b = -h / (pp * lambda), c2 = 1.0 / lambda;
+          const double d0 = a * bl0 + b * bl1, d1 = c2 * bl1;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            acc[36 + r] += B0[r] * d0 + B1[r] * d1;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[6 * r + c] += a * B0[r] * B0[c] + b * B0[r] * B1[c] + c2 * B1[r] * B1[c];
+          }
+        }
+      }
+      cluster_reduce<42, false>(acc, 0.0, R, phase);
+      if (tid == 0) {
+        for (int k = 0; k < 36; ++k) S.Sm[k] = S.Hpp[k] - R.tot[k];
+        for (int k = 0; k < 6; ++k) { S.Sm[7 * k] += lambda; S.g[k] = S.bp[k] - R.tot[36 + k]; }
+        for (int k = 0; k < 4; ++k) S.qbk[k] = S.q[k];
+        for (int k = 0; k < 3; ++k) S.tbk[k] = S.t[k];
+        S.ok2 = solve6_lower(S.Sm, S.g, S.x, S.L, S.y) ? 1 : 0;
+        if (S.ok2) for (int k = 0; k < 6; ++k) S.xp[k] = S.x[k];      // a failed solve leaves the previous x in place
+        se3_oplus(S.q, S.t, S.xp);
+        quat_to_rot(S.q, S.R);
+      }
+      __syncthreads();
+      double scale = 0.0;
+      {
+        const int ok2 = S.ok2;
+        for (int j = tid; j < nloc; j += FC_THREADS) {
+          const int i = i0 + j;
+          const double bl0 = PT(C_BL, j), bl1 = PT(C_BL + 1, j);
+          if (ok2) {
+            const double w = PT(C_W, j), h = PT(C_H, j), pp = h + lambda;
+            double J[12]; jac(j, J);
+            double cu = bl0, cv = bl1;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { cu -= w * J[r] * S.xp[r]; cv -= w * J[6 + r] * S.xp[r]; }
+            if (!d.quirk) { PT(C_DL, j) = cu / pp; PT(C_DL + 1, j) = cv / pp; }
+            else { PT(C_DL, j) = cu / pp - h * cv / (pp * lambda) + (i >= 1 ? cu / lambda : 0.0); PT(C_DL + 1, j) = cv / lambda; }
+          }
+          const double d0 = PT(C_DL, j), d1 = PT(C_DL + 1, j);
+          PT(C_F, j) += d0; PT(C_F + 1, j) += d1;
+          scale += d0 * (lambda * d0 + bl0) + d1 * (lambda * d1 + bl1);
+        }
+      }
+      chi_pass(scale);
+      if (tid == 0) {
+        const double temp = R.tot[0];
+        double sc_all = R.tot[1];
+        for (int r = 0; r < 6; ++r) sc_all += S.xp[r] * (lambda * S.xp[r] + S.bp[r]);
+        S.last_trial_chi = temp;
+        double tchi = S.ok2 ? temp : 1.7976931348623157e308;
+        double rho = (S.current - tchi) / (sc_all + 1e-3);
+        S.rho = rho;
+        if (rho > 0 && isfinite(tchi)) {
+          double alpha = 1. - pow(2 * rho - 1, 3.0);
+          alpha = fmin(alpha, 2. / 3.);
+          S.lambda *= fmax(1. / 3., alpha); S.ni = 2; S.current = tchi; S.accept = 1;
+        } else {
+          S.lambda *= S.ni; S.ni *= 2; S.accept = 0;
+          for (int k = 0; k < 4; ++k) S.q[k] = S.qbk[k];
+          for (int k = 0; k < 3; ++k) S.t[k] = S.tbk[k];
+          quat_to_rot(S.q, S.R);
+        }
+        if (d.debug && crank == 0) printf("[flow2 dbg] it %d trial %d lambda %.6g ok2 %d temp %.9g current %.9g scale %.6g rho %.6g\n", it, S.qmax, lambda, S.ok2, temp, S.current, sc_all, rho);
+        S.qmax++; S.trials++;
+        S.stop_trials = !(rho < 0 && S.qmax < 10);
+      }
+      __syncthreads();
+      if (!S.accept)
+        for (int j = tid; j < nloc; j += FC_THREADS) { PT(C_F, j) = PT(C_FBK, j); PT(C_F + 1, j) = PT(C_FBK + 1, j); }
+      __syncthreads();
+      if (S.stop_trials) break;
+    }
+    if (tid == 0) {
+      S.iters++;
+      if (S.qmax == 10 || S.rho == 0) S.ok = 0;
+      else { if ((ini - S.current) * 1e3 < ini) S.nbad++; else S.nbad = 0; if (S.nbad >= 3) S.ok = 0; }
+      if (S.chi2_check < S.last_trial_chi && it > 0) S.ok = 0;
+      S.chi2_check = S.last_trial_chi;
+    }
+    __syncthreads();
+  }
+  // ---- classification (on _error as left by the last trial), outputs ----
+  double nin[1] = {0};
+  for (int j = tid; j < nloc; j += FC_THREADS) {
+    const int i = i0 + j;
+    const float c = (float)(w_rep * (PT(C_ERR, j) * PT(C_ERR, j) + PT(C_ERR + 1, j) * PT(C_ERR + 1, j)));
+    const unsigned char in = !(c > 0.04f);
+    d.inlier[P.offset + i] = in; nin[0] += in;
+    d.flow_out[2 * (size_t)(P.offset + i)] = PT(C_F, j); d.flow_out[2 * (size_t)(P.offset + i) + 1] = PT(C_F + 1, j);
+  }
+  cluster_reduce<1, false>(nin, 0.0, R, phase);
+  if (tid == 0 && crank == 0) {
+    float* To = d.T_out + 16 * prob;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) To[4 * r + c] = (float)S.R[3 * r + c]; To[4 * r + 3] = (float)S.t[r]; }
+    To[12] = To[13] = To[14] = 0.f; To[15] = 1.f;
+    double* st = d.stats + 8 * prob;
+    st[0] = S.iters; st[1] = S.trials; st[2] = S.current; st[3] = S.lambda; st[4] = R.tot[0];
+    st[5] = 0; st[6] = 0; st[7] = 0;
+  }
+  cl.sync();       // no CTA may leave while another still reads its partial sums
+#undef PT
+}
+
 // ---- host side: a persistent device arena per context stream ----
 struct FlowArena {
   size_t cap_pts = 0, cap_prob = 0;
@@ -433,11 +753,23 @@ struct FlowArena {
   FlowProb* prob = 0;
   FlowProb* h_prob = 0;       // pinned
   float* h_T = 0; double* h_stats = 0;
-  int launches = 0;
+  int launches = 0, last_max_n = 0;
 };
 std::mutex g_mu;
 std::map<uint64_t, FlowArena> g_arenas;
 
+static int flow_launch(const FlowDev& d, int nprob, int max_n, cudaStream_t st) {
+  // cluster kernel when every problem's points fit the clusters' shared memory (18 doubles per point, FC_CL CTAs), else one CTA per problem
+  const int npc = (max_n + FC_CL - 1) / FC_CL;
+  const size_t smem = (size_t)FC_FIELDS * (size_t)(npc > 0 ? npc : 1) * sizeof(double);
+  static const bool force_single = std::getenv("VDO_FLOW_SINGLE_CTA") != nullptr;
+  if (!force_single && smem <= 200 * 1024) {
+    static bool opted = false;
+    if (!opted) { cudaFuncSetAttribute(k_flow2_lm_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); opted = true; }
+    k_flow2_lm_cl<<<nprob * FC_CL, FC_THREADS, smem, st>>>(d, npc > 0 ? npc : 1);
+  } else k_flow2_lm<<<nprob, FL_THREADS, 0, st>>>(d);
+  return 0;
+}
 #define FCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "[vdo_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return VDO_ERR_CUDA; } } while (0)
 
 }  // namespace
@@ -476,7 +808,10 @@ extern "C" int vdo_pose_opt_flow2_batch(vdo_ctx* ctx, int quirk, int nprob, cons
     FCK(cudaMemcpyAsync(A.flow, flow, total * 8, cudaMemcpyHostToDevice, st));
   }
   FlowDev d{A.prob, A.pts, A.depth, A.flow, A.scratch, A.T_out, A.flow_out, A.inlier, A.stats, quirk & 1, (quirk >> 1) & 1};
-  k_flow2_lm<<<nprob, FL_THREADS, 0, st>>>(d);
+  int max_n = 0;
+  for (int p = 0; p < nprob; ++p) max_n = std::max(max_n, offset[p + 1] - offset[p]);
+  A.last_max_n = max_n;
+  flow_launch(d, nprob, max_n, st);
   A.launches++;
   FCK(cudaGetLastError());
   FCK(cudaMemcpyAsync(A.h_T, A.T_out, (size_t)nprob * 64, cudaMemcpyDeviceToHost, st));
@@ -509,9 +844,9 @@ extern "C" int vdo_pose_opt_flow2_time(vdo_ctx* ctx, int quirk, int nprob, int r
   FlowDev d{A.prob, A.pts, A.depth, A.flow, A.scratch, A.T_out, A.flow_out, A.inlier, A.stats, quirk & 1, (quirk >> 1) & 1};
   cudaEvent_t e0, e1;
   FCK(cudaEventCreate(&e0)); FCK(cudaEventCreate(&e1));
-  k_flow2_lm<<<nprob, FL_THREADS, 0, st>>>(d);
+  flow_launch(d, nprob, A.last_max_n, st);
   FCK(cudaEventRecord(e0, st));
-  for (int i = 0; i < reps; ++i) k_flow2_lm<<<nprob, FL_THREADS, 0, st>>>(d);
+  for (int i = 0; i < reps; ++i) flow_launch(d, nprob, A.last_max_n, st);
   FCK(cudaEventRecord(e1, st));
   FCK(cudaEventSynchronize(e1));
   float ms = 0; FCK(cudaEventElapsedTime(&ms, e0, e1));
