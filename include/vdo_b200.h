@@ -250,6 +250,11 @@ int vdo_frame_sample_objects(vdo_frame *f, float th_depth_obj, int step, int max
 int vdo_scene_flow(vdo_ctx *ctx, int n, const float *u_prev, const float *v_prev, const float *z_prev, const float *Tcw_prev,
                    const float *u_cur, const float *v_cur, const float *z_cur, const float *Tcw_cur, const float *K,
                    const int *label_prev, const int *label_cur, float *flow3d, float *Xw_prev, unsigned char *valid);
+/* 7x7 sigma-2 Gaussian blur of every pyramid level + rotated-BRIEF descriptors (src/ORBextractor.cc:1083-1084, 97-136, pattern :139-397) of the
+ * keypoints of the last vdo_orb_extract call (which must have returned angles).  The reference allocates the descriptor matrix and never fills
+ * it (the computeDescriptors call is commented out, :1091); this is that call.  desc_out: n x 32 bytes in vdo_orb_extract's keypoint order. */
+int vdo_orb_describe(vdo_frame *f, int n, unsigned char *desc_out);
+int vdo_frame_debug_blur(vdo_frame *f, int level, unsigned char *img_out);   /* test hook: blurred level of the last vdo_orb_describe */
 /* test hook: pyramid level and FAST score map (u8, cv::cornerScore clipped at 0) of the last vdo_orb_extract call */
 int vdo_frame_debug_level(vdo_frame *f, int level, unsigned char *img_out, unsigned char *score_out, int *w_out, int *h_out);
 /* measurement: device time of the ORB front end (pyramid + FAST score maps) on the resident image */
@@ -380,6 +385,13 @@ int vdo_tracker_graph_export(vdo_tracker *t, int mode, const char *name, void *o
  * each, entry 0 = camera motion), vmRigidCentre (3 f32 each, same order), vnRMLabel (i32, same order), n_per_frame (entries per frame,
  * i32), n_frames (i32) */
 int vdo_tracker_map_get(const vdo_tracker *t, const char *name, void *out, int cap_elems, int *n_elems);
+/* Externally built maps -- the input of Optimizer::FullBatchOptimization(Map*, K) / PartialBatchOptimization(Map*, K, WINDOW_SIZE)
+ * (include/Optimizer.h:29-30): create a handle with params.width == params.height == 0 (intrinsics, window_size and overlap_size are used),
+ * push the Map frame by frame, run vdo_tracker_batch_optimize and read vmCameraPose[_RF] / vmRigidMotion[_RF] / vp3DPointSta / vp3DPointDyn
+ * (xyz per feature, all frames concatenated) back with vdo_tracker_map_get.  Frame 0: n_mot = 0, asso / label arrays ignored. */
+int vdo_tracker_map_push(vdo_tracker *t, int n_sta, const float *feat_sta, const float *dep_sta, const float *p3d_sta, const int *asso_sta, int n_dyn,
+                         const float *feat_dyn, const float *dep_dyn, const float *p3d_dyn, const int *asso_dyn, const int *feat_label,
+                         const float *camera_pose16, int n_mot, const float *rigid_motion16, const int *rm_label);
 
 /* Measurement hook (bench.py roofline): runs one kernel (or kernel group) of the batch path `reps` times back to back
  * on the context stream between two CUDA events, after one untimed warm-up launch, and returns the average in ms.

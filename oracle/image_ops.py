@@ -239,7 +239,7 @@ def orb_extract(gray: np.ndarray, prm: OrbParams, with_angle=True):
     """ORBextractor::operator(): returns dict(x, y (float32, level-0 coordinates), octave, response, angle, size) in output order,
     plus per-level candidate counts."""
     levels = compute_pyramid(gray, prm)
-    xs, ys, octv, resp, ang, size, ncand = [], [], [], [], [], [], []
+    xs, ys, octv, resp, ang, size, ncand, lxs, lys = [], [], [], [], [], [], [], [], []
     for lv, img in enumerate(levels):
         h, w = img.shape
         _, (minX, maxX, minY, maxY) = level_cells(w, h)
@@ -254,10 +254,66 @@ def orb_extract(gray: np.ndarray, prm: OrbParams, with_angle=True):
                 fx, fy = np.float32(lx * prm.scale_factor[lv]), np.float32(ly * prm.scale_factor[lv])
             else:
                 fx, fy = lx, ly
-            xs.append(fx); ys.append(fy); octv.append(lv); resp.append(r); ang.append(a); size.append(sps)
+            xs.append(fx); ys.append(fy); octv.append(lv); resp.append(r); ang.append(a); size.append(sps); lxs.append(lx); lys.append(ly)
     return dict(x=np.asarray(xs, np.float32), y=np.asarray(ys, np.float32), octave=np.asarray(octv, np.int32),
                 response=np.asarray(resp, np.float32), angle=np.asarray(ang, np.float32), size=np.asarray(size, np.int32),
-                n_candidates=ncand, levels=levels)
+                n_candidates=ncand, levels=levels, level_x=np.asarray(lxs, np.float32), level_y=np.asarray(lys, np.float32))
+
+
+# ------------------------------------------------------------------------------------------------- descriptors (A6)
+def orb_pattern():
+    """The 256 point pairs of ORB's learned sampling pattern (src/ORBextractor.cc:139-397; OpenCV's bit_pattern_31_), read from the
+    data file the CUDA kernel includes (vdo_slam_b200/csrc/orb_pattern.inc).  Pinned below against cv2.ORB, which carries the same table."""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vdo_slam_b200", "csrc", "orb_pattern.inc")
+    txt = "".join(l for l in open(path) if not l.lstrip().startswith("//"))
+    v = np.array([int(t) for t in re.findall(r"-?\d+", txt)], np.int32)
+    assert len(v) == 1024
+    return v.reshape(512, 2)
+
+
+def blur_level(img: np.ndarray) -> np.ndarray:
+    """GaussianBlur(workingMat, Size(7, 7), 2, 2, BORDER_REFLECT_101) (src/ORBextractor.cc:1083-1084): OpenCV's own (cv2 4.13; 3.4.0 filtered
+    in float -- version drift stated)."""
+    return cv2.GaussianBlur(img, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+
+
+def blur_level_fixed_point(img: np.ndarray) -> np.ndarray:
+    """The arithmetic cv2 4.13 uses for that call on CV_8U, restated (what k_blur7 implements): Q8.8 kernel {18, 34, 48, 56, 48, 34, 18},
+    horizontal pass in Q8.8, vertical in Q16.16, (v + 2^15) >> 16."""
+    k = np.array([18, 34, 48, 56, 48, 34, 18], np.int64)
+    p = cv2.copyMakeBorder(img, 3, 3, 3, 3, cv2.BORDER_REFLECT_101).astype(np.int64)
+    H, W = img.shape
+    h = sum(k[i] * p[:, i:i + W] for i in range(7))
+    v = sum(k[i] * h[i:i + H, :] for i in range(7))
+    return ((v + (1 << 15)) >> 16).astype(np.uint8)
+
+
+def orb_descriptor(blurred: np.ndarray, x: float, y: float, angle_deg: float, pattern=None) -> np.ndarray:
+    """computeOrbDescriptor (src/ORBextractor.cc:97-136) on a blurred level image; (x, y) in level coordinates.  float arithmetic as written
+    there (products and sums in float, cvRound = round-half-even)."""
+    pat = orb_pattern() if pattern is None else pattern
+    f32 = np.float32
+    ang = f32(f32(angle_deg) * f32(np.pi / f32(180.0)))
+    a, b = f32(np.cos(np.float64(ang))), f32(np.sin(np.float64(ang)))
+    cy, cx = cvround(float(y)), cvround(float(x))
+    px, py = pat[:, 0].astype(f32), pat[:, 1].astype(f32)
+    iy = np.rint(px * b + py * a).astype(np.int64)
+    ix = np.rint(px * a - py * b).astype(np.int64)
+    vals = blurred[cy + iy, cx + ix].astype(np.int32).reshape(256, 2)
+    bits = (vals[:, 0] < vals[:, 1]).astype(np.uint8).reshape(32, 8)
+    return (bits << np.arange(8, dtype=np.uint8)).sum(1).astype(np.uint8)
+
+
+def orb_describe(res: dict) -> np.ndarray:
+    """Descriptors (n x 32 u8) of an orb_extract() result: per level blur + rotated pair tests (src/ORBextractor.cc:1075-1091)."""
+    pat = orb_pattern()
+    blurred = [blur_level(im) for im in res["levels"]]
+    out = np.zeros((len(res["x"]), 32), np.uint8)
+    for i in range(len(out)):
+        out[i] = orb_descriptor(blurred[int(res["octave"][i])], res["level_x"][i], res["level_y"][i], res["angle"][i], pat)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- Frame sampling

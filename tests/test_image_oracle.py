@@ -86,3 +86,44 @@ def test_sampling_oracle_properties():
     assert len(s["x"]) > 100 and (s["label"] > 0).all() and (s["x"] % 4 == 0).all() and (s["y"] % 4 == 0).all()
     key = s["y"].astype(np.int64) * 10000 + s["x"]
     assert (np.diff(key) > 0).all()                                           # raster order
+
+
+# ---- A6: 7x7 blur + rotated-BRIEF descriptors (src/ORBextractor.cc:1083-1084, 97-136) ----
+def test_blur_restatement_is_cv2_gaussianblur_bit_for_bit():
+    rng = np.random.default_rng(3)
+    for shape in ((64, 80), (37, 129), (375, 1242)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert np.array_equal(io.blur_level(img), io.blur_level_fixed_point(img))      # the fixed-point arithmetic k_blur7 implements
+
+
+def test_descriptors_match_cv2_orb_up_to_blur_rounding():
+    """cv2.ORB carries the same sampling pattern, the same rotation arithmetic and the same blur call; its internal blur (on a view of its
+    bordered pyramid) differs from a stand-alone cv2.GaussianBlur by +-1 in a few pixels, so descriptor bits may differ only where the two
+    samples of a pair are within 2 of each other (each off by at most 1) -- every other bit must be identical."""
+    import cv2
+    from vdo_slam_b200.synth import make_frame
+    g = make_frame(0)["gray"]
+    res = io.orb_extract(g, io.OrbParams())
+    D = io.orb_describe(res)
+    m = np.nonzero(res["octave"] == 0)[0]
+    orb = cv2.ORB_create(nfeatures=5000, scaleFactor=1.2, nlevels=1, edgeThreshold=19, patchSize=31)
+    kps = [cv2.KeyPoint(float(res["x"][i]), float(res["y"][i]), 31.0, float(res["angle"][i]), float(res["response"][i]), 0) for i in m]
+    kps2, des = orb.compute(g, kps)
+    where = {(k.pt[0], k.pt[1]): i for i, k in enumerate(kps2)}
+    pat, bl, f32 = io.orb_pattern(), io.blur_level(g), np.float32
+    n_cmp = n_same = 0
+    for j, i in enumerate(m):
+        c = des[where[(kps[j].pt[0], kps[j].pt[1])]]
+        n_cmp += 1
+        if np.array_equal(c, D[i]):
+            n_same += 1
+            continue
+        ang = f32(f32(res["angle"][i]) * f32(np.pi / f32(180.0)))
+        a, b = f32(np.cos(np.float64(ang))), f32(np.sin(np.float64(ang)))
+        cy, cx = io.cvround(float(res["y"][i])), io.cvround(float(res["x"][i]))
+        for bit in np.nonzero(np.unpackbits((c ^ D[i])[:, None], axis=1, bitorder="little").reshape(-1))[0]:
+            p = pat[2 * bit:2 * bit + 2].astype(f32)
+            iy = np.rint(p[:, 0] * b + p[:, 1] * a).astype(int); ix = np.rint(p[:, 0] * a - p[:, 1] * b).astype(int)
+            t = bl[cy + iy, cx + ix].astype(int)
+            assert abs(int(t[0]) - int(t[1])) <= 2, (i, bit, t)      # each sample off by at most 1
+    assert n_cmp > 300 and n_same > n_cmp // 2

@@ -352,6 +352,17 @@ class Frame:
         g, d, f, m = self._keep
         self.ctx.check(self.ctx.L.vdo_frame_upload(self.h_, ptr(g, C.c_ubyte), ptr(d, C.c_float), ptr(f, C.c_float), ptr(m, C.c_int)), "vdo_frame_upload")
 
+    def orb_describe(self, n):
+        """vdo_orb_describe: descriptors (n x 32 u8) of the keypoints of the last orb_extract()."""
+        out = np.zeros((max(n, 1), 32), np.uint8)
+        self.ctx.check(self.ctx.L.vdo_orb_describe(self.h_, C.c_int(n), out.ctypes.data_as(C.POINTER(C.c_ubyte))), "vdo_orb_describe")
+        return out[:n]
+
+    def debug_blur(self, level, shape):
+        out = np.zeros(shape, np.uint8)
+        self.ctx.check(self.ctx.L.vdo_frame_debug_blur(self.h_, C.c_int(level), out.ctypes.data_as(C.POINTER(C.c_ubyte))), "vdo_frame_debug_blur")
+        return out
+
     def depth_prep(self, bf, factor):
         out = np.zeros((self.h, self.w), np.float32)
         self.ctx.check(self.ctx.L.vdo_frame_depth_prep(self.h_, C.c_float(bf), C.c_float(factor), out.ctypes.data_as(C.POINTER(C.c_float))), "vdo_frame_depth_prep")

@@ -642,6 +642,13 @@ int BaGraph::finalize() {
   d.n_part_pap = tiled ? std::max(1, (C + 127) / 128) : 148;    // tiled: one partial of p.Ap per CTA of the finalize kernel (128 vertices each)
   d.n_part_rz = std::max(1, n_paths) * 8;
   d.part_pap = dalloc<double>(d.n_part_pap); d.part_rz = dalloc<double>(d.n_part_rz);
+  {
+    const bool sharded = be_->shard_paths(d);          // collective; on success d.z / d.part_rz point into the exchange buffer
+    std::vector<int> own;
+    for (int pth = 0; pth < n_paths; ++pth) if (!sharded || pth % world == rank) own.push_back(pth);
+    d.n_own_paths = (int)own.size();
+    d.own_paths = upload(own);
+  }
   be_->sync();
   lap("alloc + upload");
   // host staging is no longer needed (keep the landmark map for read-back)
@@ -750,7 +757,8 @@ bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   }
   }
   *pcg_iters = (int)sc[SC_ITERS];
-  if (sc[SC_DONE] == 2.0 || !std::isfinite(sc[SC_RZ])) ok = false;   // breakdown (p.Ap <= 0 or NaN)
+  if (sc[SC_DONE] >= 2.0 || !std::isfinite(sc[SC_RZ])) ok = false;   // breakdown (p.Ap <= 0 or NaN), or 3: a peer never answered
+  if (d.xg_paths) be_->allreduce_sum(d.xp, 6 * (size_t)d.C);           // path-sharded preconditioner: every rank updated x on its own paths only
   // back substitution: xl = Hll^-1 (bl - Hlp xp)
   Phase ph(be_, &prof_ms_[3], prof);
   be_->vertex_transform(d, d.xp);

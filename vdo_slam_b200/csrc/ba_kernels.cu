@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128) k_hpp_mul(BaDev d, const double* __restri
 // ---- parallel cyclic reduction: one thread-block CLUSTER (PCR_CL CTAs) per chain, cluster.sync() between levels ----
 __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcr_factor(BaDev d, double lambda) {
   cg::cluster_group cl = cg::this_cluster();
-  const int path = blockIdx.x / PCR_CL;
+  const int path = d.own_paths[blockIdx.x / PCR_CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
   const int nl = pcr_num_levels(pe - pb);
   const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
@@ -430,10 +430,50 @@ __device__ __forceinline__ double pcr_solve_path(const BaDev& d, cg::cluster_gro
   return rz;
 }
 
+// Path-sharded preconditioner: the CTAs of one path publish their part of z (already in this rank's d.z) and their partial of r.z to
+// every other rank; the last CTA of the launch to finish fences and raises this rank's flag of the second exchange on every rank.
+__device__ __forceinline__ void xchg_publish_z(const BaDev& d, cg::cluster_group& cl, int path, int pb, int pe, double rz_part, int* is_last_sm) {
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  const int pidx = path * PCR_CL + (int)cl.block_rank();
+  if (threadIdx.x == 0) d.part_rz[pidx] = rz_part;
+  if (!d.xg_paths) return;
+  cl.sync();                                           // every CTA of the cluster wrote its share of z
+  for (int r = 0; r < d.xg_world; ++r) {
+    if (r == d.xg_rank) continue;
+    double* zr = d.xg_slots[r] + d.xg_off_z;
+    for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; zr[q] = d.z[q]; }
+    if (threadIdx.x == 0) (d.xg_slots[r] + d.xg_off_prz)[pidx] = rz_part;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(d.ticket + 2, 1u);
+    *is_last_sm = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!*is_last_sm || threadIdx.x != 0) return;
+  __threadfence_system();
+  d.ticket[2] = 0u;
+  const unsigned long long epoch = d.xg_epoch[192] + 1ull;
+  d.xg_epoch[192] = epoch;
+  for (int r = 0; r < d.xg_world; ++r) { volatile unsigned long long* f = d.xg_flags[r] + 320 + d.xg_rank; *f = epoch; }
+}
+// thread 0 of a CTA: wait until every rank's z part of the current epoch has arrived.  Returns false after ~2 s (a peer died).
+__device__ __forceinline__ bool xchg_wait_z(const BaDev& d) {
+  const unsigned long long epoch = d.xg_epoch[192];
+  volatile unsigned long long* f = d.xg_flags[d.xg_rank] + 320;
+  const long long t0 = clock64();
+  for (int r = 0; r < d.xg_world; ++r)
+    while (f[r] < epoch) if (clock64() - t0 > 4000000000ll) return false;
+  __threadfence_system();
+  return true;
+}
+
 __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_init(BaDev d) {
   __shared__ double red[32];
+  __shared__ int is_last;
   cg::cluster_group cl = cg::this_cluster();
-  const int path = blockIdx.x / PCR_CL;
+  const int path = d.own_paths[blockIdx.x / PCR_CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
   const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
   for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.r[q] = d.rhs[q]; d.xp[q] = 0.0; }
@@ -442,10 +482,18 @@ __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_init
   // p = z: each thread copies exactly the items it produced in the last loop of pcr_solve_path
   for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.p[q] = d.z[q]; }
   rz = block_sum(rz, red);
-  if (threadIdx.x == 0) d.part_rz[blockIdx.x] = rz;
+  if (threadIdx.x == 0) red[0] = rz;
+  __syncthreads();
+  xchg_publish_z(d, cl, path, pb, pe, red[0], &is_last);
 }
 __global__ void __launch_bounds__(256) k_pcg_init_fin(BaDev d) {
   __shared__ double red[33];
+  __shared__ int okw;
+  if (d.xg_paths) {
+    if (threadIdx.x == 0) okw = xchg_wait_z(d) ? 1 : 0;
+    __syncthreads();
+    if (!okw) { if (threadIdx.x == 0) d.scal[SC_DONE] = 3.0; return; }
+  }
   const double rz = det_sum(d.part_rz, d.n_paths * PCR_CL, red);
   if (threadIdx.x != 0) return;
   d.scal[SC_RZ] = rz; d.scal[SC_RZ0] = rz; d.scal[SC_RZ_NEW] = 0.0; d.scal[SC_PAP] = 0.0; d.scal[SC_ITERS] = 0.0; d.scal[SC_BETA] = 0.0;
@@ -470,15 +518,17 @@ __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step
   cg::cluster_group cl = cg::this_cluster();
   const double pap = det_sum(d.part_pap, d.n_part_pap, red), rz = d.scal[SC_RZ];
   const double alpha = (pap > 0.0) ? rz / pap : 0.0;
-  const int path = blockIdx.x / PCR_CL;
+  const int path = d.own_paths[blockIdx.x / PCR_CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
   const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
   for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.xp[q] += alpha * p[q]; d.r[q] -= alpha * d.Ap[q]; }
   if (pe - pb > 1) cl.sync();
   double rzn = pcr_solve_path(d, cl, pb, pe, d.r, d.z);
   rzn = block_sum(rzn, red);
-  if (threadIdx.x == 0) d.part_rz[blockIdx.x] = rzn;
-  if (!FUSED) return;
+  if (threadIdx.x == 0) red[0] = rzn;
+  __syncthreads();
+  xchg_publish_z(d, cl, path, pb, pe, red[0], &is_last);     // part_rz (and, path-sharded, z / part_rz on the other ranks)
+  if (!FUSED || d.xg_paths) return;                           // path-sharded: k_pcg_scalars_x does the scalars once every part has arrived
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicAdd(d.ticket, 1u);
@@ -645,6 +695,23 @@ __global__ void __launch_bounds__(256) k_pcg_scalars(BaDev d) {
   if (rzn <= tol2 * d.scal[SC_RZ0]) d.scal[SC_DONE] = 1.0;
 }
 
+// path-sharded preconditioner: waits for every rank's part of z / r.z, then the scalars of k_pcg_step_a<true>'s last CTA (identical on all ranks)
+__global__ void __launch_bounds__(256) k_pcg_scalars_x(BaDev d) {
+  __shared__ double red[33];
+  __shared__ int okw;
+  if (d.scal[SC_DONE] != 0.0) return;
+  if (threadIdx.x == 0) okw = xchg_wait_z(d) ? 1 : 0;
+  __syncthreads();
+  if (!okw) { if (threadIdx.x == 0) d.scal[SC_DONE] = 3.0; return; }
+  const double pap = det_sum(d.part_pap, d.n_part_pap, red);
+  const double rz_new = det_sum(d.part_rz, d.n_paths * PCR_CL, red);
+  if (threadIdx.x != 0) return;
+  const double rz = d.scal[SC_RZ];
+  if (!(pap > 0.0) || !isfinite(pap) || !isfinite(rz_new)) { d.scal[SC_DONE] = 2.0; return; }
+  d.scal[SC_BETA] = rz_new / rz; d.scal[SC_RZ] = rz_new; d.scal[SC_ITERS] += 1.0;
+  if (rz_new <= d.scal[SC_TOL2] * d.scal[SC_RZ0]) d.scal[SC_DONE] = 1.0;
+}
+
 __global__ void __launch_bounds__(128) k_apply_update(BaDev d, double lambda, int reortho) {
   __shared__ double red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -704,7 +771,7 @@ struct CudaBackend : BaBackend {
   // ---- peer-memory exchange of the sharded PCG iteration: one buffer per rank (flags + 2 x world slots of 6C doubles), mapped into every
   //      other rank through CUDA IPC (handles all-gathered over NCCL once per buffer size) ----
   struct Xchg {
-    char* local = nullptr; size_t bytes = 0; int C = 0; bool ok = false, tried = false;
+    char* local = nullptr; size_t bytes = 0, off_z = 0, off_prz = 0; int C = 0, n_paths = 0; bool ok = false, tried = false;
     std::vector<char*> peer;                 // peer[r]: this process' mapping of rank r's buffer (peer[rank] == local)
     double** d_slots = nullptr; unsigned long long** d_flags = nullptr; unsigned long long* d_epoch = nullptr;
   } xg;
@@ -719,14 +786,16 @@ struct CudaBackend : BaBackend {
     xg = Xchg();
   }
   // collective: every rank calls it with the same C.  Returns false (and the caller falls back to NCCL all-reduces) when peer mapping is unavailable.
-  bool xchg_setup(int C) {
-    if (xg.ok && xg.C >= C) return true;
+  bool xchg_setup(int C, int n_paths) {
+    if (xg.ok && xg.C >= C && xg.n_paths >= n_paths) return true;
     if (xg.tried && !xg.ok) return false;
     if (std::getenv("VDO_NO_PEER_EXCHANGE")) { xg.tried = true; return false; }
     CK(cudaStreamSynchronize(st));
     xchg_release();
-    xg.tried = true; xg.C = C;
-    xg.bytes = XG_HDR + sizeof(double) * 2 * (size_t)world * 6 * (size_t)C;
+    xg.tried = true; xg.C = C; xg.n_paths = n_paths;
+    // header | 2 x world slots of 6C | z (6C) | part_rz (n_paths x PCR_CL)
+    xg.off_z = 2 * (size_t)world * 6 * (size_t)C; xg.off_prz = xg.off_z + 6 * (size_t)C;
+    xg.bytes = XG_HDR + sizeof(double) * (xg.off_prz + (size_t)n_paths * PCR_CL + 2);
     bool good = g_nccl.AllGather != nullptr;
     if (good && cudaMalloc(&xg.local, xg.bytes) != cudaSuccess) { cudaGetLastError(); xg.local = nullptr; good = false; }
     if (good) CK(cudaMemsetAsync(xg.local, 0, xg.bytes, st));
@@ -896,7 +965,7 @@ struct CudaBackend : BaBackend {
     auto k = k_vertex_sym<1, true>; LAUNCH(k, d.n_obs_chunks, 128, d);
   }
   void precond_vertex_ter(BaDev& d) override { if (d.tiled) return; auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
-  void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_paths * PCR_CL, 256, d, lambda); }
+  void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_own_paths * PCR_CL, 256, d, lambda); }
   void schur_landmarks(BaDev& d, int mode, const double* v) override {
     if (d.tiled) { tile_schur(d, mode, -1, st); return; }
     const int g = nblk((d.T - d.Tstat) * 8, 128), gs = nblk(d.Tstat, 256);
@@ -931,13 +1000,14 @@ struct CudaBackend : BaBackend {
   void hpp_mul(BaDev& d, double lambda, const double* x, double* out) override { set_scalars(d, lambda, cur_tol2 < 0 ? 0.0 : cur_tol2); LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, x, out); }
   void pcg_init(BaDev& d) override {
     zero(d.scal + SC_PAP, 6 * sizeof(double));   // PAP, RZ, RZ_NEW, RZ0, DONE, ITERS
-    LAUNCH(k_pcg_init, d.n_paths * PCR_CL, 256, d);
+    if (d.xg_paths) zero(d.xp, 48 * (size_t)d.C);        // path-sharded: a rank touches x on its own paths only; the rest must read 0 in the final sum
+    LAUNCH(k_pcg_init, d.n_own_paths * PCR_CL, 256, d);
     LAUNCH(k_pcg_init_fin, 1, 256, d);
   }
   void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, d.n_part_pap, 256, d); }   // one CTA per slot of part_pap
   void pcg_step(BaDev& d, double tol2) override {
     set_scalars(d, cur_lambda, tol2);
-    LAUNCH(k_pcg_step_a<false>, d.n_paths * PCR_CL, 256, d, (const double*)d.p);
+    LAUNCH(k_pcg_step_a<false>, d.n_own_paths * PCR_CL, 256, d, (const double*)d.p);
     LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
     LAUNCH(k_pcg_scalars, 1, 256, d);
   }
@@ -949,9 +1019,8 @@ struct CudaBackend : BaBackend {
     // without peer mapping (or with the chunked layout) plain launches + one NCCL all-reduce per iteration
     bool peer = false;
     if (world > 1) {
-      peer = d.tiled && xchg_setup(d.C);
+      peer = d.tiled && d.xg_paths && xg.ok;            // decided (collectively) at finalize: shard_paths
       if (!peer) { BaBackend::pcg_iterate(d, lambda, tol2, n); return; }
-      d.xg_rank = rank; d.xg_world = world; d.xg_slots = xg.d_slots; d.xg_flags = xg.d_flags; d.xg_epoch = xg.d_epoch;
     }
     set_scalars(d, lambda, tol2);
     auto key = std::make_pair((const void*)d.scal, n);
@@ -975,7 +1044,8 @@ struct CudaBackend : BaBackend {
             LAUNCH(k_xchg_reduce, nblk(d.C, 128), 128, d, d.Ap, (const double*)p_out);      // sum of the slots in rank order, partials of p.Ap
           } else
             LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1, p_out);  // Ap -= B^T sums, and the partials of p.Ap
-          LAUNCH(k_pcg_step_a<true>, d.n_paths * PCR_CL, 256, d, (const double*)p_out);
+          LAUNCH(k_pcg_step_a<true>, d.n_own_paths * PCR_CL, 256, d, (const double*)p_out);
+          if (d.xg_paths) LAUNCH(k_pcg_scalars_x, 1, 256, d);
           continue;
         }
         LAUNCH(k_hpp_mul, nblk(d.C, 128), 128, d, (const double*)d.p, d.Ap);
@@ -990,7 +1060,7 @@ struct CudaBackend : BaBackend {
         if (d.n_ter_chunks > 0) { k_schur_vertex<false><<<d.n_ter_chunks, 128, 0, st2>>>(d, -1.0, d.Ap, 1); ++n_launch; }
         CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
         LAUNCH(k_pcg_dot, d.n_part_pap, 256, d);
-        LAUNCH(k_pcg_step_a<false>, d.n_paths * PCR_CL, 256, d, (const double*)d.p);
+        LAUNCH(k_pcg_step_a<false>, d.n_own_paths * PCR_CL, 256, d, (const double*)d.p);
         LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
         LAUNCH(k_pcg_scalars, 1, 256, d);
       }
@@ -1005,6 +1075,16 @@ struct CudaBackend : BaBackend {
     n_launch += per_batch[key];
   }
   std::map<std::pair<const void*, int>, int> per_batch;
+  // sharded graphs with the tiled layout: map the exchange buffer, move z / part_rz into it and shard the preconditioner by path
+  bool shard_paths(BaDev& d) override {
+    if (world <= 1 || !d.tiled || d.n_paths < world) return false;      // (every rank must own at least one path: it raises a flag per solve)
+    if (!xchg_setup(d.C, d.n_paths)) return false;
+    d.xg_rank = rank; d.xg_world = world; d.xg_slots = xg.d_slots; d.xg_flags = xg.d_flags; d.xg_epoch = xg.d_epoch;
+    d.xg_paths = 1; d.xg_off_z = xg.off_z; d.xg_off_prz = xg.off_prz;
+    d.z = (double*)(xg.local + XG_HDR) + xg.off_z;
+    d.part_rz = (double*)(xg.local + XG_HDR) + xg.off_prz;
+    return true;
+  }
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     graphs.clear(); per_batch.clear();

@@ -78,7 +78,12 @@ struct BaDev {
   int xg_rank = 0, xg_world = 1;
   double** xg_slots = 0;             // device array [world]: base of every rank's slot buffer (2 parities x world senders x 6C doubles)
   unsigned long long** xg_flags = 0; // device array [world]: every rank's flag array (world entries: epoch of the last vector received from each sender)
-  unsigned long long* xg_epoch = 0;  // local epoch counter
+  unsigned long long* xg_epoch = 0;  // local epoch counter (second exchange: flags at +320, epoch at +192 entries)
+  // Path sharding of the preconditioner (only with the peer exchange): rank r factors and solves the paths p with p % world == r, stores
+  // its part of z = M^-1 r and its partial sums of r.z straight into every rank's copy (d.z / d.part_rz then live in the exchange buffer)
+  int xg_paths = 0;
+  size_t xg_off_z = 0, xg_off_prz = 0;   // offsets (doubles, from a rank's slot base) of its z vector and its part_rz array
+  int* own_paths = 0; int n_own_paths = 0;   // the paths this rank factors / solves (all of them unless xg_paths)
   double *zl = 0, *xl = 0;                                    // 3P each
   double *vw = 0;   // 6C: per-vertex world-frame image [gamma, beta] of the vector the landmark pass multiplies (see body_vertex_transform)
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each
@@ -217,6 +222,9 @@ struct BaBackend {
     }
   }
   virtual void release(BaDev& d) { (void)d; }   // drop anything cached for this graph (called before its buffers are freed)
+  // multi-GPU: may turn on path sharding of the preconditioner for this graph (collective; called once from finalize after d is complete).
+  // Returns the list of paths this rank owns (default: every path).
+  virtual bool shard_paths(BaDev& d) { (void)d; return false; }
   // --- update / acceptance ---
   virtual void apply_update(BaDev& d, double lambda, bool reorthogonalize) = 0;  // oplus; scal[SC_SCALE] = sum x (lambda x + b)
 };

@@ -484,6 +484,61 @@ static std::vector<OKey> distribute_octtree(const std::vector<OKey>& in, int min
 }  // namespace
 
 // ================================================================================================ C ABI
+
+// ------------------------------------------------------------------------------------------------ descriptors (A6)
+// GaussianBlur(level, Size(7,7), 2, 2, BORDER_REFLECT_101) as OpenCV computes it for CV_8U (fixed point, bit-exact against cv2 4.13):
+// Q8.8 kernel {18, 34, 48, 56, 48, 34, 18} / 256, horizontal pass kept in Q8.8, vertical pass in Q16.16, (v + 2^15) >> 16.
+// (src/ORBextractor.cc:1083-1084.  OpenCV 3.4.0, which the reference's Dockerfile builds, still filtered in float: version drift.)
+__device__ __forceinline__ int reflect101(int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; return p; }
+__global__ void k_blur7(const unsigned char* __restrict__ src, int w, int h, unsigned char* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int kq[7] = {18, 34, 48, 56, 48, 34, 18};
+  int xs[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) xs[i] = reflect101(x + i - 3, w);
+  unsigned int v = 0;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const unsigned char* row = src + (size_t)reflect101(y + j - 3, h) * w;
+    unsigned int hsum = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) hsum += (unsigned int)kq[i] * row[xs[i]];
+    v += (unsigned int)kq[j] * hsum;
+  }
+  dst[(size_t)y * w + x] = (unsigned char)((v + (1u << 15)) >> 16);
+}
+// computeOrbDescriptor (src/ORBextractor.cc:97-136): one warp per keypoint, one descriptor byte (8 pair tests) per lane.
+__constant__ signed char c_orb_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+struct BlurLevels { const unsigned char* img[MAX_LEVELS]; int w[MAX_LEVELS], h[MAX_LEVELS]; };
+__global__ void k_orb_descriptors(const KpLvl* __restrict__ kps, const float* __restrict__ ang, int n, BlurLevels L, unsigned char* __restrict__ desc) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= n) return;
+  const KpLvl kp = kps[k];
+  const float factorPI = (float)(3.14159265358979323846 / 180.f);
+  const float angle = __fmul_rn(ang[k], factorPI);
+  const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+  const int w = L.w[kp.level];
+  const unsigned char* center = L.img[kp.level] + (size_t)__float2int_rn(kp.y) * w + __float2int_rn(kp.x);
+  int val = 0;
+#pragma unroll
+  for (int bit = 0; bit < 8; ++bit) {
+    const signed char* pt = c_orb_pattern + 4 * (8 * lane + bit);
+    int t[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float px = (float)pt[2 * q], py = (float)pt[2 * q + 1];
+      const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+      const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+      t[q] = center[iy * w + ix];
+    }
+    val |= (t[0] < t[1]) << bit;
+  }
+  desc[(size_t)k * 32 + lane] = (unsigned char)val;
+}
+
 struct vdo_frame {
   vdo_ctx* ctx; cudaStream_t st;
   int w, h;
@@ -491,7 +546,8 @@ struct vdo_frame {
   unsigned char* pyr[MAX_LEVELS] = {nullptr}; unsigned char* score[MAX_LEVELS] = {nullptr}; int lw[MAX_LEVELS], lh[MAX_LEVELS];
   Cell* cells = nullptr; KpOut* cell_out = nullptr; int* cell_cnt = nullptr; int cells_cap = 0;
   int* cell_off = nullptr; KpOut* cell_dense = nullptr; int* h_cnt_off = nullptr; KpOut* h_dense = nullptr; size_t h_dense_cap = 0;   // packed candidates (pinned host side)
-  KpLvl* kps = nullptr; float* ang = nullptr; int kp_cap = 0;
+  KpLvl* kps = nullptr; float* ang = nullptr; int kp_cap = 0, n_kps = -1;    // keypoints (level coordinates) / angles of the last vdo_orb_extract
+  unsigned char* blur[MAX_LEVELS] = {nullptr};
   void* scratch = nullptr; size_t scratch_cap = 0; int* d_count = nullptr;
   std::vector<KpOut> h_cell_out; std::vector<int> h_cell_cnt;
   OrbSetup orb; bool orb_ready = false;
@@ -520,7 +576,7 @@ extern "C" void vdo_frame_destroy(vdo_frame* f) {
   if (!f) return;
   cudaFree(f->gray); cudaFree(f->depth); cudaFree(f->flow); cudaFree(f->mask); cudaFree(f->d_count);
   for (int l = 1; l < MAX_LEVELS; ++l) cudaFree(f->pyr[l]);
-  for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(f->score[l]);
+  for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(f->score[l]); cudaFree(f->blur[l]); }
   cudaFree(f->cells); cudaFree(f->cell_out); cudaFree(f->cell_cnt); cudaFree(f->kps); cudaFree(f->ang); cudaFree(f->scratch);
   cudaFree(f->cell_off); cudaFree(f->cell_dense); cudaFreeHost(f->h_cnt_off); cudaFreeHost(f->h_dense);
   delete f;
@@ -635,6 +691,7 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
   }
   const int n = (int)sel.size();
   *n_out = std::min(n, max_out);
+  f->n_kps = angle ? n : -1;
   if (n == 0) return VDO_OK;
   if (n > f->kp_cap) { cudaFree(f->kps); cudaFree(f->ang); FRK(cudaMalloc(&f->kps, sizeof(KpLvl) * n * 2)); FRK(cudaMalloc(&f->ang, sizeof(float) * n * 2)); f->kp_cap = n * 2; }
   std::vector<float> h_ang(n, -1.f);
@@ -655,6 +712,34 @@ extern "C" int vdo_orb_extract(vdo_frame* f, int nfeatures, float scale_factor, 
     if (angle) angle[i] = h_ang[i];
     if (size) size[i] = (int)(PATCH_SIZE * P.scale_factor[l]);
   }
+  return VDO_OK;
+}
+
+// Descriptors of the keypoints of the last vdo_orb_extract call (which must have asked for angles): 7x7 sigma-2 blur of every level that has
+// keypoints, then the 256 rotated pair tests.  desc_out: n x 32 bytes, in the order vdo_orb_extract returned the keypoints.
+extern "C" int vdo_orb_describe(vdo_frame* f, int n, unsigned char* desc_out) {
+  if (!f || !f->orb_ready || n < 0 || (n && !desc_out)) return VDO_ERR_ARG;
+  if (f->n_kps < 0 || n > f->n_kps) return VDO_ERR_STATE;
+  if (n == 0) return VDO_OK;
+  BlurLevels L; std::memset(&L, 0, sizeof L);
+  for (int l = 0; l < f->orb.nlevels; ++l) {
+    if (!f->blur[l]) FRK(cudaMalloc(&f->blur[l], (size_t)f->lw[l] * f->lh[l]));
+    dim3 b(32, 8), g((f->lw[l] + 31) / 32, (f->lh[l] + 7) / 8);
+    k_blur7<<<g, b, 0, f->st>>>(f->pyr[l], f->lw[l], f->lh[l], f->blur[l]); f->launches++;
+    L.img[l] = f->blur[l]; L.w[l] = f->lw[l]; L.h[l] = f->lh[l];
+  }
+  if (int rc = ensure_scratch(f, (size_t)n * 32 + 64)) return rc;
+  unsigned char* d_desc = (unsigned char*)f->scratch;
+  k_orb_descriptors<<<(n * 32 + 255) / 256, 256, 0, f->st>>>(f->kps, f->ang, n, L, d_desc); f->launches++;
+  FRK(cudaMemcpyAsync(desc_out, d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, f->st));
+  FRK(cudaStreamSynchronize(f->st));
+  return VDO_OK;
+}
+// test hook: the blurred level of the last vdo_orb_describe call
+extern "C" int vdo_frame_debug_blur(vdo_frame* f, int level, unsigned char* img_out) {
+  if (!f || !f->orb_ready || level < 0 || level >= f->orb.nlevels || !f->blur[level] || !img_out) return VDO_ERR_ARG;
+  FRK(cudaMemcpyAsync(img_out, f->blur[level], (size_t)f->lw[level] * f->lh[level], cudaMemcpyDeviceToHost, f->st));
+  FRK(cudaStreamSynchronize(f->st));
   return VDO_OK;
 }
 

@@ -386,17 +386,45 @@ extern "C" void vdo_tracker_params_default(vdo_tracker_params* p) {       // exa
 }
 
 extern "C" int vdo_tracker_create(vdo_ctx* ctx, const vdo_tracker_params* params, vdo_tracker** out) {
-  if (!ctx || !params || !out || params->width < 64 || params->height < 64) return VDO_ERR_ARG;
+  // width == height == 0: a MAP-ONLY handle (no frame buffers): frames are pushed with vdo_tracker_map_push and optimised with
+  // vdo_tracker_batch_optimize -- the form Optimizer::FullBatchOptimization(Map*, K) / PartialBatchOptimization take their input in
+  const bool map_only = params && params->width == 0 && params->height == 0;
+  if (!ctx || !params || !out || (!map_only && (params->width < 64 || params->height < 64))) return VDO_ERR_ARG;
   vdo_tracker* t = new vdo_tracker;
   t->ctx = ctx; t->p = *params;
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2 && !map_only; ++i)
     if (vdo_frame_create(ctx, params->width, params->height, &t->fr[i].img) != VDO_OK) { vdo_tracker_destroy(t); return VDO_ERR_CUDA; }
   *out = t;
   return VDO_OK;
 }
+// One frame of an externally built Map (include/Map.h:34-84; what Tracking::Track pushes per frame, src/Tracking.cc:1016-1105).  Frame 0
+// carries no associations / motions (n_mot == 0).  Arrays: feat (x, y) pairs, p3d xyz triples, asso / label one int per feature,
+// camera_pose16 = vmCameraPose[i] (Twc, row-major), rigid_motion16 = vmRigidMotion[i - 1] (n_mot matrices, entry 0 = camera), rm_label likewise.
+extern "C" int vdo_tracker_map_push(vdo_tracker* t, int n_sta, const float* feat_sta, const float* dep_sta, const float* p3d_sta, const int* asso_sta, int n_dyn,
+                                    const float* feat_dyn, const float* dep_dyn, const float* p3d_dyn, const int* asso_dyn, const int* feat_label,
+                                    const float* camera_pose16, int n_mot, const float* rigid_motion16, const int* rm_label) {
+  if (!t || n_sta < 0 || n_dyn < 0 || n_mot < 0 || !camera_pose16) return VDO_ERR_ARG;
+  if ((n_sta && (!feat_sta || !dep_sta || !p3d_sta)) || (n_dyn && (!feat_dyn || !dep_dyn || !p3d_dyn)) || (n_mot && (!rigid_motion16 || !rm_label))) return VDO_ERR_ARG;
+  MapSlice& m = t->map;
+  const bool first = m.featSta.empty();
+  if (first != (n_mot == 0)) { t->err = "vdo_tracker_map_push: frame 0 has no motions, every later frame has at least the camera motion"; return VDO_ERR_ARG; }
+  if (!first && ((n_sta && !asso_sta) || (n_dyn && (!asso_dyn || !feat_label)))) return VDO_ERR_ARG;
+  m.featSta.emplace_back(feat_sta, feat_sta + 2 * (size_t)n_sta); m.depSta.emplace_back(dep_sta, dep_sta + n_sta); m.p3dSta.emplace_back(p3d_sta, p3d_sta + 3 * (size_t)n_sta);
+  m.featDyn.emplace_back(feat_dyn, feat_dyn + 2 * (size_t)n_dyn); m.depDyn.emplace_back(dep_dyn, dep_dyn + n_dyn); m.p3dDyn.emplace_back(p3d_dyn, p3d_dyn + 3 * (size_t)n_dyn);
+  M4 P; std::memcpy(P.data(), camera_pose16, 64);
+  m.cameraPose.push_back(P); m.cameraPose_RF.push_back(P);
+  if (first) return VDO_OK;
+  m.assoSta.emplace_back(asso_sta, asso_sta + n_sta); m.assoDyn.emplace_back(asso_dyn, asso_dyn + n_dyn); m.featLabel.emplace_back(feat_label, feat_label + n_dyn);
+  std::vector<M4> mot(n_mot);
+  for (int j = 0; j < n_mot; ++j) std::memcpy(mot[j].data(), rigid_motion16 + 16 * (size_t)j, 64);
+  m.rigidMotion.push_back(mot); m.rigidMotion_RF.push_back(mot);
+  m.rmLabel.emplace_back(rm_label, rm_label + n_mot); m.smLabel.emplace_back(rm_label, rm_label + n_mot);
+  m.rigidCentre.emplace_back(3 * (size_t)n_mot, 0.f);
+  return VDO_OK;
+}
 extern "C" void vdo_tracker_destroy(vdo_tracker* t) {
   if (!t) return;
-  for (int i = 0; i < 2; ++i) vdo_frame_destroy(t->fr[i].img);
+  for (int i = 0; i < 2; ++i) if (t->fr[i].img) vdo_frame_destroy(t->fr[i].img);
   delete t;
 }
 extern "C" const char* vdo_tracker_last_error(const vdo_tracker* t) { return t ? t->err.c_str() : "null tracker"; }
@@ -406,6 +434,7 @@ extern "C" int vdo_tracker_track(vdo_tracker* t, int width, int height, const un
                                  const int* gt_sem_ids, int writeback, float* Tcw_out) {
   if (!t || !gray || !depth || !flow || !mask || n_gt < 0) return VDO_ERR_ARG;
   const vdo_tracker_params& p = t->p;
+  if (!t->fr[0].img) { t->err = "vdo_tracker_track on a map-only handle"; return VDO_ERR_STATE; }
   if (width != p.width || height != p.height) {
     t->err = "vdo_tracker_track: buffers are " + std::to_string(width) + "x" + std::to_string(height) + " but the tracker was created for " + std::to_string(p.width) + "x" +
              std::to_string(p.height);
@@ -767,6 +796,8 @@ extern "C" int vdo_tracker_map_get(const vdo_tracker* t, const char* name, void*
   else if (s == "vmRigidMotion_RF") { for (auto& fr : t->map.rigidMotion_RF) for (auto& T : fr) f.insert(f.end(), T.begin(), T.end()); }
   else if (s == "vmRigidCentre") { for (auto& fr : t->map.rigidCentre) f.insert(f.end(), fr.begin(), fr.end()); }
   else if (s == "n_per_frame") { is_f = false; for (auto& fr : t->map.rmLabel) iv.push_back((int)fr.size()); }
+  else if (s == "vp3DPointSta") { for (auto& fr : t->map.p3dSta) f.insert(f.end(), fr.begin(), fr.end()); }      // all frames concatenated, xyz per feature
+  else if (s == "vp3DPointDyn") { for (auto& fr : t->map.p3dDyn) f.insert(f.end(), fr.begin(), fr.end()); }
   else if (s == "vnRMLabel") { is_f = false; for (auto& fr : t->map.rmLabel) iv.insert(iv.end(), fr.begin(), fr.end()); }
   else if (s == "n_frames") { is_f = false; iv.push_back((int)t->map.featSta.size()); }
   else return VDO_ERR_ARG;
