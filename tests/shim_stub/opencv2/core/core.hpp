@@ -19,6 +19,14 @@
 #define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
 
 namespace cv {
+struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float a, float b) : x(a), y(b) {} };
+struct Point3f { float x = 0, y = 0, z = 0; };
+struct Point { int x = 0, y = 0; };
+struct KeyPoint {
+  Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1;
+  KeyPoint() {}
+  KeyPoint(float x, float y, float s, float a = -1, float r = 0, int o = 0, int c = -1) : pt(x, y), size(s), angle(a), response(r), octave(o), class_id(c) {}
+};
 class Mat {
  public:
   int rows = 0, cols = 0;
@@ -44,5 +52,7 @@ class Mat {
   int type_ = 0;
   std::shared_ptr<std::vector<unsigned char>> buf_;
 };
+typedef const Mat& InputArray;      // enough for the shim: the reference passes cv::Mat for both
+typedef Mat& OutputArray;
 }  // namespace cv
 #endif

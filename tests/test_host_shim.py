@@ -111,3 +111,111 @@ def test_shim_rejects_mismatched_image_sizes(tmp_path):
     sys_cc = open(os.path.join(ROOT, "vdo_slam_b200", "host", "System.cc")).read()
     for needle in ("depthmap.cols != cols", "flowmap.cols != cols", "masksem.cols != cols", "frame size changed"):
         assert needle in sys_cc
+
+
+# ---- class-level shims: VDO_SLAM::ORBextractor / VDO_SLAM::Optimizer with the reference's signatures over the C ABI ----
+CLS = os.path.join(SHIM, "shim_classes")
+
+
+def _build_classes():
+    subprocess.check_call(["make", "-C", SHIM, "shim_classes"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(CLS)
+
+
+def test_class_shims_build():
+    _build_classes()
+    for hdr, needles in (("Optimizer.h", ["int static PoseOptimizationFlow2Cam(Frame *pCurFrame, Frame *pLastFrame, vector<int> &TemperalMatch);",
+                                          "cv::Mat static PoseOptimizationFlow2(Frame *pCurFrame, Frame *pLastFrame, const vector<int> &ObjId, std::vector<int> &InlierID);",
+                                          "void static FullBatchOptimization(Map *pMap, const cv::Mat Calib_K);",
+                                          "void static PartialBatchOptimization(Map *pMap, const cv::Mat Calib_K, const int WINDOW_SIZE);"]),
+                         ("ORBextractor.h", ["ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);",
+                                             "void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors);"])):
+        src = open(os.path.join(ROOT, "vdo_slam_b200", "host", hdr)).read()
+        for n in needles:                                   # the reference's declarations (include/Optimizer.h:25-32, include/ORBextractor.h:41-49)
+            assert n in src, n
+
+
+@pytest.mark.gpu
+def test_orbextractor_class_matches_oracle(tmp_path):
+    from oracle import image_ops as io
+    from vdo_slam_b200.synth import make_frame
+    _build_classes()
+    g = make_frame(3)["gray"]
+    h, w = g.shape
+    g.tofile(str(tmp_path / "g.bin"))
+    r = subprocess.run([CLS, "orb", str(tmp_path / "g.bin"), str(w), str(h), str(tmp_path / "o.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw = open(tmp_path / "o.bin", "rb").read()
+    n = int(np.frombuffer(raw, np.int32, 1)[0])
+    rec = np.frombuffer(raw, np.uint8, n * 24, 4).reshape(n, 24)
+    f5 = rec[:, :20].copy().view(np.float32).reshape(n, 5); octave = rec[:, 20:].copy().view(np.int32).reshape(n)
+    desc = np.frombuffer(raw, np.uint8, n * 32, 4 + n * 24).reshape(n, 32)
+    res = io.orb_extract(g, io.OrbParams())
+    assert n == len(res["x"]) and np.array_equal(f5[:, 0], res["x"]) and np.array_equal(f5[:, 1], res["y"]) and np.array_equal(octave, res["octave"])
+    assert np.array_equal(f5[:, 2], res["size"].astype(np.float32)) and np.array_equal(f5[:, 4], res["response"]) and np.abs(f5[:, 3] - res["angle"]).max() <= 1e-3
+    assert int(np.unpackbits(desc ^ io.orb_describe(res)).sum()) <= 8
+    tail = np.frombuffer(raw, np.int32, 1 + 16, 4 + n * 56)
+    assert tail[0] == 8 and [(int(tail[1 + 2 * l]), int(tail[2 + 2 * l])) for l in range(8)] == [im.shape[::-1] for im in res["levels"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_optimizer_flow_statics_match_oracle(tmp_path, mode):
+    from oracle import pyoracle as po
+    from vdo_slam_b200.synth import make_flow_problem
+    _build_classes()
+    p = make_flow_problem(n=700, seed=11 + mode)
+    with open(tmp_path / "p.bin", "wb") as f:
+        f.write(np.array([mode, len(p["depth"])], np.int32).tobytes()); f.write(p["K"].astype(np.float32).tobytes())
+        f.write(p["Tcw_last"].astype(np.float32).tobytes()); f.write(p["T_init"].astype(np.float32).tobytes())
+        f.write(p["pts"].astype(np.float32).tobytes()); f.write(p["depth"].astype(np.float32).tobytes()); f.write(p["flow"].astype(np.float32).tobytes())
+    r = subprocess.run([CLS, "flow", str(tmp_path / "p.bin"), str(tmp_path / "o.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw = open(tmp_path / "o.bin", "rb").read()
+    T = np.frombuffer(raw, np.float32, 16).reshape(4, 4); n_in = int(np.frombuffer(raw, np.int32, 1, 64)[0])
+    inl = np.frombuffer(raw, np.int32, n_in, 68)
+    ref = po.flow2(p, mode=mode, quirk=1)
+    assert np.abs(T - ref["T"]).max() <= 1e-6 and n_in == int(ref["inlier"].sum()) and np.array_equal(inl, np.nonzero(ref["inlier"])[0])
+    keys = np.frombuffer(raw, np.float32, 2 * len(p["depth"]), 68 + 4 * n_in).reshape(-1, 2)
+    want = (p["pts"].astype(np.float64) + ref["flow"]).astype(np.float32)
+    assert np.abs(keys[ref["inlier"]] - want[ref["inlier"]]).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_optimizer_batch_statics_match_oracle_pipeline(tmp_path):
+    """Optimizer::PartialBatchOptimization / FullBatchOptimization(Map*, K) on the oracle pipeline's Map, against the oracle's own run."""
+    import copy
+    from oracle.tracking_pipeline import OracleTracker
+    from vdo_slam_b200.synth import make_sequence_frame
+    _build_classes()
+    orc = OracleTracker(window_size=6, overlap_size=2, local_batch=False)
+    for t in range(8):
+        f = make_sequence_frame(t, seed=4)
+        orc.track(f["gray"], f["depth_raw"], f["flow"], f["mask"], f["obj_ids"])
+    m = orc.map
+    with open(tmp_path / "map.bin", "wb") as f:
+        f.write(np.asarray(orc.K4, np.float32).tobytes()); f.write(np.array([len(m["featSta"])], np.int32).tobytes())
+        for i in range(len(m["featSta"])):
+            for feat, dep, p3 in ((m["featSta"][i], m["depSta"][i], m["p3dSta"][i]), (m["featDyn"][i], m["depDyn"][i], m["p3dDyn"][i])):
+                f.write(np.array([len(dep)], np.int32).tobytes()); f.write(np.asarray(feat, np.float32).reshape(-1, 2).tobytes())
+                f.write(np.asarray(dep, np.float32).tobytes()); f.write(np.asarray(p3, np.float32).reshape(-1, 3).tobytes())
+            f.write(np.asarray(m["cameraPose"][i], np.float32).tobytes())
+            if i == 0:
+                continue
+            f.write(np.asarray(m["assoSta"][i - 1], np.int32).tobytes()); f.write(np.asarray(m["assoDyn"][i - 1], np.int32).tobytes())
+            f.write(np.asarray(m["featLabel"][i - 1], np.int32).tobytes())
+            f.write(np.array([len(m["rmLabel"][i - 1])], np.int32).tobytes())
+            for T in m["rigidMotion"][i - 1]:
+                f.write(np.asarray(T, np.float32).tobytes())
+            f.write(np.asarray(m["rmLabel"][i - 1], np.int32).tobytes())
+    N = len(m["featSta"])
+    for mode, name in ((0, "partial"), (1, "full")):
+        ref = copy.deepcopy(orc)
+        ref.batch_optimize(name)
+        r = subprocess.run([CLS, "ba", str(tmp_path / "map.bin"), str(mode), "6", str(tmp_path / "o.bin")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        out = np.fromfile(str(tmp_path / "o.bin"), np.float32)
+        cams = out[: N * 32].reshape(N, 2, 4, 4)
+        want = np.array(ref.map["cameraPose"] if mode == 0 else ref.map["cameraPose_RF"])
+        assert np.abs(cams[:, mode] - want).max() <= 1e-4
+        assert np.abs(cams[:, 1 - mode] - np.array(m["cameraPose"])).max() == 0      # the other set is left alone

@@ -644,8 +644,13 @@ int BaGraph::finalize() {
   d.part_pap = dalloc<double>(d.n_part_pap); d.part_rz = dalloc<double>(d.n_part_rz);
   {
     const bool sharded = be_->shard_paths(d);          // collective; on success d.z / d.part_rz point into the exchange buffer
-    std::vector<int> own;
-    for (int pth = 0; pth < n_paths; ++pth) if (!sharded || pth % world == rank) own.push_back(pth);
+    std::vector<int> own, shorts;
+    for (int pth = 0; pth < n_paths; ++pth) {
+      if (sharded && pth % world != rank) continue;
+      if (path_begin[pth + 1] - path_begin[pth] > VDO_PCR_SHORT) own.push_back(pth); else shorts.push_back(pth);
+    }
+    d.n_own_long = (int)own.size();
+    own.insert(own.end(), shorts.begin(), shorts.end());
     d.n_own_paths = (int)own.size();
     d.own_paths = upload(own);
   }

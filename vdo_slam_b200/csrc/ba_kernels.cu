@@ -30,7 +30,7 @@ namespace cg = cooperative_groups;
 
 namespace vdo {
 
-constexpr int PCR_CL = 8;   // CTAs per thread-block cluster working on one chain of the preconditioner
+constexpr int PCR_CL = 8;   // CTAs per thread-block cluster working on one LONG chain of the preconditioner (short chains: one CTA)
 
 #define CK(x)                                                                                       \
   do {                                                                                              \
@@ -342,12 +342,16 @@ __global__ void __launch_bounds__(128) k_hpp_mul(BaDev d, const double* __restri
 }
 
 // ---- parallel cyclic reduction: one thread-block CLUSTER (PCR_CL CTAs) per chain, cluster.sync() between levels ----
-__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcr_factor(BaDev d, double lambda) {
+// CL = CTAs per cluster: PCR_CL for long paths, 1 (plain CTA, the cluster barrier degenerates to a CTA barrier) for paths of at most
+// PCR_SHORT vertices -- most paths are short (objects seen for a few frames, single motion vertices) and a cluster of 8 CTAs each would only
+// multiply the number of waves the launch needs.  path0: position of the launch's first path in own_paths (long paths first).
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) k_pcr_factor(BaDev d, double lambda, int path0) {
   cg::cluster_group cl = cg::this_cluster();
-  const int path = d.own_paths[blockIdx.x / PCR_CL];
+  const int path = d.own_paths[path0 + blockIdx.x / CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
   const int nl = pcr_num_levels(pe - pb);
-  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = CL * blockDim.x;
   const size_t N36 = 36 * (size_t)d.C;
   int bad = 0, cur = 0;
   for (int v = pb + tid; v < pe; v += nth) body_pcr_setup(d, v, d.pcr_D, d.pcr_L);
@@ -371,9 +375,10 @@ __global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcr_fact
 
 // z = M^-1 r for the cluster's chain (r final for the whole chain on entry); returns this thread's share of r.z.
 // Work item = (vertex, row): 6 items per vertex so that A / G rows are read coalesced.
+template <int CL>
 __device__ __forceinline__ double pcr_solve_path(const BaDev& d, cg::cluster_group& cl, int pb, int pe, const double* __restrict__ r, double* __restrict__ z) {
   const int nl = pcr_num_levels(pe - pb);
-  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = CL * blockDim.x;
   const int n_items = 6 * (pe - pb);
   const size_t N6 = 6 * (size_t)d.C, N36 = 36 * (size_t)d.C;
   const double* src = r;
@@ -432,8 +437,9 @@ __device__ __forceinline__ double pcr_solve_path(const BaDev& d, cg::cluster_gro
 
 // Path-sharded preconditioner: the CTAs of one path publish their part of z (already in this rank's d.z) and their partial of r.z to
 // every other rank; the last CTA of the launch to finish fences and raises this rank's flag of the second exchange on every rank.
-__device__ __forceinline__ void xchg_publish_z(const BaDev& d, cg::cluster_group& cl, int path, int pb, int pe, double rz_part, int* is_last_sm) {
-  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+template <int CL>
+__device__ __forceinline__ void xchg_publish_z(const BaDev& d, cg::cluster_group& cl, int path, int pb, int pe, double rz_part, int* is_last_sm, unsigned int total_ctas) {
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = CL * blockDim.x;
   const int pidx = path * PCR_CL + (int)cl.block_rank();
   if (threadIdx.x == 0) d.part_rz[pidx] = rz_part;
   if (!d.xg_paths) return;
@@ -448,7 +454,7 @@ __device__ __forceinline__ void xchg_publish_z(const BaDev& d, cg::cluster_group
   if (threadIdx.x == 0) {
     __threadfence_system();
     const unsigned int t = atomicAdd(d.ticket + 2, 1u);
-    *is_last_sm = (t == gridDim.x - 1) ? 1 : 0;
+    *is_last_sm = (t == total_ctas - 1) ? 1 : 0;
   }
   __syncthreads();
   if (!*is_last_sm || threadIdx.x != 0) return;
@@ -469,22 +475,23 @@ __device__ __forceinline__ bool xchg_wait_z(const BaDev& d) {
   return true;
 }
 
-__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_init(BaDev d) {
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) k_pcg_init(BaDev d, int path0, unsigned int total_ctas) {
   __shared__ double red[32];
   __shared__ int is_last;
   cg::cluster_group cl = cg::this_cluster();
-  const int path = d.own_paths[blockIdx.x / PCR_CL];
+  const int path = d.own_paths[path0 + blockIdx.x / CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
-  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = CL * blockDim.x;
   for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.r[q] = d.rhs[q]; d.xp[q] = 0.0; }
   if (pe - pb > 1) cl.sync();
-  double rz = pcr_solve_path(d, cl, pb, pe, d.r, d.z);
+  double rz = pcr_solve_path<CL>(d, cl, pb, pe, d.r, d.z);
   // p = z: each thread copies exactly the items it produced in the last loop of pcr_solve_path
   for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.p[q] = d.z[q]; }
   rz = block_sum(rz, red);
   if (threadIdx.x == 0) red[0] = rz;
   __syncthreads();
-  xchg_publish_z(d, cl, path, pb, pe, red[0], &is_last);
+  xchg_publish_z<CL>(d, cl, path, pb, pe, red[0], &is_last, total_ctas);
 }
 __global__ void __launch_bounds__(256) k_pcg_init_fin(BaDev d) {
   __shared__ double red[33];
@@ -510,29 +517,29 @@ __global__ void __launch_bounds__(256) k_pcg_dot(BaDev d) {
 }
 // x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new += r.z.  FUSED: p is passed explicitly (double-buffered) and the last CTA to
 // finish does the work of k_pcg_step_b's beta and of k_pcg_scalars.
-template <bool FUSED>
-__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(256) k_pcg_step_a(BaDev d, const double* __restrict__ p) {
+template <bool FUSED, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) k_pcg_step_a(BaDev d, const double* __restrict__ p, int path0, unsigned int total_ctas) {
   __shared__ double red[33];
   __shared__ int is_last;
   if (d.scal[SC_DONE] != 0.0) return;
   cg::cluster_group cl = cg::this_cluster();
   const double pap = det_sum(d.part_pap, d.n_part_pap, red), rz = d.scal[SC_RZ];
   const double alpha = (pap > 0.0) ? rz / pap : 0.0;
-  const int path = d.own_paths[blockIdx.x / PCR_CL];
+  const int path = d.own_paths[path0 + blockIdx.x / CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
-  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = PCR_CL * blockDim.x;
+  const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = CL * blockDim.x;
   for (int w = tid; w < 6 * (pe - pb); w += nth) { const size_t q = 6 * (size_t)pb + w; d.xp[q] += alpha * p[q]; d.r[q] -= alpha * d.Ap[q]; }
   if (pe - pb > 1) cl.sync();
-  double rzn = pcr_solve_path(d, cl, pb, pe, d.r, d.z);
+  double rzn = pcr_solve_path<CL>(d, cl, pb, pe, d.r, d.z);
   rzn = block_sum(rzn, red);
   if (threadIdx.x == 0) red[0] = rzn;
   __syncthreads();
-  xchg_publish_z(d, cl, path, pb, pe, red[0], &is_last);     // part_rz (and, path-sharded, z / part_rz on the other ranks)
+  xchg_publish_z<CL>(d, cl, path, pb, pe, red[0], &is_last, total_ctas);     // part_rz (and, path-sharded, z / part_rz on the other ranks)
   if (!FUSED || d.xg_paths) return;                           // path-sharded: k_pcg_scalars_x does the scalars once every part has arrived
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicAdd(d.ticket, 1u);
-    is_last = (t == gridDim.x - 1) ? 1 : 0;
+    is_last = (t == total_ctas - 1) ? 1 : 0;
   }
   __syncthreads();
   if (!is_last) return;
@@ -965,7 +972,16 @@ struct CudaBackend : BaBackend {
     auto k = k_vertex_sym<1, true>; LAUNCH(k, d.n_obs_chunks, 128, d);
   }
   void precond_vertex_ter(BaDev& d) override { if (d.tiled) return; auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
-  void precond_factor(BaDev& d, double lambda) override { LAUNCH(k_pcr_factor, d.n_own_paths * PCR_CL, 256, d, lambda); }
+  // long paths (clusters of PCR_CL CTAs) first in own_paths, then the short ones (one CTA each)
+  void precond_factor(BaDev& d, double lambda) override {
+    LAUNCH(k_pcr_factor<PCR_CL>, d.n_own_long * PCR_CL, 256, d, lambda, 0);
+    LAUNCH(k_pcr_factor<1>, d.n_own_paths - d.n_own_long, 256, d, lambda, d.n_own_long);
+  }
+  template <bool FUSED> void launch_step_a(BaDev& d, const double* p) {
+    const unsigned int total = (unsigned int)(d.n_own_long * PCR_CL + (d.n_own_paths - d.n_own_long));
+    LAUNCH((k_pcg_step_a<FUSED, PCR_CL>), d.n_own_long * PCR_CL, 256, d, p, 0, total);
+    LAUNCH((k_pcg_step_a<FUSED, 1>), d.n_own_paths - d.n_own_long, 256, d, p, d.n_own_long, total);
+  }
   void schur_landmarks(BaDev& d, int mode, const double* v) override {
     if (d.tiled) { tile_schur(d, mode, -1, st); return; }
     const int g = nblk((d.T - d.Tstat) * 8, 128), gs = nblk(d.Tstat, 256);
@@ -1001,13 +1017,17 @@ struct CudaBackend : BaBackend {
   void pcg_init(BaDev& d) override {
     zero(d.scal + SC_PAP, 6 * sizeof(double));   // PAP, RZ, RZ_NEW, RZ0, DONE, ITERS
     if (d.xg_paths) zero(d.xp, 48 * (size_t)d.C);        // path-sharded: a rank touches x on its own paths only; the rest must read 0 in the final sum
-    LAUNCH(k_pcg_init, d.n_own_paths * PCR_CL, 256, d);
+    {
+      const unsigned int total = (unsigned int)(d.n_own_long * PCR_CL + (d.n_own_paths - d.n_own_long));
+      LAUNCH(k_pcg_init<PCR_CL>, d.n_own_long * PCR_CL, 256, d, 0, total);
+      LAUNCH(k_pcg_init<1>, d.n_own_paths - d.n_own_long, 256, d, d.n_own_long, total);
+    }
     LAUNCH(k_pcg_init_fin, 1, 256, d);
   }
   void pcg_dot_pAp(BaDev& d) override { LAUNCH(k_pcg_dot, d.n_part_pap, 256, d); }   // one CTA per slot of part_pap
   void pcg_step(BaDev& d, double tol2) override {
     set_scalars(d, cur_lambda, tol2);
-    LAUNCH(k_pcg_step_a<false>, d.n_own_paths * PCR_CL, 256, d, (const double*)d.p);
+    launch_step_a<false>(d, (const double*)d.p);
     LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
     LAUNCH(k_pcg_scalars, 1, 256, d);
   }
@@ -1044,7 +1064,7 @@ struct CudaBackend : BaBackend {
             LAUNCH(k_xchg_reduce, nblk(d.C, 128), 128, d, d.Ap, (const double*)p_out);      // sum of the slots in rank order, partials of p.Ap
           } else
             LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Ap, 1, p_out);  // Ap -= B^T sums, and the partials of p.Ap
-          LAUNCH(k_pcg_step_a<true>, d.n_own_paths * PCR_CL, 256, d, (const double*)p_out);
+          launch_step_a<true>(d, (const double*)p_out);
           if (d.xg_paths) LAUNCH(k_pcg_scalars_x, 1, 256, d);
           continue;
         }
@@ -1060,7 +1080,7 @@ struct CudaBackend : BaBackend {
         if (d.n_ter_chunks > 0) { k_schur_vertex<false><<<d.n_ter_chunks, 128, 0, st2>>>(d, -1.0, d.Ap, 1); ++n_launch; }
         CK(cudaEventRecord(ev_join, st2)); CK(cudaStreamWaitEvent(st, ev_join, 0));
         LAUNCH(k_pcg_dot, d.n_part_pap, 256, d);
-        LAUNCH(k_pcg_step_a<false>, d.n_own_paths * PCR_CL, 256, d, (const double*)d.p);
+        launch_step_a<false>(d, (const double*)d.p);
         LAUNCH(k_pcg_step_b, min(nblk(d.C * 6, 256), 148), 256, d);
         LAUNCH(k_pcg_scalars, 1, 256, d);
       }

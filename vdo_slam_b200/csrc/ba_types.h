@@ -34,6 +34,7 @@
 // layout do not exist in this mode.
 #define VDO_TILE_L 256
 #define VDO_TILE_E 768
+#define VDO_PCR_SHORT 256
 #define VDO_SEG 64
 #define VDO_SEG2 15   // Schur kernels: runs of one vertex cut at 15 entries (odd: threads walking consecutive full runs hit distinct shared-memory banks), one thread per (run, component pair)
 
@@ -83,7 +84,8 @@ struct BaDev {
   // its part of z = M^-1 r and its partial sums of r.z straight into every rank's copy (d.z / d.part_rz then live in the exchange buffer)
   int xg_paths = 0;
   size_t xg_off_z = 0, xg_off_prz = 0;   // offsets (doubles, from a rank's slot base) of its z vector and its part_rz array
-  int* own_paths = 0; int n_own_paths = 0;   // the paths this rank factors / solves (all of them unless xg_paths)
+  int* own_paths = 0; int n_own_paths = 0;   // the paths this rank factors / solves (all of them unless xg_paths), the LONG ones first
+  int n_own_long = 0;                        // ... of which this many have more than VDO_PCR_SHORT vertices (solved by a cluster of CTAs; the rest by one CTA each)
   double *zl = 0, *xl = 0;                                    // 3P each
   double *vw = 0;   // 6C: per-vertex world-frame image [gamma, beta] of the vector the landmark pass multiplies (see body_vertex_transform)
   double *obs_cls_w = 0, *obs_cls_d = 0, *ter_cls_w = 0, *ter_cls_d = 0;  // 256 each

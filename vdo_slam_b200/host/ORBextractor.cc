@@ -52,7 +52,7 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray, std::vector
   if (n == 0) desc = cv::Mat();
   else {
     desc.create(n, 32, CV_8U);
-    if (vdo_orb_describe(mpFrame, n, x.data(), y.data(), oct.data(), ang.data(), desc.data) != VDO_OK) {
+    if (vdo_orb_describe(mpFrame, n, desc.data) != VDO_OK) {
       std::cerr << "vdo_b200: ORB descriptors failed: " << vdo_last_error(Optimizer::Context()) << std::endl;
       exit(-1);
     }
