@@ -106,6 +106,14 @@ typedef struct vdo_lm_stats {
   int kernel_launches;      /* kernels launched by this optimize() call */
 } vdo_lm_stats;
 
+/* Converter (src/Converter.cc:25-41, 151-166) and the cv::Mat 4x4 product as the reference's float / double rounding rules (host-only):
+ * toSE3Quat (rotation -> Eigen quaternion, w >= 0, normalised; q = x y z w), toCvMat (quaternion -> rotation, rounded to float),
+ * toInvMatrix ([R^T | -R^T t], the translation accumulated in double and rounded once), A * B of two 4x4 CV_32F (float accumulation). */
+int vdo_convert_to_se3quat(const float *T16, double *q4, double *t3);
+int vdo_convert_to_cvmat(const double *q4, const double *t3, float *T16);
+int vdo_convert_inv_matrix(const float *T16, float *out16);
+int vdo_convert_mul4(const float *A16, const float *B16, float *out16);
+
 /* sizeof() of a public struct as this library was built ("vdo_lm_options", "vdo_lm_stats", "vdo_tracker_params"; -1: unknown name): FFI
  * bindings that mirror the structs by hand (ctypes, cgo, JNI) check it at load time -- a binding that lags a struct extension would
  * otherwise have the library write past its buffer. */
@@ -325,6 +333,7 @@ int vdo_renew_frame_info(vdo_frame *cur, int n_tm, const int *tm_sta, int n_stat
 /* depth and mask label at the truncated pixel of each key (x, y interleaved, n x 2 f32); 0 / 0 outside the image.  The
  * "update current frame from last" look-ups of Tracking::GrabImageRGBD (src/Tracking.cc:262-312). */
 int vdo_frame_gather(vdo_frame *f, int n, const float *keys, float *depth_out, int *mask_out);
+int vdo_frame_read_mask(vdo_frame *f, int *mask_out);   /* D2H of the resident (possibly updated) semantic mask */
 
 /* ------------------------------------------------------------------------------------------------
  * Whole per-frame path: System::TrackRGBD -> Tracking::GrabImageRGBD -> Tracking::Track (include/System.h:49-51,

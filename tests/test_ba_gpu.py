@@ -72,6 +72,26 @@ def test_partial_batch_constants_static_only(ctx):
     assert max(_pose_err(se3, ro["se3"])) <= 1e-5 and np.abs(pt - ro["pt"]).max() <= 1e-5
 
 
+def test_dense_reduced_system_path_matches_oracle_and_pcg(ctx, monkeypatch):
+    """NS1: small static-only graphs (the 20-camera sliding window) form S explicitly and factor it on the fp64 tensor cores (mma.sync m8n8k4)
+    instead of running the matrix-free PCG: a direct solve, so the LM run coincides with the oracle's to rounding; the PCG path agrees."""
+    g = make_batch_graph(n_frames=20, n_objects=0, n_static=2500, n_dynamic=0, seed=13, consts=PARTIAL_BATCH)
+    ro = po.ba_optimize(g, max_iters=100, gain_threshold=1e-3)
+    G = capi.BatchGraph(ctx, g)                                   # qualifies: tiled, static only, 6C = 120 <= 168
+    r = G.optimize(max_iterations=100, gain_threshold=1e-3)
+    assert r["iterations"] == ro["iters"] and r["pcg_iterations"] == 0        # no PCG ran
+    n = r["iterations"] + 1
+    np.testing.assert_allclose(r["chi2"][:n], ro["chi2"][:n], rtol=1e-9)
+    se3, pt = G.vertices()
+    assert max(_pose_err(se3, ro["se3"])) <= 1e-8 and np.abs(pt - ro["pt"]).max() <= 1e-8
+    monkeypatch.setenv("VDO_BA_DENSE", "0")
+    G2 = capi.BatchGraph(ctx, g)
+    r2 = G2.optimize(max_iterations=100, gain_threshold=1e-3, pcg_rel_tol=1e-10)
+    assert r2["iterations"] == ro["iters"] and r2["pcg_iterations"] > 0
+    se3b, ptb = G2.vertices()
+    assert max(_pose_err(se3, se3b)) <= 1e-7 and np.abs(pt - ptb).max() <= 1e-7
+
+
 def test_reset_and_repeat_is_reproducible_to_rounding(ctx):
     g = make_batch_graph(n_frames=15, n_objects=1, n_static=500, n_dynamic=100, seed=4)
     G = capi.BatchGraph(ctx, g)

@@ -635,6 +635,11 @@ int BaGraph::finalize() {
   d.xp = dalloc<double>(6 * (size_t)C); d.r = dalloc<double>(6 * (size_t)C); d.z = dalloc<double>(6 * (size_t)C);
   d.p = dalloc<double>(6 * (size_t)C); d.Ap = dalloc<double>(6 * (size_t)C); d.rhs = dalloc<double>(6 * (size_t)C);
   d.p2 = dalloc<double>(6 * (size_t)C); d.ticket = dalloc<unsigned int>(4);
+  {
+    const char* env = std::getenv("VDO_BA_DENSE");   // "0": never; default: whenever the graph qualifies
+    const bool want = !(env && std::string(env) == "0");
+    if (want && tiled && world == 1 && Tstat == T && 6 * C <= be_->dense_capacity()) d.Sdense = dalloc<double>((size_t)36 * C * C + 6 * (size_t)C + 8);
+  }
   d.zl = tiled ? nullptr : dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P); d.vw = dalloc<double>(6 * (size_t)C);
   oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
   d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
@@ -726,6 +731,15 @@ double BaGraph::robust_chi2() {
 bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   BaDev& d = d_;
   const bool prof = prof_on_;
+  if (d.Sdense) {                              // small static-only graph: explicit reduced matrix + tensor-core Cholesky
+    Phase ph(be_, &prof_ms_[2], prof);
+    be_->factor_landmarks(d, lambda);
+    *pcg_iters = 0;
+    const bool ok = be_->dense_solve(d, lambda);
+    be_->vertex_transform(d, d.xp);
+    be_->schur_landmarks(d, 2, d.xp);
+    return ok;
+  }
   {
   Phase ph(be_, &prof_ms_[0], prof);
   be_->factor_landmarks(d, lambda);

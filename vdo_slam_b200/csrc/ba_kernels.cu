@@ -719,6 +719,171 @@ __global__ void __launch_bounds__(256) k_pcg_scalars_x(BaDev d) {
   if (rz_new <= d.scal[SC_TOL2] * d.scal[SC_RZ0]) d.scal[SC_DONE] = 1.0;
 }
 
+// ---- dense reduced system for small static-only graphs (NS1) ----
+// S (n x n, n = 6C, row-major, lower triangle used) = Hpp + lambda I (+ se3-se3 off-diagonal blocks) - sum_j (1 / s_j) H_pl,j H_pl,j^T, rhs = bp - sum_j H_pl,j b_l,j / s_j
+// with H_pl for an EdgeSE3PointXYZ = om J_c^T J_p, J_c = [-I | 2 [Zc]x], J_p = R_c^T (edge_se3_pointxyz.cpp:99-140).
+__global__ void __launch_bounds__(128) k_dense_init(BaDev d, double lambda, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double* S = d.Sdense; double* rhs = S + (size_t)n * n;
+  if (i < n * n) {
+    const int r = i / n, c = i % n, vr = r / 6, vc = c / 6;
+    double v = 0.0;
+    if (vr == vc) { v = d.Hpp[36 * (size_t)vr + 6 * (r % 6) + (c % 6)]; if (r == c) v += lambda; }
+    S[i] = v;
+  }
+  if (i < n) rhs[i] = d.bp[i];
+  if (i == 0) rhs[n] = 0.0;                       // status word: != 0 after the factorisation means "not positive definite"
+}
+__global__ void __launch_bounds__(64) k_dense_se3_edges(BaDev d, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.Ese || d.se_j[e] < 0) return;
+  const int i = d.se_i[e], j = d.se_j[e];
+  const double* H = d.se_Hoff + 36 * (size_t)e;    // J_i^T W J_j: rows i, columns j
+  double* S = d.Sdense;
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) {
+      if (i > j) atomicAdd(S + (size_t)(6 * i + r) * n + 6 * j + c, H[6 * r + c]);
+      else atomicAdd(S + (size_t)(6 * j + c) * n + 6 * i + r, H[6 * r + c]);
+    }
+}
+__global__ void __launch_bounds__(128) k_dense_schur(BaDev d, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d.P) return;
+  const int eb = d.lm_obs_begin[k], ee = d.lm_obs_begin[k + 1];
+  if (ee <= eb) return;
+  const double is = 1.0 / d.pt_s[k];
+  const double p[3] = {d.pt[3 * (size_t)k], d.pt[3 * (size_t)k + 1], d.pt[3 * (size_t)k + 2]};
+  const double bls[3] = {d.bl[3 * (size_t)k] * is, d.bl[3 * (size_t)k + 1] * is, d.bl[3 * (size_t)k + 2] * is};
+  double* S = d.Sdense; double* rhs = S + (size_t)n * n;
+  // M_c = om J_c^T R_c^T (6 x 3): rows 0-2 = -om R^T, rows 3-5 = om (2 [Zc]x)^T R^T
+  auto make_M = [&](int e, double* M) -> int {
+    const int c = d.lm_cam[e];
+    const double* T = d.se3 + 12 * (size_t)c;
+    const double w[3] = {p[0] - T[9], p[1] - T[10], p[2] - T[11]};
+    double Zc[3]; rot_t_apply(T, w, Zc);
+    const double om = d.lm_omega[e];
+    // 2 [Zc]x = [[0, -2z, 2y], [2z, 0, -2x], [-2y, 2x, 0]];  J_c^T rows 3-5 = (2 [Zc]x)^T
+    const double A[9] = {0, 2 * Zc[2], -2 * Zc[1], -2 * Zc[2], 0, 2 * Zc[0], 2 * Zc[1], -2 * Zc[0], 0};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        M[3 * r + q] = -om * T[3 * q + r];                                                  // -om R^T
+        M[9 + 3 * r + q] = om * (A[3 * r] * T[3 * q] + A[3 * r + 1] * T[3 * q + 1] + A[3 * r + 2] * T[3 * q + 2]);   // om A R^T
+      }
+    return c;
+  };
+  for (int e1 = eb; e1 < ee; ++e1) {
+    double M1[18]; const int c1 = make_M(e1, M1);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) atomicAdd(rhs + 6 * c1 + r, -(M1[3 * r] * bls[0] + M1[3 * r + 1] * bls[1] + M1[3 * r + 2] * bls[2]));
+    for (int e2 = eb; e2 < ee; ++e2) {
+      double M2[18]; const int c2 = make_M(e2, M2);
+      if (c2 > c1) continue;                                                                  // lower triangle (blocks with c1 >= c2)
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          atomicAdd(S + (size_t)(6 * c1 + r) * n + 6 * c2 + q, -is * (M1[3 * r] * M2[3 * q] + M1[3 * r + 1] * M2[3 * q + 1] + M1[3 * r + 2] * M2[3 * q + 2]));
+        }
+    }
+  }
+}
+// One CTA: blocked right-looking Cholesky of the lower triangle of S in shared memory (8-column panels; the trailing update
+// A[i][j] -= L[i][k] L[j][k]^T over 8x8 tiles is two mma.sync.m8n8k4.f64 per tile), then the two triangular solves.  n <= DENSE_MAX.
+constexpr int DENSE_MAX = 168;
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256) k_dense_chol(BaDev d, int n) {
+  extern __shared__ double sA[];                    // npad x ld, row-major; ld = npad + 1 (bank spread)
+  const int npad = (n + 7) & ~7, ld = npad + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  double* S = d.Sdense; double* rhs = S + (size_t)n * n;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int i = tid; i < npad * npad; i += blockDim.x) {
+    const int r = i / npad, c = i % npad;
+    double v = 0.0;
+    if (r < n && c < n) v = (c <= r) ? S[(size_t)r * n + c] : S[(size_t)c * n + r];   // mirror the lower triangle (block (c1 == c2) parts were written in full)
+    else if (r == c) v = 1.0;                                                        // padding: identity
+    sA[r * ld + c] = v;
+  }
+  __syncthreads();
+  const int nb = npad / 8;
+  for (int kb = 0; kb < nb; ++kb) {
+    const int k0 = 8 * kb;
+    if (warp == 0) {                                // 8 x 8 diagonal block, unblocked (lanes = rows)
+      for (int j = 0; j < 8; ++j) {
+        double djj = sA[(k0 + j) * ld + k0 + j];
+        if (!(djj > 0.0)) { if (lane == 0) bad = 1; djj = 1.0; }
+        const double l = sqrt(djj);
+        __syncwarp();
+        if (lane == j) sA[(k0 + j) * ld + k0 + j] = l;
+        if (lane > j && lane < 8) sA[(k0 + lane) * ld + k0 + j] /= l;
+        __syncwarp();
+        if (lane > j && lane < 8) {
+          const double lij = sA[(k0 + lane) * ld + k0 + j];
+          for (int c = j + 1; c <= lane; ++c) sA[(k0 + lane) * ld + k0 + c] -= lij * sA[(k0 + c) * ld + k0 + j];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // panel: rows below the diagonal block solve x L_kk^T = a (one thread per row)
+    for (int r = k0 + 8 + tid; r < npad; r += blockDim.x) {
+      double x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double s = sA[r * ld + k0 + j];
+#pragma unroll
+        for (int c = 0; c < j; ++c) s -= x[c] * sA[(k0 + j) * ld + k0 + c];
+        x[j] = s / sA[(k0 + j) * ld + k0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sA[r * ld + k0 + j] = x[j];
+    }
+    __syncthreads();
+    // trailing update on the fp64 tensor cores: tile (ib, jb), ib >= jb > kb:  A_ij -= L_ik L_jk^T
+    const int nt = nb - kb - 1, ntiles = nt * (nt + 1) / 2;
+    for (int t = warp; t < ntiles; t += nw) {
+      int a = 0, rem = t;
+      while (rem >= nt - a) { rem -= nt - a; ++a; }
+      const int jb = kb + 1 + a, ib = jb + rem;
+      const int g = lane >> 2, q = lane & 3;        // fragment coordinates: A row g / col q (+4), B row q (+4) / col g, C row g / cols 2q, 2q + 1
+      double c0 = 0.0, c1 = 0.0;
+      dmma_m8n8k4(c0, c1, sA[(8 * ib + g) * ld + k0 + q], sA[(8 * jb + g) * ld + k0 + q]);
+      dmma_m8n8k4(c0, c1, sA[(8 * ib + g) * ld + k0 + 4 + q], sA[(8 * jb + g) * ld + k0 + 4 + q]);
+      sA[(8 * ib + g) * ld + 8 * jb + 2 * q] -= c0;
+      sA[(8 * ib + g) * ld + 8 * jb + 2 * q + 1] -= c1;
+    }
+    __syncthreads();
+  }
+  // L y = rhs, L^T x = y (warp 0; n is small)
+  __shared__ double y[DENSE_MAX];
+  for (int i = tid; i < npad; i += blockDim.x) y[i] = i < n ? rhs[i] : 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int c = lane; c < i; c += 32) s += sA[i * ld + c] * y[c];
+      s = warp_sum(s);
+      if (lane == 0) y[i] = (y[i] - s) / sA[i * ld + i];
+      __syncwarp();
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = 0.0;
+      for (int c = i + 1 + lane; c < n; c += 32) s += sA[c * ld + i] * y[c];
+      s = warp_sum(s);
+      if (lane == 0) y[i] = (y[i] - s) / sA[i * ld + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) d.xp[i] = y[i];
+  if (tid == 0) rhs[n] = bad ? 1.0 : 0.0;
+}
+
 __global__ void __launch_bounds__(128) k_apply_update(BaDev d, double lambda, int reortho) {
   __shared__ double red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1115,6 +1280,19 @@ struct CudaBackend : BaBackend {
     }
     if (cur_scal == d.scal) cur_scal = nullptr;
   }
+  // dense reduced system + tensor-core Cholesky (small static-only graphs)
+  int dense_capacity() const override { return DENSE_MAX; }
+  bool dense_solve(BaDev& d, double lambda) override {
+    const int n = 6 * d.C, npad = (n + 7) & ~7;
+    LAUNCH(k_dense_init, nblk(n * n, 128), 128, d, lambda, n);
+    LAUNCH(k_dense_se3_edges, nblk(d.Ese, 64), 64, d, n);
+    LAUNCH(k_dense_schur, nblk(d.P, 128), 128, d, n);
+    const size_t smem = sizeof(double) * (size_t)npad * (npad + 1);
+    k_dense_chol<<<1, 256, smem, st>>>(d, n); ++n_launch;
+    double status = 0.0;
+    d2h(&status, d.Sdense + (size_t)n * n + n, sizeof(double));
+    return status == 0.0;
+  }
   void apply_update(BaDev& d, double lambda, bool reortho) override { LAUNCH(k_apply_update, nblk(d.C + d.P, 128), 128, d, lambda, reortho ? 1 : 0); }
 };
 
@@ -1135,6 +1313,7 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
     optin((const void*)k_tile_precond<false>, SMEM_PRE_ST); optin((const void*)k_tile_precond<true>, SMEM_PRE_CH);
     optin((const void*)k_tile_schur2<false, 0>, smem_sch2(false, VDO_TILE_E, 255, 1)); optin((const void*)k_tile_schur2<false, 1>, smem_sch2(false, VDO_TILE_E, 255, 1));
     optin((const void*)k_tile_schur2<true, 0>, smem_sch2(true, VDO_TILE_E, 255, 255)); optin((const void*)k_tile_schur2<true, 1>, smem_sch2(true, VDO_TILE_E, 255, 255));
+    optin((const void*)k_dense_chol, sizeof(double) * (size_t)DENSE_MAX * (DENSE_MAX + 1));
     optin((const void*)k_tile_schur<true, 0>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 1>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 2>, SMEM_SCH_CH);
   }
   CudaBackend* b = new CudaBackend;

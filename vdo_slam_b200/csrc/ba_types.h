@@ -34,7 +34,7 @@
 // layout do not exist in this mode.
 #define VDO_TILE_L 256
 #define VDO_TILE_E 768
-#define VDO_PCR_SHORT 256
+#define VDO_PCR_SHORT 32    // paths up to this many vertices: one CTA (one (vertex, row) item per thread); longer: a cluster of PCR_CL CTAs
 #define VDO_SEG 64
 #define VDO_SEG2 15   // Schur kernels: runs of one vertex cut at 15 entries (odd: threads walking consecutive full runs hit distinct shared-memory banks), one thread per (run, component pair)
 
@@ -73,6 +73,7 @@ struct BaDev {
   double *pcr_A = 0, *pcr_G = 0;  // pcr_levels * C * 36 : elimination operators per level
   double *pcr_b = 0;              // 2 * C * 6 scratch of the solve   // per landmark: diagonal scalar of Hll^-1; per ternary edge: g_k + g_k+1 - 2 g_k,k+1
   double *xp = 0, *r = 0, *z = 0, *p = 0, *Ap = 0, *rhs = 0; // 6C each
+  double* Sdense = 0;       // (6C)^2 + 6C + 8: dense reduced matrix, right-hand side and status of the dense path (only allocated for small static-only graphs)
   double* p2 = 0;           // 6C: second buffer of the search direction (the fused PCG kernels write p_{k+1} = z + beta p_k out of place)
   unsigned int* ticket = 0; // "last CTA done" counters of the fused PCG step ([0]) and of the peer exchange ([1])
   // ---- multi-GPU exchange of the sharded PCG iteration (CUDA backend, peer memory over NVLink; see k_xchg_scatter / k_xchg_reduce) ----
@@ -224,6 +225,12 @@ struct BaBackend {
     }
   }
   virtual void release(BaDev& d) { (void)d; }   // drop anything cached for this graph (called before its buffers are freed)
+  // Dense reduced system (small static-only graphs, e.g. the 20-camera sliding window): S = Hpp + lambda I - Hpl Hll^-1 Hlp formed explicitly
+  // (6C x 6C) and solved by a Cholesky factorisation whose trailing updates run on the fp64 tensor cores (mma.sync m8n8k4) -- the
+  // BlockSolver Schur path of g2o/core/block_solver.hpp:352-486 instead of the matrix-free PCG.  dense_capacity(): largest 6C (0: unsupported);
+  // dense_solve(): xp = S^-1 (bp - Hpl Hll^-1 bl) after factor_landmarks(lambda); returns false when S is not positive definite.
+  virtual int dense_capacity() const { return 0; }
+  virtual bool dense_solve(BaDev& d, double lambda) { (void)d; (void)lambda; return false; }
   // multi-GPU: may turn on path sharding of the preconditioner for this graph (collective; called once from finalize after d is complete).
   // Returns the list of paths this rank owns (default: every path).
   virtual bool shard_paths(BaDev& d) { (void)d; return false; }

@@ -581,6 +581,13 @@ extern "C" void vdo_frame_destroy(vdo_frame* f) {
   cudaFree(f->cell_off); cudaFree(f->cell_dense); cudaFreeHost(f->h_cnt_off); cudaFreeHost(f->h_dense);
   delete f;
 }
+// D2H of the resident mask (the tracker writes it back into the caller's buffer only when UpdateMask changed it)
+extern "C" int vdo_frame_read_mask(vdo_frame* f, int* mask_out) {
+  if (!f || !mask_out) return VDO_ERR_ARG;
+  FRK(cudaMemcpyAsync(mask_out, f->mask, sizeof(int) * (size_t)f->w * f->h, cudaMemcpyDeviceToHost, f->st));
+  FRK(cudaStreamSynchronize(f->st));
+  return VDO_OK;
+}
 // internal: device pointers of a resident frame for the other translation units (tracking_ops.cu)
 extern "C" int vdo_frame_device_ptrs(vdo_frame* f, unsigned char** gray, float** depth, float** flow, int** mask, int* w, int* h, void** stream) {
   if (!f) return VDO_ERR_ARG;

@@ -457,7 +457,8 @@ extern "C" int vdo_tracker_track(vdo_tracker* t, int width, int height, const un
     for (int i = 0; i < n; ++i) { cx[i] = L.objCorres[2 * i]; cy[i] = L.objCorres[2 * i + 1]; }
     int nw = 0;
     StageTimer stage_timer_1(&t->stage_ms[1]);
-    TK(vdo_update_mask(C.img, L.img, n, L.semObjLabel.data(), cx.data(), cy.data(), writeback ? mask : nullptr, &nw, nullptr));
+    TK(vdo_update_mask(C.img, L.img, n, L.semObjLabel.data(), cx.data(), cy.data(), nullptr, &nw, nullptr));
+    if (writeback && nw > 0) TK(vdo_frame_read_mask(C.img, mask));        // the caller's buffer already holds the mask unless an object was warped into it
   }
   {
     StageTimer stage_timer_2(&t->stage_ms[2]);
