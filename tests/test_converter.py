@@ -90,3 +90,20 @@ def test_to_se3quat_and_back(L):
         assert np.abs(back[:3, :3] - Rq.astype(np.float32)).max() <= 6e-8 and np.array_equal(back[:3, 3], T[:3, 3]) and back[3].tolist() == [0, 0, 0, 1]
         if it % 3:                                                      # orthonormal input: the round trip is the identity to float rounding
             assert np.abs(back - T).max() <= 3e-7
+
+
+def test_shim_gray_conversion_follows_opencv_3_4_and_is_within_one_of_cv2_4():
+    """System::TrackRGBD converts colour input with cvtColor(RGB2GRAY / BGR2GRAY) (src/Tracking.cc:209-222).  The shim restates the 8-bit
+    fixed-point formula of the OpenCV the reference builds (3.4.0: 14-bit coefficients 4899 / 9617 / 1868); the cv2 in this image (4.13) uses
+    15-bit coefficients (9798 / 19235 / 3735) -- version drift of at most one grey level, checked here against cv2.cvtColor itself."""
+    import cv2
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (97, 211, 3), dtype=np.uint8)
+    r, g, b = img[..., 0].astype(np.int64), img[..., 1].astype(np.int64), img[..., 2].astype(np.int64)
+    v34 = ((r * 4899 + g * 9617 + b * 1868 + (1 << 13)) >> 14)
+    v4 = ((r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15)
+    ref = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY).astype(np.int64)
+    assert np.array_equal(v4, ref)                                     # the 4.x arithmetic, restated, is cv2's
+    assert np.abs(v34 - ref).max() <= 1 and (v34 != ref).mean() < 0.01  # 3.4 vs 4.13: at most one level, < 1 % of the pixels
+    src = open(os.path.join(ROOT, "vdo_slam_b200", "host", "System.cc")).read()
+    assert "R * 4899 + G * 9617 + B * 1868 + (1 << 13)) >> 14" in src

@@ -106,3 +106,21 @@ def test_unsupported_png_flavours_are_refused(ectx, tmp_path):
         capi.io_read_png(ectx, p)
     with pytest.raises(capi.VdoError):
         capi.io_read_png(ectx, str(tmp_path / "missing.png"))
+
+
+def test_decoders_reject_corrupt_headers_and_directories(tmp_path):
+    """Untrusted sizes behind the C ABI: a PNG whose IHDR claims a gigantic image, a truncated .flo and a directory must come back as an
+    error code, not as std::bad_alloc through extern "C"."""
+    import struct, zlib
+    from vdo_slam_b200 import capi
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    bogus = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 60000, 60000, 16, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    p = tmp_path / "bogus.png"; p.write_bytes(bogus)
+    L = capi.load(EMUL) if "EMUL" in globals() else capi.load()
+    import ctypes as C
+    buf = (C.c_ubyte * 16)()
+    assert L.vdo_io_read_png(str(p).encode(), buf, C.c_size_t(16)) != 0
+    assert L.vdo_io_read_png(str(tmp_path).encode(), buf, C.c_size_t(16)) != 0          # a directory
+    out = C.c_void_p()
+    assert L.vdo_g2o_read(str(tmp_path).encode(), C.byref(out)) != 0

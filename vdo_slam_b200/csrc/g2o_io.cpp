@@ -83,9 +83,12 @@ int vdo_g2o_read(const char* path, vdo_g2o** out) {
   std::fseek(f, 0, SEEK_END);
   const long sz = std::ftell(f);
   std::fseek(f, 0, SEEK_SET);
-  std::vector<char> buf((size_t)sz + 1);
+  if (sz < 0 || (unsigned long)sz > ((unsigned long)1 << 33)) { std::fclose(f); return VDO_ERR_ARG; }   // directory / pipe / absurd size
+  std::vector<char> buf;
+  try { buf.resize((size_t)sz + 1); } catch (...) { std::fclose(f); return VDO_ERR_ARG; }
   const size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
   std::fclose(f);
+  if (got != (size_t)sz) return VDO_ERR_ARG;                         // short read
   buf[got] = 0;
   vdo_g2o* g = new vdo_g2o;
   std::map<int, int> se3_of, pt_of;             // file id -> compact index

@@ -29,8 +29,8 @@ bool read_file(const char* path, std::vector<unsigned char>& buf) {
   std::fseek(f, 0, SEEK_END);
   const long sz = std::ftell(f);
   std::fseek(f, 0, SEEK_SET);
-  if (sz < 0) { std::fclose(f); return false; }
-  buf.resize((size_t)sz);
+  if (sz < 0 || (unsigned long)sz > ((unsigned long)1 << 31)) { std::fclose(f); return false; }    // directories, pipes, > 2 GiB: not an input file of this path
+  try { buf.resize((size_t)sz); } catch (...) { std::fclose(f); return false; }
   const size_t got = sz ? std::fread(buf.data(), 1, (size_t)sz, f) : 0;
   std::fclose(f);
   return got == (size_t)sz;
@@ -80,7 +80,11 @@ int png_decode(const char* path, PngHeader& H, std::vector<unsigned char>& out) 
   int rc = png_parse(file, H, &idat);
   if (rc != VDO_OK) return rc;
   const size_t bpp = (size_t)H.channels * H.depth / 8, row = (size_t)H.w * bpp;
-  std::vector<unsigned char> raw((row + 1) * (size_t)H.h);
+  // the header's size is untrusted: deflate expands at most ~1032x, so an image that claims more bytes than the compressed stream could
+  // possibly hold (or an absurd size) is rejected before anything is allocated
+  if ((size_t)H.w > 65536 || (size_t)H.h > 65536 || (row + 1) * (size_t)H.h > idat.size() * 1100 + 4096) return VDO_ERR_ARG;
+  std::vector<unsigned char> raw;
+  try { raw.resize((row + 1) * (size_t)H.h); out.reserve(row * (size_t)H.h); } catch (...) { return VDO_ERR_ARG; }
   uLongf n = (uLongf)raw.size();
   if (uncompress(raw.data(), &n, idat.data(), (uLong)idat.size()) != Z_OK || n != raw.size()) return VDO_ERR_ARG;
   out.assign(row * (size_t)H.h, 0);
