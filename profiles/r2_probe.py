@@ -41,7 +41,7 @@ for var in os.environ.get("TOLS", "1e-8,1e-6,1e-5,1e-4").split(","):
     print(f"tol {tol}:", json.dumps(out[f"tol{tol}"]), flush=True)
 G.reset(); G.optimize()
 kt = {}
-for k in ["schur_static", "schur_chains", "schur_vertex_obs", "hpp_mul", "pcg_step", "pcg_iterate8", "lin_static", "lin_chains", "lin_vertex_obs", "precond", "chi2_tracklets", "factor_landmarks"]:
+for k in ["schur_static", "schur_chains", "schur_vertex_obs", "hpp_mul", "pcg_step", "pcg_iterate8", "lin_static", "lin_chains", "lin_vertex_obs", "precond", "band_form", "precond_tiles", "pcr_factor", "pcg_step_a", "chi2_tracklets", "factor_landmarks"]:
     try:
         kt[k] = G.time_kernel(k, 20)
     except Exception as e:

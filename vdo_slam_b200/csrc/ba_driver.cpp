@@ -640,6 +640,31 @@ int BaGraph::finalize() {
     const bool want = !(env && std::string(env) == "0");
     if (want && tiled && world == 1 && Tstat == T && 6 * C <= be_->dense_capacity()) d.Sdense = dalloc<double>((size_t)36 * C * C + 6 * (size_t)C + 8);
   }
+  if (tiled && !d.Sdense && Tstat > 0 && be_->band_max_width() > 0) {
+    // Explicit static block of the reduced matrix (banded in the se3 numbering): possible when every static landmark lists its
+    // observing vertices in strictly increasing order within a window of band_max_width() consecutive vertex numbers (tracks over
+    // consecutive frames).  Otherwise the matrix-free static tile kernel stays in the PCG.
+    const char* env = std::getenv("VDO_BA_BAND");      // "0": never
+    const int Wmax = be_->band_max_width();
+    std::vector<int> w_W(NT, 0), w_v0(NT, C), w_v1(NT, -1), w_bad(NT, 0);
+    parallel_for(NT, [&](int t, int n) {
+      const int a = (int)((int64_t)Tstat * t / n), b = (int)((int64_t)Tstat * (t + 1) / n);
+      int W = 0, v0 = C, v1 = -1, bad = 0;
+      for (int k = a; k < b && !bad; ++k) {
+        const int e0 = lm_begin[k], e1 = lm_begin[k + 1];
+        if (e1 <= e0) continue;
+        for (int e = e0 + 1; e < e1; ++e) if (lm_cam[e] <= lm_cam[e - 1]) { bad = 1; break; }
+        W = std::max(W, lm_cam[e1 - 1] - lm_cam[e0] + 1); v0 = std::min(v0, lm_cam[e0]); v1 = std::max(v1, lm_cam[e1 - 1]);
+      }
+      w_W[t] = W; w_v0[t] = v0; w_v1[t] = v1; w_bad[t] = bad;
+    });
+    int W = 0, v0 = C, v1 = -1, bad = 0;
+    for (int t = 0; t < NT; ++t) { W = std::max(W, w_W[t]); v0 = std::min(v0, w_v0[t]); v1 = std::max(v1, w_v1[t]); bad |= w_bad[t]; }
+    if (!(env && std::string(env) == "0") && !bad && v1 >= v0 && W <= Wmax && (size_t)(v1 - v0 + 1) * W * 80 <= ((size_t)512 << 20)) {
+      d.band_W = W; d.band_v0 = v0; d.band_n = v1 - v0 + 1;
+      d.band = dalloc<double>((size_t)d.band_n * W * 10);
+    }
+  }
   d.zl = tiled ? nullptr : dalloc<double>(3 * (size_t)P); d.xl = dalloc<double>(3 * (size_t)P); d.vw = dalloc<double>(6 * (size_t)C);
   oc.w.resize(256, 0.0); oc.d.resize(256, 0.0); tc.w.resize(256, 0.0); tc.d.resize(256, 0.0);
   d.obs_cls_w = upload(oc.w); d.obs_cls_d = upload(oc.d); d.ter_cls_w = upload(tc.w); d.ter_cls_d = upload(tc.d);
@@ -743,6 +768,7 @@ bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   {
   Phase ph(be_, &prof_ms_[0], prof);
   be_->factor_landmarks(d, lambda);
+  if (d.band) be_->band_form(d);
   be_->zero(d.scal + SC_BAD, sizeof(double));
   be_->precond_begin(d, lambda);
   be_->precond_vertex_obs(d);
@@ -909,6 +935,9 @@ int BaGraph::time_kernel(const char* name, int reps, float* ms_avg) {
     else if (n == "linearize") linearize();
     else if (n == "factor_landmarks") be_->factor_landmarks(d, lam);
     else if (n == "precond") { be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); be_->precond_factor(d, lam); }
+    else if (n == "band_form") be_->band_form(d);
+    else if (n == "precond_tiles") { be_->precond_begin(d, lam); be_->precond_vertex_obs(d); be_->precond_vertex_ter(d); }
+    else if (n == "pcr_factor") be_->precond_factor(d, lam);
     else if (n == "schur_landmarks") be_->schur_landmarks(d, 1, d.p);
     else if (n == "schur_static") be_->schur_landmarks_part(d, 1, d.p, 0);
     else if (n == "schur_chains") be_->schur_landmarks_part(d, 1, d.p, 1);

@@ -345,31 +345,159 @@ __global__ void __launch_bounds__(128) k_hpp_mul(BaDev d, const double* __restri
 // CL = CTAs per cluster: PCR_CL for long paths, 1 (plain CTA, the cluster barrier degenerates to a CTA barrier) for paths of at most
 // PCR_SHORT vertices -- most paths are short (objects seen for a few frames, single motion vertices) and a cluster of 8 CTAs each would only
 // multiply the number of waves the launch needs.  path0: position of the launch's first path in own_paths (long paths first).
+// In-place Gauss-Jordan inverse of an SPD 6x6 whose row i lives in lane i of an aligned 8-lane group (lanes 6, 7 of the group and groups
+// without a vertex carry the identity; every lane of the warp executes the shuffles).  The pivots are those of the LDL^T factorisation:
+// a non-positive (or non-finite) one reports "not SPD" exactly where the Cholesky of body_pcr_invert does.
+__device__ __forceinline__ bool gj6_rows(double (&a)[6], int i) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double rk[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) rk[c] = __shfl_sync(0xffffffffu, a[c], k, 8);
+    const double piv = rk[k];
+    if (!(piv > 0.0) || !(piv < 1e300)) ok = false;
+    const double pinv = 1.0 / piv;
+    if (i == k) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a[c] = (c == k) ? pinv : rk[c] * pinv;
+    } else {
+      const double f = a[k] * pinv;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a[c] = (c == k) ? -f : a[c] - f * rk[c];
+    }
+  }
+  return ok;
+}
+// Factorisation of the block-tridiagonal preconditioner of one se3 path by parallel cyclic reduction: ONE pass and one cluster barrier per
+// level (the first version ran three passes of (vertex, row, column) items per level, each behind a barrier and a round trip through L2:
+// 0.55 ms for the 1000-vertex camera path, 12 % of a solve).  An 8-lane group owns a vertex, lane i its row i of every block:
+//   A_v = -L_v Dinv_{v-s},  G_v = -L_{v+s}^T Dinv_{v+s},  D'_v = D_v + A_v L_v^T + G_v L_{v+s},  L'_v = A_v L_{v-s},  Dinv'_v = (D'_v)^-1
+// all from level-l data of v and v +- s (Dinv' is formed by the group at the end of the level, in registers, with shuffles), so the only
+// exchange between groups is the barrier that closes the level.  D is updated in place (a group reads only its own rows); L and Dinv are
+// double buffered (Dinv: pcr_Dinv / second half of pcr_D).  The arrays are read with plain loads: other CTAs of the cluster wrote them.
 template <int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) k_pcr_factor(BaDev d, double lambda, int path0) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_pcr_factor(BaDev d, double lambda, int path0) {
   cg::cluster_group cl = cg::this_cluster();
   const int path = d.own_paths[path0 + blockIdx.x / CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
   const int nl = pcr_num_levels(pe - pb);
   const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = CL * blockDim.x;
+  const int grp = tid >> 3, i = tid & 7, ngrp = nth >> 3;
   const size_t N36 = 36 * (size_t)d.C;
-  int bad = 0, cur = 0;
-  for (int v = pb + tid; v < pe; v += nth) body_pcr_setup(d, v, d.pcr_D, d.pcr_L);
+  double* const Dm = d.pcr_D;                                // level matrix D, in place
+  double* const DI[2] = {d.pcr_Dinv, d.pcr_D + N36};
+  int bad = 0;
+  const int n_round = (pe - pb + ngrp - 1) / ngrp;
+  // identity rows for the lanes without work (keeps gj6_rows finite)
+  auto idle_row = [&](double (&a)[6]) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a[c] = (c == (i % 6)) ? 1.0 : 0.0;
+  };
+  auto finish = [&](double (&a)[6], bool act, int v, double* out) {      // a = row i of D'_v on entry; writes row i of its inverse
+    double dii = 1.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) if (act && c == i) dii = a[c];
+    const bool ok = gj6_rows(a, i);
+    if (!act) return;
+    if (!ok) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a[c] = (c == i) ? 1.0 / (fabs(dii) + lambda) : 0.0;
+      if (i == 0) bad = 1;
+    }
+    double* o = out + 36 * (size_t)v + 6 * i;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) o[c] = a[c];
+  };
+  // level 0: D = assembled diagonal block (in Minv), L = M(v, v-1) from the se3-se3 edge block; Dinv_0
+  for (int r = 0; r < n_round; ++r) {
+    const int v = pb + r * ngrp + grp;
+    const bool act = v < pe && i < 6;
+    double a[6];
+    idle_row(a);
+    if (act) {
+      const double* S = d.Minv + 36 * (size_t)v + 6 * i;
+      double* Dv = Dm + 36 * (size_t)v + 6 * i;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { a[c] = S[c]; Dv[c] = a[c]; }
+      const int e = d.pcr_edge[v];
+      double* Lv = d.pcr_L + 36 * (size_t)v + 6 * i;
+      if (e < 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Lv[c] = 0.0;
+      } else {
+        const double* B = d.se_Hoff + 36 * (size_t)e;
+        const bool tr = d.pcr_tr[v] != 0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Lv[c] = tr ? B[6 * c + i] : B[6 * i + c];
+      }
+    }
+    finish(a, act, v, nl > 0 ? DI[0] : d.Minv);
+  }
   if (nl > 0) cl.sync();
+  int cur = 0;
   for (int l = 0; l < nl; ++l) {
-    const double *D = d.pcr_D + cur * N36, *L = d.pcr_L + cur * N36;
-    double *Dn = d.pcr_D + (1 - cur) * N36, *Ln = d.pcr_L + (1 - cur) * N36;
+    const double* L = d.pcr_L + cur * N36; double* Ln = d.pcr_L + (1 - cur) * N36;
+    const double* Di = DI[cur]; double* Dout = (l + 1 < nl) ? DI[1 - cur] : d.Minv;
     double *A = d.pcr_A + l * N36, *G = d.pcr_G + l * N36;
-    const int n_items = 36 * (pe - pb), s = 1 << l;
-    for (int v = pb + tid; v < pe; v += nth) body_pcr_invert(d, v, D, d.pcr_Dinv, lambda, &bad);
-    cl.sync();
-    for (int w = tid; w < n_items; w += nth) { const int v = pb + w / 36, rc = w % 36; body_pcr_AG(v, rc / 6, rc % 6, pb, pe, s, L, d.pcr_Dinv, A, G); }
-    cl.sync();
-    for (int w = tid; w < n_items; w += nth) { const int v = pb + w / 36, rc = w % 36; body_pcr_DL(v, rc / 6, rc % 6, pb, pe, s, D, L, A, G, Dn, Ln); }
-    cl.sync();
+    const int s = 1 << l;
+    for (int r = 0; r < n_round; ++r) {
+      const int v = pb + r * ngrp + grp;
+      const bool act = v < pe && i < 6;
+      double dn[6];
+      idle_row(dn);
+      if (act) {
+        const bool hm = v - s >= pb, hp = v + s < pe, hmm = v - 2 * s >= pb;
+        const double* Lv = L + 36 * (size_t)v;
+        double av[6] = {0, 0, 0, 0, 0, 0}, gv[6] = {0, 0, 0, 0, 0, 0}, ln[6] = {0, 0, 0, 0, 0, 0};
+        double* Dv = Dm + 36 * (size_t)v + 6 * i;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dn[c] = Dv[c];
+        if (hm) {
+          const double* Dim = Di + 36 * (size_t)(v - s);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const double lk = Lv[6 * i + k];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) av[c] -= lk * Dim[6 * k + c];
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dn[c] += av[k] * Lv[6 * c + k];
+          }
+          if (hmm) {
+            const double* Lm = L + 36 * (size_t)(v - s);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) ln[c] += av[k] * Lm[6 * k + c];
+            }
+          }
+        }
+        if (hp) {
+          const double* Lp = L + 36 * (size_t)(v + s); const double* Dip = Di + 36 * (size_t)(v + s);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const double lk = Lp[6 * k + i];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) gv[c] -= lk * Dip[6 * k + c];
+          }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) dn[c] += gv[k] * Lp[6 * k + c];
+          }
+        }
+        double* Ao = A + 36 * (size_t)v + 6 * i; double* Go = G + 36 * (size_t)v + 6 * i; double* Lo = Ln + 36 * (size_t)v + 6 * i;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { Ao[c] = av[c]; Go[c] = gv[c]; Lo[c] = ln[c]; Dv[c] = dn[c]; }
+      }
+      finish(dn, act, v, Dout);
+    }
+    if (l + 1 < nl) cl.sync();
     cur = 1 - cur;
   }
-  for (int v = pb + tid; v < pe; v += nth) body_pcr_invert(d, v, d.pcr_D + cur * N36, d.Minv, lambda, &bad);
   if (bad) atomicAdd(d.scal + SC_BAD, 1.0);
 }
 
@@ -1090,7 +1218,9 @@ struct CudaBackend : BaBackend {
   void tile_schur(BaDev& d, int mode, int part, cudaStream_t chain_stream) {
     const int ns = d.n_tiles_stat, nc = d.n_tiles - d.n_tiles_stat;
     const size_t bs = SMEM_SCH_ST, bc = SMEM_SCH_CH;
-    if (part != 1 && ns > 0) {
+    if (part != 1 && ns > 0 && mode == 1 && d.band) {
+      k_band_mul<<<nblk(d.band_n, 8), 256, 0, st>>>(d); ++n_launch;
+    } else if (part != 1 && ns > 0) {
       const size_t sm2 = smem_sch2(false, d.capE_st, d.capV_st, 1);
       if (mode == 0) k_tile_schur2<false, 0><<<ns, VDO_TILE_L, sm2, st>>>(d, 0, d.capE_st, d.capV_st, 1);
       else if (mode == 1) k_tile_schur2<false, 1><<<ns, VDO_TILE_L, sm2, st>>>(d, 0, d.capE_st, d.capV_st, 1);
@@ -1125,6 +1255,13 @@ struct CudaBackend : BaBackend {
     int n = d.C * 6 + d.P;
     LAUNCH(k_max_diagonal, min(nblk(n, 256), 148 * 8), 256, d);
   }
+  int band_max_width() const override { return 32; }
+  void band_form(BaDev& d) override {
+    if (!d.band || d.n_tiles_stat <= 0) return;
+    zero(d.band, sizeof(double) * 10 * (size_t)d.band_n * d.band_W);
+    const int per = max(1, (d.n_tiles_stat + 148 * 3 - 1) / (148 * 3));          // 3 CTAs per SM, each a run of consecutive tiles
+    k_band_form<<<nblk(d.n_tiles_stat, per), VDO_TILE_L, smem_band(d.capE_st), st>>>(d, per, d.capE_st); ++n_launch;
+  }
   void factor_landmarks(BaDev& d, double lambda) override { LAUNCH(k_factor_landmarks, nblk(d.T, 128), 128, d, lambda); }
   void precond_begin(BaDev& d, double lambda) override { LAUNCH(k_precond_begin, nblk(d.C * 36, 128), 128, d, lambda); }
   void precond_vertex_obs(BaDev& d) override {
@@ -1139,7 +1276,8 @@ struct CudaBackend : BaBackend {
   void precond_vertex_ter(BaDev& d) override { if (d.tiled) return; auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
   // long paths (clusters of PCR_CL CTAs) first in own_paths, then the short ones (one CTA each)
   void precond_factor(BaDev& d, double lambda) override {
-    LAUNCH(k_pcr_factor<PCR_CL>, d.n_own_long * PCR_CL, 256, d, lambda, 0);
+    static const int thr = [] { const char* e = std::getenv("VDO_PCR_FACTOR_THREADS"); const int t = e ? std::atoi(e) : 512; return (t >= 64 && t <= 512 && t % 32 == 0) ? t : 512; }();
+    LAUNCH(k_pcr_factor<PCR_CL>, d.n_own_long * PCR_CL, thr, d, lambda, 0);
     LAUNCH(k_pcr_factor<1>, d.n_own_paths - d.n_own_long, 256, d, lambda, d.n_own_long);
   }
   template <bool FUSED> void launch_step_a(BaDev& d, const double* p) {
@@ -1312,6 +1450,7 @@ BaBackend* make_backend(int device, char* err, size_t errlen) {
     optin((const void*)k_tile_schur<false, 0>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 1>, SMEM_SCH_ST); optin((const void*)k_tile_schur<false, 2>, SMEM_SCH_ST);
     optin((const void*)k_tile_precond<false>, SMEM_PRE_ST); optin((const void*)k_tile_precond<true>, SMEM_PRE_CH);
     optin((const void*)k_tile_schur2<false, 0>, smem_sch2(false, VDO_TILE_E, 255, 1)); optin((const void*)k_tile_schur2<false, 1>, smem_sch2(false, VDO_TILE_E, 255, 1));
+    optin((const void*)k_band_form, smem_band(VDO_TILE_E));
     optin((const void*)k_tile_schur2<true, 0>, smem_sch2(true, VDO_TILE_E, 255, 255)); optin((const void*)k_tile_schur2<true, 1>, smem_sch2(true, VDO_TILE_E, 255, 255));
     optin((const void*)k_dense_chol, sizeof(double) * (size_t)DENSE_MAX * (DENSE_MAX + 1));
     optin((const void*)k_tile_schur<true, 0>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 1>, SMEM_SCH_CH); optin((const void*)k_tile_schur<true, 2>, SMEM_SCH_CH);

@@ -553,6 +553,163 @@ __global__ void __launch_bounds__(VDO_TILE_L, CHAINS ? 4 : 5) k_tile_schur2(BaDe
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------------------
+// Banded static block of the reduced matrix.  band[(a - band_v0) * W + k] holds the 10 moments  sum_l g [1, p_l, p_l p_l^T],
+// g = om_la om_l(a+k) / s_l, over the static landmarks seen by both vertex a and vertex a + k (k = 0: om_la^2 / s_l): everything S_static
+// needs (the Jacobians are [I ; p x] up to the per-vertex frame change the finalize kernel applies).  It is re-formed for every LM trial
+// (s_l = sum om + lambda) and turns the PCG's static product from a 79 MB pass over the edges into a 2.4 MB banded multiply (k_band_mul).
+//
+// Formation: CTAs own runs of consecutive static tiles (tiles are ordered by first vertex, so a run meets a window of ~40 vertices).  Per tile,
+// a WARP takes a vertex c of the tile and walks c's edges in the tile's vertex-sorted order, four edges per step: lane = (edge of the step, offset
+// k < 8).  A landmark's edges are sorted by vertex, so the partner edge of edge i for offset k is at most k places further.  All lanes of a warp
+// run the same trip count (a first version with one thread per (vertex, k) ran at the longest edge list of the 32 vertices in its warp: 0.8 ms).
+// The few pairs with offset >= 8 (tracks longer than 8 frames) are done by a thread per landmark.  Sums go to a shared-memory window of the
+// CTA (vertex x offset x 10 moments) and from there to the band with atomics when the run ends: 10 atomics per (vertex, k) and RUN of tiles.
+constexpr int BAND_SPAN = 40, BAND_KS = 16, BAND_NEAR = 8;   // window: vertices x offsets kept in shared memory (the rest goes straight to global atomics)
+inline size_t smem_band(int capE) {
+  return sb(3 * VDO_TILE_L * 8) + sb(VDO_TILE_L * 8) + sb((VDO_TILE_L + 1) * 4) + sb((size_t)capE * 8) + sb((size_t)capE) + sb((size_t)capE * 4) + 3 * sb(256 * 4) +
+         sb((size_t)BAND_SPAN * BAND_KS * 10 * 8);
+}
+__global__ void __launch_bounds__(VDO_TILE_L, 3) k_band_form(BaDev d, int tiles_per_cta, int capE) {
+  extern __shared__ __align__(16) unsigned char tile_sh[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* c0 = tile_sh;
+  auto carve = [&](size_t bytes) { unsigned char* p = c0; c0 += sb(bytes); return p; };
+  double* sP = (double*)carve(3 * VDO_TILE_L * 8);
+  double* sIS = (double*)carve(VDO_TILE_L * 8);
+  int* sLB = (int*)carve((VDO_TILE_L + 1) * 4);
+  double* sOM = (double*)carve((size_t)capE * 8);
+  uint8_t* sCS = (uint8_t*)carve((size_t)capE);
+  uint32_t* sPS = (uint32_t*)carve((size_t)capE * 4);
+  int* sTV = (int*)carve(256 * 4);
+  int* sQ0 = (int*)carve(256 * 4);
+  int* sQ1 = (int*)carve(256 * 4);
+  double* sACC = (double*)carve((size_t)BAND_SPAN * BAND_KS * 10 * 8);
+  __shared__ int sML[2];                                       // longest track of the current tile (double buffered: reset one tile ahead)
+  if (tid < 2) sML[tid] = 0;
+  const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, d.n_tiles_stat);
+  if (t_begin >= t_end) return;
+  for (int i = tid; i < BAND_SPAN * BAND_KS * 10; i += VDO_TILE_L) sACC[i] = 0.0;
+  const int W = d.band_W;
+  const int vbase = d.tile_verts[d.tiles[t_begin].vs0];
+  auto moments = [&](double g, int l, double (&acc)[10]) {
+    const double px = sP[3 * l], py = sP[3 * l + 1], pz = sP[3 * l + 2];
+    const double gx = g * px, gy = g * py, gz = g * pz;
+    acc[0] += g; acc[1] += gx; acc[2] += gy; acc[3] += gz;
+    acc[4] += gx * px; acc[5] += gx * py; acc[6] += gx * pz; acc[7] += gy * py; acc[8] += gy * pz; acc[9] += gz * pz;
+  };
+  for (int t = t_begin; t < t_end; ++t) {
+    const Tile tl = d.tiles[t];
+    const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0, ncam = tl.nv & 0xFFFF, n_os = tl.qo1 - tl.qo0;
+    __syncthreads();                                           // the previous tile is done with the staged arrays
+    if (tid < nl) {
+      const size_t k = (size_t)tl.k0 + tid;
+      sP[3 * tid] = d.pt[3 * k]; sP[3 * tid + 1] = d.pt[3 * k + 1]; sP[3 * tid + 2] = d.pt[3 * k + 2];
+      sIS[tid] = 1.0 / d.pt_s[k];
+    }
+    for (int i = tid; i <= nl; i += VDO_TILE_L) sLB[i] = d.lm_obs_begin[tl.k0 + i] - tl.e0;
+    for (int e = tid; e < ne; e += VDO_TILE_L) { sOM[e] = d.lm_omega[tl.e0 + e]; sCS[e] = d.lm_cslot[tl.e0 + e]; sPS[e] = d.ob_ps[tl.e0 + e]; }
+    if (tid < ncam) sTV[tid] = d.tile_verts[tl.vs0 + tid];
+    __syncthreads();
+    for (int s = tid; s < n_os; s += VDO_TILE_L) {
+      const Seg g = d.osegs2[tl.qo0 + s];
+      const int q0 = g.begin - tl.e0, slot = sCS[sPS[q0] & 0xFFFFu];
+      if (s == 0 || d.osegs2[tl.qo0 + s - 1].v != g.v) sQ0[slot] = q0;
+      if (s == n_os - 1 || d.osegs2[tl.qo0 + s + 1].v != g.v) sQ1[slot] = q0 + g.n;
+    }
+    if (tid < nl && sLB[tid + 1] > sLB[tid]) atomicMax(&sML[t & 1], sTV[sCS[sLB[tid + 1] - 1]] - sTV[sCS[sLB[tid]]] + 1);
+    if (tid == 0) sML[(t + 1) & 1] = 0;
+    __syncthreads();
+    const int vlast = sTV[ncam - 1];
+    // warp per vertex, lane = (sub-edge, offset within a sweep of 8 offsets); sweeps beyond the first only when the tile has tracks that long
+    const int sub = lane >> 3, maxlen = sML[t & 1];
+    for (int c = warp; c < ncam; c += VDO_TILE_L / 32) {
+      const int vc = sTV[c], qb = sQ0[c], qe = sQ1[c];
+      const int kmax = min(min(W, maxlen), vlast - vc + 1);      // offsets that can have a pair at all
+      for (int k0 = 0; k0 < kmax; k0 += 8) {
+        const int k = k0 + (lane & 7), target = vc + k;
+        double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (k < kmax)
+          for (int q = qb + sub; q < qe; q += 4) {
+            const uint32_t ps = sPS[q];
+            const int i = (int)(ps & 0xFFFFu), l = (int)(ps >> 16);
+            int j = i;
+            if (k > 0) {
+              j = min(i + k, sLB[l + 1] - 1);
+              while (j > i && sTV[sCS[j]] > target) --j;
+              if (j == i || sTV[sCS[j]] != target) continue;
+            }
+            moments(sOM[i] * sOM[j] * sIS[l], l, acc);
+          }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 10; ++m) { acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 8); acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 16); }
+        if (lane < 8 && acc[0] != 0.0) {
+          const int r = vc - vbase;
+          if (r >= 0 && r < BAND_SPAN && k < BAND_KS) {
+            double* dst = sACC + ((size_t)r * BAND_KS + k) * 10;    // this warp is the only writer of vertex vc's entries in this tile
+#pragma unroll
+            for (int m = 0; m < 10; ++m) dst[m] += acc[m];
+          } else {
+            double* dst = d.band + ((size_t)(vc - d.band_v0) * W + k) * 10;
+#pragma unroll
+            for (int m = 0; m < 10; ++m) atomicAdd(dst + m, acc[m]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < BAND_SPAN * BAND_KS; e += VDO_TILE_L) {
+    const int r = e / BAND_KS, k = e - r * BAND_KS;
+    const double* src = sACC + (size_t)e * 10;
+    if (src[0] == 0.0 || k >= W) continue;
+    double* dst = d.band + ((size_t)(vbase + r - d.band_v0) * W + k) * 10;
+#pragma unroll
+    for (int m = 0; m < 10; ++m) atomicAdd(dst + m, src[m]);
+  }
+}
+
+// S_static * p from the band (replaces k_tile_schur2<static, 1> inside the PCG): one warp per row a, lanes over the offsets -(W-1) .. W-1.
+// With vw_b = [gamma_b ; beta_b] and the moments (M0, M1, M2) of the pair (a, b):
+//   F_o[a] -= M0 gamma_b + 2 M1 x beta_b,      M_o[a] -= 2 (M1 x gamma_b + 2 (M2 - tr(M2) I) beta_b)
+// (the sums the static tile kernel leaves in acc6: p x (p x beta) = (p p^T - |p|^2 I) beta).  The band is 2.4 MB for 1000 cameras and W = 30:
+// L2-resident, against 79 MB of edge data per product for the matrix-free kernel.
+__global__ void __launch_bounds__(256) k_band_mul(BaDev d) {
+  if (d.scal[SC_DONE] != 0.0) return;
+  const int a = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (a >= d.band_n) return;
+  const int W = d.band_W;
+  double F[3] = {0, 0, 0}, M[3] = {0, 0, 0};
+  for (int o = lane; o < 2 * W - 1; o += 32) {
+    const int kk = o - (W - 1), b = a + kk;
+    if (b < 0 || b >= d.band_n) continue;
+    const double* m = d.band + (kk >= 0 ? ((size_t)a * W + kk) : ((size_t)b * W - kk)) * 10;
+    const double m0 = m[0];
+    if (m0 == 0.0) continue;
+    const double* w = d.vw + 6 * (size_t)(d.band_v0 + b);
+    const double g[3] = {w[0], w[1], w[2]}, be[3] = {w[3], w[4], w[5]};
+    const double m1[3] = {m[1], m[2], m[3]};
+    double c1[3], c2[3];
+    cross3(m1, be, c1); cross3(m1, g, c2);
+    const double tr = m[4] + m[7] + m[9];
+    const double q0 = m[4] * be[0] + m[5] * be[1] + m[6] * be[2] - tr * be[0];
+    const double q1 = m[5] * be[0] + m[7] * be[1] + m[8] * be[2] - tr * be[1];
+    const double q2 = m[6] * be[0] + m[8] * be[1] + m[9] * be[2] - tr * be[2];
+    F[0] -= m0 * g[0] + 2 * c1[0]; F[1] -= m0 * g[1] + 2 * c1[1]; F[2] -= m0 * g[2] + 2 * c1[2];
+    M[0] -= 2 * (c2[0] + 2 * q0); M[1] -= 2 * (c2[1] + 2 * q1); M[2] -= 2 * (c2[2] + 2 * q2);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { F[i] += __shfl_down_sync(0xffffffffu, F[i], s); M[i] += __shfl_down_sync(0xffffffffu, M[i], s); }
+  }
+  if (lane == 0) {
+    double* dst = d.acc6 + 12 * (size_t)(d.band_v0 + a);
+    atomicAdd(dst, F[0]); atomicAdd(dst + 1, F[1]); atomicAdd(dst + 2, F[2]); atomicAdd(dst + 3, M[0]); atomicAdd(dst + 4, M[1]); atomicAdd(dst + 5, M[2]);
+  }
+}
+
 // per vertex: out_v += sign * B^T [F ; M - t x (2 F_o + F_t)] (torque moved to the vertex origin); clears the sums.
 // With pdot != NULL also the CTA's share of pdot . out (fixed order) into part_pap[blockIdx.x]: the PCG's p.Ap without another launch.
 __global__ void __launch_bounds__(128) k_tile_finalize_schur2(BaDev d, double sign, double* __restrict__ out, int check_done, const double* __restrict__ pdot) {

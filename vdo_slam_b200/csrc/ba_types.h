@@ -73,6 +73,9 @@ struct BaDev {
   double *pcr_A = 0, *pcr_G = 0;  // pcr_levels * C * 36 : elimination operators per level
   double *pcr_b = 0;              // 2 * C * 6 scratch of the solve   // per landmark: diagonal scalar of Hll^-1; per ternary edge: g_k + g_k+1 - 2 g_k,k+1
   double *xp = 0, *r = 0, *z = 0, *p = 0, *Ap = 0, *rhs = 0; // 6C each
+  // banded static block of the reduced matrix (see k_band_mul): for rows [band_v0, band_v0 + band_n) of se3 vertices and offsets 0..band_W-1,
+  // the 10 moments sum_l (om_la om_lb / s_l) [1, p_l, p_l p_l^T] over the static landmarks seen by both; re-formed per trial (s_l holds lambda)
+  double* band = 0; int band_W = 0, band_v0 = 0, band_n = 0;
   double* Sdense = 0;       // (6C)^2 + 6C + 8: dense reduced matrix, right-hand side and status of the dense path (only allocated for small static-only graphs)
   double* p2 = 0;           // 6C: second buffer of the search direction (the fused PCG kernels write p_{k+1} = z + beta p_k out of place)
   unsigned int* ticket = 0; // "last CTA done" counters of the fused PCG step ([0]) and of the peer exchange ([1])
@@ -230,6 +233,9 @@ struct BaBackend {
   // BlockSolver Schur path of g2o/core/block_solver.hpp:352-486 instead of the matrix-free PCG.  dense_capacity(): largest 6C (0: unsupported);
   // dense_solve(): xp = S^-1 (bp - Hpl Hll^-1 bl) after factor_landmarks(lambda); returns false when S is not positive definite.
   virtual int dense_capacity() const { return 0; }
+  // widest supported band of the explicit static block (0: the backend has no band path); band_form(): fill d.band after factor_landmarks
+  virtual int band_max_width() const { return 0; }
+  virtual void band_form(BaDev& d) { (void)d; }
   virtual bool dense_solve(BaDev& d, double lambda) { (void)d; (void)lambda; return false; }
   // multi-GPU: may turn on path sharding of the preconditioner for this graph (collective; called once from finalize after d is complete).
   // Returns the list of paths this rank owns (default: every path).
