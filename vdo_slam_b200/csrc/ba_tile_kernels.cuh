@@ -565,9 +565,9 @@ __global__ void __launch_bounds__(VDO_TILE_L, CHAINS ? 4 : 5) k_tile_schur2(BaDe
 // run the same trip count (a first version with one thread per (vertex, k) ran at the longest edge list of the 32 vertices in its warp: 0.8 ms).
 // The few pairs with offset >= 8 (tracks longer than 8 frames) are done by a thread per landmark.  Sums go to a shared-memory window of the
 // CTA (vertex x offset x 10 moments) and from there to the band with atomics when the run ends: 10 atomics per (vertex, k) and RUN of tiles.
-constexpr int BAND_SPAN = 40, BAND_KS = 16, BAND_NEAR = 8;   // window: vertices x offsets kept in shared memory (the rest goes straight to global atomics)
+constexpr int BAND_SPAN = 36, BAND_KS = 16;   // window: vertices x offsets kept in shared memory (the rest goes straight to global atomics)
 inline size_t smem_band(int capE) {
-  return sb(3 * VDO_TILE_L * 8) + sb(VDO_TILE_L * 8) + sb((VDO_TILE_L + 1) * 4) + sb((size_t)capE * 8) + sb((size_t)capE) + sb((size_t)capE * 4) + 3 * sb(256 * 4) +
+  return sb(3 * VDO_TILE_L * 8) + sb(VDO_TILE_L * 8) + sb((VDO_TILE_L + 1) * 4) + sb((size_t)capE * 8) + 2 * sb((size_t)capE) + 2 * sb((size_t)capE * 4) + 3 * sb(256 * 4) +
          sb((size_t)BAND_SPAN * BAND_KS * 10 * 8);
 }
 __global__ void __launch_bounds__(VDO_TILE_L, 3) k_band_form(BaDev d, int tiles_per_cta, int capE) {
@@ -581,6 +581,8 @@ __global__ void __launch_bounds__(VDO_TILE_L, 3) k_band_form(BaDev d, int tiles_
   double* sOM = (double*)carve((size_t)capE * 8);
   uint8_t* sCS = (uint8_t*)carve((size_t)capE);
   uint32_t* sPS = (uint32_t*)carve((size_t)capE * 4);
+  int* sCAM = (int*)carve((size_t)capE * 4);                  // per edge (landmark-major): its vertex number
+  uint8_t* sREM = (uint8_t*)carve((size_t)capE);              // ... and how many edges of the same landmark follow it
   int* sTV = (int*)carve(256 * 4);
   int* sQ0 = (int*)carve(256 * 4);
   int* sQ1 = (int*)carve(256 * 4);
@@ -618,27 +620,31 @@ __global__ void __launch_bounds__(VDO_TILE_L, 3) k_band_form(BaDev d, int tiles_
       if (s == n_os - 1 || d.osegs2[tl.qo0 + s + 1].v != g.v) sQ1[slot] = q0 + g.n;
     }
     if (tid < nl && sLB[tid + 1] > sLB[tid]) atomicMax(&sML[t & 1], sTV[sCS[sLB[tid + 1] - 1]] - sTV[sCS[sLB[tid]]] + 1);
+    for (int e = tid; e < ne; e += VDO_TILE_L) { sCAM[e] = sTV[sCS[e]]; sREM[e] = (uint8_t)min(255, sLB[(int)d.lm_lml[tl.e0 + e] + 1] - 1 - e); }
     if (tid == 0) sML[(t + 1) & 1] = 0;
     __syncthreads();
     const int vlast = sTV[ncam - 1];
-    // warp per vertex, lane = (sub-edge, offset within a sweep of 8 offsets); sweeps beyond the first only when the tile has tracks that long
+    // Each warp takes an equal share [qa, qb) of the tile's edges in vertex-sorted order (a vertex's edges are contiguous there) and walks it
+    // vertex by vertex, 4 edges per step: lane = (sub-edge, offset within a sweep of 8 offsets); sweeps beyond the first only when the tile has
+    // tracks that long.  A vertex whose edges straddle two shares is summed by both warps: the window is updated with shared-memory atomics.
     const int sub = lane >> 3, maxlen = sML[t & 1];
-    for (int c = warp; c < ncam; c += VDO_TILE_L / 32) {
-      const int vc = sTV[c], qb = sQ0[c], qe = sQ1[c];
+    const int qa = (int)((long long)ne * warp / (VDO_TILE_L / 32)), qb = (int)((long long)ne * (warp + 1) / (VDO_TILE_L / 32));
+    int c = 0;
+    if (qa < qb) { int lo = 0, hi = ncam - 1; while (lo < hi) { const int mid = (lo + hi) >> 1; if (sQ1[mid] > qa) hi = mid; else lo = mid + 1; } c = lo; }
+    for (int q0 = qa; q0 < qb; ++c) {
+      const int q1 = min(sQ1[c], qb), vc = sTV[c];
       const int kmax = min(min(W, maxlen), vlast - vc + 1);      // offsets that can have a pair at all
       for (int k0 = 0; k0 < kmax; k0 += 8) {
         const int k = k0 + (lane & 7), target = vc + k;
         double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (k < kmax)
-          for (int q = qb + sub; q < qe; q += 4) {
+          for (int q = q0 + sub; q < q1; q += 4) {
             const uint32_t ps = sPS[q];
             const int i = (int)(ps & 0xFFFFu), l = (int)(ps >> 16);
-            int j = i;
-            if (k > 0) {
-              j = min(i + k, sLB[l + 1] - 1);
-              while (j > i && sTV[sCS[j]] > target) --j;
-              if (j == i || sTV[sCS[j]] != target) continue;
-            }
+            int j = i + min(k, (int)sREM[i]);                        // a landmark's edges are sorted by vertex: the partner is at most k places on
+            int cj = sCAM[j];
+            while (cj > target) cj = sCAM[--j];                     // (stops at j == i at the latest: vertex vc <= target)
+            if (cj != target) continue;
             moments(sOM[i] * sOM[j] * sIS[l], l, acc);
           }
         __syncwarp();
@@ -646,10 +652,15 @@ __global__ void __launch_bounds__(VDO_TILE_L, 3) k_band_form(BaDev d, int tiles_
         for (int m = 0; m < 10; ++m) { acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 8); acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 16); }
         if (lane < 8 && acc[0] != 0.0) {
           const int r = vc - vbase;
-          if (r >= 0 && r < BAND_SPAN && k < BAND_KS) {
-            double* dst = sACC + ((size_t)r * BAND_KS + k) * 10;    // this warp is the only writer of vertex vc's entries in this tile
+          const bool win = r >= 0 && r < BAND_SPAN && k < BAND_KS;
+          if (win && q0 == sQ0[c] && q1 == sQ1[c]) {               // the whole vertex is this warp's: plain update
+            double* dst = sACC + ((size_t)r * BAND_KS + k) * 10;
 #pragma unroll
             for (int m = 0; m < 10; ++m) dst[m] += acc[m];
+          } else if (win) {
+            double* dst = sACC + ((size_t)r * BAND_KS + k) * 10;
+#pragma unroll
+            for (int m = 0; m < 10; ++m) atomicAdd(dst + m, acc[m]);
           } else {
             double* dst = d.band + ((size_t)(vc - d.band_v0) * W + k) * 10;
 #pragma unroll
@@ -657,6 +668,7 @@ __global__ void __launch_bounds__(VDO_TILE_L, 3) k_band_form(BaDev d, int tiles_
           }
         }
       }
+      q0 = q1;
     }
   }
   __syncthreads();
