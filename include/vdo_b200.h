@@ -134,6 +134,10 @@ int vdo_graph_reset_vertices(vdo_graph *g);
 /* sizes after finalize: out[0]=n_se3 out[1]=n_pt out[2]=n_pointxyz_edges out[3]=n_motion_edges out[4]=n_se3_edges
  * out[5]=n_prior out[6]=n_tracklets out[7]=device bytes held */
 int vdo_graph_info(const vdo_graph *g, int64_t out[8]);
+/* which solver paths the finalized graph uses: out[0]=tiled layout (0/1) out[1]=tiles out[2]=static tiles out[3]=width of the explicit
+ * banded static block of the reduced matrix (0: matrix-free static product) out[4]=rows of that band out[5]=dense reduced-matrix path (0/1)
+ * out[6]=preconditioner sharded by se3 path over the ranks (0/1) out[7]=se3 paths */
+int vdo_graph_solver_info(const vdo_graph *g, int64_t out[8]);
 
 /* Test hooks: one linearisation at the current estimates, returned in the caller's vertex numbering.
  * Hpp_diag: n_se3 x 36 (row-major 6x6 diagonal blocks), bp: n_se3 x 6, Hll_diag: n_pt (scalar: the 3x3

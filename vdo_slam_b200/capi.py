@@ -285,6 +285,11 @@ class BatchGraph:
         self.ctx.check(self.ctx.L.vdo_graph_info(self.h, out), "vdo_graph_info")
         return dict(zip(["n_se3", "n_pt", "n_pointxyz_edges", "n_motion_edges", "n_se3_edges", "n_prior", "n_tracklets", "device_bytes"], list(out)))
 
+    def solver_info(self):
+        out = (C.c_int64 * 8)()
+        self.ctx.check(self.ctx.L.vdo_graph_solver_info(self.h, out), "vdo_graph_solver_info")
+        return dict(zip(["tiled", "n_tiles", "n_static_tiles", "band_width", "band_rows", "dense", "path_sharded", "n_paths"], list(out)))
+
     def time_kernel(self, name: str, reps: int = 20) -> float:
         ms = C.c_float(0)
         self.ctx.check(self.ctx.L.vdo_graph_time_kernel(self.h, name.encode(), C.c_int(reps), C.byref(ms)), f"vdo_graph_time_kernel({name})")

@@ -732,6 +732,12 @@ int BaGraph::info(int64_t out[8]) const {
   return VDO_OK;
 }
 
+int BaGraph::solver_info(int64_t out[8]) const {
+  out[0] = d_.tiled; out[1] = d_.n_tiles; out[2] = d_.n_tiles_stat; out[3] = d_.band ? d_.band_W : 0; out[4] = d_.band ? d_.band_n : 0;
+  out[5] = d_.Sdense ? 1 : 0; out[6] = d_.xg_paths; out[7] = d_.n_paths;
+  return VDO_OK;
+}
+
 // ---- buildSystem (g2o/core/block_solver.hpp:501-560) ----
 void BaGraph::linearize() {
   be_->zero(d_.Hpp, 336 * (size_t)d_.C);          // H_pp diagonal blocks and b_p are one buffer (one all-reduce)
@@ -768,13 +774,13 @@ bool BaGraph::solve(double lambda, const vdo_lm_options& opt, int* pcg_iters) {
   {
   Phase ph(be_, &prof_ms_[0], prof);
   be_->factor_landmarks(d, lambda);
-  if (d.band) be_->band_form(d);
   be_->zero(d.scal + SC_BAD, sizeof(double));
   be_->precond_begin(d, lambda);
   be_->precond_vertex_obs(d);
   be_->precond_vertex_ter(d);
   be_->allreduce_sum(d.Minv, 36 * (size_t)d.C);
   be_->precond_factor(d, lambda);
+  if (d.band) be_->band_form(d);
   }
   {
   Phase ph(be_, &prof_ms_[1], prof);
@@ -940,6 +946,7 @@ int BaGraph::time_kernel(const char* name, int reps, float* ms_avg) {
     else if (n == "pcr_factor") be_->precond_factor(d, lam);
     else if (n == "schur_landmarks") be_->schur_landmarks(d, 1, d.p);
     else if (n == "schur_static") be_->schur_landmarks_part(d, 1, d.p, 0);
+    else if (n == "schur_static_mf") { double* b = d.band; d.band = nullptr; be_->schur_landmarks_part(d, 1, d.p, 0); d.band = b; }   // the matrix-free tile kernel even when the band is on
     else if (n == "schur_chains") be_->schur_landmarks_part(d, 1, d.p, 1);
     else if (n == "lin_static") be_->lin_tracklets_part(d, true, 0);
     else if (n == "lin_chains") be_->lin_tracklets_part(d, true, 1);

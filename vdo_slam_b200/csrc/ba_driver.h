@@ -36,6 +36,7 @@ class BaGraph {
   int get_vertices(double* se3, double* pt);
   int reset_vertices();
   int info(int64_t out[8]) const;
+  int solver_info(int64_t out[8]) const;
   int debug_linearize(double* Hpp, double* bp, double* Hll, double* bl, double* chi2);
   int time_kernel(const char* name, int reps, float* ms_avg);
   const std::string& error() const { return err_; }

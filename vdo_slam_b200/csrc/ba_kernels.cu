@@ -377,7 +377,7 @@ __device__ __forceinline__ bool gj6_rows(double (&a)[6], int i) {
 // exchange between groups is the barrier that closes the level.  D is updated in place (a group reads only its own rows); L and Dinv are
 // double buffered (Dinv: pcr_Dinv / second half of pcr_D).  The arrays are read with plain loads: other CTAs of the cluster wrote them.
 template <int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_pcr_factor(BaDev d, double lambda, int path0) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 2) k_pcr_factor(BaDev d, double lambda, int path0) {
   cg::cluster_group cl = cg::this_cluster();
   const int path = d.own_paths[path0 + blockIdx.x / CL];
   const int pb = d.path_begin[path], pe = d.path_begin[path + 1];
@@ -385,6 +385,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_pcr_factor(B
   const int tid = cl.block_rank() * blockDim.x + threadIdx.x, nth = CL * blockDim.x;
   const int grp = tid >> 3, i = tid & 7, ngrp = nth >> 3;
   const size_t N36 = 36 * (size_t)d.C;
+  __shared__ double sblk[32 * 180];                          // per 8-lane group: the five neighbour blocks of the current round
   double* const Dm = d.pcr_D;                                // level matrix D, in place
   double* const DI[2] = {d.pcr_Dinv, d.pcr_D + N36};
   int bad = 0;
@@ -443,51 +444,45 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(512) k_pcr_factor(B
     const int s = 1 << l;
     for (int r = 0; r < n_round; ++r) {
       const int v = pb + r * ngrp + grp;
-      const bool act = v < pe && i < 6;
+      const bool has_v = v < pe, act = has_v && i < 6;
+      // stage the five blocks the group needs (L_v, Dinv_{v-s}, L_{v-s}, L_{v+s}, Dinv_{v+s}; zeros outside the path) with all loads in flight
+      // at once: read in place they cost one L2 round trip per block, serialised behind the branches (4 us per round, measured)
+      double* blk = sblk + 180 * (threadIdx.x >> 3);
+      __syncwarp();
+      if (has_v) {
+        const bool hm = v - s >= pb, hp = v + s < pe, hmm = v - 2 * s >= pb;
+        const double *s0 = L + 36 * (size_t)v, *s1 = Di + 36 * (size_t)(hm ? v - s : v), *s2 = L + 36 * (size_t)(hm ? v - s : v), *s3 = L + 36 * (size_t)(hp ? v + s : v),
+                     *s4 = Di + 36 * (size_t)(hp ? v + s : v);
+        double tmp[23];
+#pragma unroll
+        for (int u = 0; u < 23; ++u) {
+          const int e = (threadIdx.x & 7) + 8 * u, bq = e / 36, o = e - 36 * bq;
+          const double* sp = bq == 0 ? s0 : bq == 1 ? s1 : bq == 2 ? s2 : bq == 3 ? s3 : s4;
+          const bool on = bq == 0 ? true : bq == 1 ? hm : bq == 2 ? hmm : hp;
+          tmp[u] = (e < 180 && on) ? sp[o] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 23; ++u) { const int e = (threadIdx.x & 7) + 8 * u; if (e < 180) blk[e] = tmp[u]; }
+      }
+      __syncwarp();
       double dn[6];
       idle_row(dn);
       if (act) {
-        const bool hm = v - s >= pb, hp = v + s < pe, hmm = v - 2 * s >= pb;
-        const double* Lv = L + 36 * (size_t)v;
+        const double *Lv = blk, *Dim = blk + 36, *Lm = blk + 72, *Lp = blk + 108, *Dip = blk + 144;
         double av[6] = {0, 0, 0, 0, 0, 0}, gv[6] = {0, 0, 0, 0, 0, 0}, ln[6] = {0, 0, 0, 0, 0, 0};
         double* Dv = Dm + 36 * (size_t)v + 6 * i;
 #pragma unroll
         for (int c = 0; c < 6; ++c) dn[c] = Dv[c];
-        if (hm) {
-          const double* Dim = Di + 36 * (size_t)(v - s);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            const double lk = Lv[6 * i + k];
+        for (int k = 0; k < 6; ++k) {
+          const double lk = Lv[6 * i + k], lp = Lp[6 * k + i];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) av[c] -= lk * Dim[6 * k + c];
-          }
-#pragma unroll
-          for (int c = 0; c < 6; ++c) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) dn[c] += av[k] * Lv[6 * c + k];
-          }
-          if (hmm) {
-            const double* Lm = L + 36 * (size_t)(v - s);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-#pragma unroll
-              for (int c = 0; c < 6; ++c) ln[c] += av[k] * Lm[6 * k + c];
-            }
-          }
+          for (int c = 0; c < 6; ++c) { av[c] -= lk * Dim[6 * k + c]; gv[c] -= lp * Dip[6 * k + c]; }
         }
-        if (hp) {
-          const double* Lp = L + 36 * (size_t)(v + s); const double* Dip = Di + 36 * (size_t)(v + s);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            const double lk = Lp[6 * k + i];
+        for (int k = 0; k < 6; ++k) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) gv[c] -= lk * Dip[6 * k + c];
-          }
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) dn[c] += gv[k] * Lp[6 * k + c];
-          }
+          for (int c = 0; c < 6; ++c) { dn[c] += av[k] * Lv[6 * c + k] + gv[k] * Lp[6 * k + c]; ln[c] += av[k] * Lm[6 * k + c]; }
         }
         double* Ao = A + 36 * (size_t)v + 6 * i; double* Go = G + 36 * (size_t)v + 6 * i; double* Lo = Ln + 36 * (size_t)v + 6 * i;
 #pragma unroll
@@ -1276,8 +1271,7 @@ struct CudaBackend : BaBackend {
   void precond_vertex_ter(BaDev& d) override { if (d.tiled) return; auto k = k_vertex_sym<1, false>; LAUNCH(k, d.n_ter_chunks, 128, d); }
   // long paths (clusters of PCR_CL CTAs) first in own_paths, then the short ones (one CTA each)
   void precond_factor(BaDev& d, double lambda) override {
-    static const int thr = [] { const char* e = std::getenv("VDO_PCR_FACTOR_THREADS"); const int t = e ? std::atoi(e) : 512; return (t >= 64 && t <= 512 && t % 32 == 0) ? t : 512; }();
-    LAUNCH(k_pcr_factor<PCR_CL>, d.n_own_long * PCR_CL, thr, d, lambda, 0);
+    LAUNCH(k_pcr_factor<PCR_CL>, d.n_own_long * PCR_CL, 256, d, lambda, 0);
     LAUNCH(k_pcr_factor<1>, d.n_own_paths - d.n_own_long, 256, d, lambda, d.n_own_long);
   }
   template <bool FUSED> void launch_step_a(BaDev& d, const double* p) {

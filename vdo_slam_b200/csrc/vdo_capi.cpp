@@ -93,6 +93,7 @@ int vdo_graph_optimize(vdo_graph* g, const vdo_lm_options* opt, vdo_lm_stats* st
 int vdo_graph_get_vertices(const vdo_graph* g, double* se3, double* pt) { VDO_FWD(get_vertices(se3, pt)) }
 int vdo_graph_reset_vertices(vdo_graph* g) { VDO_FWD(reset_vertices()) }
 int vdo_graph_info(const vdo_graph* g, int64_t out[8]) { VDO_FWD(info(out)) }
+int vdo_graph_solver_info(const vdo_graph* g, int64_t out[8]) { VDO_FWD(solver_info(out)) }
 int vdo_graph_debug_linearize(vdo_graph* g, double* Hpp, double* bp, double* Hll, double* bl, double* chi2) { VDO_FWD(debug_linearize(Hpp, bp, Hll, bl, chi2)) }
 
 int vdo_graph_time_kernel(vdo_graph* g, const char* name, int reps, float* ms_avg) { VDO_FWD(time_kernel(name, reps, ms_avg)) }
