@@ -14,7 +14,7 @@ g = make_batch_graph(**WORKLOADS[a.workload])
 ctx = capi.Context(0, lib_path=a.lib) if a.lib else capi.Context(0)
 for rep in range(4):
     t = time.perf_counter(); G = capi.BatchGraph(ctx, g); t1 = time.perf_counter() - t
-    t = time.perf_counter(); r = G.optimize(max_iterations=2, gain_threshold=0.0); t2 = time.perf_counter() - t
+    t = time.perf_counter(); r = G.optimize(max_iterations=int(os.environ.get("ITERS", "2")), gain_threshold=0.0) if int(os.environ.get("ITERS", "2")) > 0 else None; t2 = time.perf_counter() - t
     t = time.perf_counter(); G.vertices(); t3 = time.perf_counter() - t
     t = time.perf_counter(); G.close(); t4 = time.perf_counter() - t
     print(f"rep {rep}: ingest {t1*1e3:.1f} ms | 2 LM iterations {t2*1e3:.1f} ms | read-back {t3*1e3:.1f} ms | free {t4*1e3:.1f} ms", flush=True)

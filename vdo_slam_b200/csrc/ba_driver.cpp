@@ -10,7 +10,11 @@
 #include <map>
 #include <numeric>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
+#include <unistd.h>
 
 namespace vdo {
 
@@ -22,12 +26,69 @@ int host_threads() {
   const int v = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
   return std::max(1, std::min(v, 64));
 }
+// Worker pool of the host-side ingest: the ~30 parallel sections of one finalize() would otherwise create and join their threads each time
+// (15 threads x 30 sections: milliseconds of pure thread start-up per graph).  Sections are serialised (one pool per process); a section
+// started from inside a worker runs inline.
+class HostPool {
+ public:
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+    cv_work_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void run(int nthreads, const std::function<void(int, int)>& fn) {
+    if (nthreads <= 1 || inside_) { for (int t = 0; t < nthreads; ++t) fn(t, nthreads); return; }
+    std::lock_guard<std::mutex> section(run_);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      if (pid_ != getpid()) {          // forked child: the parent's workers do not exist here (their std::thread objects are abandoned, not joined)
+        new std::vector<std::thread>(std::move(th_));
+        th_.clear(); pid_ = getpid();
+      }
+      while ((int)th_.size() < nthreads - 1) { const int id = (int)th_.size() + 1; th_.emplace_back([this, id] { worker(id); }); }
+      fn_ = &fn; n_ = nthreads; pending_ = nthreads - 1; ++gen_;
+    }
+    cv_work_.notify_all();
+    inside_ = true; fn(0, nthreads); inside_ = false;
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  void worker(int id) {
+    inside_ = true;
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void(int, int)>* fn = nullptr; int n = 0;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_work_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        if (id < n_) { fn = fn_; n = n_; }
+      }
+      if (!fn) continue;
+      (*fn)(id, n);
+      std::lock_guard<std::mutex> lk(m_);
+      if (--pending_ == 0) cv_done_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_, run_;
+  std::condition_variable cv_work_, cv_done_;
+  const std::function<void(int, int)>* fn_ = nullptr;
+  int n_ = 0, pending_ = 0;
+  unsigned long gen_ = 0;
+  bool stop_ = false;
+  pid_t pid_ = getpid();
+  static thread_local bool inside_;
+};
+thread_local bool HostPool::inside_ = false;
+HostPool& host_pool() { static HostPool* p = new HostPool; return *p; }     // leaked on purpose: no joins during static destruction
 template <typename F> void parallel_for(int nthreads, F fn) {   // fn(thread index, thread count)
   if (nthreads <= 1) { fn(0, 1); return; }
-  std::vector<std::thread> th;
-  for (int t = 1; t < nthreads; ++t) th.emplace_back([=] { fn(t, nthreads); });
-  fn(0, nthreads);
-  for (auto& x : th) x.join();
+  const std::function<void(int, int)> f = fn;
+  host_pool().run(nthreads, f);
 }
 struct Phase {
   BaBackend* be; float* acc; bool on;
@@ -221,17 +282,43 @@ int BaGraph::finalize() {
     }
   });
   lap("  first_cam scan");
-  auto counting_sort = [&](std::vector<int>& ids, const HostBuf<int>& key_of_id, int nkeys) {   // stable
-    std::vector<int> cntk(nkeys + 1, 0), out(ids.size());
-    for (int id : ids) cntk[key_of_id[id] + 1]++;
-    for (int k = 0; k < nkeys; ++k) cntk[k + 1] += cntk[k];
-    for (int id : ids) out[cntk[key_of_id[id]]++] = id;
+  // stable counting sort of ids by key_of_id[id], in parallel: chunk t of the list counts its keys, the (key, chunk) prefix gives every chunk
+  // its output cursor per key, every chunk scatters its ids in order -- the result of a stable sort does not depend on the thread count
+  auto counting_sort = [&](std::vector<int>& ids, const HostBuf<int>& key_of_id, int nkeys) {
+    const size_t n = ids.size();
+    if (n == 0) return;
+    const int W = (n < 65536 || (size_t)nkeys * NT > 4 * n) ? 1 : NT;
+    std::vector<int> keys(n), out(n);
+    std::vector<int> hist((size_t)W * nkeys, 0);
+    parallel_for(W, [&](int t, int w) {
+      const size_t a = n * t / w, b = n * (t + 1) / w;
+      int* h = &hist[(size_t)t * nkeys];
+      for (size_t i = a; i < b; ++i) { const int k = key_of_id[ids[i]]; keys[i] = k; h[k]++; }
+    });
+    { int run = 0; for (int k = 0; k < nkeys; ++k) for (int t = 0; t < W; ++t) { int& h = hist[(size_t)t * nkeys + k]; const int c = h; h = run; run += c; } }
+    parallel_for(W, [&](int t, int w) {
+      const size_t a = n * t / w, b = n * (t + 1) / w;
+      int* h = &hist[(size_t)t * nkeys];
+      for (size_t i = a; i < b; ++i) out[h[keys[i]]++] = ids[i];
+    });
     ids.swap(out);
   };
   std::vector<int> stat_ids, chain_heads;
-  for (int p = 0; p < P; ++p) {
-    if (prev[p] != -1) continue;
-    if (next[p] == -1) stat_ids.push_back(p); else chain_heads.push_back(p);
+  {   // heads of tracklets, in landmark order (parallel count, then fill)
+    std::vector<size_t> ns(NT + 1, 0), nc(NT + 1, 0);
+    parallel_for(NT, [&](int t, int n) {
+      const int a = (int)((int64_t)P * t / n), b = (int)((int64_t)P * (t + 1) / n);
+      size_t s0 = 0, c0 = 0;
+      for (int p = a; p < b; ++p) if (prev[p] == -1) { if (next[p] == -1) ++s0; else ++c0; }
+      ns[t + 1] = s0; nc[t + 1] = c0;
+    });
+    for (int t = 0; t < NT; ++t) { ns[t + 1] += ns[t]; nc[t + 1] += nc[t]; }
+    stat_ids.resize(ns[NT]); chain_heads.resize(nc[NT]);
+    parallel_for(NT, [&](int t, int n) {
+      const int a = (int)((int64_t)P * t / n), b = (int)((int64_t)P * (t + 1) / n);
+      size_t s0 = ns[t], c0 = nc[t];
+      for (int p = a; p < b; ++p) if (prev[p] == -1) { if (next[p] == -1) stat_ids[s0++] = p; else chain_heads[c0++] = p; }
+    });
   }
   lap("  collect heads");
   {   // static landmarks: by first observing camera, inside one camera by DESCENDING edge count -- the lanes of a warp that loops over
@@ -239,7 +326,10 @@ int BaGraph::finalize() {
     int mx = 0;
     for (int p : stat_ids) mx = std::max(mx, cnt_old[p]);
     HostBuf<int> neg = stage<int>(P);
-    for (int p : stat_ids) neg[p] = mx - cnt_old[p];
+    parallel_for(NT, [&](int t, int n) {
+      const size_t a = stat_ids.size() * t / n, b = stat_ids.size() * (t + 1) / n;
+      for (size_t i = a; i < b; ++i) neg[stat_ids[i]] = mx - cnt_old[stat_ids[i]];
+    });
     counting_sort(stat_ids, neg, mx + 1);
   }
   counting_sort(stat_ids, first_cam, C + 1);
