@@ -23,7 +23,7 @@ namespace {
 // graph construction is single-threaded, src/Optimizer.cc:1232-1930).  VDO_HOST_THREADS overrides the default.
 int host_threads() {
   const char* e = std::getenv("VDO_HOST_THREADS");
-  const int v = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  const int v = e ? std::atoi(e) : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
   return std::max(1, std::min(v, 64));
 }
 // Worker pool of the host-side ingest: the ~30 parallel sections of one finalize() would otherwise create and join their threads each time
@@ -98,8 +98,8 @@ struct Phase {
 }  // namespace
 
 void BaGraph::copy_bytes(void* dst, const void* src, size_t bytes) {
-  if (bytes < ((size_t)8 << 20)) { std::memcpy(dst, src, bytes); return; }
-  parallel_for(std::min(host_threads(), 8), [&](int t, int n) {
+  if (bytes < ((size_t)4 << 20)) { std::memcpy(dst, src, bytes); return; }
+  parallel_for(std::min(host_threads(), 16), [&](int t, int n) {
     const size_t a = (bytes * t / n) & ~(size_t)63, b = t + 1 == n ? bytes : ((bytes * (t + 1) / n) & ~(size_t)63);
     std::memcpy((char*)dst + a, (const char*)src + a, b - a);
   });
@@ -442,28 +442,50 @@ int BaGraph::finalize() {
   {
     const char* env = std::getenv("VDO_BA_LAYOUT");
     if (env && std::string(env) == "chunked") tiled = false;
-    Tile cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    // a tile also meets at most 255 distinct cameras (edges address them by an 8-bit slot): cam_tile[c] = serial of the tile that saw camera c last
-    std::vector<int> cam_tile(C, -1), fresh;
-    int tile_serial = 0, ncam_cur = 0;
-    auto close = [&](int t) {
-      if (cur.t1 > cur.t0) tiles.push_back(cur);
-      cur.t0 = cur.t1 = t; cur.k0 = cur.k1 = tk_begin[t]; cur.e0 = cur.e1 = lm_begin[tk_begin[t]];
-      ++tile_serial; ncam_cur = 0;
+    // Greedy packing of whole tracklets into tiles, inside FIXED segments of the tracklet order (their number depends on the graph only, so
+    // the layout is the same for any thread count); a tile never spans two segments, hence the segments pack in parallel.  A tile also meets
+    // at most 255 distinct cameras (edges address them by an 8-bit slot): cam_tile[c] = serial of the tile that saw camera c last.
+    const int nseg_st = std::max(1, std::min(48, Tstat / 8192)), nseg_ch = std::max(1, std::min(16, (T - Tstat) / 2048));
+    struct SegOut { std::vector<Tile> tiles; int bad = 0; };
+    std::vector<SegOut> segs((size_t)nseg_st + nseg_ch);
+    auto pack = [&](int t_lo, int t_hi, SegOut& out) {
+      if (t_lo >= t_hi) return;
+      Tile cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      std::vector<int> cam_tile(C, -1), fresh;
+      int tile_serial = 0, ncam_cur = 0;
+      auto close = [&](int t) {
+        if (cur.t1 > cur.t0) out.tiles.push_back(cur);
+        cur.t0 = cur.t1 = t; cur.k0 = cur.k1 = tk_begin[t]; cur.e0 = cur.e1 = lm_begin[tk_begin[t]];
+        ++tile_serial; ncam_cur = 0;
+      };
+      close(t_lo);
+      for (int t = t_lo; t < t_hi; ++t) {
+        const int nl = tk_begin[t + 1] - tk_begin[t], ea = lm_begin[tk_begin[t]], eb = lm_begin[tk_begin[t + 1]], ne = eb - ea;
+        if (nl > VDO_TILE_L || ne > VDO_TILE_E) { out.bad = 1; return; }
+        auto count_fresh = [&]() { fresh.clear(); for (int e = ea; e < eb; ++e) if (cam_tile[lm_cam[e]] != tile_serial) { cam_tile[lm_cam[e]] = tile_serial; fresh.push_back(lm_cam[e]); } };
+        count_fresh();
+        if ((cur.k1 - cur.k0) + nl > VDO_TILE_L || (cur.e1 - cur.e0) + ne > VDO_TILE_E || ncam_cur + (int)fresh.size() > 255) { close(t); count_fresh(); }
+        if ((int)fresh.size() > 255) { out.bad = 1; return; }                 // one tracklet seen by more than 255 cameras
+        ncam_cur += (int)fresh.size();
+        cur.t1 = t + 1; cur.k1 = tk_begin[t + 1]; cur.e1 = eb;
+      }
+      if (cur.t1 > cur.t0) out.tiles.push_back(cur);
     };
-    for (int t = 0; t < T && tiled; ++t) {
-      if (t == Tstat) { close(t); n_tiles_stat = (int)tiles.size(); }
-      const int nl = tk_begin[t + 1] - tk_begin[t], ea = lm_begin[tk_begin[t]], eb = lm_begin[tk_begin[t + 1]], ne = eb - ea;
-      if (nl > VDO_TILE_L || ne > VDO_TILE_E) { tiled = false; break; }
-      auto count_fresh = [&]() { fresh.clear(); for (int e = ea; e < eb; ++e) if (cam_tile[lm_cam[e]] != tile_serial) { cam_tile[lm_cam[e]] = tile_serial; fresh.push_back(lm_cam[e]); } };
-      count_fresh();
-      if ((cur.k1 - cur.k0) + nl > VDO_TILE_L || (cur.e1 - cur.e0) + ne > VDO_TILE_E || ncam_cur + (int)fresh.size() > 255) { close(t); count_fresh(); }
-      if ((int)fresh.size() > 255) { tiled = false; break; }                 // one tracklet seen by more than 255 cameras
-      ncam_cur += (int)fresh.size();
-      cur.t1 = t + 1; cur.k1 = tk_begin[t + 1]; cur.e1 = eb;
+    if (tiled) {
+      const int nseg = nseg_st + nseg_ch;
+      parallel_for(std::min(NT, nseg), [&](int w, int n) {
+        for (int sg = w; sg < nseg; sg += n) {
+          if (sg < nseg_st) pack((int)((int64_t)Tstat * sg / nseg_st), (int)((int64_t)Tstat * (sg + 1) / nseg_st), segs[sg]);
+          else { const int c = sg - nseg_st, Tc = T - Tstat; pack(Tstat + (int)((int64_t)Tc * c / nseg_ch), Tstat + (int)((int64_t)Tc * (c + 1) / nseg_ch), segs[sg]); }
+        }
+      });
+      for (int sg = 0; sg < nseg && tiled; ++sg) {
+        if (segs[sg].bad) tiled = false;
+        if (sg == nseg_st) n_tiles_stat = (int)tiles.size();
+        tiles.insert(tiles.end(), segs[sg].tiles.begin(), segs[sg].tiles.end());
+      }
+      if (!tiled) tiles.clear();
     }
-    if (tiled) { if (cur.t1 > cur.t0) tiles.push_back(cur); if (Tstat == T) n_tiles_stat = (int)tiles.size(); }
-    else tiles.clear();
   }
   std::vector<int> vm_begin(C + 1, 0), vm_pt;
   std::vector<double> vm_z;
