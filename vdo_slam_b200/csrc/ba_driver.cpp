@@ -752,7 +752,7 @@ int BaGraph::finalize() {
     const bool want = !(env && std::string(env) == "0");
     if (want && tiled && world == 1 && Tstat == T && 6 * C <= be_->dense_capacity()) d.Sdense = dalloc<double>((size_t)36 * C * C + 6 * (size_t)C + 8);
   }
-  if (tiled && !d.Sdense && Tstat > 0 && be_->band_max_width() > 0) {
+  if (tiled && Tstat > 0 && be_->band_max_width() > 0) {
     // Explicit static block of the reduced matrix (banded in the se3 numbering): possible when every static landmark lists its
     // observing vertices in strictly increasing order within a window of band_max_width() consecutive vertex numbers (tracks over
     // consecutive frames).  Otherwise the matrix-free static tile kernel stays in the PCG.

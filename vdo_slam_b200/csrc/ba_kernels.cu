@@ -912,6 +912,61 @@ __global__ void __launch_bounds__(128) k_dense_schur(BaDev d, int n) {
     }
   }
 }
+// S += the static Schur term from the band (see k_band_form / k_band_mul): block (row vertex b = a + k, column vertex a) = Y_b Kc X_a with
+//   X_a = [[-R, -2 [t]x R], [0, R]]  (local increment -> the world-frame vector vw of body_vertex_transform),
+//   Kc  = [[M0 I, 2 [M1]x], [2 [M1]x, 4 (M2 - tr(M2) I)]]  (the band product, sign folded in),
+//   Y_b = [[R^T, 0], [-2 R^T [t]x, R^T]]  (k_tile_finalize_schur2: torque moved to the vertex origin, rotated into the vertex frame).
+// One thread per (a, k); every block is written by exactly one thread (no atomics -- the thread-per-landmark k_dense_schur issued
+// ~600 fp64 atomics per landmark onto the 20 x 20 blocks: 0.4 ms per trial on the 20-camera window, mostly contention).
+__global__ void __launch_bounds__(128) k_dense_from_band(BaDev d, int n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = d.band_W;
+  if (idx >= d.band_n * W) return;
+  const int a = idx / W, k = idx - a * W, b = a + k;
+  if (b >= d.band_n) return;
+  const double* m = d.band + (size_t)idx * 10;
+  if (m[0] == 0.0) return;
+  const int va = d.band_v0 + a, vb = d.band_v0 + b;
+  const double* Ta = d.se3 + 12 * (size_t)va; const double* Tb = d.se3 + 12 * (size_t)vb;
+  auto skew = [](const double* t, double* K) { K[0] = 0; K[1] = -t[2]; K[2] = t[1]; K[3] = t[2]; K[4] = 0; K[5] = -t[0]; K[6] = -t[1]; K[7] = t[0]; K[8] = 0; };
+  double X[36], Kc[36], Z[36];
+  {   // X_a
+    double tx[9]; skew(Ta + 9, tx);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        const double txr = tx[3 * r] * Ta[c] + tx[3 * r + 1] * Ta[3 + c] + tx[3 * r + 2] * Ta[6 + c];     // ([t]x R)[r][c]
+        X[6 * r + c] = -Ta[3 * r + c]; X[6 * r + 3 + c] = -2.0 * txr;
+        X[6 * (r + 3) + c] = 0.0; X[6 * (r + 3) + 3 + c] = Ta[3 * r + c];
+      }
+  }
+  {   // Kc
+    const double m1[3] = {m[1], m[2], m[3]};
+    double m1x[9]; skew(m1, m1x);
+    const double M2[9] = {m[4], m[5], m[6], m[5], m[7], m[8], m[6], m[8], m[9]};
+    const double tr = m[4] + m[7] + m[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        Kc[6 * r + c] = (r == c) ? m[0] : 0.0; Kc[6 * r + 3 + c] = 2.0 * m1x[3 * r + c];
+        Kc[6 * (r + 3) + c] = 2.0 * m1x[3 * r + c]; Kc[6 * (r + 3) + 3 + c] = 4.0 * (M2[3 * r + c] - (r == c ? tr : 0.0));
+      }
+  }
+  mat6_mul(Kc, X, Z);
+  double Y[36];
+  {   // Y_b
+    double tx[9]; skew(Tb + 9, tx);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        const double rtx = Tb[r] * tx[c] + Tb[3 + r] * tx[3 + c] + Tb[6 + r] * tx[6 + c];                   // (R^T [t]x)[r][c]
+        Y[6 * r + c] = Tb[3 * c + r]; Y[6 * r + 3 + c] = 0.0;
+        Y[6 * (r + 3) + c] = -2.0 * rtx; Y[6 * (r + 3) + 3 + c] = Tb[3 * c + r];
+      }
+  }
+  double B[36];
+  mat6_mul(Y, Z, B);
+  double* S = d.Sdense;
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) S[(size_t)(6 * vb + r) * n + 6 * va + c] += B[6 * r + c];
+}
 // One CTA: blocked right-looking Cholesky of the lower triangle of S in shared memory (8-column panels; the trailing update
 // A[i][j] -= L[i][k] L[j][k]^T over 8x8 tiles is two mma.sync.m8n8k4.f64 per tile), then the two triangular solves.  n <= DENSE_MAX.
 constexpr int DENSE_MAX = 168;
@@ -1418,7 +1473,15 @@ struct CudaBackend : BaBackend {
     const int n = 6 * d.C, npad = (n + 7) & ~7;
     LAUNCH(k_dense_init, nblk(n * n, 128), 128, d, lambda, n);
     LAUNCH(k_dense_se3_edges, nblk(d.Ese, 64), 64, d, n);
-    LAUNCH(k_dense_schur, nblk(d.P, 128), 128, d, n);
+    if (d.band) {
+      // static Schur term from the band moments (one writer per block), right-hand side through the mode-0 tile kernel + finalize
+      band_form(d);
+      LAUNCH(k_dense_from_band, nblk(d.band_n * d.band_W, 128), 128, d, n);
+      tile_schur(d, 0, -1, st);
+      LAUNCH(k_tile_finalize_schur2, nblk(d.C, 128), 128, d, -1.0, d.Sdense + (size_t)n * n, 0, (const double*)nullptr);
+    } else {
+      LAUNCH(k_dense_schur, nblk(d.P, 128), 128, d, n);
+    }
     const size_t smem = sizeof(double) * (size_t)npad * (npad + 1);
     k_dense_chol<<<1, 256, smem, st>>>(d, n); ++n_launch;
     double status = 0.0;

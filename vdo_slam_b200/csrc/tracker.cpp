@@ -9,6 +9,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -728,7 +729,11 @@ int build_graph(vdo_tracker* t, bool full, GraphArrays& G) {
 extern "C" int vdo_tracker_batch_optimize(vdo_tracker* t, int mode, const vdo_lm_options* opt, vdo_lm_stats* stats, int* info) {
   if (!t || (mode != 0 && mode != 1)) return VDO_ERR_ARG;
   GraphArrays G;
+  const bool prof = std::getenv("VDO_PROFILE") != nullptr;
+  const auto tp0 = std::chrono::steady_clock::now();
+  auto lap_ms = [&](const std::chrono::steady_clock::time_point& a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
   TK(build_graph(t, mode == 1, G));
+  const double ms_build = lap_ms(tp0);
   const int ns = (int)G.se3.size() / 12, np = (int)G.pt.size() / 3;
   if (info) { info[0] = ns; info[1] = np; info[2] = (int)G.prior_v.size(); info[3] = (int)G.se3e_w.size(); info[4] = (int)G.obs_w.size(); info[5] = (int)G.ter_w.size(); }
   vdo_graph* g = nullptr;
@@ -739,12 +744,17 @@ extern "C" int vdo_tracker_batch_optimize(vdo_tracker* t, int mode, const vdo_lm
   if (rc == VDO_OK && !G.obs_w.empty()) rc = vdo_graph_add_edges_se3_pointxyz(g, (int)G.obs_w.size(), G.obs_cp.data(), G.obs_z.data(), G.obs_w.data(), G.obs_delta.data());
   if (rc == VDO_OK && !G.ter_w.empty()) rc = vdo_graph_add_edges_landmark_motion(g, (int)G.ter_w.size(), G.ter_pph.data(), G.ter_w.data(), G.ter_delta.data());
   if (rc == VDO_OK) rc = vdo_graph_finalize(g);
+  const double ms_ingest = lap_ms(tp0) - ms_build;
   vdo_lm_options o;
   if (opt) o = *opt; else { vdo_lm_options_default(&o); o.max_iterations = G.max_iters; o.gain_threshold = G.gain; }
-  if (rc == VDO_OK) rc = vdo_graph_optimize(g, &o, stats, nullptr);
+  vdo_lm_stats st_local;
+  if (rc == VDO_OK) rc = vdo_graph_optimize(g, &o, stats ? stats : &st_local, nullptr);
+  const double ms_opt = lap_ms(tp0) - ms_build - ms_ingest;
   std::vector<double> se3(12 * (size_t)ns + 12), pt(3 * (size_t)np + 3);
   if (rc == VDO_OK) rc = vdo_graph_get_vertices(g, se3.data(), pt.data());
   vdo_graph_destroy(g);
+  if (prof) std::fprintf(stderr, "[vdo_b200] batch_optimize mode %d: %d se3, %d points, %d obs | build %.2f ms | ingest %.2f | optimise %.2f (%d LM it) | read-back+free %.2f\n", mode, ns, np,
+                         (int)G.obs_w.size(), ms_build, ms_ingest, ms_opt, (stats ? stats : &st_local)->iterations, lap_ms(tp0) - ms_build - ms_ingest - ms_opt);
   if (rc != VDO_OK) { t->err = std::string("batch optimisation failed: ") + vdo_last_error(t->ctx); return rc; }
   MapSlice& m = t->map;
   const int N = (int)m.featSta.size();
