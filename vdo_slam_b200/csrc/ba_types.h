@@ -23,6 +23,8 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #define VDO_CHUNK 512
@@ -135,6 +137,7 @@ struct HostArena {
     bytes = (bytes + 255) & ~(size_t)255;
     for (Block& b : blocks) if (b.cap - b.used >= bytes) { void* r = b.p + b.used; b.used += bytes; return r; }
     const size_t cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+    if (std::getenv("VDO_ARENA_TRACE")) std::fprintf(stderr, "[vdo_b200] staging arena: new block of %zu MB for a request of %zu bytes (%zu blocks, users %d)\n", cap >> 20, bytes, blocks.size(), users);
     Block nb{raw_alloc(cap), cap, bytes};
     blocks.push_back(nb);
     return nb.p;
