@@ -346,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
                           "step": f"one full LM solve (<= {LM_MAX_ITERS} iterations, gain < {LM_GAIN}) from the same initial estimates",
                           "l2": "device-resident graph (%.0f MB) exceeds the 126 MB L2 and every kernel streams > L2-size of it; no explicit flush" % (info["device_bytes"] / 1e6),
                           "layout": "tiled (one CTA per <=256-landmark / <=768-edge tile, TMA bulk staging)",
-                          "multi_gpu": (f"tracklets sharded round-robin over {world} ranks, se3 state replicated, NCCL all-reduce of H_pp/b_p per linearisation, of S*p per PCG iteration, of chi2/scale per LM trial" if world > 1 else "single GPU")},
+                          "multi_gpu": (f"tracklets sharded round-robin over {world} ranks, se3 state replicated, preconditioner sharded by se3 path; per PCG iteration S*p and z are exchanged through peer memory (CUDA IPC, NVLink stores + flags) inside the captured CUDA graph (NCCL all-reduce fallback); NCCL all-reduce of H_pp/b_p per linearisation, of the preconditioner diagonal / rhs / chi2 per LM trial" if world > 1 else "single GPU")},
                "lm_iters_per_step": iters / args.steps, "pcg_iters_per_lm_iter": pcg / max(iters, 1),
                "ms_linearize_per_lm_iter": lin_ms_per_iter, "ms_solve_per_lm_iter": ms_solve / max(iters, 1),
                "clocks": clocks, "gpu_launches": launches, "parity": parity,
