@@ -114,10 +114,60 @@ struct EmulBackend : BaBackend {
     }
     for (int v = 0; v < d.C; ++v) tile_finalize_precond(d, v);
   }
+  // ---- banded static block of the reduced matrix, restated serially: the moments per (vertex, offset) over the static landmarks,
+  //      and the product in this backend's accumulator convention (acc6 = 6 per vertex: force, torque about the VERTEX origin) ----
+  int band_max_width() const override { return 32; }
+  void band_form(BaDev& d) override {
+    if (!d.band) return;
+    ++n_launch;
+    const int W = d.band_W;
+    for (size_t i = 0; i < (size_t)d.band_n * W * 10; ++i) d.band[i] = 0.0;
+    for (int k = 0; k < d.Tstat; ++k) {
+      const int e0 = d.lm_obs_begin[k], e1 = d.lm_obs_begin[k + 1];
+      const double is = 1.0 / d.pt_s[k];
+      const double* p = d.pt + 3 * (size_t)k;
+      const double m[10] = {1.0, p[0], p[1], p[2], p[0] * p[0], p[0] * p[1], p[0] * p[2], p[1] * p[1], p[1] * p[2], p[2] * p[2]};
+      for (int i = e0; i < e1; ++i)
+        for (int j = i; j < e1; ++j) {
+          const double g = d.lm_omega[i] * d.lm_omega[j] * is;
+          double* dst = d.band + ((size_t)(d.lm_cam[i] - d.band_v0) * W + (d.lm_cam[j] - d.lm_cam[i])) * 10;
+          for (int q = 0; q < 10; ++q) dst[q] += g * m[q];
+        }
+    }
+  }
+  void band_mul(BaDev& d) {
+    const int W = d.band_W;
+    for (int a = 0; a < d.band_n; ++a) {
+      double F[3] = {0, 0, 0}, M[3] = {0, 0, 0};
+      for (int kk = -(W - 1); kk <= W - 1; ++kk) {
+        const int b = a + kk;
+        if (b < 0 || b >= d.band_n) continue;
+        const double* m = d.band + (kk >= 0 ? ((size_t)a * W + kk) : ((size_t)b * W - kk)) * 10;
+        if (m[0] == 0.0) continue;
+        const double* w = d.vw + 6 * (size_t)(d.band_v0 + b);
+        const double m1[3] = {m[1], m[2], m[3]};
+        double c1[3], c2[3];
+        cross3(m1, w + 3, c1); cross3(m1, w, c2);
+        const double tr = m[4] + m[7] + m[9];
+        const double q0 = m[4] * w[3] + m[5] * w[4] + m[6] * w[5] - tr * w[3], q1 = m[5] * w[3] + m[7] * w[4] + m[8] * w[5] - tr * w[4],
+                     q2 = m[6] * w[3] + m[8] * w[4] + m[9] * w[5] - tr * w[5];
+        F[0] -= m[0] * w[0] + 2 * c1[0]; F[1] -= m[0] * w[1] + 2 * c1[1]; F[2] -= m[0] * w[2] + 2 * c1[2];
+        M[0] -= 2 * (c2[0] + 2 * q0); M[1] -= 2 * (c2[1] + 2 * q1); M[2] -= 2 * (c2[2] + 2 * q2);
+      }
+      const int v = d.band_v0 + a;
+      const double* t = d.se3 + 12 * (size_t)v + 9;
+      double txf[3]; cross3(t, F, txf);
+      double* acc = d.acc6 + 6 * (size_t)v;
+      acc[0] += F[0]; acc[1] += F[1]; acc[2] += F[2];
+      acc[3] += M[0] - 2 * txf[0]; acc[4] += M[1] - 2 * txf[1]; acc[5] += M[2] - 2 * txf[2];       // torque moved from the world origin to the vertex origin
+    }
+  }
   template <int MODE> void tile_schur(BaDev& d) {
+    if (MODE == 1 && d.band) band_mul(d);
     for (int ti = 0; ti < d.n_tiles; ++ti) {
       const Tile tl = d.tiles[ti];
       const bool chains = ti >= d.n_tiles_stat;
+      if (MODE == 1 && d.band && !chains) continue;           // the static tiles' product comes from the band
       const int nl = tl.k1 - tl.k0, ne = tl.e1 - tl.e0;
       TileSm& sm = sb.bind(d, tl, false, false);
       if (!chains) {

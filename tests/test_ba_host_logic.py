@@ -187,3 +187,36 @@ def test_ingest_is_independent_of_the_host_thread_count(ectx, monkeypatch):
         for x, y in zip(lin, res[0][0]):
             assert np.array_equal(x, y)
         assert np.array_equal(v[0], res[0][1][0]) and np.array_equal(v[1], res[0][1][1])
+
+
+def test_banded_static_block_decision_and_result(ectx, monkeypatch):
+    """Driver logic of the explicit banded static block on the emulated backend, which restates the band formation and the band
+    product serially: it is chosen exactly when every static landmark lists its observing vertices in increasing order inside a window of 32
+    vertex numbers, and the LM run is the same with and without it (and equal to the oracle's)."""
+    g = make_batch_graph(n_frames=24, n_objects=2, n_static=500, n_dynamic=120, seed=11)
+    ro = po.ba_optimize(g)
+    G = capi.BatchGraph(ectx, g)
+    si = G.solver_info()
+    assert si["tiled"] == 1 and 0 < si["band_width"] <= 32 and si["band_rows"] >= 24 and si["dense"] == 0
+    r = G.optimize(pcg_rel_tol=1e-10)
+    a, b = G.vertices()
+    assert r["iterations"] == ro["iters"] and np.abs(a - ro["se3"]).max() < 1e-7 and np.abs(b - ro["pt"]).max() < 1e-7
+    # edge list reversed: a landmark's vertices now DEcrease along its edge list -> refused, matrix-free product, same answer
+    h = dict(g)
+    for k in ("obs_cp", "obs_z", "obs_w", "obs_delta"):
+        h[k] = np.ascontiguousarray(g[k][::-1])
+    H = capi.BatchGraph(ectx, h)
+    assert H.solver_info()["band_width"] == 0
+    r2 = H.optimize(pcg_rel_tol=1e-10)
+    c, d = H.vertices()
+    assert r2["iterations"] == ro["iters"] and np.abs(a - c).max() < 1e-7 and np.abs(b - d).max() < 1e-7
+    # a landmark seen by two cameras 40 frames apart: wider than the widest band
+    w = make_batch_graph(n_frames=48, n_objects=0, n_static=200, n_dynamic=0, seed=12)
+    w = dict(w)
+    cp = w["obs_cp"].copy()
+    first = np.flatnonzero(cp[:, 1] == cp[0, 1])
+    cp[first[0], 0] = 0; cp[first[-1], 0] = 45                  # (vertex numbers of the camera path follow the frame order)
+    w["obs_cp"] = cp
+    assert capi.BatchGraph(ectx, w).solver_info()["band_width"] == 0
+    monkeypatch.setenv("VDO_BA_BAND", "0")
+    assert capi.BatchGraph(ectx, g).solver_info()["band_width"] == 0
