@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(128) k_hpp_mul(BaDev d, const double* __restri
 // CL = CTAs per cluster: PCR_CL for long paths, 1 (plain CTA, the cluster barrier degenerates to a CTA barrier) for paths of at most
 // PCR_SHORT vertices -- most paths are short (objects seen for a few frames, single motion vertices) and a cluster of 8 CTAs each would only
 // multiply the number of waves the launch needs.  path0: position of the launch's first path in own_paths (long paths first).
+
 // In-place Gauss-Jordan inverse of an SPD 6x6 whose row i lives in lane i of an aligned 8-lane group (lanes 6, 7 of the group and groups
 // without a vertex carry the identity; every lane of the warp executes the shuffles).  The pivots are those of the LDL^T factorisation:
 // a non-positive (or non-finite) one reports "not SPD" exactly where the Cholesky of body_pcr_invert does.

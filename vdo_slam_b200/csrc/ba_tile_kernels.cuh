@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(VDO_TILE_L) k_tile_schur(BaDev d, int tile0) {
 //    bulk copies are in flight; edges address them by an 8-bit slot (lm_cslot / tk_hslot, 1 B instead of a 4 B vertex index),
 //    so the landmark loop has no global gather on its critical path.
 //  * the vertex side is ONE THREAD PER (RUN, COMPONENT): the tile's edges in vertex-sorted order are cut into runs of one
-//    vertex and at most VDO_SEG2 = 16 entries (osegs2 / tsegs2); a thread adds its component over its run from shared memory
+//    vertex and at most VDO_SEG2 = 15 entries (osegs2 / tsegs2; odd, so that threads walking consecutive full runs hit distinct banks); a thread adds its component over its run from shared memory
 //    and issues one fp64 atomic.  No shuffles, no selects, no idle lanes on short runs (chain tiles average 8 entries per
 //    vertex: the warp-per-segment scheme of k_tile_schur ran them at 12 % lane utilisation).
 //  * chains: the two scalar recurrences of the tracklet solve (forward y_j = c_j + f_{j-1} y_{j-1}, backward
