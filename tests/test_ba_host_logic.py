@@ -220,3 +220,30 @@ def test_banded_static_block_decision_and_result(ectx, monkeypatch):
     assert capi.BatchGraph(ectx, w).solver_info()["band_width"] == 0
     monkeypatch.setenv("VDO_BA_BAND", "0")
     assert capi.BatchGraph(ectx, g).solver_info()["band_width"] == 0
+
+
+def test_two_contexts_ingest_concurrently(ectx):
+    """The ingest's worker pool is process-wide and its sections are serialised: two host threads building graphs on two contexts at the
+    same time (ctypes releases the GIL) must get the layouts and results of the serial runs."""
+    import threading
+    g = make_batch_graph(n_frames=30, n_objects=2, n_static=4000, n_dynamic=600, seed=5)
+    ref = capi.BatchGraph(ectx, g)
+    r0 = ref.optimize(max_iterations=3, gain_threshold=0)
+    a0, b0 = ref.vertices()
+    ctxs = [capi.Context(0, lib_path=EMUL) for _ in range(2)]
+    out = [None, None]
+
+    def work(i):
+        for _ in range(3):
+            G = capi.BatchGraph(ctxs[i], g)
+            r = G.optimize(max_iterations=3, gain_threshold=0)
+            out[i] = (r["chi2"].copy(), *G.vertices())
+            G.close()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for i in range(2):
+        assert out[i] is not None
+        np.testing.assert_array_equal(out[i][0], r0["chi2"])
+        np.testing.assert_array_equal(out[i][1], a0); np.testing.assert_array_equal(out[i][2], b0)
